@@ -1,0 +1,155 @@
+/*
+ * ib200.h -- C ABI of libib200.so: the B200 (sm_100a) implementation of INTREPPPID's sequence-encoder hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain structs, raw DEVICE pointers, sizes
+ * and a cudaStream_t (as void*); no C++ or torch types cross it.  The caller (PyTorch caching allocator) owns every
+ * buffer, including the workspace that carries saved activations from *_fwd to *_bwd.  Launchers are stateless and
+ * re-entrant, enqueue on the given stream only, never allocate, never synchronise.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/intrepppid/):
+ *   ib200_encoder_fwd / _bwd    encoders/awd_lstm.py:147-155 (AWDLSTMEncoder.forward: truncation + embedding dropout)
+ *                               utils/embedding_do.py:20-44  (embedding_dropout)
+ *                               utils/weightdrop.py:65-111   (WeightDrop._setweights + forward on nn.LSTM)
+ *                               encoders/awd_lstm.py:51-56   (AWDLSTM.forward: 2nd truncation + nn.LSTM -> _VF.lstm)
+ *   ib200_pool_fc_fwd / _bwd    encoders/awd_lstm.py:58-71   (bi_reduce on h_n[-2:], fc Linear)
+ *   ib200_loss_head_fwd / _bwd  e2e/e2e_triplet.py:113-136   (TripletE2ENet.step: triplet projection, TripletMarginLoss,
+ *                               classifier/head/mlp.py:35-68  MLPHead, BCEWithLogitsLoss, beta mix)
+ *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
+ *
+ * Conventions
+ *   - weights are in PyTorch layout: weight_ih [4H,in], weight_hh [4H,H], gate row-blocks in order (i,f,g,o); two biases.
+ *   - E == H (nn.LSTM(embedding_size, embedding_size, ...), awd_lstm.py:35-41).  Supported H: 32, 64.
+ *   - "group" = one encoder call of the reference.  A training step fuses G=5 calls (anchor, positive, negative, p1, p2 --
+ *     e2e_triplet.py:116-129) into one launch set; every group has its own masks and its own truncation lengths.
+ *   - masks are INPUTS (nullptr = no drop).  emb_row_scale[g][v] = keep/(1-p) per vocabulary row; whh_l0_mask[g] = scaled
+ *     DropConnect mask for weight_hh_l0 (forward direction of layer 0 only).
+ *   - return value: 0 ok; <0 invalid argument (IB200_E_*); >0 a cudaError_t.  ib200_last_error() gives text (thread-local).
+ */
+#ifndef IB200_H_
+#define IB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IB200_VERSION 100
+#define IB200_MAX_LAYERS 4
+
+enum { IB200_REDUCE_LAST = 0, IB200_REDUCE_MEAN = 1, IB200_REDUCE_MAX = 2 };
+/* IB200_PREC_FP32: bf16 hi/lo split operands (3 tensor-core MMAs per product, ~2^-16 operand error), fp32 state, exact-ish
+ * exp/rcp activations, fp32 activation storage.  IB200_PREC_BF16: single bf16 MMA, tanh.approx, bf16 activation storage. */
+enum { IB200_PREC_FP32 = 0, IB200_PREC_BF16 = 1 };
+enum {
+  IB200_E_NULL = -1, IB200_E_SHAPE = -2, IB200_E_UNSUPPORTED = -3, IB200_E_WORKSPACE = -4, IB200_E_ALIGN = -5
+};
+
+typedef struct ib200_cfg {
+  int32_t G;          /* groups (encoder calls) fused in this launch set */
+  int32_t B;          /* sequences per group */
+  int32_t T;          /* token row width == trunc_len */
+  int32_t V;          /* vocabulary rows */
+  int32_t H;          /* embedding size == LSTM hidden size */
+  int32_t L;          /* rnn_num_layers (1..IB200_MAX_LAYERS) */
+  int32_t bi_reduce;  /* IB200_REDUCE_* ("concat" is not functional in the reference either) */
+  int32_t precision;  /* IB200_PREC_* */
+  int32_t training;   /* 1: keep activations for ib200_encoder_bwd in the workspace */
+  int32_t reserved;
+} ib200_cfg;
+
+/* Parameters of the encoder, PyTorch layout (state_dict names in comments; d=0 forward, d=1 "_reverse"). */
+typedef struct ib200_encoder_params {
+  const float* emb;                         /* encoder.embedder.weight                [V,H] */
+  const float* w_ih[IB200_MAX_LAYERS][2];   /* encoder.encoder.rnn.weight_ih_l{l}{d}  [4H,H] (l=0) / [4H,2H] */
+  const float* w_hh[IB200_MAX_LAYERS][2];   /* ...weight_hh_l{l}{d} ([0][0] = weight_hh_l0_raw)  [4H,H] */
+  const float* b_ih[IB200_MAX_LAYERS][2];   /* ...bias_ih_l{l}{d}  [4H] */
+  const float* b_hh[IB200_MAX_LAYERS][2];   /* ...bias_hh_l{l}{d}  [4H] */
+} ib200_encoder_params;
+
+/* Gradients, same shapes; every non-null tensor is OVERWRITTEN (not accumulated).  Dead tensors (top-layer forward
+ * chain under bi_reduce=last) are written as exact zeros. */
+typedef struct ib200_encoder_grads {
+  float* emb;
+  float* w_ih[IB200_MAX_LAYERS][2];
+  float* w_hh[IB200_MAX_LAYERS][2];
+  float* b_ih[IB200_MAX_LAYERS][2];
+  float* b_hh[IB200_MAX_LAYERS][2];
+} ib200_encoder_grads;
+
+int ib200_version(void);
+const char* ib200_last_error(void);
+
+/* Bytes of workspace ib200_encoder_fwd needs for cfg (includes everything _bwd needs when cfg.training). 0 on bad cfg. */
+size_t ib200_workspace_bytes(const ib200_cfg* cfg);
+
+/*
+ * Encoder forward for G groups.
+ *   tokens          int64 [G*B, T] row-major, pad id 0, ids in [0,V)                         (data/ppi_oma.py:388-390)
+ *   emb_row_scale   float [G,V] or NULL
+ *   whh_l0_mask     float [G,4H,H] or NULL
+ *   lengths_out     int32 [2,G]: row 0 = T1 (awd_lstm.py:149-150), row 1 = T_eff (awd_lstm.py:53-54); exact integers.
+ *                   A group with T_eff==0 is NOT run (the reference raises there, Q13); callers check lengths_out.
+ *   hn_top          float [2, G*B, H]: final hidden state of the top layer, [0]=forward dir, [1]=reverse dir.  Under
+ *                   bi_reduce=last only [1] is produced ([0] is zero-filled: the dead chain is skipped, Q16).
+ */
+int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* params,
+                      const float* emb_row_scale, const float* whh_l0_mask, int32_t* lengths_out, float* hn_top,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Encoder backward.  `workspace` is the buffer the matching _fwd call filled (cfg.training must have been 1).
+ *   d_hn_top        float [2, G*B, H] gradient w.r.t. hn_top (entries of a dead direction are ignored)
+ *   grads           overwritten; w_hh[0][0] receives the gradient of the RAW tensor (mask applied per group).
+ */
+int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* params, const float* emb_row_scale,
+                      const float* whh_l0_mask, const float* d_hn_top, const ib200_encoder_grads* grads,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* bi_reduce + fc.  hn_top [2,N,H] -> z [N,H].  pooled_out [N,H] and (max only) argmax_out uint8 [N,H] are saved for bwd. */
+int ib200_pool_fc_fwd(int32_t N, int32_t H, int32_t bi_reduce, const float* hn_top, const float* fc_w, const float* fc_b,
+                      float* z, float* pooled_out, uint8_t* argmax_out, void* stream);
+/* dz [N,H] -> d_hn_top [2,N,H], d_fc_w [H,H], d_fc_b [H] (all overwritten). */
+int ib200_pool_fc_bwd(int32_t N, int32_t H, int32_t bi_reduce, const float* dz, const float* pooled, const uint8_t* argmax,
+                      const float* fc_w, float* d_hn_top, float* d_fc_w, float* d_fc_b, void* stream);
+
+/* Triplet + head + BCE.  z is [5,B,H] in group order (anchor, positive, negative, p1, p2). */
+typedef struct ib200_head_params {
+  const float* fc1_w; /* head.classify.fc1.module.weight_raw [H/2,H] */
+  const float* fc1_b; /* [H/2] */
+  const float* fc2_w; /* head.classify.fc2.module.weight_raw [1,H/2] */
+  const float* fc2_b; /* [1] */
+  const float* proj_w; /* triplet_projection.1.weight [H,H] or NULL (use_projection=False) */
+  const float* proj_b; /* [H] or NULL */
+} ib200_head_params;
+typedef struct ib200_head_grads {
+  float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *proj_w, *proj_b;
+} ib200_head_grads;
+typedef struct ib200_head_masks { /* all already scaled by 1/(1-p); NULL = identity */
+  const float* fc1_w; /* [H/2,H] */
+  const float* do1;   /* [B,H/2] */
+  const float* do2;   /* [B,H/2] */
+  const float* fc2_w; /* [1,H/2] */
+} ib200_head_masks;
+
+/* losses_out float[3] = {loss, classifier_loss, triplet_loss}; y_hat_out float [B] logits.  y: int64 [B] labels. */
+int ib200_loss_head_fwd(int32_t B, int32_t H, float beta_classifier, const float* z, const int64_t* y,
+                        const ib200_head_params* params, const ib200_head_masks* masks, float* losses_out,
+                        float* y_hat_out, void* stream);
+/* d_loss: device scalar (upstream gradient of `loss`); d_y_hat: float [B] upstream gradient of the logits or NULL.
+ * dz_out [5,B,H] and grads are overwritten.  Recomputes the forward intermediates from z (they are tiny), so no
+ * workspace is carried.  (A stand-alone MLPHead backward is d_loss = 0 with d_y_hat given.) */
+int ib200_loss_head_bwd(int32_t B, int32_t H, float beta_classifier, const float* z, const int64_t* y,
+                        const ib200_head_params* params, const ib200_head_masks* masks, const float* d_loss,
+                        const float* d_y_hat, float* dz_out, const ib200_head_grads* grads, void* stream);
+
+/* Eval-mode head + sigmoid over pairs of cached embeddings: prob_out[p] = sigmoid(head(z[idx_a[p]], z[idx_b[p]])).
+ * idx_a/idx_b int32 [P]; if both NULL, P must equal M*(M+1)/2 and pairs are the upper triangle (i<=j) in row-major order. */
+int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a, const int32_t* idx_b, int64_t P,
+                     const ib200_head_params* params, float* prob_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IB200_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libib200.so (include/ib200.h).  There is NO fallback: if the CUDA library is missing or cannot be
+loaded, importing the compute path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libib200.so")
+
+MAX_LAYERS = 4
+REDUCE = {"last": 0, "mean": 1, "max": 2}
+PRECISION = {"fp32": 0, "bf16": 1}
+
+F = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("G", "B", "T", "V", "H", "L", "bi_reduce", "precision", "training", "reserved")]
+
+
+class EncoderParams(C.Structure):
+    _fields_ = [("emb", vp), ("w_ih", vp * 2 * MAX_LAYERS), ("w_hh", vp * 2 * MAX_LAYERS), ("b_ih", vp * 2 * MAX_LAYERS),
+                ("b_hh", vp * 2 * MAX_LAYERS)]
+
+
+class HeadParams(C.Structure):
+    _fields_ = [(n, vp) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b", "proj_w", "proj_b")]
+
+
+class HeadMasks(C.Structure):
+    _fields_ = [(n, vp) for n in ("fc1_w", "do1", "do2", "fc2_w")]
+
+
+EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_encoder_fwd", "ib200_encoder_bwd",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score")
+
+_lib = None
+
+
+class IB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IB200Error(f"{LIB_PATH} is missing: build it with `python -m intrepppid_b200.build` "
+                         "(intrepppid_b200 has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.ib200_version.restype = C.c_int
+    L.ib200_last_error.restype = C.c_char_p
+    L.ib200_workspace_bytes.restype = C.c_size_t
+    L.ib200_workspace_bytes.argtypes = [C.POINTER(Cfg)]
+    L.ib200_encoder_fwd.argtypes = [C.POINTER(Cfg), vp, C.POINTER(EncoderParams), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.ib200_encoder_bwd.argtypes = [C.POINTER(Cfg), C.POINTER(EncoderParams), vp, vp, vp, C.POINTER(EncoderParams), vp,
+                                    C.c_size_t, vp]
+    L.ib200_pool_fc_fwd.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
+    L.ib200_pool_fc_bwd.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ib200_loss_head_fwd.argtypes = [C.c_int32, C.c_int32, C.c_float, vp, vp, C.POINTER(HeadParams), C.POINTER(HeadMasks), vp,
+                                      vp, vp]
+    L.ib200_loss_head_bwd.argtypes = [C.c_int32, C.c_int32, C.c_float, vp, vp, C.POINTER(HeadParams), C.POINTER(HeadMasks), vp,
+                                      vp, vp, C.POINTER(HeadParams), vp]
+    L.ib200_pair_score.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.POINTER(HeadParams), vp, vp]
+    for name in EXPORTS:
+        if name not in ("ib200_version", "ib200_last_error", "ib200_workspace_bytes"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().ib200_last_error().decode("utf-8", "replace")
+        kind = "invalid argument" if status < 0 else "CUDA error"
+        raise IB200Error(f"{what}: {kind} {status}: {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

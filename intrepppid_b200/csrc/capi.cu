@@ -1,0 +1,322 @@
+// C ABI of libib200.so (see include/ib200.h): argument validation, workspace carve-up and the launch sequences.
+#include <algorithm>
+#include <cstdio>
+#include <string>
+
+#include "../../include/ib200.h"
+#include "kernels.h"
+#include "small.h"
+
+using namespace ib200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+#define CK(call, where)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+  } while (0)
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Workspace layout.  Everything the backward needs is inside, so the caller only keeps one buffer alive.
+struct Plan {
+  int G, B, T, V, H, L, N;
+  size_t R;  // token rows = N*T
+  bool train;
+  bool live[IB200_MAX_LAYERS][2];
+  size_t lens, tok32, table;
+  size_t wih_gi[IB200_MAX_LAYERS][2], b_gi[IB200_MAX_LAYERS][2], wihT_gi[IB200_MAX_LAYERS][2];
+  size_t Y[IB200_MAX_LAYERS];
+  size_t X[2];
+  size_t gates[IB200_MAX_LAYERS][2], cst[IB200_MAX_LAYERS][2];
+  size_t bwd_scratch;  // dY [R,2H] then dX0 [R,H]
+  size_t partial;
+  int ctas_per_group;
+  size_t total;
+};
+
+bool cfg_ok(const ib200_cfg* c) {
+  return c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64) && c->L >= 1 &&
+         c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1);
+}
+
+Plan make_plan(const ib200_cfg* c) {
+  Plan p{};
+  p.G = c->G; p.B = c->B; p.T = c->T; p.V = c->V; p.H = c->H; p.L = c->L;
+  p.N = c->G * c->B;
+  p.R = (size_t)p.N * p.T;
+  p.train = c->training != 0;
+  const int H = p.H;
+  for (int l = 0; l < p.L; ++l) {
+    p.live[l][0] = !(l == p.L - 1 && c->bi_reduce == IB200_REDUCE_LAST);  // dead chain under "last" 
+    p.live[l][1] = true;
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  p.lens = take(sizeof(int) * 2 * p.G);
+  p.tok32 = take(sizeof(int) * p.R);
+  p.table = take(sizeof(float) * (size_t)p.G * 2 * p.V * 4 * H);
+  for (int l = 0; l < p.L; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const size_t K = l == 0 ? H : 2 * H;
+      if (l > 0) {
+        p.wih_gi[l][d] = take(sizeof(float) * 4 * H * K);
+        p.b_gi[l][d] = take(sizeof(float) * 4 * H);
+      }
+      if (p.train) p.wihT_gi[l][d] = take(sizeof(float) * 4 * H * K);
+    }
+  for (int l = 0; l < p.L; ++l)
+    if (p.train || l < p.L - 1) p.Y[l] = take(sizeof(float) * p.R * 2 * H);
+  if (p.L > 1)
+    for (int d = 0; d < 2; ++d) p.X[d] = take(sizeof(float) * p.R * 4 * H);
+  if (p.train) {
+    for (int l = 0; l < p.L; ++l)
+      for (int d = 0; d < 2; ++d)
+        if (p.live[l][d]) {
+          p.gates[l][d] = take(sizeof(float) * p.R * 4 * H);
+          p.cst[l][d] = take(sizeof(float) * p.R * H);
+        }
+    p.bwd_scratch = p.L > 1 ? p.X[0] : take(sizeof(float) * p.R * 3 * H);  // X is dead once the forward is done
+    p.ctas_per_group = std::max(1, 148 / p.G);
+    p.partial = take(sizeof(float) * (size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 2 * H + 4 * H));
+  }
+  p.total = off;
+  return p;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
+
+}  // namespace
+
+extern "C" {
+
+int ib200_version(void) { return IB200_VERSION; }
+const char* ib200_last_error(void) { return g_err.c_str(); }
+
+size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
+  if (!cfg_ok(cfg)) return 0;
+  return make_plan(cfg).total;
+}
+
+int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
+                      const float* whh_l0_mask, int32_t* lengths_out, float* hn_top, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H must be 32 or 64, 1<=L<=4, bi_reduce in last/mean/max)");
+  if (!tokens || !P || !hn_top || !ws || !P->emb) return fail(IB200_E_NULL, "ib200_encoder_fwd: null pointer");
+  const Plan p = make_plan(cfg);
+  if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_fwd: workspace too small");
+  if (((uintptr_t)ws & 255) != 0) return fail(IB200_E_ALIGN, "ib200_encoder_fwd: workspace must be 256-byte aligned");
+  for (int l = 0; l < p.L; ++l)
+    for (int d = 0; d < 2; ++d)
+      if (!P->w_ih[l][d] || !P->w_hh[l][d] || !P->b_ih[l][d] || !P->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_fwd: null LSTM parameter");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = p.H, prec = cfg->precision;
+
+  LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens)};
+  CK(launch_lengths(la, st), "lengths");
+  if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
+
+  TableArgs ta{p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
+               {P->b_hh[0][0], P->b_hh[0][1]}, at<float>(ws, p.table)};
+  CK(launch_l0_table(ta, st), "l0 table");
+
+  for (int l = 0; l < p.L; ++l)
+    for (int d = 0; d < 2; ++d) {
+      if (!p.live[l][d]) continue;
+      const int K = l == 0 ? H : 2 * H;
+      float* w = l > 0 ? at<float>(ws, p.wih_gi[l][d]) : nullptr;
+      float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
+      float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
+      if (w || wT) CK(launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
+    }
+
+  if (!p.live[p.L - 1][0]) CK(launch_fill_zero(hn_top, (size_t)p.N * H, st), "hn zero");
+
+  for (int l = 0; l < p.L; ++l) {
+    const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
+    if (l > 0) {
+      for (int d = dir0; d < 2; ++d) {
+        GemmNTArgs ga{};
+        ga.G = p.G; ga.B = p.B; ga.Tmax = p.T; ga.lens = at<int>(ws, p.lens);
+        ga.nsrc = 1; ga.A[0] = at<float>(ws, p.Y[l - 1]); ga.lda = 2 * H; ga.K = 2 * H;
+        ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
+        ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
+        CK(launch_gemm_nt(ga, prec, st), "input projection gemm");
+      }
+    }
+    LstmFwdArgs fa{};
+    fa.G = p.G; fa.B = p.B; fa.Tmax = p.T; fa.V = p.V; fa.dir0 = dir0; fa.ndir = ndir;
+    fa.lens = at<int>(ws, p.lens);
+    if (l == 0) {
+      fa.tok = at<int>(ws, p.tok32);
+      fa.table = at<float>(ws, p.table);
+    } else {
+      fa.xproj[0] = at<float>(ws, p.X[0]);
+      fa.xproj[1] = at<float>(ws, p.X[1]);
+    }
+    fa.whh[0] = P->w_hh[l][0]; fa.whh[1] = P->w_hh[l][1];
+    fa.whh_mask = l == 0 ? whh_l0_mask : nullptr;
+    const bool need_y = p.train || l < p.L - 1;
+    fa.y = need_y ? at<float>(ws, p.Y[l]) : nullptr;
+    fa.y_stride = 2 * H;
+    for (int d = 0; d < 2; ++d) {
+      fa.gates[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.gates[l][d]) : nullptr;
+      fa.cstate[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.cst[l][d]) : nullptr;
+    }
+    fa.hn = l == p.L - 1 ? hn_top : nullptr;
+    CK(launch_lstm_fwd(fa, H, prec, st), "lstm fwd");
+  }
+  return 0;
+}
+
+int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const float* emb_row_scale, const float* whh_l0_mask,
+                      const float* d_hn_top, const ib200_encoder_grads* Gr, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg_ok(cfg) || !cfg->training) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_bwd: cfg must be the training cfg used for _fwd");
+  if (!P || !d_hn_top || !Gr || !ws) return fail(IB200_E_NULL, "ib200_encoder_bwd: null pointer");
+  const Plan p = make_plan(cfg);
+  if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_bwd: workspace too small");
+  for (int l = 0; l < p.L; ++l)
+    for (int d = 0; d < 2; ++d)
+      if (!Gr->w_ih[l][d] || !Gr->w_hh[l][d] || !Gr->b_ih[l][d] || !Gr->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_bwd: null gradient tensor");
+  if (!Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = p.H, prec = cfg->precision;
+  const int* lens = at<int>(ws, p.lens);
+  float* dY = at<float>(ws, p.bwd_scratch);
+  float* dX0 = dY + p.R * 2 * H;
+  float* partial = at<float>(ws, p.partial);
+
+  for (int l = p.L - 1; l >= 0; --l) {
+    const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
+    LstmBwdArgs ba{};
+    ba.G = p.G; ba.B = p.B; ba.Tmax = p.T; ba.dir0 = dir0; ba.ndir = ndir; ba.lens = lens;
+    ba.whh[0] = P->w_hh[l][0]; ba.whh[1] = P->w_hh[l][1];
+    ba.whh_mask = l == 0 ? whh_l0_mask : nullptr;
+    for (int d = 0; d < 2; ++d) {
+      ba.gates[d] = p.live[l][d] ? at<float>(ws, p.gates[l][d]) : nullptr;
+      ba.cstate[d] = p.live[l][d] ? at<float>(ws, p.cst[l][d]) : nullptr;
+    }
+    ba.dy = l == p.L - 1 ? nullptr : dY;
+    ba.dy_stride = 2 * H;
+    ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
+    CK(launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
+
+    // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
+    for (int d = 0; d < 2; ++d) {
+      const int K = l == 0 ? H : 2 * H;
+      if (!p.live[l][d]) {  // dead chain: exact zeros
+        CK(launch_fill_zero(Gr->w_ih[l][d], (size_t)4 * H * K, st), "zero");
+        CK(launch_fill_zero(Gr->w_hh[l][d], (size_t)4 * H * H, st), "zero");
+        CK(launch_fill_zero(Gr->b_ih[l][d], (size_t)4 * H, st), "zero");
+        CK(launch_fill_zero(Gr->b_hh[l][d], (size_t)4 * H, st), "zero");
+        continue;
+      }
+      GemmTNArgs ta{};
+      ta.G = p.G; ta.B = p.B; ta.Tmax = p.T; ta.lens = lens;
+      ta.A = at<float>(ws, p.gates[l][d]); ta.KA = 4 * H;
+      ta.partial = partial; ta.ctas_per_group = p.ctas_per_group;
+      // dW_ih
+      if (l == 0) {
+        ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V; ta.NB = H;
+      } else {
+        ta.Bsrc = at<float>(ws, p.Y[l - 1]); ta.ldb = 2 * H; ta.col0 = 0; ta.shift = 0; ta.NB = 2 * H;
+      }
+      ta.colsum = 0;
+      CK(launch_gemm_tn(ta, prec, st), "dW_ih gemm");
+      DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], nullptr, nullptr};
+      CK(launch_dw_reduce(ra, st), "dW_ih reduce");
+      // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
+      ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
+      ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H;
+      ta.colsum = 1;
+      CK(launch_gemm_tn(ta, prec, st), "dW_hh gemm");
+      DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, (l == 0 && d == 0) ? whh_l0_mask : nullptr,
+                      Gr->w_hh[l][d], Gr->b_ih[l][d], Gr->b_hh[l][d]};
+      CK(launch_dw_reduce(rb, st), "dW_hh reduce");
+    }
+
+    // input gradient of this layer
+    GemmNTArgs ga{};
+    ga.G = p.G; ga.B = p.B; ga.Tmax = p.T; ga.lens = lens;
+    ga.nsrc = 0;
+    for (int d = 0; d < 2; ++d)
+      if (p.live[l][d]) {
+        ga.A[ga.nsrc] = at<float>(ws, p.gates[l][d]);
+        ga.W[ga.nsrc] = at<float>(ws, p.wihT_gi[l][d]);
+        ++ga.nsrc;
+      }
+    ga.lda = 4 * H; ga.K = 4 * H; ga.bias = nullptr; ga.accumulate = 0;
+    if (l > 0) {
+      ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
+      CK(launch_gemm_nt(ga, prec, st), "dY gemm");
+    } else {
+      ga.C = dX0; ga.ldc = H; ga.NC = H;
+      CK(launch_gemm_nt(ga, prec, st), "dX0 gemm");
+      EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
+      CK(launch_emb_grad(ea, st), "embedding grad");
+    }
+  }
+  return 0;
+}
+
+int ib200_pool_fc_fwd(int32_t N, int32_t H, int32_t bi_reduce, const float* hn_top, const float* fc_w, const float* fc_b, float* z,
+                      float* pooled_out, uint8_t* argmax_out, void* stream) {
+  if (!hn_top || !fc_w || !fc_b || !z) return fail(IB200_E_NULL, "ib200_pool_fc_fwd: null pointer");
+  if (N < 1 || H < 1 || H > 1024 || bi_reduce < 0 || bi_reduce > 2) return fail(IB200_E_SHAPE, "ib200_pool_fc_fwd: bad shape / bi_reduce");
+  CK(launch_pool_fc_fwd(N, H, bi_reduce, hn_top, fc_w, fc_b, z, pooled_out, argmax_out, (cudaStream_t)stream), "pool_fc fwd");
+  return 0;
+}
+
+int ib200_pool_fc_bwd(int32_t N, int32_t H, int32_t bi_reduce, const float* dz, const float* pooled, const uint8_t* argmax,
+                      const float* fc_w, float* d_hn_top, float* d_fc_w, float* d_fc_b, void* stream) {
+  if (!dz || !pooled || !fc_w || !d_hn_top || !d_fc_w || !d_fc_b) return fail(IB200_E_NULL, "ib200_pool_fc_bwd: null pointer");
+  if (bi_reduce == IB200_REDUCE_MAX && !argmax) return fail(IB200_E_NULL, "ib200_pool_fc_bwd: max needs argmax");
+  if (N < 1 || H < 1 || H > 1024 || bi_reduce < 0 || bi_reduce > 2) return fail(IB200_E_SHAPE, "ib200_pool_fc_bwd: bad shape / bi_reduce");
+  CK(launch_pool_fc_bwd(N, H, bi_reduce, dz, pooled, argmax, fc_w, d_hn_top, d_fc_w, d_fc_b, (cudaStream_t)stream), "pool_fc bwd");
+  return 0;
+}
+
+int ib200_loss_head_fwd(int32_t B, int32_t H, float beta, const float* z, const int64_t* y, const ib200_head_params* hp,
+                        const ib200_head_masks* hm, float* losses_out, float* y_hat_out, void* stream) {
+  if (!z || !y || !hp || !losses_out || !y_hat_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b)
+    return fail(IB200_E_NULL, "ib200_loss_head_fwd: null pointer");
+  if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_fwd: bad shape");
+  ib200_head_masks none{};
+  CK(launch_loss_head_fwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, losses_out, y_hat_out, (cudaStream_t)stream), "loss_head fwd");
+  return 0;
+}
+
+int ib200_loss_head_bwd(int32_t B, int32_t H, float beta, const float* z, const int64_t* y, const ib200_head_params* hp,
+                        const ib200_head_masks* hm, const float* d_loss, const float* d_y_hat, float* dz_out, const ib200_head_grads* hg,
+                        void* stream) {
+  if (!z || !y || !hp || !d_loss || !dz_out || !hg || !hg->fc1_w || !hg->fc1_b || !hg->fc2_w || !hg->fc2_b)
+    return fail(IB200_E_NULL, "ib200_loss_head_bwd: null pointer");
+  if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_bwd: bad shape");
+  ib200_head_masks none{};
+  CK(launch_loss_head_bwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, d_loss, d_y_hat, dz_out, *hg, (cudaStream_t)stream),
+     "loss_head bwd");
+  return 0;
+}
+
+int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a, const int32_t* idx_b, int64_t P,
+                     const ib200_head_params* hp, float* prob_out, void* stream) {
+  if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score: null pointer");
+  if ((idx_a == nullptr) != (idx_b == nullptr)) return fail(IB200_E_NULL, "ib200_pair_score: idx_a and idx_b must both be given or both be null");
+  if (M < 1 || (H != 32 && H != 64) || P < 0) return fail(IB200_E_SHAPE, "ib200_pair_score: bad shape");
+  if (!idx_a && P != (int64_t)M * (M + 1) / 2) return fail(IB200_E_SHAPE, "ib200_pair_score: P must be M(M+1)/2 for the implicit upper triangle");
+  CK(launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, (cudaStream_t)stream), "pair_score");
+  return 0;
+}
+
+}  // extern "C"

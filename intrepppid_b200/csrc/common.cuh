@@ -1,0 +1,96 @@
+// Shared device helpers for libib200 (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ib200 {
+
+constexpr int kBC = 8;  // sequences per CTA in the recurrent kernels (= N of mma.m16n8k16)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gate-interleaved ("GI") column order used for every [.,4H] activation tensor (input projections, saved gates, dgates):
+//   gi(u, q) = 4*u + q     u = hidden unit, q = gate in PyTorch order (0=i, 1=f, 2=g, 3=o)
+// so that the four gates of one cell are one aligned float4.  PyTorch row r = q*H + u.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int gi_to_torch_row(int gi, int H) { return (gi & 3) * H + (gi >> 2); }
+
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x (low 16 bits) = lo_elem
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// (x,y) -> packed bf16 pair `hi` = round(x,y) and `lo` = round((x,y) - hi): x ~= hi + lo to ~2^-17 relative.
+__device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// activations.  ACCURATE: ex2.approx + rcp.approx (abs error ~3e-7) for the fp32 mode; FAST: one MUFU.TANH each.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float x) {
+  if constexpr (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+  } else {
+    return __fdividef(1.0f, 1.0f + __expf(-x));
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float tanh_f(float x) {
+  if constexpr (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+  } else {
+    // 1 - 2/(1+e^{2x}); saturates cleanly (e^{2x} -> inf gives 1, -> 0 gives -1)
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+  }
+}
+
+__device__ __forceinline__ float mish_f(float x) {
+  // x * tanh(softplus(x)); softplus with PyTorch's threshold=20 (nn.Mish -> F.mish)
+  float sp = x > 20.0f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+__device__ __forceinline__ float mish_grad_f(float x) {
+  float sp = x > 20.0f ? x : log1pf(expf(x));
+  float tsp = tanhf(sp);
+  float sig = 1.0f / (1.0f + expf(-x));
+  return tsp + x * (1.0f - tsp * tsp) * sig;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  int sz = valid ? 16 : 0;  // src-size 0 => zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ib200

@@ -1,0 +1,131 @@
+// Internal launcher interface between capi.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace ib200 {
+
+// ---- K0: truncation lengths + int32 token copy (A1/A3) ------------------------------------------------------------------
+struct LengthArgs {
+  int G, B, Tin, V, H;
+  const long long* tokens;     // [G*B, Tin] int64
+  const float* emb;            // [V,H]
+  const float* emb_row_scale;  // [G,V] or null
+  int* tok32;                  // [G*B, Tin]
+  int* lens;                   // [2,G]: T1 then T_eff (zeroed by the launcher)
+};
+cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st);
+
+// ---- K1a: layer-0 input-projection table P[g][d][v][4H] (GI order) --------------------------------------------------------
+struct TableArgs {
+  int G, V, H;
+  const float* emb;            // [V,H]
+  const float* emb_row_scale;  // [G,V] or null
+  const float* w_ih[2];        // [4H,H]
+  const float* b_ih[2];
+  const float* b_hh[2];
+  float* table;                // [G,2,V,4H]
+};
+cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st);
+
+// ---- weight preparation: GI-permuted copies used by the GEMMs ------------------------------------------------------------
+// out_w[gi][k] = w[torch_row(gi)][k]  (rows permuted), out_wT[k][gi] = same transposed, out_b[gi] = b_ih + b_hh permuted
+cudaError_t launch_prep_wih(const float* w, const float* b_ih, const float* b_hh, int H, int K, float* out_w, float* out_wT,
+                            float* out_b, cudaStream_t st);
+
+// ---- K2: recurrent forward ----------------------------------------------------------------------------------------------
+struct LstmFwdArgs {
+  int G, B, Tmax, V;
+  int dir0, ndir;            // directions run: dir0 .. dir0+ndir-1 (grid.z)
+  const int* lens;           // [2,G]
+  const int* tok;            // [N,Tmax] (layer 0) or null
+  const float* table;        // layer 0: [G,2,V,4H]
+  const float* xproj[2];     // layer >= 1: per direction [N,Tmax,4H] (GI)
+  const float* whh[2];       // [4H,H] per direction
+  const float* whh_mask;     // [G,4H,H] or null; direction 0 only
+  float* y;                  // [N,Tmax,y_stride] (+dir*H) or null
+  int y_stride;
+  float* gates[2];           // per direction [N,Tmax,H,4] (training) or null
+  float* cstate[2];          // per direction [N,Tmax,H]
+  float* hn;                 // [2,N,H] or null
+};
+cudaError_t launch_lstm_fwd(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
+
+// ---- K3: recurrent backward (BPTT); dgates overwrite the saved gates in place ------------------------------------------------
+struct LstmBwdArgs {
+  int G, B, Tmax;
+  int dir0, ndir;
+  const int* lens;
+  const float* whh[2];
+  const float* whh_mask;
+  float* gates[2];           // in: (i,f,g,o) ; out: (da_i,da_f,da_g,da_o), GI order
+  const float* cstate[2];
+  const float* dy;           // [N,Tmax,dy_stride] (+dir*H) gradient w.r.t. this layer's output, or null
+  int dy_stride;
+  const float* dhn;          // [2,N,H] gradient w.r.t. the final hidden state, or null
+};
+cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
+
+// ---- tensor-core GEMMs over token rows -------------------------------------------------------------------------------------
+// NT:  C[row, NC] (=|+=) sum_s A_s[row, K] * W_s[NC, K]^T (+ bias)   for rows (n,t), t < T_eff[group(n)]
+struct GemmNTArgs {
+  int G, B, Tmax;
+  const int* lens;
+  int nsrc;                  // 1 or 2 A/W source pairs (K-concatenation, e.g. both directions' dgates)
+  const float* A[2];         // [N*Tmax, lda]
+  int lda;
+  int K;                     // per source
+  const float* W[2];         // [NC, K] row-major
+  const float* bias;         // [NC] or null
+  float* C;                  // [N*Tmax, ldc]
+  int ldc;
+  int NC;
+  int accumulate;            // C += instead of C =
+};
+cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st);
+
+// TN:  P[cta][KA, NB] = sum_{rows of cta} A[row, KA]^T * Bop[row, NB]   (partials; reduced by launch_dw_reduce)
+struct GemmTNArgs {
+  int G, B, Tmax;
+  const int* lens;
+  const float* A;            // dgates [N*Tmax, KA] (GI)
+  int KA;                    // 4H
+  // B operand: either dense rows Bsrc[(n, t+shift), col0 .. col0+NB) with zero outside [0,T_eff), or gathered embeddings
+  const float* Bsrc;
+  int ldb, col0, shift;
+  const int* tok;            // if non-null: Bop[row] = scale[g][tok] * emb[tok] (layer-0 input), Bsrc/ldb unused
+  const float* emb;
+  const float* emb_row_scale;
+  int V;
+  int NB;
+  float* partial;            // [G][ctas_per_group][KA*NB (+ KA if colsum)]
+  int ctas_per_group;
+  int colsum;                // also produce column sums of A (bias gradient) after the KA*NB block
+};
+cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st);
+
+// out[torch_row(gi)][c] = sum_g mask_g[torch_row][c] * sum_cta partial[g][cta][gi][c];  optional bias outputs
+struct DwReduceArgs {
+  int G, ctas_per_group, KA, NB, H;
+  const float* partial;
+  int has_colsum;
+  const float* mask;         // [G, KA, NB] in torch row order, or null
+  float* out;                // [KA, NB] torch row order
+  float* out_b1;             // [KA] or null (bias_ih grad)
+  float* out_b2;             // [KA] or null (bias_hh grad, identical values)
+};
+cudaError_t launch_dw_reduce(const DwReduceArgs& a, cudaStream_t st);
+
+// embedding gradient: demb[v] = sum_g scale[g][v] * sum_{(n,t): tok=v, t<T_eff} dx[n,t]   (row 0 = padding_idx gets zero)
+struct EmbGradArgs {
+  int G, B, Tmax, V, H;
+  const int* lens;
+  const int* tok;
+  const float* dx;           // [N*Tmax, H]
+  const float* emb_row_scale;
+  float* demb;               // [V,H], zero-filled by the launcher
+};
+cudaError_t launch_emb_grad(const EmbGradArgs& a, cudaStream_t st);
+
+cudaError_t launch_fill_zero(float* p, size_t n, cudaStream_t st);
+
+}  // namespace ib200

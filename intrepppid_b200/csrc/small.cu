@@ -1,0 +1,181 @@
+// K0 / K1a / K4: truncation lengths, layer-0 input-projection table, bi_reduce pooling + fc.
+#include "kernels.h"
+#include "small.h"
+
+namespace ib200 {
+namespace {
+
+// ---- A1: T1[g] = max_b #{t : tok != 0} (a COUNT, encoders/awd_lstm.py:149-150) + int32 copy of the ids ---------------------
+__global__ void len1_kernel(const LengthArgs p) {
+  const int n = blockIdx.x, g = n / p.B;
+  const long long* __restrict__ src = p.tokens + (size_t)n * p.Tin;
+  int* __restrict__ dst = p.tok32 + (size_t)n * p.Tin;
+  int cnt = 0;
+  for (int t = threadIdx.x; t < p.Tin; t += blockDim.x) {
+    const int v = (int)src[t];
+    dst[t] = v;
+    cnt += (v != 0);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  __shared__ int ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += ws[i];
+    atomicMax(p.lens + g, tot);
+  }
+}
+
+// ---- A3: T_eff[g] = max_{b,e} #{t < T1 : (scale[g][tok] * emb[tok][e]) != 0} (encoders/awd_lstm.py:53-54, quirk Q2) -----------
+// count[b][e] = sum_v hist_b[v] * [scale[g][v] != 0 && emb[v][e] != 0]   (scale >= 1 when non-zero, so no underflow to 0)
+__global__ void len2_kernel(const LengthArgs p) {
+  extern __shared__ int hist[];  // [V]
+  const int n = blockIdx.x, g = n / p.B;
+  const int T1 = p.lens[g];
+  for (int v = threadIdx.x; v < p.V; v += blockDim.x) hist[v] = 0;
+  __syncthreads();
+  const int* __restrict__ tk = p.tok32 + (size_t)n * p.Tin;
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
+    const int v = tk[t];
+    if (v >= 0 && v < p.V) atomicAdd(&hist[v], 1);
+  }
+  __syncthreads();
+  int best = 0;
+  for (int e = threadIdx.x; e < p.H; e += blockDim.x) {
+    int cnt = 0;
+    for (int v = 0; v < p.V; ++v) {
+      const int hv = hist[v];
+      if (hv == 0) continue;
+      const bool keep = p.emb_row_scale == nullptr || p.emb_row_scale[(size_t)g * p.V + v] != 0.0f;
+      if (keep && p.emb[(size_t)v * p.H + e] != 0.0f) cnt += hv;
+    }
+    best = max(best, cnt);
+  }
+  best = __reduce_max_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(p.lens + p.G + g, best);
+}
+
+__global__ void zero_int_kernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+// ---- K1a: P[g][d][v][gi] = (scale[g][v] * emb[v]) . w_ih_d[row(gi)] + b_ih_d[row] + b_hh_d[row] -----------------------------------
+// (utils/embedding_do.py:26-43 folded with the layer-0 x W_ih^T of nn.LSTM: the lookup-table identity)
+template <int H>
+__global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int v_per_block) {
+  const int gi = threadIdx.x, row = gi_to_torch_row(gi, H);
+  const int g = blockIdx.y >> 1, d = blockIdx.y & 1;
+  float w[H];
+  const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
+#pragma unroll
+  for (int k = 0; k < H; ++k) w[k] = wr[k];
+  const float bias = p.b_ih[d][row] + p.b_hh[d][row];
+  __shared__ float x[H];
+  const int vend = min(p.V, (int)(blockIdx.x + 1) * v_per_block);
+  for (int v = blockIdx.x * v_per_block; v < vend; ++v) {
+    __syncthreads();
+    if (gi < H) {
+      const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
+      x[gi] = sc * p.emb[(size_t)v * H + gi];  // the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
+    }
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) s = fmaf(x[k], w[k], s);
+    p.table[(((size_t)(g * 2 + d)) * p.V + v) * 4 * H + gi] = s + bias;
+  }
+}
+
+// ---- K4: bi_reduce on h_n[-2:] + fc (encoders/awd_lstm.py:58-71) -----------------------------------------------------------------
+__global__ void pool_fc_fwd_kernel(int N, int H, int mode, const float* __restrict__ hn, const float* __restrict__ fc_w,
+                                   const float* __restrict__ fc_b, float* __restrict__ z, float* __restrict__ pooled_out,
+                                   uint8_t* __restrict__ argmax_out) {
+  extern __shared__ float pooled[];
+  const int n = blockIdx.x;
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
+    const float f = hn[(size_t)n * H + e], r = hn[((size_t)N + n) * H + e];
+    float v;
+    if (mode == 0) v = r;                 // "last": h_n[-1] = top-layer REVERSE final state (quirk Q4)
+    else if (mode == 1) v = (f + r) * 0.5f;  // "mean"
+    else {                                // "max" (ties -> first = forward, as torch.max(dim=0))
+      v = f >= r ? f : r;
+      if (argmax_out != nullptr) argmax_out[(size_t)n * H + e] = f >= r ? 0 : 1;
+    }
+    pooled[e] = v;
+    if (pooled_out != nullptr) pooled_out[(size_t)n * H + e] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
+    float s = fc_b[e];
+    for (int k = 0; k < H; ++k) s = fmaf(pooled[k], fc_w[(size_t)e * H + k], s);
+    z[(size_t)n * H + e] = s;
+  }
+}
+
+__global__ void pool_fc_bwd_dh_kernel(int N, int H, int mode, const float* __restrict__ dz, const uint8_t* __restrict__ argmax,
+                                      const float* __restrict__ fc_w, float* __restrict__ d_hn) {
+  extern __shared__ float dzs[];
+  const int n = blockIdx.x;
+  for (int e = threadIdx.x; e < H; e += blockDim.x) dzs[e] = dz[(size_t)n * H + e];
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float s = 0.f;
+    for (int e = 0; e < H; ++e) s = fmaf(dzs[e], fc_w[(size_t)e * H + k], s);
+    float df, dr;
+    if (mode == 0) { df = 0.f; dr = s; }
+    else if (mode == 1) { df = 0.5f * s; dr = 0.5f * s; }
+    else { const bool rev = argmax[(size_t)n * H + k] != 0; df = rev ? 0.f : s; dr = rev ? s : 0.f; }
+    d_hn[(size_t)n * H + k] = df;
+    d_hn[((size_t)N + n) * H + k] = dr;
+  }
+}
+
+__global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz, const float* __restrict__ pooled,
+                                      float* __restrict__ d_fc_w, float* __restrict__ d_fc_b) {
+  const int e = blockIdx.x;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float s = 0.f, sb = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = dz[(size_t)n * H + e];
+      s = fmaf(d, pooled[(size_t)n * H + k], s);
+      sb += d;
+    }
+    d_fc_w[(size_t)e * H + k] = s;
+    if (k == 0) d_fc_b[e] = sb;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
+  zero_int_kernel<<<1, 64, 0, st>>>(a.lens, 2 * a.G);
+  len1_kernel<<<a.G * a.B, 256, 0, st>>>(a);
+  len2_kernel<<<a.G * a.B, 128, a.V * sizeof(int), st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
+  const int vpb = 8;
+  dim3 grid((a.V + vpb - 1) / vpb, a.G * 2);
+  if (a.H == 64) l0_table_kernel<64><<<grid, 256, 0, st>>>(a, vpb);
+  else if (a.H == 32) l0_table_kernel<32><<<grid, 128, 0, st>>>(a, vpb);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_fc_fwd(int N, int H, int mode, const float* hn, const float* fc_w, const float* fc_b, float* z,
+                               float* pooled_out, uint8_t* argmax_out, cudaStream_t st) {
+  pool_fc_fwd_kernel<<<N, 64, H * sizeof(float), st>>>(N, H, mode, hn, fc_w, fc_b, z, pooled_out, argmax_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_fc_bwd(int N, int H, int mode, const float* dz, const float* pooled, const uint8_t* argmax,
+                               const float* fc_w, float* d_hn, float* d_fc_w, float* d_fc_b, cudaStream_t st) {
+  pool_fc_bwd_dh_kernel<<<N, 64, H * sizeof(float), st>>>(N, H, mode, dz, argmax, fc_w, d_hn);
+  pool_fc_bwd_dw_kernel<<<H, 64, 0, st>>>(N, H, dz, pooled, d_fc_w, d_fc_b);
+  return cudaGetLastError();
+}
+
+}  // namespace ib200

@@ -1,0 +1,150 @@
+"""TripletE2ENet on the sm_100a kernels -- drop-in for intrepppid/e2e/e2e_triplet.py:43-255 (same constructor, forward /
+step / *_step / configure_optimizers, same state_dict keys).
+
+`step()` fuses the reference's five encoder calls (anchor, positive, negative, then p1, p2 -- e2e_triplet.py:116-129) into one
+G=5 launch set with per-group masks and truncation lengths, then runs triplet + head + BCE + beta mix in one kernel.
+Lightning / torchmetrics are optional: when they are importable the class is a LightningModule and logs exactly what the
+reference logs; otherwise it is a plain nn.Module and `log` is a no-op (the arithmetic is identical).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+from torch.optim import AdamW
+from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts, OneCycleLR
+
+from .. import ops
+
+try:  # optional orchestration dependencies (absent in the build image)
+    import pytorch_lightning as pl
+
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover
+    pl = None
+
+    class _Base(nn.Module):
+        def log(self, *a, **k):
+            pass
+
+try:
+    import torchmetrics
+except Exception:  # pragma: no cover
+    torchmetrics = None
+
+
+class StepMasks:
+    """Explicit masks for one training step (SURVEY Q6 draw order); any field may be None (= no drop).
+    emb_row_scale [5,V] (keep/(1-p)), whh_mask [5,4H,H], head = (fc1_w [H/2,H], do1 [B,H/2], do2 [B,H/2], fc2_w [1,H/2])."""
+
+    def __init__(self, emb_row_scale=None, whh_mask=None, head=(None, None, None, None)):
+        self.emb_row_scale, self.whh_mask, self.head = emb_row_scale, whh_mask, tuple(head)
+
+
+class TripletE2ENet(_Base):
+    def __init__(self, embedding_size: int, encoder: nn.Module, head: nn.Module, embedding_droprate: float, num_epochs: int,
+                 steps_per_epoch: int, beta_classifier: float, use_projection: bool, optimizer_type: str, lr: float):
+        super().__init__()
+        self.encoder = encoder
+        self.embedding_droprate = embedding_droprate
+        self.classifier_criterion = nn.BCEWithLogitsLoss()   # kept for attribute compatibility; evaluated in the fused kernel
+        self.num_epochs = num_epochs
+        self.steps_per_epoch = steps_per_epoch
+        self.triplet_criterion = nn.TripletMarginLoss(margin=1.0, p=2)
+        if use_projection:
+            self.triplet_projection = nn.Sequential(nn.Mish(), nn.Linear(embedding_size, embedding_size))
+        if torchmetrics is not None:
+            self.auroc = torchmetrics.AUROC(task="binary")
+            self.average_precision = torchmetrics.AveragePrecision(task="binary")
+            self.mcc = torchmetrics.MatthewsCorrCoef(task="binary", threshold=0.5)
+            self.precision_metric = torchmetrics.Precision(task="binary")
+            self.recall = torchmetrics.Recall(task="binary")
+        self.do_rate = 0.3
+        self.head = head
+        self.beta_classifier = beta_classifier
+        self.optimizer_type = optimizer_type
+        self.lr = lr
+        self.use_projection = use_projection
+        self.last_step = None  # dict of detached tensors from the most recent step()
+
+    # -- inference API (e2e_triplet.py:105-111): no projection here (quirk Q11); the caller applies sigmoid ---------------------
+    def forward(self, x1, x2):
+        z = self.encoder.forward_groups(torch.stack((x1, x2), dim=0))
+        return self.head(z[0], z[1])
+
+    @torch.no_grad()
+    def embed(self, x, batch_size: int = 512):
+        """Eval-mode embeddings [M,E] of M sequences, for encode-once / score-all-pairs inference."""
+        out = []
+        for i in range(0, x.shape[0], batch_size):
+            out.append(self.encoder(x[i:i + batch_size]))
+        return torch.cat(out, dim=0)
+
+    @torch.no_grad()
+    def score_pairs(self, z, idx_a=None, idx_b=None):
+        """sigmoid(head(z[i], z[j])) for explicit pairs or the whole upper triangle (eval mode)."""
+        return ops.pair_score(z, *self.head.tensors(), idx_a, idx_b)
+
+    # -- training step (e2e_triplet.py:113-187) ---------------------------------------------------------------------------------
+    def step(self, batch, stage, masks: Optional[StepMasks] = None):
+        p1_seq, p2_seq, omid_anchor_seq, omid_positive_seq, omid_negative_seq, y = batch
+        tokens = torch.stack((omid_anchor_seq, omid_positive_seq, omid_negative_seq, p1_seq, p2_seq), dim=0)
+        if masks is None:
+            ers, whm = self.encoder.draw_masks(5)
+            head_masks = None
+        else:
+            ers, whm, head_masks = masks.emb_row_scale, masks.whh_mask, masks.head
+        # draw order of the reference: 5 x (row mask, W_hh mask), then the 4 head masks
+        z = self.encoder.forward_groups(tokens, ers, whm, draw=False)
+        if head_masks is None:
+            head_masks = self.head.draw_masks(y.shape[0])
+        proj_w = proj_b = None
+        if self.use_projection:
+            proj_w, proj_b = self.triplet_projection[1].weight, self.triplet_projection[1].bias
+        losses, y_hat = ops.loss_head(self.beta_classifier, z, y, *self.head.tensors(), proj_w, proj_b, masks=head_masks)
+        loss, classifier_loss, triplet_loss = losses[0], losses[1].detach(), losses[2].detach()
+        self.last_step = {"loss": loss.detach(), "classifier_loss": classifier_loss, "triplet_loss": triplet_loss,
+                          "y_hat": y_hat.detach(), "z": z.detach(), "lengths": self.encoder.last_lengths}
+
+        self.log(f"{stage}_classifier_loss", classifier_loss, on_epoch=True, on_step=False, prog_bar=True)
+        self.log(f"{stage}_triplet_loss", triplet_loss, on_epoch=True, on_step=False, prog_bar=True)
+        self.log(f"{stage}_loss", loss, on_epoch=True, on_step=False, prog_bar=True)
+        self.log(f"{stage}_classifier_loss_step", classifier_loss, on_epoch=False, on_step=True, prog_bar=False)
+        self.log(f"{stage}_triplet_loss_step", triplet_loss, on_epoch=False, on_step=True, prog_bar=False)
+        self.log(f"{stage}_loss_step", loss, on_epoch=False, on_step=True, prog_bar=False)
+        if torchmetrics is not None:
+            yh = y_hat.detach()
+            self.log(f"{stage}_auroc", self.auroc(yh, y).detach(), on_epoch=True, on_step=False)
+            self.log(f"{stage}_ap", self.average_precision(yh, y).detach(), on_epoch=True, on_step=False)
+            self.log(f"{stage}_mcc", self.mcc(yh, y).detach(), on_epoch=True, on_step=False)
+            self.log(f"{stage}_precision", self.precision_metric(yh, y).detach(), on_epoch=True, on_step=False)
+            self.log(f"{stage}_rec", self.recall(yh, y).detach(), on_epoch=True, on_step=False)
+        return loss
+
+    def training_step(self, batch, batch_idx):
+        return self.step(batch, "train")
+
+    def validation_step(self, batch, batch_idx):
+        return self.step(batch, "val")
+
+    def test_step(self, batch, batch_idx):
+        return self.step(batch, "test")
+
+    # -- optimizers (e2e_triplet.py:198-255; the step after the hot path, unchanged) -----------------------------------------------
+    def configure_optimizers(self):
+        if self.optimizer_type in ("ranger21", "ranger21_xx"):
+            from ranger21 import Ranger21  # third-party, same pin as the reference; imported lazily
+
+            xx = self.optimizer_type == "ranger21_xx"
+            return Ranger21(self.parameters(), use_warmup=xx, warmdown_active=xx, lr=self.lr, weight_decay=1e-2,
+                            num_batches_per_epoch=self.steps_per_epoch, num_epochs=self.num_epochs, warmdown_start_pct=0.72)
+        if self.optimizer_type == "adamw":
+            return AdamW(self.parameters(), lr=self.lr)
+        if self.optimizer_type == "adamw_1cycle":
+            optimizer = AdamW(self.parameters(), lr=self.lr)
+            return [optimizer], [OneCycleLR(optimizer, self.lr, epochs=self.num_epochs, steps_per_epoch=self.steps_per_epoch)]
+        if self.optimizer_type == "adamw_cosine":
+            optimizer = AdamW(self.parameters(), lr=self.lr)
+            return [optimizer], [CosineAnnealingWarmRestarts(optimizer, T_0=10, T_mult=2, eta_min=1e-6)]
+        raise ValueError('Expected one of "ranger21", "adamw", "ranger21_xx", or "adamw_1cycle" as the optimizer type.')

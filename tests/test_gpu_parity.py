@@ -1,0 +1,171 @@
+"""GPU parity: the CUDA path (through the C ABI, via the reference-shaped modules) against the CPU oracle on the same seeded
+inputs and the same explicit masks, and against the golden vectors produced by the unmodified reference.
+
+Gates (BASELINE.json north_star / SURVEY 8d): fp32 mode -- embeddings, losses and every gradient within 1e-4 relative L2;
+bf16 mode -- within 2e-2; truncation lengths (T1, T_eff) bit-exact; dead-chain gradients exactly zero."""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, assert_grad_close, load_golden, rel_l2
+from helpers import build_product, product_masks, run_oracle_step, run_product_step
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _golden_inputs(gold):
+    c = gold["config"]
+    mk = gold["masks"]
+    masks = R.StepMasks(mk["emb_row_keep"], mk["whh_mask"], mk["fc1_w"], mk["do1"], mk["do2"], mk["fc2_w"])
+    batch = gold["tokens"] + [gold["y"]]
+    kw = dict(L=c["L"], bi=c["bi"], beta=c["beta"], use_projection=c["proj"], p_emb=c["p_emb"])
+    return c, masks, batch, kw
+
+
+def _check(got, ref, tol, grads=True):
+    assert torch.equal(got["lengths"].cpu(), ref["lengths"]), "T1 / T_eff must be bit-exact"
+    for g in range(5):
+        assert rel_l2(got["z"][g], ref["z"][g]) < tol, f"z[{g}]"
+    for k in ("loss", "classifier_loss", "triplet_loss"):
+        assert abs(float(got[k]) - float(ref[k])) <= tol * max(1.0, abs(float(ref[k]))), k
+    assert rel_l2(got["y_hat"], ref["y_hat"]) < tol * 10 or float((got["y_hat"] - ref["y_hat"]).abs().max()) < tol
+    if grads:
+        for n, g in ref["grads"].items():
+            assert got["grads"][n] is not None, f"missing gradient {n}"
+            assert_grad_close(got["grads"][n], g, tol, n)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_training_step_vs_reference_golden(name):
+    """fp32 mode against numbers produced by the reference itself (tests/golden, oracle/make_golden.py)."""
+    gold = load_golden(name)
+    c, masks, batch, kw = _golden_inputs(gold)
+    got = run_product_step(gold["params"], batch, masks, p_rnn=c["p_rnn"], p_do=c["p_do"], **kw)
+    t = gold["train"]
+    ref = {"lengths": run_oracle_step(gold["params"], batch, masks, **kw)["lengths"], "z": torch.stack(t["z"]), "loss": t["loss"],
+           "classifier_loss": t["classifier_loss"], "triplet_loss": t["triplet_loss"], "y_hat": t["y_hat"], "grads": t["grads"]}
+    _check(got, ref, 2e-4)  # the golden numbers are fp32 themselves (oracle noise ~5e-6..2e-5 on small-norm tensors)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_vs_fp64_oracle(name, precision):
+    gold = load_golden(name)
+    c, masks, batch, kw = _golden_inputs(gold)
+    got = run_product_step(gold["params"], batch, masks, p_rnn=c["p_rnn"], p_do=c["p_do"], precision=precision, **kw)
+    ref = run_oracle_step(gold["params"], batch, masks, **kw)
+    _check(got, ref, TOL[precision])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_eval_forward_vs_reference_golden(name):
+    gold = load_golden(name)
+    c = gold["config"]
+    net = build_product(gold["params"], L=c["L"], bi=c["bi"], beta=c["beta"], use_projection=c["proj"], p_emb=c["p_emb"],
+                        p_rnn=c["p_rnn"], p_do=c["p_do"]).eval()
+    with torch.no_grad():
+        logits = net(gold["tokens"][0].cuda(), gold["tokens"][1].cuda()).cpu()
+    assert logits.shape == gold["eval"]["logits"].shape
+    assert float((logits - gold["eval"]["logits"]).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("E,L,bi,B,T", [(64, 2, "last", 13, 257), (32, 3, "mean", 9, 100), (64, 1, "max", 8, 64)])
+def test_seeded_cases_vs_oracle(E, L, bi, B, T):
+    """Ragged batches whose sizes are not multiples of the kernel tiles (8 sequences per CTA, 32/128-row GEMM tiles)."""
+    V = 97
+    P = R.init_params(vocab=V, E=E, L=L, seed=21)
+    batch = list(R.synthetic_batch(B, T, V, seed=22, padded=True))
+    masks = R.draw_step_masks(B, V, E, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=23)
+    kw = dict(L=L, bi=bi, beta=2.0, use_projection=False, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+    ref = run_oracle_step(P, batch, masks, **kw)
+    _check(got, ref, 1e-4)
+
+
+def test_all_pad_batch_raises_like_the_reference():
+    P = R.init_params(E=32, L=2)
+    net = build_product(P, L=2, bi="last").eval()
+    with pytest.raises(RuntimeError, match="sequence length"):
+        net.encoder(torch.zeros(4, 16, dtype=torch.long, device="cuda"))
+
+
+def test_all_pad_row_is_legal_and_bias_driven():
+    """Q13: a row of pads inside a batch yields a non-zero embedding."""
+    P = R.init_params(E=32, L=2)
+    net = build_product(P, L=2, bi="last").eval()
+    x = torch.randint(1, 250, (4, 16))
+    x[2] = 0
+    with torch.no_grad():
+        z = net.encoder(x.cuda()).cpu()
+        zr, _ = R.encoder_forward(x, P, num_layers=2, bi_reduce="last", training=False)
+    assert float(z[2].norm()) > 0
+    assert rel_l2(z, zr) < 1e-4
+
+
+def test_concat_rejected():
+    P = R.init_params(E=32, L=2)
+    net = build_product(P, L=2, bi="last")
+    net.encoder.encoder.bi_reduce = "concat"
+    with pytest.raises(ValueError):
+        net.encoder(torch.ones(2, 8, dtype=torch.long, device="cuda"))
+
+
+def test_cpu_tensors_are_refused():
+    """No CPU fallback: the ops raise instead of silently running elsewhere."""
+    from intrepppid_b200._lib import IB200Error
+
+    P = R.init_params(E=32, L=2)
+    net = build_product(P, L=2, bi="last", device="cpu").eval()
+    with pytest.raises(IB200Error):
+        net.encoder(torch.ones(2, 8, dtype=torch.long))
+
+
+def test_pair_score_block_vs_oracle():
+    """Config 4 parity: head + sigmoid on all pairs of a block of embeddings (explicit indices and implicit upper triangle)."""
+    P = R.init_params(E=64, L=2, seed=5)
+    net = build_product(P, L=2, bi="last").eval()
+    z = torch.randn(96, 64)
+    ia, ib = torch.triu_indices(96, 96)
+    with torch.no_grad():
+        ref = torch.sigmoid(R.mlp_head(z[ia], z[ib], P).squeeze(1))
+    got_tri = net.score_pairs(z.cuda()).cpu()
+    got_idx = net.score_pairs(z.cuda(), ia.cuda(), ib.cuda()).cpu()
+    assert float((got_tri - ref).abs().max()) < 1e-5
+    assert float((got_idx - ref).abs().max()) < 1e-5
+
+
+def test_headline_shape_determinism_and_group_fusion():
+    """Full-size (B=80, T=1500) properties that need no oracle: the step is deterministic run to run, and the per-group
+    embeddings of the fused G=5 launch equal five separate encoder calls with the same masks (bit for bit)."""
+    import intrepppid_b200 as ib
+
+    torch.manual_seed(0)
+    net = ib.intrepppid_network(1).cuda().train()
+    batch = [t.cuda() for t in R.synthetic_batch(80, 1500, 250, seed=1234)]
+    m = R.draw_step_masks(80, 250, 64, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=5)
+    pm = product_masks(m, 0.3)
+    emb_w = net.encoder.embedder.weight
+    l1 = net.step(batch, "train", masks=pm)
+    l1.backward()
+    g1 = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    z_fused, lens = net.last_step["z"].clone(), net.last_step["lengths"].clone()
+    net.zero_grad()
+    l2 = net.step(batch, "train", masks=pm)
+    l2.backward()
+    assert float(l1) == float(l2)
+    for n, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        if p is emb_w:  # the embedding scatter uses float atomics: equal to rounding, not bitwise
+            assert rel_l2(p.grad, g1[n]) < 1e-5
+        else:
+            assert torch.equal(p.grad, g1[n]), n
+    order = [batch[2], batch[3], batch[4], batch[0], batch[1]]
+    with torch.no_grad():
+        for g in range(5):
+            zg = net.encoder(order[g], pm.emb_row_scale[g], pm.whh_mask[g])
+            assert torch.equal(net.encoder.last_lengths[:, 0], lens[:, g])
+            assert float((zg - z_fused[g]).abs().max()) == 0.0
+    assert int(lens[1].max()) <= 1500 and int(lens[1].min()) > 900

@@ -1,0 +1,134 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports every symbol include/ib200.h declares,
+host-only entry points behave, and the Python mirror keeps the reference's names, signatures and checkpoint keys.
+No compute entry point is called here (no GPU in this tier)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from intrepppid_b200 import build as b
+
+    b.build()
+    from intrepppid_b200 import _lib
+
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ib200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ib200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ib200.h but not exported by libib200.so"
+    from intrepppid_b200 import _lib
+
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_and_workspace_are_host_only(lib):
+    from intrepppid_b200._lib import Cfg
+
+    assert lib.ib200_version() == 100
+    train = Cfg(5, 80, 1500, 250, 64, 2, 0, 0, 1, 0)
+    infer = Cfg(1, 512, 1500, 250, 64, 2, 0, 0, 0, 0)
+    wt, wi = lib.ib200_workspace_bytes(train), lib.ib200_workspace_bytes(infer)
+    # training keeps gates/c/h for 3 live chains: a few GB at the headline shape, far below 180 GB
+    assert 3e9 < wt < 8e9 and 1e9 < wi < 3e9
+    assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 48, 2, 0, 0, 1, 0)) == 0      # unsupported H
+    assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 64, 9, 0, 0, 1, 0)) == 0      # too many layers
+    assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 64, 2, 3, 0, 1, 0)) == 0      # "concat" is not a mode
+
+
+def test_null_arguments_are_rejected_before_any_launch(lib):
+    from intrepppid_b200._lib import Cfg
+
+    cfg = Cfg(1, 2, 8, 10, 32, 1, 0, 0, 0, 0)
+    st = lib.ib200_encoder_fwd(cfg, None, None, None, None, None, None, None, 0, None)
+    assert st == -1 and b"null" in lib.ib200_last_error()
+    assert lib.ib200_pair_score(4, 48, None, None, None, 10, None, None, None) < 0
+
+
+def test_reference_signatures_are_mirrored():
+    import intrepppid_b200 as ib
+    from intrepppid_b200.classifier.head import MLPHead
+    from intrepppid_b200.encoders import AWDLSTMEncoder
+    from intrepppid_b200.e2e.e2e_triplet import TripletE2ENet
+
+    sig = inspect.signature(ib.intrepppid_network)
+    want = ["steps_per_epoch", "vocab_size", "embedding_size", "rnn_num_layers", "rnn_dropout_rate", "variational_dropout",
+            "bi_reduce", "embedding_droprate", "num_epochs", "do_rate", "beta_classifier", "lr", "use_projection", "optimizer_type"]
+    assert list(sig.parameters)[:len(want)] == want
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["vocab_size"], d["embedding_size"], d["rnn_num_layers"], d["bi_reduce"], d["beta_classifier"]) == (250, 64, 2, "last", 2)
+    assert list(inspect.signature(AWDLSTMEncoder.__init__).parameters)[1:] == [
+        "embedder", "embedding_size", "embedding_droprate", "rnn_num_layers", "rnn_dropout_rate", "variational_dropout", "bi_reduce"]
+    assert list(inspect.signature(MLPHead.__init__).parameters)[1:] == ["embedding_size", "do_rate"]
+    assert list(inspect.signature(TripletE2ENet.__init__).parameters)[1:] == [
+        "embedding_size", "encoder", "head", "embedding_droprate", "num_epochs", "steps_per_epoch", "beta_classifier",
+        "use_projection", "optimizer_type", "lr"]
+
+
+def test_checkpoint_keys_match_the_reference_recorded_in_golden():
+    import intrepppid_b200 as ib
+    from conftest import load_golden
+
+    torch.manual_seed(0)
+    net = ib.intrepppid_network(1)
+    assert sorted(net.state_dict().keys()) == load_golden("train_last_E64")["state_dict_keys"]
+    assert sum(p.numel() for p in net.parameters()) == 216498
+    torch.manual_seed(0)
+    net_p = ib.intrepppid_network(0, use_projection=True)   # cli/infer.py:170 builds it this way
+    assert "triplet_projection.1.weight" in net_p.state_dict()
+
+
+@pytest.mark.reference
+def test_same_seed_same_initial_weights_and_cross_loading():
+    import intrepppid_b200 as ib
+    from oracle import ref_shim
+
+    torch.manual_seed(0)
+    mine = ib.intrepppid_network(1)
+    torch.manual_seed(0)
+    ref = ref_shim.build_reference_net()
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in b)
+    ref.load_state_dict(a, strict=True)
+    mine.load_state_dict(b, strict=True)
+
+
+def test_product_refuses_to_run_without_cuda():
+    """The compute path fails loudly instead of falling back (this container has no GPU)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import intrepppid_b200 as ib
+    from intrepppid_b200._lib import IB200Error
+
+    net = ib.intrepppid_network(1).eval()
+    with pytest.raises(IB200Error):
+        net.encoder(torch.ones(2, 8, dtype=torch.long))
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess
+    import sys
+
+    code = "import sys; import intrepppid_b200, intrepppid_b200.ops; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "intrepppid_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", ""), f
