@@ -81,6 +81,16 @@ typedef struct ib200_encoder_grads {
 int ib200_version(void);
 const char* ib200_last_error(void);
 
+/* Instrumentation (used by bench.py).  ib200_launch_count: kernels launched by this library in this process so far.
+ * ib200_timing_enable(1) makes every launcher bracket its kernels with CUDA events on the launching stream;
+ * ib200_timing_read sums the elapsed ms and the number of timed launcher calls per kernel family since the last read
+ * (arrays of ib200_timing_families() entries, names from ib200_timing_family_name) and synchronises on those events. */
+unsigned long long ib200_launch_count(void);
+int ib200_timing_enable(int on);
+int ib200_timing_families(void);
+const char* ib200_timing_family_name(int family);
+int ib200_timing_read(int n, float* ms_out, int* launches_out);
+
 /* Bytes of workspace ib200_encoder_fwd needs for cfg (includes everything _bwd needs when cfg.training). 0 on bad cfg. */
 size_t ib200_workspace_bytes(const ib200_cfg* cfg);
 

@@ -33,7 +33,8 @@ class HeadMasks(C.Structure):
     _fields_ = [(n, vp) for n in ("fc1_w", "do1", "do2", "fc2_w")]
 
 
-EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_encoder_fwd", "ib200_encoder_bwd",
+EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
+           "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_bwd",
            "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score")
 
 _lib = None
@@ -65,8 +66,14 @@ def lib() -> C.CDLL:
     L.ib200_loss_head_bwd.argtypes = [C.c_int32, C.c_int32, C.c_float, vp, vp, C.POINTER(HeadParams), C.POINTER(HeadMasks), vp,
                                       vp, vp, C.POINTER(HeadParams), vp]
     L.ib200_pair_score.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.POINTER(HeadParams), vp, vp]
+    L.ib200_launch_count.restype = C.c_ulonglong
+    L.ib200_timing_family_name.restype = C.c_char_p
+    L.ib200_timing_family_name.argtypes = [C.c_int]
+    L.ib200_timing_enable.argtypes = [C.c_int]
+    L.ib200_timing_read.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     for name in EXPORTS:
-        if name not in ("ib200_version", "ib200_last_error", "ib200_workspace_bytes"):
+        if name not in ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count",
+                        "ib200_timing_family_name"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -82,3 +89,20 @@ def check(status: int, what: str) -> None:
 def ptr(t) -> int | None:
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def timing_enable(on: bool) -> None:
+    check(lib().ib200_timing_enable(1 if on else 0), "ib200_timing_enable")
+
+
+def timing_read() -> dict:
+    """{family: (total_ms, timed_launcher_calls)} since the last read (synchronises on the recorded events)."""
+    L = lib()
+    n = L.ib200_timing_families()
+    ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+    check(L.ib200_timing_read(n, ms, cnt), "ib200_timing_read")
+    return {L.ib200_timing_family_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
+
+
+def launch_count() -> int:
+    return int(lib().ib200_launch_count())

@@ -1,7 +1,10 @@
 // C ABI of libib200.so (see include/ib200.h): argument validation, workspace carve-up and the launch sequences.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/ib200.h"
 #include "kernels.h"
@@ -28,6 +31,50 @@ int cuda_fail(cudaError_t e, const char* where) {
   } while (0)
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
+enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_COUNT };
+const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
+                                     "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero"};
+std::atomic<unsigned long long> g_launches{0};
+struct TimingState {
+  std::mutex mu;
+  bool on = false;
+  std::vector<cudaEvent_t> pool;   // pairs (start, stop)
+  std::vector<int> fam;            // family of pair i
+  size_t used = 0;                 // pairs in use
+} g_timing;
+
+struct TimedScope {
+  cudaEvent_t stop = nullptr;
+  cudaStream_t st;
+  TimedScope(int fam, int nkernels, cudaStream_t s) : st(s) {
+    g_launches.fetch_add((unsigned long long)nkernels);
+    if (!g_timing.on) return;
+    std::lock_guard<std::mutex> lk(g_timing.mu);
+    if (g_timing.used * 2 + 2 > g_timing.pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      g_timing.pool.push_back(a);
+      g_timing.pool.push_back(b);
+      g_timing.fam.push_back(fam);
+    }
+    g_timing.fam[g_timing.used] = fam;
+    cudaEventRecord(g_timing.pool[g_timing.used * 2], st);
+    stop = g_timing.pool[g_timing.used * 2 + 1];
+    ++g_timing.used;
+  }
+  ~TimedScope() {
+    if (stop) cudaEventRecord(stop, st);
+  }
+};
+#define TIMED(fam, nk, call, where)  \
+  do {                               \
+    TimedScope ts__(fam, nk, st);    \
+    CK(call, where);                 \
+  } while (0)
 
 // Workspace layout.  Everything the backward needs is inside, so the caller only keeps one buffer alive.
 struct Plan {
@@ -105,6 +152,35 @@ extern "C" {
 int ib200_version(void) { return IB200_VERSION; }
 const char* ib200_last_error(void) { return g_err.c_str(); }
 
+unsigned long long ib200_launch_count(void) { return g_launches.load(); }
+
+int ib200_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  g_timing.on = on != 0;
+  g_timing.used = 0;
+  return 0;
+}
+
+int ib200_timing_families(void) { return F_COUNT; }
+const char* ib200_timing_family_name(int i) { return (i >= 0 && i < F_COUNT) ? kFamilyNames[i] : ""; }
+
+int ib200_timing_read(int n, float* ms_out, int* launches_out) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  if (!ms_out || !launches_out || n < F_COUNT) return fail(IB200_E_SHAPE, "ib200_timing_read: need arrays of ib200_timing_families() entries");
+  for (int i = 0; i < F_COUNT; ++i) { ms_out[i] = 0.f; launches_out[i] = 0; }
+  for (size_t i = 0; i < g_timing.used; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_timing.pool[2 * i + 1]);
+    if (e != cudaSuccess) return cuda_fail(e, "timing sync");
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_timing.pool[2 * i], g_timing.pool[2 * i + 1]);
+    if (e != cudaSuccess) return cuda_fail(e, "timing elapsed");
+    ms_out[g_timing.fam[i]] += ms;
+    launches_out[g_timing.fam[i]] += 1;
+  }
+  g_timing.used = 0;
+  return 0;
+}
+
 size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
   if (!cfg_ok(cfg)) return 0;
   return make_plan(cfg).total;
@@ -124,12 +200,12 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
   const int H = p.H, prec = cfg->precision;
 
   LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens)};
-  CK(launch_lengths(la, st), "lengths");
+  TIMED(F_LENGTHS, 3, launch_lengths(la, st), "lengths");
   if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
 
   TableArgs ta{p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
                {P->b_hh[0][0], P->b_hh[0][1]}, at<float>(ws, p.table)};
-  CK(launch_l0_table(ta, st), "l0 table");
+  TIMED(F_L0_TABLE, 1, launch_l0_table(ta, st), "l0 table");
 
   for (int l = 0; l < p.L; ++l)
     for (int d = 0; d < 2; ++d) {
@@ -138,10 +214,10 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       float* w = l > 0 ? at<float>(ws, p.wih_gi[l][d]) : nullptr;
       float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
       float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
-      if (w || wT) CK(launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
+      if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
     }
 
-  if (!p.live[p.L - 1][0]) CK(launch_fill_zero(hn_top, (size_t)p.N * H, st), "hn zero");
+  if (!p.live[p.L - 1][0]) TIMED(F_FILL, 1, launch_fill_zero(hn_top, (size_t)p.N * H, st), "hn zero");
 
   for (int l = 0; l < p.L; ++l) {
     const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
@@ -152,7 +228,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
         ga.nsrc = 1; ga.A[0] = at<float>(ws, p.Y[l - 1]); ga.lda = 2 * H; ga.K = 2 * H;
         ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
         ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
-        CK(launch_gemm_nt(ga, prec, st), "input projection gemm");
+        TIMED(F_GEMM_XPROJ, 1, launch_gemm_nt(ga, prec, st), "input projection gemm");
       }
     }
     LstmFwdArgs fa{};
@@ -175,7 +251,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       fa.cstate[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.cst[l][d]) : nullptr;
     }
     fa.hn = l == p.L - 1 ? hn_top : nullptr;
-    CK(launch_lstm_fwd(fa, H, prec, st), "lstm fwd");
+    TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, launch_lstm_fwd(fa, H, prec, st), "lstm fwd");
   }
   return 0;
 }
@@ -210,16 +286,16 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ba.dy = l == p.L - 1 ? nullptr : dY;
     ba.dy_stride = 2 * H;
     ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
-    CK(launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
+    TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
     for (int d = 0; d < 2; ++d) {
       const int K = l == 0 ? H : 2 * H;
       if (!p.live[l][d]) {  // dead chain: exact zeros
-        CK(launch_fill_zero(Gr->w_ih[l][d], (size_t)4 * H * K, st), "zero");
-        CK(launch_fill_zero(Gr->w_hh[l][d], (size_t)4 * H * H, st), "zero");
-        CK(launch_fill_zero(Gr->b_ih[l][d], (size_t)4 * H, st), "zero");
-        CK(launch_fill_zero(Gr->b_hh[l][d], (size_t)4 * H, st), "zero");
+        TIMED(F_FILL, 1, launch_fill_zero(Gr->w_ih[l][d], (size_t)4 * H * K, st), "zero");
+        TIMED(F_FILL, 1, launch_fill_zero(Gr->w_hh[l][d], (size_t)4 * H * H, st), "zero");
+        TIMED(F_FILL, 1, launch_fill_zero(Gr->b_ih[l][d], (size_t)4 * H, st), "zero");
+        TIMED(F_FILL, 1, launch_fill_zero(Gr->b_hh[l][d], (size_t)4 * H, st), "zero");
         continue;
       }
       GemmTNArgs ta{};
@@ -233,17 +309,17 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         ta.Bsrc = at<float>(ws, p.Y[l - 1]); ta.ldb = 2 * H; ta.col0 = 0; ta.shift = 0; ta.NB = 2 * H;
       }
       ta.colsum = 0;
-      CK(launch_gemm_tn(ta, prec, st), "dW_ih gemm");
+      TIMED(F_GEMM_DW, 1, launch_gemm_tn(ta, prec, st), "dW_ih gemm");
       DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], nullptr, nullptr};
-      CK(launch_dw_reduce(ra, st), "dW_ih reduce");
+      TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW_ih reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
       ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H;
       ta.colsum = 1;
-      CK(launch_gemm_tn(ta, prec, st), "dW_hh gemm");
+      TIMED(F_GEMM_DW, 1, launch_gemm_tn(ta, prec, st), "dW_hh gemm");
       DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, (l == 0 && d == 0) ? whh_l0_mask : nullptr,
                       Gr->w_hh[l][d], Gr->b_ih[l][d], Gr->b_hh[l][d]};
-      CK(launch_dw_reduce(rb, st), "dW_hh reduce");
+      TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rb, st), "dW_hh reduce");
     }
 
     // input gradient of this layer
@@ -259,12 +335,12 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ga.lda = 4 * H; ga.K = 4 * H; ga.bias = nullptr; ga.accumulate = 0;
     if (l > 0) {
       ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
-      CK(launch_gemm_nt(ga, prec, st), "dY gemm");
+      TIMED(F_GEMM_DGRAD, 1, launch_gemm_nt(ga, prec, st), "dY gemm");
     } else {
       ga.C = dX0; ga.ldc = H; ga.NC = H;
-      CK(launch_gemm_nt(ga, prec, st), "dX0 gemm");
+      TIMED(F_GEMM_DGRAD, 1, launch_gemm_nt(ga, prec, st), "dX0 gemm");
       EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
-      CK(launch_emb_grad(ea, st), "embedding grad");
+      TIMED(F_EMB_GRAD, 2, launch_emb_grad(ea, st), "embedding grad");
     }
   }
   return 0;
@@ -274,7 +350,8 @@ int ib200_pool_fc_fwd(int32_t N, int32_t H, int32_t bi_reduce, const float* hn_t
                       float* pooled_out, uint8_t* argmax_out, void* stream) {
   if (!hn_top || !fc_w || !fc_b || !z) return fail(IB200_E_NULL, "ib200_pool_fc_fwd: null pointer");
   if (N < 1 || H < 1 || H > 1024 || bi_reduce < 0 || bi_reduce > 2) return fail(IB200_E_SHAPE, "ib200_pool_fc_fwd: bad shape / bi_reduce");
-  CK(launch_pool_fc_fwd(N, H, bi_reduce, hn_top, fc_w, fc_b, z, pooled_out, argmax_out, (cudaStream_t)stream), "pool_fc fwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_POOL_FC, 1, launch_pool_fc_fwd(N, H, bi_reduce, hn_top, fc_w, fc_b, z, pooled_out, argmax_out, st), "pool_fc fwd");
   return 0;
 }
 
@@ -283,7 +360,8 @@ int ib200_pool_fc_bwd(int32_t N, int32_t H, int32_t bi_reduce, const float* dz, 
   if (!dz || !pooled || !fc_w || !d_hn_top || !d_fc_w || !d_fc_b) return fail(IB200_E_NULL, "ib200_pool_fc_bwd: null pointer");
   if (bi_reduce == IB200_REDUCE_MAX && !argmax) return fail(IB200_E_NULL, "ib200_pool_fc_bwd: max needs argmax");
   if (N < 1 || H < 1 || H > 1024 || bi_reduce < 0 || bi_reduce > 2) return fail(IB200_E_SHAPE, "ib200_pool_fc_bwd: bad shape / bi_reduce");
-  CK(launch_pool_fc_bwd(N, H, bi_reduce, dz, pooled, argmax, fc_w, d_hn_top, d_fc_w, d_fc_b, (cudaStream_t)stream), "pool_fc bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_POOL_FC, 2, launch_pool_fc_bwd(N, H, bi_reduce, dz, pooled, argmax, fc_w, d_hn_top, d_fc_w, d_fc_b, st), "pool_fc bwd");
   return 0;
 }
 
@@ -293,7 +371,8 @@ int ib200_loss_head_fwd(int32_t B, int32_t H, float beta, const float* z, const 
     return fail(IB200_E_NULL, "ib200_loss_head_fwd: null pointer");
   if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_fwd: bad shape");
   ib200_head_masks none{};
-  CK(launch_loss_head_fwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, losses_out, y_hat_out, (cudaStream_t)stream), "loss_head fwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_LOSS_HEAD, 1, launch_loss_head_fwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, losses_out, y_hat_out, st), "loss_head fwd");
   return 0;
 }
 
@@ -304,8 +383,8 @@ int ib200_loss_head_bwd(int32_t B, int32_t H, float beta, const float* z, const 
     return fail(IB200_E_NULL, "ib200_loss_head_bwd: null pointer");
   if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_bwd: bad shape");
   ib200_head_masks none{};
-  CK(launch_loss_head_bwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, d_loss, d_y_hat, dz_out, *hg, (cudaStream_t)stream),
-     "loss_head bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_LOSS_HEAD, 1, launch_loss_head_bwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, d_loss, d_y_hat, dz_out, *hg, st), "loss_head bwd");
   return 0;
 }
 
@@ -315,7 +394,8 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
   if ((idx_a == nullptr) != (idx_b == nullptr)) return fail(IB200_E_NULL, "ib200_pair_score: idx_a and idx_b must both be given or both be null");
   if (M < 1 || (H != 32 && H != 64) || P < 0) return fail(IB200_E_SHAPE, "ib200_pair_score: bad shape");
   if (!idx_a && P != (int64_t)M * (M + 1) / 2) return fail(IB200_E_SHAPE, "ib200_pair_score: P must be M(M+1)/2 for the implicit upper triangle");
-  CK(launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, (cudaStream_t)stream), "pair_score");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, st), "pair_score");
   return 0;
 }
 

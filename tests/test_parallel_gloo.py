@@ -1,0 +1,87 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: bucketed gradient mean-allreduce launched from grad hooks."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class Toy(nn.Module):
+    """Same naming shape as the product net: an early bucket (head, fc) and a late one (rnn, embedder), plus a dead branch."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder = nn.Module()
+        self.encoder.embedder = nn.Embedding(10, 4)
+        self.encoder.rnn = nn.Linear(4, 4)
+        self.encoder.fc = nn.Linear(4, 4)
+        self.encoder.projection = nn.Linear(4, 4)  # never used in forward (quirk Q10)
+        self.head = nn.Linear(4, 1)
+
+    def forward(self, x):
+        return self.head(self.encoder.fc(torch.tanh(self.encoder.rnn(self.encoder.embedder(x).mean(1))))).mean()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from intrepppid_b200.parallel import GradientAllReducer, default_buckets, shard_range
+
+    torch.manual_seed(0)
+    net = Toy()
+    buckets = default_buckets(net)
+    names = {id(p): n for n, p in net.named_parameters()}
+    assert len(buckets) == 2
+    assert all("projection" not in names[id(p)] for b in buckets for p in b)
+    assert all(("rnn" in names[id(p)] or "embedder" in names[id(p)]) for p in buckets[1])
+    red = GradientAllReducer(net)
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randint(0, 10, (world * 3, 5), generator=g)
+    lo, hi = shard_range(x_all.shape[0], rank, world)
+    for _ in range(2):  # two steps: the reducer must re-arm itself
+        net.zero_grad(set_to_none=True)
+        net(x_all[lo:hi]).backward()
+        red.finish()
+    mine = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    # single-process reference: mean over ranks of per-shard gradients == gradient of the mean of shard losses
+    torch.manual_seed(0)
+    ref = Toy()
+    loss = sum(ref(x_all[shard_range(x_all.shape[0], r, world)[0]:shard_range(x_all.shape[0], r, world)[1]]) for r in range(world)) / world
+    loss.backward()
+    ok = all(torch.allclose(mine[n], p.grad, atol=1e-6) for n, p in ref.named_parameters() if p.grad is not None)
+    ok = ok and net.encoder.projection.weight.grad is None
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_allreduce_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_range_partitions_exactly():
+    from intrepppid_b200.parallel import shard_range
+
+    for n in (0, 1, 7, 20000):
+        for w in (1, 2, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
