@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -251,6 +252,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       fa.cstate[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.cst[l][d]) : nullptr;
     }
     fa.hn = l == p.L - 1 ? hn_top : nullptr;
+    { const char* e = getenv("IB200_DBG"); fa.dbg = e ? atoi(e) : 0; }
     TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, launch_lstm_fwd(fa, H, prec, st), "lstm fwd");
   }
   return 0;

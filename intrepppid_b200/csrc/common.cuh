@@ -42,6 +42,16 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // ---------------------------------------------------------------------------------------------------------------------
 // activations.  ACCURATE: ex2.approx + rcp.approx (abs error ~3e-7) for the fp32 mode; FAST: one MUFU.TANH each.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_f(float x) {
   if constexpr (FAST) {
@@ -49,7 +59,8 @@ __device__ __forceinline__ float sigmoid_f(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
     return fmaf(0.5f, t, 0.5f);
   } else {
-    return __fdividef(1.0f, 1.0f + __expf(-x));
+    // 1/(1+2^(-x log2 e)): FMUL, MUFU.EX2, FADD, MUFU.RCP.  ex2 -> +inf gives 0, -> 0 gives 1: no special cases needed.
+    return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
   }
 }
 template <bool FAST>
@@ -60,8 +71,23 @@ __device__ __forceinline__ float tanh_f(float x) {
     return t;
   } else {
     // 1 - 2/(1+e^{2x}); saturates cleanly (e^{2x} -> inf gives 1, -> 0 gives -1)
-    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+    return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
   }
+}
+
+// four 8x8 b16 matrices from smem, transposed on load: with rows = k (8 b16 = one 16-byte row of 8 sequences) this yields
+// the mma B fragments {b0,b1} of two consecutive k16 tiles directly.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row_ptr) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
 }
 
 __device__ __forceinline__ float mish_f(float x) {
@@ -79,12 +105,12 @@ __device__ __forceinline__ float mish_grad_f(float x) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   int sz = valid ? 16 : 0;  // src-size 0 => zero-fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -47,6 +47,7 @@ struct LstmFwdArgs {
   float* gates[2];           // per direction [N,Tmax,H,4] (training) or null
   float* cstate[2];          // per direction [N,Tmax,H]
   float* hn;                 // [2,N,H] or null
+  int dbg;                   // ablation flags for timing experiments (env IB200_DBG; 0 in production)
 };
 cudaError_t launch_lstm_fwd(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
 

@@ -10,24 +10,28 @@
 // Mapping (H=64: 8 warps): dh^T[H,8] = W_hh^T[H,4H] * da[4H,8] with mma.m16n8k16; W_hh^T lives in registers (A operand), each warp
 // owns one 16-unit output tile and one half of K (two partial sums, exchanged through smem).  The K order is chosen so that
 // the B fragment of lane (col n, unit%4) is exactly the cell's (da_i,da_f | da_g,da_o) pair of packed bf16x2 words.
-// Two __syncthreads per step.  fp32 mode: bf16 hi/lo split, 3 MMAs per product.
+// Saved gates, c and dy are prefetched kD steps ahead with cp.async into per-thread smem slots.
+// Two __syncthreads per step.  fp32 mode: bf16 hi/lo split, 3 MMAs per product, every product on short accumulator chains.
 #include "kernels.h"
 
 namespace ib200 {
 namespace {
 
-constexpr int kPF = 2;
+constexpr int kD = 8;  // async prefetch depth in steps (power of two)
 
-struct CellIn {
-  float4 g;     // saved (i,f,g,o)
-  float cprev;  // c at the previous scan position (0 at the chain start)
-  float dy;     // upstream gradient of h_t
+template <int H>
+struct BwdSmem {
+  static constexpr int NT = H * 4, NW = H / 8, KTT = H / 4;
+  float4 rg[kD][2][NT];            // saved (i,f,g,o) of my two cells
+  float rc[kD][2][NT];             // c at the scan predecessor (0 at the chain start)
+  float rdy[kD][2][NT];            // upstream gradient of h_t
+  uint32_t dafrag[2][KTT][32][2];  // da as mma B fragments: [hi/lo][k tile][lane][2 words]
+  float2 xch[NW][32];              // partial dh handed to the partner warp
 };
 
-template <int H, bool SPLIT, bool FAST_ACT>
+template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY>
 __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p) {
-  constexpr int NW = H / 8, MT = H / 16, KTT = H / 4, KTH = KTT / 2;
-  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr int NT = H * 4, MT = H / 16, KTT = H / 4, KTH = KTT / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int mt = warp % MT, kh = warp / MT;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
@@ -39,23 +43,22 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
   const int Tmax = p.Tmax;
   const size_t N = (size_t)p.G * p.B;
 
-  __shared__ __align__(16) uint32_t dafrag[NPART][KTT][32][2];
-  __shared__ __align__(8) float2 xch[NW][32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<H>& sm = *reinterpret_cast<BwdSmem<H>*>(smem_raw);
 
   // ---- A fragments: W_hh^T, K ordered as (unit, gate) with the fragment positions {2tig,2tig+1,2tig+8,2tig+9} = gates i,f,g,o ----
   uint32_t Ahi[KTH][4], Alo[KTH][4];
   {
-    const float* __restrict__ W = p.whh[dir];
+    const float* __restrict__ W = (dir ? p.whh[1] : p.whh[0]);
     const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
-    const int j0 = 16 * mt + gq, j1 = j0 + 8;
+    const int j0 = 16 * mt + gq;
 #pragma unroll
     for (int ktl = 0; ktl < KTH; ++ktl) {
       const int uu = 4 * (kh * KTH + ktl) + tig;
-      const int jj[4] = {j0, j1, j0, j1};
-      const int qa[4] = {0, 0, 2, 2};
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int ia = (qa[r] * H + uu) * H + jj[r], ib = ((qa[r] + 1) * H + uu) * H + jj[r];
+        const int jj = j0 + ((r & 1) ? 8 : 0), q = (r & 2) ? 2 : 0;
+        const int ia = (q * H + uu) * H + jj, ib = ((q + 1) * H + uu) * H + jj;
         float w0 = W[ia], w1 = W[ib];
         if (M != nullptr) {
           w0 *= M[ia];
@@ -75,67 +78,89 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
   const int j = 16 * mt + gq + 8 * kh;
   const int n0 = 2 * tig, n1 = n0 + 1;
   const bool v0 = n0 < nvalid, v1 = n1 < nvalid;
-  float4* __restrict__ G4 = reinterpret_cast<float4*>(p.gates[dir]);
-  const float* __restrict__ C = p.cstate[dir];
+  // columns beyond the batch read a valid sequence (clamped) and never store
+  const int rb0 = (nbase + min(n0, nvalid - 1)) * Tmax, rb1 = (nbase + min(n1, nvalid - 1)) * Tmax;
+  // backward scan: s = 0..T-1 visits t = T-1..0 (forward chain) or t = 0..T-1 (reverse chain)
+  const int t_first = dir ? 0 : T - 1, dt = dir ? 1 : -1;
+  float4* __restrict__ G4 = reinterpret_cast<float4*>((dir ? p.gates[1] : p.gates[0]));
+  const float* __restrict__ C = (dir ? p.cstate[1] : p.cstate[0]);
+  const ptrdiff_t gstride = (ptrdiff_t)dt * H;
+  // running pointers of the prefetch (kD steps ahead): gates at t(s), c of the scan predecessor = c at t(s+1), dy at t(s)
+  const float4* gp0 = G4 + (size_t)(rb0 + t_first) * H + j;
+  const float4* gp1 = G4 + (size_t)(rb1 + t_first) * H + j;
+  const float* cp0 = C + (size_t)(rb0 + t_first) * H + j;  // advanced BEFORE use: first use is t(1)
+  const float* cp1 = C + (size_t)(rb1 + t_first) * H + j;
+  const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + t_first) * p.dy_stride + dir * H + j : nullptr;
+  const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + t_first) * p.dy_stride + dir * H + j : nullptr;
+  const ptrdiff_t dstride = (ptrdiff_t)dt * p.dy_stride;
+  constexpr int kStage = 2 * NT;
 
-  auto time_of = [&](int s) { return dir ? s : (T - 1 - s); };  // reverse of the forward scan order
-  auto fetch = [&](int s, CellIn (&q)[2]) {
-    q[0].g = make_float4(0.f, 0.f, 0.f, 0.f);
-    q[0].cprev = 0.f;
-    q[0].dy = 0.f;
-    q[1] = q[0];
-    if (s < T) {
-      const int t = time_of(s);
-      const int tp = dir ? t + 1 : t - 1;            // scan predecessor of t in the forward pass
-      const bool has_prev = dir ? (t + 1 < T) : (t > 0);
-      const bool vv[2] = {v0, v1};
-      const int nn[2] = {n0, n1};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (vv[c]) {
-          const size_t row = (size_t)(nbase + nn[c]) * Tmax + t;
-          q[c].g = G4[row * H + j];
-          if (has_prev) q[c].cprev = __ldg(C + ((size_t)(nbase + nn[c]) * Tmax + tp) * H + j);
-          if (p.dy != nullptr) q[c].dy = __ldg(p.dy + row * p.dy_stride + dir * H + j);
-        }
+  auto issue = [&](int s) {
+    const int st = s & (kD - 1);
+    const bool in = s < T, has_prev = s + 1 < T;
+    cp_async16(&sm.rg[st][0][tid], gp0, in);
+    cp_async16(&sm.rg[st][1][tid], gp1, in);
+    if (has_prev) {
+      cp0 += gstride;
+      cp1 += gstride;
+      gp0 += gstride;
+      gp1 += gstride;
+    }
+    cp_async4(&sm.rc[st][0][tid], cp0, has_prev);  // zero-filled at the chain start (c_{-1} = 0)
+    cp_async4(&sm.rc[st][1][tid], cp1, has_prev);
+    if constexpr (HAS_DY) {
+      cp_async4(&sm.rdy[st][0][tid], dp0, in);
+      cp_async4(&sm.rdy[st][1][tid], dp1, in);
+      if (has_prev) {
+        dp0 += dstride;
+        dp1 += dstride;
       }
     }
+    cp_async_commit();
   };
 
-  CellIn q[kPF][2];
-  fetch(0, q[0]);
-  fetch(1, q[1]);
-  float ccur[2] = {0.f, 0.f}, dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f};
-  {
-    const int t = time_of(0);
-    if (v0) ccur[0] = C[((size_t)(nbase + n0) * Tmax + t) * H + j];
-    if (v1) ccur[1] = C[((size_t)(nbase + n1) * Tmax + t) * H + j];
-    if (p.dhn != nullptr) {
-      if (v0) dhrec[0] = p.dhn[((size_t)dir * N + nbase + n0) * H + j];
-      if (v1) dhrec[1] = p.dhn[((size_t)dir * N + nbase + n1) * H + j];
-    }
+  float ccur[2], dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f};
+  ccur[0] = cp0[0];
+  ccur[1] = cp1[0];
+  if (p.dhn != nullptr) {
+    dhrec[0] = p.dhn[((size_t)dir * N + nbase + min(n0, nvalid - 1)) * H + j];
+    dhrec[1] = p.dhn[((size_t)dir * N + nbase + min(n1, nvalid - 1)) * H + j];
   }
+#pragma unroll
+  for (int s = 0; s < kD; ++s) issue(s);
 
-  auto step = [&](const int s, CellIn (&slot)[2]) {
-    const int t = time_of(s);
-    CellIn in[2] = {slot[0], slot[1]};
-    fetch(s + kPF, slot);
+  float4* gs0 = G4 + (size_t)(rb0 + t_first) * H + j;  // da store pointers at t(s)
+  float4* gs1 = G4 + (size_t)(rb1 + t_first) * H + j;
+  uint32_t* dst_hi0 = &sm.dafrag[0][j >> 2][n0 * 4 + (j & 3)][0];
+  constexpr int kFragPart = KTT * 32 * 2;  // words per hi/lo part
+  const uint32_t* bsrc = &sm.dafrag[0][kh * KTH][lane][0];
 
-    const int nn[2] = {n0, n1};
-    const bool vv[2] = {v0, v1};
+  for (int s = 0; s < T; ++s) {
+    cp_async_wait<kD - 1>();
+    const int st = s & (kD - 1);
+    const float4 gin[2] = {sm.rg[st][0][tid], sm.rg[st][1][tid]};
+    const float cprev[2] = {sm.rc[st][0][tid], sm.rc[st][1][tid]};
+    float dyin[2] = {0.f, 0.f};
+    if constexpr (HAS_DY) {
+      dyin[0] = sm.rdy[st][0][tid];
+      dyin[1] = sm.rdy[st][1][tid];
+    }
+    issue(s + kD);
+
+    float4 sv[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float gi = in[c].g.x, gf = in[c].g.y, gg = in[c].g.z, go = in[c].g.w;
-      const float dh = dhrec[c] + in[c].dy;
+      const float gi = gin[c].x, gf = gin[c].y, gg = gin[c].z, go = gin[c].w;
+      const float dh = dhrec[c] + dyin[c];
       const float tc = tanh_f<FAST_ACT>(ccur[c]);
       const float d_o = dh * tc;
-      const float dct = fmaf(dh * go, 1.0f - tc * tc, dc[c]);
-      const float d_i = dct * gg, d_g = dct * gi, d_f = dct * in[c].cprev;
+      const float dct = fmaf(dh * go, fmaf(-tc, tc, 1.0f), dc[c]);
+      const float d_i = dct * gg, d_g = dct * gi, d_f = dct * cprev[c];
       dc[c] = dct * gf;
-      ccur[c] = in[c].cprev;
+      ccur[c] = cprev[c];
       const float da_i = d_i * gi * (1.0f - gi), da_f = d_f * gf * (1.0f - gf);
-      const float da_g = d_g * (1.0f - gg * gg), da_o = d_o * go * (1.0f - go);
-      if (vv[c]) G4[((size_t)(nbase + nn[c]) * Tmax + t) * H + j] = make_float4(da_i, da_f, da_g, da_o);
+      const float da_g = d_g * fmaf(-gg, gg, 1.0f), da_o = d_o * go * (1.0f - go);
+      sv[c] = make_float4(da_i, da_f, da_g, da_o);
       // B-fragment slot of this cell: k tile j/4, lane (col*4 + j%4)
       uint32_t hi0, hi1, lo0 = 0u, lo1 = 0u;
       if constexpr (SPLIT) {
@@ -145,59 +170,69 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
         hi0 = pack_bf16(da_i, da_f);
         hi1 = pack_bf16(da_g, da_o);
       }
-      const int fl = nn[c] * 4 + (j & 3);
-      *reinterpret_cast<uint2*>(&dafrag[0][j >> 2][fl][0]) = make_uint2(hi0, hi1);
-      if constexpr (SPLIT) *reinterpret_cast<uint2*>(&dafrag[NPART - 1][j >> 2][fl][0]) = make_uint2(lo0, lo1);
+      *reinterpret_cast<uint2*>(dst_hi0 + c * 8) = make_uint2(hi0, hi1);
+      if constexpr (SPLIT) *reinterpret_cast<uint2*>(dst_hi0 + c * 8 + kFragPart) = make_uint2(lo0, lo1);
     }
     __syncthreads();  // (A) all da of this step are in smem
+    // the in-place da store goes out right AFTER the barrier (bar.sync waits for outstanding global stores)
+    if (v0) *gs0 = sv[0];
+    if (v1) *gs1 = sv[1];
+    gs0 += gstride;
+    gs1 += gstride;
 
     if (s + 1 < T) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acs[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float ac1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float ac2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
       for (int ktl = 0; ktl < KTH; ++ktl) {
-        const int kt = kh * KTH + ktl;
-        const uint2 bh = *reinterpret_cast<const uint2*>(&dafrag[0][kt][lane][0]);
-        mma_bf16(acc, Ahi[ktl], bh.x, bh.y);
+        const uint2 bh = *reinterpret_cast<const uint2*>(bsrc + ktl * 64);
+        mma_bf16(acc[ktl & 1], Ahi[ktl], bh.x, bh.y);
         if constexpr (SPLIT) {
-          const uint2 bl = *reinterpret_cast<const uint2*>(&dafrag[NPART - 1][kt][lane][0]);
-          mma_bf16(acs, Ahi[ktl], bl.x, bl.y);
-          mma_bf16(acs, Alo[ktl], bh.x, bh.y);
+          const uint2 bl = *reinterpret_cast<const uint2*>(bsrc + ktl * 64 + kFragPart);
+          mma_bf16(ac1[ktl & 1], Ahi[ktl], bl.x, bl.y);
+          mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
         }
       }
+      float r4[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += acs[r];
-      // acc: [0]=(unit 16mt+gq, col n0) [1]=(.., n1) [2]=(unit 16mt+gq+8, n0) [3]=(.., n1).  Keep the rows of my unit, hand
+      for (int r = 0; r < 4; ++r) {
+        r4[r] = acc[0][r] + acc[1][r];
+        if constexpr (SPLIT) r4[r] += (ac1[0][r] + ac1[1][r]) + (ac2[0][r] + ac2[1][r]);
+      }
+      // r4: [0]=(unit 16mt+gq, col n0) [1]=(.., n1) [2]=(unit 16mt+gq+8, n0) [3]=(.., n1).  Keep the rows of my unit, hand
       // the other two to the partner warp (same mt, other K half), which owns that unit.
-      const float2 mine = kh ? make_float2(acc[2], acc[3]) : make_float2(acc[0], acc[1]);
-      const float2 theirs = kh ? make_float2(acc[0], acc[1]) : make_float2(acc[2], acc[3]);
-      xch[warp][lane] = theirs;
+      const float2 mine = kh ? make_float2(r4[2], r4[3]) : make_float2(r4[0], r4[1]);
+      sm.xch[warp][lane] = kh ? make_float2(r4[0], r4[1]) : make_float2(r4[2], r4[3]);
       __syncthreads();  // (B)
-      const float2 other = xch[kh ? warp - MT : warp + MT][lane];
+      const float2 other = sm.xch[kh ? warp - MT : warp + MT][lane];
       dhrec[0] = mine.x + other.x;
       dhrec[1] = mine.y + other.y;
     }
-  };
-
-  for (int s = 0; s < T; s += kPF) {
-    step(s, q[0]);
-    if (s + 1 < T) step(s + 1, q[1]);
   }
+  cp_async_wait<0>();
+}
+
+template <int H, bool SPLIT, bool FAST, bool HAS_DY>
+cudaError_t launch_k(const LstmBwdArgs& a, cudaStream_t st) {
+  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir);
+  const size_t smem = sizeof(BwdSmem<H>);
+  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY><<<grid, H * 4, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int H, bool SPLIT, bool FAST>
+cudaError_t launch_b(const LstmBwdArgs& a, cudaStream_t st) {
+  return a.dy != nullptr ? launch_k<H, SPLIT, FAST, true>(a, st) : launch_k<H, SPLIT, FAST, false>(a, st);
 }
 
 }  // namespace
 
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st) {
-  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir);
-  if (H == 64) {
-    if (precision == 0) lstm_bwd_kernel<64, true, false><<<grid, 256, 0, st>>>(a);
-    else lstm_bwd_kernel<64, false, true><<<grid, 256, 0, st>>>(a);
-  } else if (H == 32) {
-    if (precision == 0) lstm_bwd_kernel<32, true, false><<<grid, 128, 0, st>>>(a);
-    else lstm_bwd_kernel<32, false, true><<<grid, 128, 0, st>>>(a);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  if (H == 64) return precision == 0 ? launch_b<64, true, false>(a, st) : launch_b<64, false, true>(a, st);
+  if (H == 32) return precision == 0 ? launch_b<32, true, false>(a, st) : launch_b<32, false, true>(a, st);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace ib200

@@ -8,27 +8,37 @@
 //   * gates^T[4H, 8] = W_hh[4H, H] * h^T[H, 8] with mma.m16n8k16 (bf16 operands, fp32 accumulate).  W_hh is the A operand and
 //     lives in REGISTERS for the whole kernel (per warp two 16-row tiles: rows (i_u, f_u) and (g_u, o_u) for its 8 units u),
 //     so after the MMAs each thread holds i,f,g,o of one unit for two sequences: no shuffles, no smem for gates.
-//   * fp32 mode: operands are split into bf16 hi + lo and three MMAs (hi*hi, hi*lo, lo*hi) are issued per product
-//     (operand error ~2^-17; measured end-to-end error at T=1500 ~2e-6).  bf16 mode: one MMA.
-//   * h is exchanged through a double-buffered smem tile (bf16 hi/lo, padded rows => conflict-free B-fragment loads);
-//     ONE __syncthreads per step.
+//     The accumulators are INITIALISED with the input projection, so the MMA result is the pre-activation.
+//   * fp32 mode: operands are split into bf16 hi + lo and three MMAs (hi*hi, hi*lo, lo*hi) are issued per product, each on its
+//     own accumulator chain (depth H/16) (operand error ~2^-17; end-to-end error at T=1500 ~1e-6).  bf16 mode: one MMA.
+//   * h is exchanged through a double-buffered smem tile laid out [unit][sequence] (16-byte rows): the producer writes one
+//     packed bf16x2 word per part, the consumer gets its B fragments with ldmatrix.x4.trans.  ONE __syncthreads per step.
 //   * the input projection is consumed as one float4 per cell (gate-interleaved layout): for layer 0 it is gathered from the
-//     per-group table P[g][dir][token] (K1, the V x 4H lookup-table identity); for layers >= 1 it is the dense
-//     xproj tensor written by the tensor-core GEMM.  It is prefetched two steps ahead into registers.
+//     per-group table P[g][dir][token] (K1, the V x 4H lookup-table identity) -- the CTA's token ids are staged
+//     once in smem as uint16 in scan order; for layers >= 1 it is the dense xproj tensor written by the tensor-core GEMM.
+//     It is prefetched kD steps ahead with cp.async into per-thread smem slots (a register prefetch ring serialises on the
+//     counting scoreboard: profiles/r1_lstm_ncu_full_summary.txt).  The step loop is branch-free: pointers advance by a
+//     constant stride, columns beyond the batch are clamped for loads and masked for stores.
 #include "kernels.h"
 
 namespace ib200 {
 
 namespace {
 
-constexpr int kTokChunk = 32;  // time steps of token ids staged in smem per refill (layer 0)
-constexpr int kPF = 2;         // xproj prefetch distance in steps
+constexpr int kD = 4;  // async prefetch depth in steps (power of two)
+
+template <int H, bool SPLIT>
+struct FwdSmem {
+  static constexpr int NT = H * 4, NPART = SPLIT ? 2 : 1;
+  float4 xring[kD][2][NT];                 // per-thread slots of the input projection
+  __nv_bfloat16 hs[2][NPART][H][kBC];      // h_{t-1}: [buffer][hi/lo][unit][sequence]
+  // followed by uint16 toks[T + kD][kBC] (layer 0)
+};
 
 template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN>
 __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p) {
-  constexpr int KT = H / 16;       // k tiles over the hidden units
-  constexpr int HS = H + 8;        // padded row stride (bf16) of the h tile: conflict-free fragment loads
-  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr int NT = H * 4, KT = H / 16, NPART = SPLIT ? 2 : 1;
+  using Smem = FwdSmem<H, SPLIT>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];  // T_eff of this group
@@ -38,14 +48,15 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
   const int nbase = g * p.B + b0;  // first global sequence index of this CTA
   const int Tmax = p.Tmax;
 
-  __shared__ __align__(16) __nv_bfloat16 hs[2][NPART][kBC][HS];
-  __shared__ int toks[2][kBC][kTokChunk];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  uint16_t* toks = reinterpret_cast<uint16_t*>(smem_raw + sizeof(Smem));
 
   // ---- A fragments: W_hh rows of this warp's 8 units, masked per group for (layer 0, forward) -----------------------------
   const int u = warp * 8 + gq;  // the unit this thread owns
   uint32_t Ahi[2][KT][4], Alo[2][KT][4];
   {
-    const float* __restrict__ W = p.whh[dir];
+    const float* __restrict__ W = (dir ? p.whh[1] : p.whh[0]);
     const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
@@ -54,14 +65,13 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
 #pragma unroll
       for (int kt = 0; kt < KT; ++kt) {
         const int k0 = kt * 16 + 2 * tig;
-        const int rr[4] = {r0, r1, r0, r1};
-        const int kk[4] = {k0, k0, k0 + 8, k0 + 8};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float w0 = W[rr[j] * H + kk[j]], w1 = W[rr[j] * H + kk[j] + 1];
+          const int idx = ((j & 1) ? r1 : r0) * H + k0 + ((j & 2) ? 8 : 0);
+          float w0 = W[idx], w1 = W[idx + 1];
           if (M != nullptr) {
-            w0 *= M[rr[j] * H + kk[j]];
-            w1 *= M[rr[j] * H + kk[j] + 1];
+            w0 *= M[idx];
+            w1 *= M[idx + 1];
           }
           if constexpr (SPLIT) {
             split_bf16(w0, w1, Ahi[tile][kt][j], Alo[tile][kt][j]);
@@ -74,139 +84,172 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
     }
   }
 
-  // ---- init h = 0 (both buffers), token chunks 0 and 1 ---------------------------------------------------------------------
-  for (int i = tid; i < 2 * NPART * kBC * HS; i += blockDim.x) (&hs[0][0][0][0])[i] = __float2bfloat16(0.0f);
-  auto load_tok_chunk = [&](int c) {
-    if constexpr (LAYER0) {
-      for (int i = tid; i < kBC * kTokChunk; i += blockDim.x) {
-        const int n = i / kTokChunk, ss = i % kTokChunk, s = c * kTokChunk + ss;
-        int v = 0;
-        if (s < T && n < nvalid) {
-          const int t = dir ? (T - 1 - s) : s;
-          v = p.tok[(size_t)(nbase + n) * Tmax + t];
-        }
-        toks[c & 1][n][ss] = v;
-      }
+  // ---- init h = 0 (both buffers); stage this CTA's token ids in scan order (layer 0) ------------------------------------------
+  for (int i = tid; i < 2 * NPART * H * kBC / 2; i += NT) reinterpret_cast<uint32_t*>(&sm.hs[0][0][0][0])[i] = 0u;
+  if constexpr (LAYER0) {
+    for (int i = tid; i < (T + kD) * kBC; i += NT) {
+      const int n = i / (T + kD), s = i % (T + kD);  // consecutive threads read consecutive time steps (coalesced)
+      int v = 0;
+      if (s < T && n < nvalid) v = p.tok[(size_t)(nbase + n) * Tmax + (dir ? (T - 1 - s) : s)];
+      toks[s * kBC + n] = (uint16_t)v;
     }
-  };
-  load_tok_chunk(0);
-  load_tok_chunk(1);
+  }
   __syncthreads();
 
   const int n0 = 2 * tig, n1 = 2 * tig + 1;  // the two sequences (columns) this thread owns
   const bool v0 = n0 < nvalid, v1 = n1 < nvalid;
+  // columns beyond the batch read a valid sequence (clamped) and never store
+  const int rb0 = (nbase + min(n0, nvalid - 1)) * Tmax, rb1 = (nbase + min(n1, nvalid - 1)) * Tmax;
+  const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
   const float4* __restrict__ xsrc =
-      LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H
-             : reinterpret_cast<const float4*>(p.xproj[dir]);
+      LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
+             : reinterpret_cast<const float4*>((dir ? p.xproj[1] : p.xproj[0])) + u;
+  // layer >= 1: running source pointers of the prefetch (kD steps ahead of the compute), advanced by one row per step
+  const float4* xp0 = xsrc + (size_t)(rb0 + t_first) * H;
+  const float4* xp1 = xsrc + (size_t)(rb1 + t_first) * H;
+  const ptrdiff_t xstride = (ptrdiff_t)dt * H;
+  float4* slot = &sm.xring[0][0][tid];
+  constexpr int kStage = 2 * NT;  // float4 per ring stage
 
-  auto fetch_x = [&](int s, float4 (&x)[2]) {
-    x[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    x[1] = x[0];
-    if (s < T) {
-      const int t = dir ? (T - 1 - s) : s;
-      if constexpr (LAYER0) {
-        const int c = (s / kTokChunk) & 1, ss = s % kTokChunk;
-        if (v0) x[0] = __ldg(xsrc + (size_t)toks[c][n0][ss] * H + u);
-        if (v1) x[1] = __ldg(xsrc + (size_t)toks[c][n1][ss] * H + u);
-      } else {
-        if (v0) x[0] = __ldg(xsrc + ((size_t)(nbase + n0) * Tmax + t) * H + u);
-        if (v1) x[1] = __ldg(xsrc + ((size_t)(nbase + n1) * Tmax + t) * H + u);
+  // one cp.async group per step; slot (s % kD) of this thread is re-armed right after it has been read
+  auto issue = [&](int s) {
+    float4* dst = slot + (s & (kD - 1)) * kStage;
+    if constexpr (LAYER0) {
+      const uint32_t tw = *reinterpret_cast<const uint32_t*>(toks + s * kBC + n0);  // tokens of (n0, n1); rows >= T hold 0
+      cp_async16(dst, xsrc + (size_t)(tw & 0xffffu) * H, true);
+      cp_async16(dst + NT, xsrc + (size_t)(tw >> 16) * H, true);
+    } else {
+      const bool in = s < T;
+      cp_async16(dst, xp0, in);
+      cp_async16(dst + NT, xp1, in);
+      if (s + 1 < T) {
+        xp0 += xstride;
+        xp1 += xstride;
       }
     }
+    cp_async_commit();
   };
-
-  float4 xq[kPF][2];
-  fetch_x(0, xq[0]);
-  fetch_x(1, xq[1]);
+#pragma unroll
+  for (int s = 0; s < kD; ++s) issue(s);
 
   float c0 = 0.f, c1 = 0.f, h0 = 0.f, h1 = 0.f;
+  // running output pointers at time t(s)
+  float4* g40 = nullptr;
+  float4* g41 = nullptr;
+  float* cs0 = nullptr;
+  float* cs1 = nullptr;
+  if constexpr (TRAIN) {
+    float4* G4 = reinterpret_cast<float4*>((dir ? p.gates[1] : p.gates[0]));
+    float* Cst = (dir ? p.cstate[1] : p.cstate[0]);
+    g40 = G4 + (size_t)(rb0 + t_first) * H + u;
+    g41 = G4 + (size_t)(rb1 + t_first) * H + u;
+    cs0 = Cst + (size_t)(rb0 + t_first) * H + u;
+    cs1 = Cst + (size_t)(rb1 + t_first) * H + u;
+  }
+  const bool has_y = p.y != nullptr;
+  float* y0 = has_y ? p.y + (size_t)(rb0 + t_first) * p.y_stride + dir * H + u : nullptr;
+  float* y1 = has_y ? p.y + (size_t)(rb1 + t_first) * p.y_stride + dir * H + u : nullptr;
+  const ptrdiff_t gstride = (ptrdiff_t)dt * H, ystride = (ptrdiff_t)dt * p.y_stride;
 
-  auto step = [&](const int s, float4 (&xslot)[2]) {
-    const int t = dir ? (T - 1 - s) : s;
-    const float4 x0 = xslot[0], x1 = xslot[1];
-    if constexpr (LAYER0) {
-      // refill the token ring: chunk (s/CH + 1) replaces chunk (s/CH - 1), whose last use was at step s - 1 - kPF
-      if (s > 0 && (s % kTokChunk) == 0) load_tok_chunk(s / kTokChunk + 1);
-    }
-    fetch_x(s + kPF, xslot);
+  const __nv_bfloat16* hrow = &sm.hs[0][0][lane % H][0];  // ldmatrix row address of this lane (k-pair block 0, buffer 0)
+  __nv_bfloat16* hput = &sm.hs[0][0][u][n0];
+  constexpr int kBufElems = NPART * H * kBC, kPartElems = H * kBC;
 
-    // B fragments: h_{t-1}^T
-    const __nv_bfloat16(*hb)[kBC][HS] = hs[s & 1];
-    uint32_t bh[KT][2], bl[KT][2];
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      bh[kt][0] = *reinterpret_cast<const uint32_t*>(&hb[0][gq][kt * 16 + 2 * tig]);
-      bh[kt][1] = *reinterpret_cast<const uint32_t*>(&hb[0][gq][kt * 16 + 2 * tig + 8]);
-      if constexpr (SPLIT) {
-        bl[kt][0] = *reinterpret_cast<const uint32_t*>(&hb[NPART - 1][gq][kt * 16 + 2 * tig]);
-        bl[kt][1] = *reinterpret_cast<const uint32_t*>(&hb[NPART - 1][gq][kt * 16 + 2 * tig + 8]);
-      }
+  const int dbg = p.dbg;
+  for (int s = 0; s < T; ++s) {
+    float4 x0 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), x1 = x0;
+    if (!(dbg & 8)) {
+      cp_async_wait<kD - 1>();  // this thread's copies for step s have landed
+      const float4* cur = slot + (s & (kD - 1)) * kStage;
+      x0 = cur[0];
+      x1 = cur[NT];
+      issue(s + kD);
     }
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float acs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // small cross terms (fp32 mode)
+
+    // accumulators start from the input projection: [0]=(row gq, col n0) [1]=(row gq, col n1) [2]=(row gq+8, n0) [3]=(row gq+8, n1)
+    // tile 0 rows: gq -> i_u, gq+8 -> f_u ; tile 1 rows: gq -> g_u, gq+8 -> o_u
+    float acc[2][4] = {{x0.x, x1.x, x0.y, x1.y}, {x0.z, x1.z, x0.w, x1.w}};
+    float ac1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float ac2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int buf = s & 1;
+    if (!(dbg & 1))
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kp = 0; kp < (KT + 1) / 2; ++kp) {
+      uint32_t bh[4], bl[4];
+      ldmatrix_x4_trans(bh, hrow + buf * kBufElems + kp * 32 * kBC);
+      if constexpr (SPLIT) ldmatrix_x4_trans(bl, hrow + buf * kBufElems + kPartElems + kp * 32 * kBC);
 #pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        mma_bf16(acc[tile], Ahi[tile][kt], bh[kt][0], bh[kt][1]);
-        if constexpr (SPLIT) {
-          mma_bf16(acs[tile], Ahi[tile][kt], bl[kt][0], bl[kt][1]);
-          mma_bf16(acs[tile], Alo[tile][kt], bh[kt][0], bh[kt][1]);
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kt = kp * 2 + kk;
+        if (kt < KT) {
+#pragma unroll
+          for (int tile = 0; tile < 2; ++tile) {
+            mma_bf16(acc[tile], Ahi[tile][kt], bh[2 * kk], bh[2 * kk + 1]);
+            if constexpr (SPLIT) {
+              mma_bf16(ac1[tile], Ahi[tile][kt], bl[2 * kk], bl[2 * kk + 1]);
+              mma_bf16(ac2[tile], Alo[tile][kt], bh[2 * kk], bh[2 * kk + 1]);
+            }
+          }
         }
       }
     }
-    // accumulator layout: [0]=(row gq, col 2tig) [1]=(row gq, col 2tig+1) [2]=(row gq+8, col 2tig) [3]=(row gq+8, col 2tig+1)
-    // tile 0 rows: gq -> i_u, gq+8 -> f_u ; tile 1 rows: gq -> g_u, gq+8 -> o_u
-    float ai0 = acc[0][0] + acs[0][0] + x0.x, af0 = acc[0][2] + acs[0][2] + x0.y;
-    float ag0 = acc[1][0] + acs[1][0] + x0.z, ao0 = acc[1][2] + acs[1][2] + x0.w;
-    float ai1 = acc[0][1] + acs[0][1] + x1.x, af1 = acc[0][3] + acs[0][3] + x1.y;
-    float ag1 = acc[1][1] + acs[1][1] + x1.z, ao1 = acc[1][3] + acs[1][3] + x1.w;
+    float ai0 = acc[0][0], af0 = acc[0][2], ag0 = acc[1][0], ao0 = acc[1][2];
+    float ai1 = acc[0][1], af1 = acc[0][3], ag1 = acc[1][1], ao1 = acc[1][3];
+    if constexpr (SPLIT) {
+      ai0 += ac1[0][0] + ac2[0][0]; af0 += ac1[0][2] + ac2[0][2]; ag0 += ac1[1][0] + ac2[1][0]; ao0 += ac1[1][2] + ac2[1][2];
+      ai1 += ac1[0][1] + ac2[0][1]; af1 += ac1[0][3] + ac2[0][3]; ag1 += ac1[1][1] + ac2[1][1]; ao1 += ac1[1][3] + ac2[1][3];
+    }
 
-    const float i0 = sigmoid_f<FAST_ACT>(ai0), f0 = sigmoid_f<FAST_ACT>(af0), gg0 = tanh_f<FAST_ACT>(ag0),
-                o0 = sigmoid_f<FAST_ACT>(ao0);
-    const float i1 = sigmoid_f<FAST_ACT>(ai1), f1 = sigmoid_f<FAST_ACT>(af1), gg1 = tanh_f<FAST_ACT>(ag1),
-                o1 = sigmoid_f<FAST_ACT>(ao1);
-    c0 = fmaf(f0, c0, i0 * gg0);
-    c1 = fmaf(f1, c1, i1 * gg1);
-    h0 = o0 * tanh_f<FAST_ACT>(c0);
-    h1 = o1 * tanh_f<FAST_ACT>(c1);
+    float i0, f0, gg0, o0, i1, f1, gg1, o1;
+    if (!(dbg & 2)) {
+      i0 = sigmoid_f<FAST_ACT>(ai0), f0 = sigmoid_f<FAST_ACT>(af0), gg0 = tanh_f<FAST_ACT>(ag0), o0 = sigmoid_f<FAST_ACT>(ao0);
+      i1 = sigmoid_f<FAST_ACT>(ai1), f1 = sigmoid_f<FAST_ACT>(af1), gg1 = tanh_f<FAST_ACT>(ag1), o1 = sigmoid_f<FAST_ACT>(ao1);
+      c0 = fmaf(f0, c0, i0 * gg0);
+      c1 = fmaf(f1, c1, i1 * gg1);
+      h0 = o0 * tanh_f<FAST_ACT>(c0);
+      h1 = o1 * tanh_f<FAST_ACT>(c1);
+    } else {
+      i0 = ai0 * 0.5f, f0 = af0 * 0.5f, gg0 = ag0 * 0.5f, o0 = ao0 * 0.5f, i1 = ai1 * 0.5f, f1 = af1 * 0.5f, gg1 = ag1 * 0.5f, o1 = ao1 * 0.5f;
+      c0 = fmaf(f0, c0, i0 * gg0) * 0.1f;
+      c1 = fmaf(f1, c1, i1 * gg1) * 0.1f;
+      h0 = o0 * c0;
+      h1 = o1 * c1;
+    }
 
-    // publish h_t for the next step
-    __nv_bfloat16(*hn)[kBC][HS] = hs[(s + 1) & 1];
+    // publish h_t for the next step: one packed word (sequences n0,n1 of unit u) per part
     {
-      const __nv_bfloat16 h0h = __float2bfloat16_rn(h0), h1h = __float2bfloat16_rn(h1);
-      hn[0][n0][u] = h0h;
-      hn[0][n1][u] = h1h;
+      __nv_bfloat16* dst = hput + (buf ^ 1) * kBufElems;
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
+      *reinterpret_cast<__nv_bfloat162*>(dst) = hh;
       if constexpr (SPLIT) {
-        hn[NPART - 1][n0][u] = __float2bfloat16_rn(h0 - __bfloat162float(h0h));
-        hn[NPART - 1][n1][u] = __float2bfloat16_rn(h1 - __bfloat162float(h1h));
+        const float2 hf = __bfloat1622float2(hh);
+        *reinterpret_cast<__nv_bfloat162*>(dst + kPartElems) = __floats2bfloat162_rn(h0 - hf.x, h1 - hf.y);
       }
     }
-    // stream out what later stages need
-    const size_t row0 = (size_t)(nbase + n0) * Tmax + t, row1 = (size_t)(nbase + n1) * Tmax + t;
-    if (p.y != nullptr) {
-      if (v0) p.y[row0 * p.y_stride + dir * H + u] = h0;
-      if (v1) p.y[row1 * p.y_stride + dir * H + u] = h1;
+    // stream out what later stages need (placement relative to the barrier makes no measurable difference: ablation in DESIGN.md)
+    if (has_y && !(dbg & 4)) {
+      if (v0) *y0 = h0;
+      if (v1) *y1 = h1;
+      y0 += ystride;
+      y1 += ystride;
     }
-    if constexpr (TRAIN) {
-      float4* G4 = reinterpret_cast<float4*>(p.gates[dir]);
-      float* C = p.cstate[dir];
+    if (TRAIN && !(dbg & 4)) {
       if (v0) {
-        G4[row0 * H + u] = make_float4(i0, f0, gg0, o0);
-        C[row0 * H + u] = c0;
+        *g40 = make_float4(i0, f0, gg0, o0);
+        *cs0 = c0;
       }
       if (v1) {
-        G4[row1 * H + u] = make_float4(i1, f1, gg1, o1);
-        C[row1 * H + u] = c1;
+        *g41 = make_float4(i1, f1, gg1, o1);
+        *cs1 = c1;
       }
+      g40 += gstride;
+      g41 += gstride;
+      cs0 += gstride;
+      cs1 += gstride;
     }
-    __syncthreads();
-  };
-
-  for (int s = 0; s < T; s += kPF) {
-    step(s, xq[0]);
-    if (s + 1 < T) step(s + 1, xq[1]);
+    if (!(dbg & 16)) __syncthreads();
   }
+  cp_async_wait<0>();
 
   if (p.hn != nullptr) {
     const size_t N = (size_t)p.G * p.B;
@@ -215,15 +258,26 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
   }
 }
 
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
+cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
+  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir), block(H * 4);
+  size_t smem = sizeof(FwdSmem<H, SPLIT>);
+  if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR><<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <int H, bool SPLIT, bool FAST>
 cudaError_t launch_h(const LstmFwdArgs& a, cudaStream_t st) {
-  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir), block(H * 4);
   const bool l0 = a.tok != nullptr, tr = a.gates[a.dir0] != nullptr;
-  if (l0 && tr) lstm_fwd_kernel<H, SPLIT, FAST, true, true><<<grid, block, 0, st>>>(a);
-  else if (l0) lstm_fwd_kernel<H, SPLIT, FAST, true, false><<<grid, block, 0, st>>>(a);
-  else if (tr) lstm_fwd_kernel<H, SPLIT, FAST, false, true><<<grid, block, 0, st>>>(a);
-  else lstm_fwd_kernel<H, SPLIT, FAST, false, false><<<grid, block, 0, st>>>(a);
-  return cudaGetLastError();
+  if (l0 && a.V > 65536) return cudaErrorInvalidValue;  // token ids are staged as uint16
+  if (l0 && tr) return launch_k<H, SPLIT, FAST, true, true>(a, st);
+  if (l0) return launch_k<H, SPLIT, FAST, true, false>(a, st);
+  if (tr) return launch_k<H, SPLIT, FAST, false, true>(a, st);
+  return launch_k<H, SPLIT, FAST, false, false>(a, st);
 }
 
 }  // namespace
