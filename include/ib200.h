@@ -159,6 +159,20 @@ int ib200_loss_head_bwd(int32_t B, int32_t H, float beta_classifier, const float
 int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a, const int32_t* idx_b, int64_t P,
                      const ib200_head_params* params, float* prob_out, void* stream);
 
+/* Test hook (tests/test_gpu_gemm.py): the token-row NT GEMM in isolation.  impl: 0 legacy mma.sync, 1 tcgen05, 2 auto.
+ * C[row,NC] (=|+=) sum_s A_s[row,K] W_s[NC,K]^T (+bias) for rows (n,t) with t < lens[G + n/B] of the [G*B, T] row space. */
+int ib200_dbg_gemm_nt(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                      int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc,
+                      int32_t NC, int32_t accumulate, int32_t precision, int32_t impl, void* stream);
+
+/* Test hook: the weight-gradient TN GEMM in isolation.  partial[g][cta][KA*NB (+KA column sums)] = sum over the token rows
+ * assigned to (g, cta) of A[row,KA]^T Bop[row,NB]; Bop = Bsrc rows shifted by `shift` steps (zero outside [0,T_eff)), or
+ * scale[g][tok]*emb[tok] when tok != NULL. */
+int ib200_dbg_gemm_tn(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, int32_t KA, const float* Bsrc,
+                      int32_t ldb, int32_t col0, int32_t shift, const int32_t* tok, const float* emb, const float* emb_row_scale,
+                      int32_t V, int32_t NB, float* partial, int32_t ctas_per_group, int32_t colsum, int32_t precision,
+                      int32_t impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,6 +143,40 @@ Plan make_plan(const ib200_cfg* c) {
   return p;
 }
 
+// GEMM dispatch: tcgen05 kernels where the shape is covered, legacy mma.sync otherwise (H=32 test shapes; IB200_GEMM=legacy)
+bool use_tc() {
+  static const bool v = [] { const char* e = getenv("IB200_GEMM"); return !(e && std::string(e) == "legacy"); }();
+  return v;
+}
+cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st) {
+  if (use_tc()) {
+    cudaError_t e = launch_gemm_nt_tc(a, prec, st);
+    if (e != cudaErrorInvalidConfiguration) return e;
+    (void)cudaGetLastError();
+    if (a.nsrc == 2) {  // W of both sources does not fit in shared memory: one source per pass, second pass accumulates
+      GemmNTArgs b = a;
+      b.nsrc = 1;
+      e = launch_gemm_nt_tc(b, prec, st);
+      if (e == cudaSuccess) {
+        b.A[0] = a.A[1]; b.W[0] = a.W[1]; b.accumulate = 1; b.bias = nullptr;
+        return launch_gemm_nt_tc(b, prec, st);
+      }
+      if (e != cudaErrorInvalidConfiguration) return e;
+      (void)cudaGetLastError();
+    }
+  }
+  return launch_gemm_nt(a, prec, st);
+}
+
+cudaError_t gemm_tn_auto(const GemmTNArgs& a, int prec, cudaStream_t st) {
+  if (use_tc()) {
+    cudaError_t e = launch_gemm_tn_tc(a, prec, st);
+    if (e != cudaErrorInvalidConfiguration) return e;
+    (void)cudaGetLastError();
+  }
+  return launch_gemm_tn(a, prec, st);
+}
+
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
 
@@ -229,7 +263,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
         ga.nsrc = 1; ga.A[0] = at<float>(ws, p.Y[l - 1]); ga.lda = 2 * H; ga.K = 2 * H;
         ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
         ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
-        TIMED(F_GEMM_XPROJ, 1, launch_gemm_nt(ga, prec, st), "input projection gemm");
+        TIMED(F_GEMM_XPROJ, 1, gemm_nt_auto(ga, prec, st), "input projection gemm");
       }
     }
     LstmFwdArgs fa{};
@@ -311,14 +345,14 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         ta.Bsrc = at<float>(ws, p.Y[l - 1]); ta.ldb = 2 * H; ta.col0 = 0; ta.shift = 0; ta.NB = 2 * H;
       }
       ta.colsum = 0;
-      TIMED(F_GEMM_DW, 1, launch_gemm_tn(ta, prec, st), "dW_ih gemm");
+      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_ih gemm");
       DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], nullptr, nullptr};
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW_ih reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
       ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H;
       ta.colsum = 1;
-      TIMED(F_GEMM_DW, 1, launch_gemm_tn(ta, prec, st), "dW_hh gemm");
+      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_hh gemm");
       DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, (l == 0 && d == 0) ? whh_l0_mask : nullptr,
                       Gr->w_hh[l][d], Gr->b_ih[l][d], Gr->b_hh[l][d]};
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rb, st), "dW_hh reduce");
@@ -337,10 +371,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ga.lda = 4 * H; ga.K = 4 * H; ga.bias = nullptr; ga.accumulate = 0;
     if (l > 0) {
       ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
-      TIMED(F_GEMM_DGRAD, 1, launch_gemm_nt(ga, prec, st), "dY gemm");
+      TIMED(F_GEMM_DGRAD, 1, gemm_nt_auto(ga, prec, st), "dY gemm");
     } else {
       ga.C = dX0; ga.ldc = H; ga.NC = H;
-      TIMED(F_GEMM_DGRAD, 1, launch_gemm_nt(ga, prec, st), "dX0 gemm");
+      TIMED(F_GEMM_DGRAD, 1, gemm_nt_auto(ga, prec, st), "dX0 gemm");
       EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
       TIMED(F_EMB_GRAD, 2, launch_emb_grad(ea, st), "embedding grad");
     }
@@ -398,6 +432,33 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
   if (!idx_a && P != (int64_t)M * (M + 1) / 2) return fail(IB200_E_SHAPE, "ib200_pair_score: P must be M(M+1)/2 for the implicit upper triangle");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, st), "pair_score");
+  return 0;
+}
+
+// ---- test hooks: the token-row GEMMs in isolation (tests/test_gpu_gemm.py) ------------------------------------------------------
+int ib200_dbg_gemm_nt(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                      int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc,
+                      int32_t NC, int32_t accumulate, int32_t precision, int32_t impl, void* stream) {
+  GemmNTArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.nsrc = nsrc; a.A[0] = A0; a.A[1] = A1; a.lda = lda; a.K = K;
+  a.W[0] = W0; a.W[1] = W1; a.bias = bias; a.C = C; a.ldc = ldc; a.NC = NC; a.accumulate = accumulate;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(impl == 0 ? launch_gemm_nt(a, precision, st) : (impl == 1 ? launch_gemm_nt_tc(a, precision, st) : gemm_nt_auto(a, precision, st)),
+     "dbg gemm nt");
+  return 0;
+}
+
+int ib200_dbg_gemm_tn(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, int32_t KA, const float* Bsrc,
+                      int32_t ldb, int32_t col0, int32_t shift, const int32_t* tok, const float* emb, const float* emb_row_scale,
+                      int32_t V, int32_t NB, float* partial, int32_t ctas_per_group, int32_t colsum, int32_t precision,
+                      int32_t impl, void* stream) {
+  GemmTNArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.A = A; a.KA = KA; a.Bsrc = Bsrc; a.ldb = ldb; a.col0 = col0; a.shift = shift;
+  a.tok = tok; a.emb = emb; a.emb_row_scale = emb_row_scale; a.V = V; a.NB = NB; a.partial = partial;
+  a.ctas_per_group = ctas_per_group; a.colsum = colsum;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(impl == 0 ? launch_gemm_tn(a, precision, st) : (impl == 1 ? launch_gemm_tn_tc(a, precision, st) : gemm_tn_auto(a, precision, st)),
+     "dbg gemm tn");
   return 0;
 }
 

@@ -1,0 +1,441 @@
+// tcgen05 (5th-gen tensor core) versions of the token-row GEMMs, H = 64 shapes.  Same contracts as gemm.cu:
+//   NT : C[row, NC] (=|+=) sum_s A_s[row, K] W_s[NC, K]^T (+ bias)     xproj (NC=256,K=128), dY (NC=128,K=256), dX0 (NC=64,K=512)
+//   TN : P[cta][KA, NB] = sum_rows A[row, KA]^T Bop[row, NB]           dW_ih / dW_hh / db partials (KA=256, NB=128|64)
+// Operands are fp32 in HBM.  Loader warps read them (coalesced, masked by T_eff, optionally gathered/shifted), split every value
+// into bf16 hi + lo and write both planes into 128-byte-swizzled shared-memory tiles; ONE thread issues tcgen05.mma
+// (kind::f16, bf16 x bf16 -> fp32 in TMEM), three MMAs per k-step in fp32 mode (hi*hi + hi*lo + lo*hi); accumulators live in TMEM
+// and are drained by four epilogue warps with tcgen05.ld.  Stages are handed over with mbarriers; tcgen05.commit releases them.
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace ib200 {
+namespace {
+
+using namespace tc;
+
+constexpr int kBM = 128;      // rows per tile (UMMA M)
+constexpr int kBK = 64;       // k elements per stage (= one 128-byte swizzle row of bf16)
+constexpr int kStagesNT = 2;
+constexpr int kTileBytes = kBM * 128;  // one [128 x 64] bf16 plane
+
+struct NTBarriers {
+  uint64_t full[kStagesNT], empty[kStagesNT], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ bool nt_tile_live(const GemmNTArgs& p, long long row0, long long nrows) {
+  const long long rl = min(row0 + kBM, nrows) - 1;
+  const int na = (int)(row0 / p.Tmax), nb = (int)(rl / p.Tmax);
+  return !(na == nb && (int)(row0 % p.Tmax) >= p.lens[p.G + na / p.B]);
+}
+
+// write 4 consecutive k (or m) values as bf16 hi / lo into the two planes of a swizzled tile
+template <bool SPLIT>
+__device__ __forceinline__ void store_split4(unsigned char* hi_plane, unsigned char* lo_plane, uint32_t off, float4 v) {
+  uint32_t h0, h1, l0 = 0u, l1 = 0u;
+  if constexpr (SPLIT) {
+    split_bf16(v.x, v.y, h0, l0);
+    split_bf16(v.z, v.w, h1, l1);
+  } else {
+    h0 = pack_bf16(v.x, v.y);
+    h1 = pack_bf16(v.z, v.w);
+  }
+  *reinterpret_cast<uint2*>(hi_plane + off) = make_uint2(h0, h1);
+  if constexpr (SPLIT) *reinterpret_cast<uint2*>(lo_plane + off) = make_uint2(l0, l1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// NT.  9 warps: 0-3 loaders (A tiles), 4-7 epilogue (TMEM -> HBM), 8 MMA issuer + TMEM owner.  W (all of K) is resident in smem.
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int NC, bool SPLIT>
+__global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) {
+  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr uint32_t kWTile = NC * 128;  // one [NC x 64] bf16 plane of W
+  constexpr uint32_t kTmemCols = 2 * NC < 32 ? 32 : 2 * NC;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int kslices = p.K / kBK, KC = p.nsrc * kslices;
+  unsigned char* Wres = smem;                                    // [KC][NPART][NC x 128 B]
+  unsigned char* Ast = Wres + (size_t)KC * NPART * kWTile;        // [stage][NPART][128 x 128 B]
+  NTBarriers* bars = reinterpret_cast<NTBarriers*>(Ast + (size_t)kStagesNT * NPART * kTileBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nrows = (long long)p.G * p.B * p.Tmax;
+  const int ntiles = (int)((nrows + kBM - 1) / kBM);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesNT; ++s) {
+      mbar_init(&bars->full[s], 128);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tfull[a], 1);
+      mbar_init(&bars->tempty[a], 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, kTmemCols);
+  // resident W: all 256 loader+epilogue threads convert fp32 -> bf16 hi/lo, swizzled K-major
+  if (warp < 8) {
+    const int f4_per_row = p.K / 4;
+    for (int src = 0; src < p.nsrc; ++src) {
+      const float* __restrict__ W = src ? p.W[1] : p.W[0];
+      for (int i = tid; i < NC * f4_per_row; i += 256) {
+        const int n = i / f4_per_row, k4 = i % f4_per_row, k = k4 * 4;
+        const float4 v = *reinterpret_cast<const float4*>(W + (size_t)n * p.K + k);
+        const int kc = src * kslices + k / kBK, kk = k % kBK;
+        unsigned char* hi = Wres + (size_t)(kc * NPART) * kWTile;
+        store_split4<SPLIT>(hi, hi + kWTile, sw128_offset(n, kk >> 3) + ((kk >> 2) & 1) * 8, v);
+      }
+    }
+    fence_async_smem();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < 4) {
+    // ===================== loaders =====================
+    const int f = tid & 15, rg = tid >> 4;  // float4 index within the 64-wide k slice, row group
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * kBM;
+      if (!nt_tile_live(p, row0, nrows)) continue;
+      // row validity of the 16 rows this thread touches
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long row = row0 + j * 8 + rg;
+        bool ok = row < nrows;
+        if (ok) ok = (int)(row % p.Tmax) < p.lens[p.G + (int)(row / p.Tmax) / p.B];
+        vmask |= (ok ? 1u : 0u) << j;
+      }
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int stage = it % kStagesNT;
+        const float* __restrict__ A = (kc / kslices) ? p.A[1] : p.A[0];
+        const int k0 = (kc % kslices) * kBK + f * 4;
+        float4 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vmask & (1u << j)) v[j] = __ldg(reinterpret_cast<const float4*>(A + (row0 + j * 8 + rg) * p.lda + k0));
+        }
+        mbar_wait(&bars->empty[stage], ((it / kStagesNT) & 1) ^ 1);
+        unsigned char* hi = Ast + (size_t)(stage * NPART) * kTileBytes;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) store_split4<SPLIT>(hi, hi + kTileBytes, sw128_offset(j * 8 + rg, f >> 1) + (f & 1) * 8, v[j]);
+        fence_async_smem();
+        mbar_arrive(&bars->full[stage]);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kBM, NC, false, false);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (!nt_tile_live(p, (long long)tile * kBM, nrows)) continue;
+        const uint32_t acc = tl & 1;
+        mbar_wait(&bars->tempty[acc], ((tl >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * NC;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int stage = it % kStagesNT;
+          mbar_wait(&bars->full[stage], (it / kStagesNT) & 1);
+          fence_after_sync();
+          const uint32_t a_hi = smem_u32(Ast + (size_t)(stage * NPART) * kTileBytes), a_lo = a_hi + kTileBytes;
+          const uint32_t b_hi = smem_u32(Wres + (size_t)(kc * NPART) * kWTile), b_lo = b_hi + kWTile;
+#pragma unroll
+          for (int k16 = 0; k16 < kBK / 16; ++k16) {
+            const uint32_t ko = k16 * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
+            const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, 0), bh = smem_desc_sw128(b_hi + ko, 1024, 0);
+            mma_bf16_ss(d_tmem, ah, bh, idesc, (kc | k16) != 0);
+            if constexpr (SPLIT) {
+              const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, 0), bl = smem_desc_sw128(b_lo + ko, 1024, 0);
+              mma_bf16_ss(d_tmem, ah, bl, idesc, true);
+              mma_bf16_ss(d_tmem, al, bh, idesc, true);
+            }
+          }
+          mma_commit(&bars->empty[stage]);  // stage free once these MMAs have read it
+        }
+        mma_commit(&bars->tfull[acc]);
+        ++tl;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * kBM;
+      if (!nt_tile_live(p, row0, nrows)) continue;
+      const uint32_t acc = tl & 1;
+      mbar_wait(&bars->tfull[acc], (tl >> 1) & 1);
+      fence_after_sync();
+      const long long row = row0 + q * 32 + lane;
+      bool ok = row < nrows;
+      if (ok) ok = (int)(row % p.Tmax) < p.lens[p.G + (int)(row / p.Tmax) / p.B];
+      float* crow = p.C + row * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < NC / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC + c * 32, r);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            const int col = c * 32 + 4 * j;
+            if (p.bias != nullptr) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(crow + col);
+            if (p.accumulate) {
+              const float4 e = *dst;
+              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
+            *dst = o;
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&bars->tempty[acc]);
+      ++tl;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int NC>
+cudaError_t launch_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st) {
+  const int npart = precision == 0 ? 2 : 1;
+  const int KC = a.nsrc * (a.K / kBK);
+  const size_t smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + sizeof(NTBarriers) + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back (one source per pass / legacy kernel)
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long nrows = (long long)a.G * a.B * a.Tmax;
+  const int ntiles = (int)((nrows + kBM - 1) / kBM);
+  const unsigned grid = (unsigned)std::min(ntiles, sms);
+  cudaError_t e;
+  if (precision == 0) {
+    e = cudaFuncSetAttribute(gemm_nt_tc_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_nt_tc_kernel<NC, true><<<grid, 288, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_nt_tc_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_nt_tc_kernel<NC, false><<<grid, 288, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// TN.  P[cta][KA=256, NB] = sum over this CTA's token rows of A[row, :]^T Bop[row, :].  Both operands are "MN-major" for the
+// tensor core: a stage holds 64 token rows (= K); each 64-column block of A / Bop is a [64 k-rows x 128 B] swizzled tile.
+// 9 warps: 0-7 loaders (fp32 -> bf16 hi/lo, masked / shifted / gathered), 8 MMA issuer + TMEM owner; warps 0-3 drain TMEM at the end.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int kStagesTN = 2;
+constexpr int kBlkBytes = 64 * 128;  // one [64 k-rows x 64 columns] bf16 block
+
+struct TNBarriers {
+  uint64_t full[kStagesTN], empty[kStagesTN], done;
+  uint32_t tmem_base;
+};
+
+template <int NB, bool SPLIT>
+__global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const GemmTNArgs p) {
+  constexpr int KA = 256, NPART = SPLIT ? 2 : 1;
+  constexpr int kABytes = (KA / 64) * kBlkBytes, kBBytes = (NB / 64) * kBlkBytes;  // per plane
+  constexpr int kStageBytes = NPART * (kABytes + kBBytes);
+  constexpr uint32_t kTmemCols = 2 * NB;
+  constexpr int FPR = NB / 4, RPP = 256 / FPR, BPASS = 64 / RPP;  // B operand: float4 per row, rows per pass, passes
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  TNBarriers* bars = reinterpret_cast<TNBarriers*>(smem + (size_t)kStagesTN * kStageBytes);
+  float* csum_sm = reinterpret_cast<float*>(bars + 1);  // [4][KA] column-sum exchange
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y, cta = blockIdx.x;
+  const int T = p.lens[p.G + g];
+  const int tiles_per_seq = (T + 63) / 64;
+  const int items = p.B * tiles_per_seq;
+  const bool gathered = p.tok != nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesTN; ++s) {
+      mbar_init(&bars->full[s], 256);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->done, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int my_items = cta < items ? (items - cta + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+
+  if (warp < 8) {
+    // ===================== loaders =====================
+    const int fa = tid & 63, ra = tid >> 6;      // A: float4 index in the 256-wide row, first row (rows ra + 4j)
+    const int fb = tid % FPR, rb = tid / FPR;    // B: float4 index in the NB-wide row, first row (rows rb + RPP*j)
+    const uint32_t a_off = (fa >> 4) * kBlkBytes + (fa & 1) * 8, a_chunk = (fa & 15) >> 1;
+    const uint32_t b_off = (fb >> 4) * kBlkBytes + (fb & 1) * 8, b_chunk = (fb & 15) >> 1;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t it = 0;
+    for (int item = cta; item < items; item += p.ctas_per_group, ++it) {
+      const int stage = it % kStagesTN;
+      const int n = g * p.B + item / tiles_per_seq, t0 = (item % tiles_per_seq) * 64;
+      float4 va[16], vb[BPASS];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int t = t0 + ra + 4 * j;
+        va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < T) va[j] = __ldg(reinterpret_cast<const float4*>(p.A + ((size_t)n * p.Tmax + t) * KA) + fa);
+      }
+#pragma unroll
+      for (int j = 0; j < BPASS; ++j) {
+        const int t = t0 + rb + RPP * j;
+        vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < T) {
+          if (gathered) {
+            const int tk = p.tok[(size_t)n * p.Tmax + t];
+            const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + tk] : 1.0f;
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB) + fb);
+            vb[j] = make_float4(sc * e.x, sc * e.y, sc * e.z, sc * e.w);
+          } else {
+            const int ts = t + p.shift;
+            if (ts >= 0 && ts < T) vb[j] = __ldg(reinterpret_cast<const float4*>(p.Bsrc + ((size_t)n * p.Tmax + ts) * p.ldb + p.col0) + fb);
+          }
+        }
+      }
+      if (p.colsum) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { csum.x += va[j].x; csum.y += va[j].y; csum.z += va[j].z; csum.w += va[j].w; }
+      }
+      mbar_wait(&bars->empty[stage], ((it / kStagesTN) & 1) ^ 1);
+      unsigned char* st_base = smem + (size_t)stage * kStageBytes;
+      unsigned char* a_hi = st_base;                     // [A hi][A lo][B hi][B lo]
+      unsigned char* b_hi = st_base + NPART * kABytes;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) store_split4<SPLIT>(a_hi, a_hi + kABytes, a_off + sw128_offset(ra + 4 * j, a_chunk), va[j]);
+#pragma unroll
+      for (int j = 0; j < BPASS; ++j) store_split4<SPLIT>(b_hi, b_hi + kBBytes, b_off + sw128_offset(rb + RPP * j, b_chunk), vb[j]);
+      fence_async_smem();
+      mbar_arrive(&bars->full[stage]);
+    }
+    if (p.colsum) *reinterpret_cast<float4*>(csum_sm + ra * KA + fa * 4) = csum;
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_bf16(128, NB, true, true);
+    for (int it = 0; it < my_items; ++it) {
+      const int stage = it % kStagesTN;
+      mbar_wait(&bars->full[stage], (it / kStagesTN) & 1);
+      fence_after_sync();
+      const uint32_t a_hi = smem_u32(smem + (size_t)stage * kStageBytes), a_lo = a_hi + kABytes;
+      const uint32_t b_hi = a_hi + NPART * kABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16) {
+        const uint32_t ko = k16 * 16 * 128;  // 16 k-rows of 128 bytes
+        const uint64_t bh = smem_desc_sw128(b_hi + ko, 1024, kBlkBytes), bl = smem_desc_sw128(b_lo + ko, 1024, kBlkBytes);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t mo = mt * 2 * kBlkBytes;  // 128 columns of A = two 64-column blocks
+          const uint64_t ah = smem_desc_sw128(a_hi + mo + ko, 1024, kBlkBytes);
+          const uint32_t d = tmem_base + mt * NB;
+          mma_bf16_ss(d, ah, bh, idesc, (it | k16) != 0);
+          if constexpr (SPLIT) {
+            const uint64_t al = smem_desc_sw128(a_lo + mo + ko, 1024, kBlkBytes);
+            mma_bf16_ss(d, ah, bl, idesc, true);
+            mma_bf16_ss(d, al, bh, idesc, true);
+          }
+        }
+      }
+      mma_commit(&bars->empty[stage]);
+    }
+    mma_commit(&bars->done);
+  }
+  __syncthreads();  // column sums visible; every role has finished issuing
+
+  float* out = p.partial + ((size_t)g * p.ctas_per_group + cta) * ((size_t)KA * NB + (p.colsum ? KA : 0));
+  if (warp < 4) {
+    // ===================== epilogue: TMEM -> partial[KA][NB] =====================
+    if (my_items > 0) {
+      mbar_wait(&bars->done, 0);
+      fence_after_sync();
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      float* orow = out + (size_t)(mt * 128 + warp * 32 + lane) * NB;
+#pragma unroll 1
+      for (int c = 0; c < NB / 32; ++c) {
+        uint32_t r[32];
+        if (my_items > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * NB + c * 32, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(orow + c * 32 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  } else if (warp < 8 && p.colsum) {
+    for (int c = tid - 128; c < KA; c += 128)
+      out[(size_t)KA * NB + c] = my_items > 0 ? (csum_sm[c] + csum_sm[KA + c]) + (csum_sm[2 * KA + c] + csum_sm[3 * KA + c]) : 0.f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int NB>
+cudaError_t launch_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st) {
+  const int npart = precision == 0 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)kStagesTN * npart * ((256 / 64) + (NB / 64)) * kBlkBytes + sizeof(TNBarriers) + 4 * 256 * sizeof(float) + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  dim3 grid(a.ctas_per_group, a.G);
+  cudaError_t e;
+  if (precision == 0) {
+    e = cudaFuncSetAttribute(gemm_tn_tc_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tn_tc_kernel<NB, true><<<grid, 288, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_tn_tc_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tn_tc_kernel<NB, false><<<grid, 288, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// returns cudaErrorInvalidConfiguration when the shape is not covered (caller uses the legacy mma.sync kernel)
+cudaError_t launch_gemm_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st) {
+  if (a.K % kBK != 0 || a.lda % 4 != 0 || a.ldc % 4 != 0) return cudaErrorInvalidConfiguration;
+  switch (a.NC) {
+    case 256: return launch_nt_tc<256>(a, precision, st);
+    case 128: return launch_nt_tc<128>(a, precision, st);
+    case 64: return launch_nt_tc<64>(a, precision, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+
+cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st) {
+  if (a.KA != 256) return cudaErrorInvalidConfiguration;
+  if (!a.tok && (a.ldb % 4 != 0 || a.col0 % 4 != 0)) return cudaErrorInvalidConfiguration;
+  if (a.NB == 128) return launch_tn_tc<128>(a, precision, st);
+  if (a.NB == 64) return launch_tn_tc<64>(a, precision, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace ib200

@@ -82,7 +82,9 @@ struct GemmNTArgs {
   int NC;
   int accumulate;            // C += instead of C =
 };
-cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st);
+cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st);      // legacy mma.sync (any supported H)
+// tcgen05 version (H=64 shapes); returns cudaErrorInvalidConfiguration when the shape / smem budget is not covered
+cudaError_t launch_gemm_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st);
 
 // TN:  P[cta][KA, NB] = sum_{rows of cta} A[row, KA]^T * Bop[row, NB]   (partials; reduced by launch_dw_reduce)
 struct GemmTNArgs {
@@ -102,7 +104,8 @@ struct GemmTNArgs {
   int ctas_per_group;
   int colsum;                // also produce column sums of A (bias gradient) after the KA*NB block
 };
-cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st);
+cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st);      // legacy mma.sync
+cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st);   // tcgen05 (KA=256, NB=128|64)
 
 // out[torch_row(gi)][c] = sum_g mask_g[torch_row][c] * sum_cta partial[g][cta][gi][c];  optional bias outputs
 struct DwReduceArgs {
