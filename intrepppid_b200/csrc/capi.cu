@@ -322,6 +322,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ba.dy = l == p.L - 1 ? nullptr : dY;
     ba.dy_stride = 2 * H;
     ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
+    { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
     TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)

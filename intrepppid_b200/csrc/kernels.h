@@ -63,6 +63,7 @@ struct LstmBwdArgs {
   const float* dy;           // [N,Tmax,dy_stride] (+dir*H) gradient w.r.t. this layer's output, or null
   int dy_stride;
   const float* dhn;          // [2,N,H] gradient w.r.t. the final hidden state, or null
+  int dbg;                   // ablation flags (env IB200_DBG)
 };
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 

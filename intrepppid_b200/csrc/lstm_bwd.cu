@@ -29,16 +29,18 @@ struct BwdSmem {
   float2 xch[NW][32];              // partial dh handed to the partner warp
 };
 
-template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY>
-__global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p) {
+// HALF: 4 sequences per CTA on the even mma columns, one cell per thread (see lstm_fwd.cu).
+template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY, bool HALF>
+__global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const LstmBwdArgs p) {
   constexpr int NT = H * 4, MT = H / 16, KTT = H / 4, KTH = KTT / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int mt = warp % MT, kh = warp / MT;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];
   if (T <= 0) return;
-  const int b0 = blockIdx.x * kBC;
-  const int nvalid = min(kBC, p.B - b0);
+  constexpr int SEQ = HALF ? kBC / 2 : kBC, NC = HALF ? 1 : 2;  // sequences per CTA, cells per thread
+  const int b0 = blockIdx.x * SEQ;
+  const int nvalid = min(SEQ, p.B - b0);
   const int nbase = g * p.B + b0;
   const int Tmax = p.Tmax;
   const size_t N = (size_t)p.G * p.B;
@@ -76,10 +78,11 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
 
   // ---- the two cells this thread owns -----------------------------------------------------------------------------------------
   const int j = 16 * mt + gq + 8 * kh;
-  const int n0 = 2 * tig, n1 = n0 + 1;
-  const bool v0 = n0 < nvalid, v1 = n1 < nvalid;
+  const int n0 = 2 * tig, n1 = n0 + 1;                   // mma columns (HALF: only n0 carries a sequence)
+  const int q0 = HALF ? tig : n0, q1 = HALF ? tig : n1;  // sequence index within the CTA
+  const bool v0 = q0 < nvalid, v1 = !HALF && q1 < nvalid;
   // columns beyond the batch read a valid sequence (clamped) and never store
-  const int rb0 = (nbase + min(n0, nvalid - 1)) * Tmax, rb1 = (nbase + min(n1, nvalid - 1)) * Tmax;
+  const int rb0 = (nbase + min(q0, nvalid - 1)) * Tmax, rb1 = (nbase + min(q1, nvalid - 1)) * Tmax;
   // backward scan: s = 0..T-1 visits t = T-1..0 (forward chain) or t = 0..T-1 (reverse chain)
   const int t_first = dir ? 0 : T - 1, dt = dir ? 1 : -1;
   float4* __restrict__ G4 = reinterpret_cast<float4*>((dir ? p.gates[1] : p.gates[0]));
@@ -99,32 +102,36 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
     const int st = s & (kD - 1);
     const bool in = s < T, has_prev = s + 1 < T;
     cp_async16(&sm.rg[st][0][tid], gp0, in);
-    cp_async16(&sm.rg[st][1][tid], gp1, in);
+    if constexpr (!HALF) cp_async16(&sm.rg[st][1][tid], gp1, in);
     if (has_prev) {
       cp0 += gstride;
-      cp1 += gstride;
       gp0 += gstride;
-      gp1 += gstride;
+      if constexpr (!HALF) {
+        cp1 += gstride;
+        gp1 += gstride;
+      }
     }
     cp_async4(&sm.rc[st][0][tid], cp0, has_prev);  // zero-filled at the chain start (c_{-1} = 0)
-    cp_async4(&sm.rc[st][1][tid], cp1, has_prev);
+    if constexpr (!HALF) cp_async4(&sm.rc[st][1][tid], cp1, has_prev);
     if constexpr (HAS_DY) {
       cp_async4(&sm.rdy[st][0][tid], dp0, in);
-      cp_async4(&sm.rdy[st][1][tid], dp1, in);
+      if constexpr (!HALF) cp_async4(&sm.rdy[st][1][tid], dp1, in);
       if (has_prev) {
         dp0 += dstride;
-        dp1 += dstride;
+        if constexpr (!HALF) dp1 += dstride;
       }
     }
     cp_async_commit();
   };
 
+  for (int i = tid; i < 2 * KTT * 32 * 2; i += NT) (&sm.dafrag[0][0][0][0])[i] = 0u;  // HALF: odd columns stay zero
+  __syncthreads();
   float ccur[2], dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f};
   ccur[0] = cp0[0];
   ccur[1] = cp1[0];
   if (p.dhn != nullptr) {
-    dhrec[0] = p.dhn[((size_t)dir * N + nbase + min(n0, nvalid - 1)) * H + j];
-    dhrec[1] = p.dhn[((size_t)dir * N + nbase + min(n1, nvalid - 1)) * H + j];
+    dhrec[0] = p.dhn[((size_t)dir * N + nbase + min(q0, nvalid - 1)) * H + j];
+    dhrec[1] = p.dhn[((size_t)dir * N + nbase + min(q1, nvalid - 1)) * H + j];
   }
 #pragma unroll
   for (int s = 0; s < kD; ++s) issue(s);
@@ -138,18 +145,21 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
   for (int s = 0; s < T; ++s) {
     cp_async_wait<kD - 1>();
     const int st = s & (kD - 1);
-    const float4 gin[2] = {sm.rg[st][0][tid], sm.rg[st][1][tid]};
-    const float cprev[2] = {sm.rc[st][0][tid], sm.rc[st][1][tid]};
-    float dyin[2] = {0.f, 0.f};
-    if constexpr (HAS_DY) {
-      dyin[0] = sm.rdy[st][0][tid];
-      dyin[1] = sm.rdy[st][1][tid];
+    float4 gin[2];
+    float cprev[2], dyin[2] = {0.f, 0.f};
+    gin[0] = sm.rg[st][0][tid];
+    cprev[0] = sm.rc[st][0][tid];
+    if constexpr (HAS_DY) dyin[0] = sm.rdy[st][0][tid];
+    if constexpr (!HALF) {
+      gin[1] = sm.rg[st][1][tid];
+      cprev[1] = sm.rc[st][1][tid];
+      if constexpr (HAS_DY) dyin[1] = sm.rdy[st][1][tid];
     }
     issue(s + kD);
 
     float4 sv[2];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const float gi = gin[c].x, gf = gin[c].y, gg = gin[c].z, go = gin[c].w;
       const float dh = dhrec[c] + dyin[c];
       const float tc = tanh_f<FAST_ACT>(ccur[c]);
@@ -176,7 +186,9 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
     __syncthreads();  // (A) all da of this step are in smem
     // the in-place da store goes out right AFTER the barrier (bar.sync waits for outstanding global stores)
     if (v0) *gs0 = sv[0];
-    if (v1) *gs1 = sv[1];
+    if constexpr (!HALF) {
+      if (v1) *gs1 = sv[1];
+    }
     gs0 += gstride;
     gs1 += gstride;
 
@@ -213,14 +225,22 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_bwd_kernel(const LstmBwdArgs p)
   cp_async_wait<0>();
 }
 
+template <int H, bool SPLIT, bool FAST, bool HAS_DY, bool HALF>
+cudaError_t launch_kh(const LstmBwdArgs& a, cudaStream_t st) {
+  constexpr int SEQ = HALF ? kBC / 2 : kBC;
+  dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir);
+  const size_t smem = sizeof(BwdSmem<H>);
+  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF><<<grid, H * 4, smem, st>>>(a);
+  return cudaGetLastError();
+}
 template <int H, bool SPLIT, bool FAST, bool HAS_DY>
 cudaError_t launch_k(const LstmBwdArgs& a, cudaStream_t st) {
-  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir);
-  const size_t smem = sizeof(BwdSmem<H>);
-  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY><<<grid, H * 4, smem, st>>>(a);
-  return cudaGetLastError();
+  const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
+  // two co-resident HALF CTAs per SM pay off in the backward only when the MMA phase is short (bf16 mode); measured, DESIGN.md
+  const bool half = full_ctas <= (((a.dbg & 128) || SPLIT) ? 74 : 148) && !(a.dbg & 64);
+  return half ? launch_kh<H, SPLIT, FAST, HAS_DY, true>(a, st) : launch_kh<H, SPLIT, FAST, HAS_DY, false>(a, st);
 }
 template <int H, bool SPLIT, bool FAST>
 cudaError_t launch_b(const LstmBwdArgs& a, cudaStream_t st) {

@@ -35,16 +35,20 @@ struct FwdSmem {
   // followed by uint16 toks[T + kD][kBC] (layer 0)
 };
 
-template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN>
-__global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p) {
+// HALF: 4 sequences per CTA on the EVEN mma columns (odd columns stay zero): one cell per thread instead of two.  Used when the
+// launch would otherwise fill at most half of the SMs (e.g. the single live top-layer chain): the MMA work per CTA is unchanged
+// but every other per-step cost (activations, loads, stores) halves and twice as many SMs work.
+template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN, bool HALF>
+__global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const LstmFwdArgs p) {
   constexpr int NT = H * 4, KT = H / 16, NPART = SPLIT ? 2 : 1;
   using Smem = FwdSmem<H, SPLIT>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];  // T_eff of this group
   if (T <= 0) return;
-  const int b0 = blockIdx.x * kBC;
-  const int nvalid = min(kBC, p.B - b0);
+  constexpr int SEQ = HALF ? kBC / 2 : kBC;  // sequences per CTA
+  const int b0 = blockIdx.x * SEQ;
+  const int nvalid = min(SEQ, p.B - b0);
   const int nbase = g * p.B + b0;  // first global sequence index of this CTA
   const int Tmax = p.Tmax;
 
@@ -87,19 +91,20 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
   // ---- init h = 0 (both buffers); stage this CTA's token ids in scan order (layer 0) ------------------------------------------
   for (int i = tid; i < 2 * NPART * H * kBC / 2; i += NT) reinterpret_cast<uint32_t*>(&sm.hs[0][0][0][0])[i] = 0u;
   if constexpr (LAYER0) {
-    for (int i = tid; i < (T + kD) * kBC; i += NT) {
+    for (int i = tid; i < (T + kD) * SEQ; i += NT) {
       const int n = i / (T + kD), s = i % (T + kD);  // consecutive threads read consecutive time steps (coalesced)
       int v = 0;
       if (s < T && n < nvalid) v = p.tok[(size_t)(nbase + n) * Tmax + (dir ? (T - 1 - s) : s)];
-      toks[s * kBC + n] = (uint16_t)v;
+      toks[s * kBC + (HALF ? 2 * n : n)] = (uint16_t)v;
     }
   }
   __syncthreads();
 
-  const int n0 = 2 * tig, n1 = 2 * tig + 1;  // the two sequences (columns) this thread owns
-  const bool v0 = n0 < nvalid, v1 = n1 < nvalid;
+  const int n0 = 2 * tig, n1 = 2 * tig + 1;  // the two mma columns this thread owns (HALF: only n0 carries a sequence)
+  const int q0 = HALF ? tig : n0, q1 = HALF ? tig : n1;  // sequence index within the CTA
+  const bool v0 = q0 < nvalid, v1 = !HALF && q1 < nvalid;
   // columns beyond the batch read a valid sequence (clamped) and never store
-  const int rb0 = (nbase + min(n0, nvalid - 1)) * Tmax, rb1 = (nbase + min(n1, nvalid - 1)) * Tmax;
+  const int rb0 = (nbase + min(q0, nvalid - 1)) * Tmax, rb1 = (nbase + min(q1, nvalid - 1)) * Tmax;
   const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
   const float4* __restrict__ xsrc =
       LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
@@ -117,14 +122,14 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
     if constexpr (LAYER0) {
       const uint32_t tw = *reinterpret_cast<const uint32_t*>(toks + s * kBC + n0);  // tokens of (n0, n1); rows >= T hold 0
       cp_async16(dst, xsrc + (size_t)(tw & 0xffffu) * H, true);
-      cp_async16(dst + NT, xsrc + (size_t)(tw >> 16) * H, true);
+      if constexpr (!HALF) cp_async16(dst + NT, xsrc + (size_t)(tw >> 16) * H, true);
     } else {
       const bool in = s < T;
       cp_async16(dst, xp0, in);
-      cp_async16(dst + NT, xp1, in);
+      if constexpr (!HALF) cp_async16(dst + NT, xp1, in);
       if (s + 1 < T) {
         xp0 += xstride;
-        xp1 += xstride;
+        if constexpr (!HALF) xp1 += xstride;
       }
     }
     cp_async_commit();
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
       cp_async_wait<kD - 1>();  // this thread's copies for step s have landed
       const float4* cur = slot + (s & (kD - 1)) * kStage;
       x0 = cur[0];
-      x1 = cur[NT];
+      if constexpr (!HALF) x1 = cur[NT];
       issue(s + kD);
     }
 
@@ -203,11 +208,15 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
     float i0, f0, gg0, o0, i1, f1, gg1, o1;
     if (!(dbg & 2)) {
       i0 = sigmoid_f<FAST_ACT>(ai0), f0 = sigmoid_f<FAST_ACT>(af0), gg0 = tanh_f<FAST_ACT>(ag0), o0 = sigmoid_f<FAST_ACT>(ao0);
-      i1 = sigmoid_f<FAST_ACT>(ai1), f1 = sigmoid_f<FAST_ACT>(af1), gg1 = tanh_f<FAST_ACT>(ag1), o1 = sigmoid_f<FAST_ACT>(ao1);
       c0 = fmaf(f0, c0, i0 * gg0);
-      c1 = fmaf(f1, c1, i1 * gg1);
       h0 = o0 * tanh_f<FAST_ACT>(c0);
-      h1 = o1 * tanh_f<FAST_ACT>(c1);
+      if constexpr (!HALF) {
+        i1 = sigmoid_f<FAST_ACT>(ai1), f1 = sigmoid_f<FAST_ACT>(af1), gg1 = tanh_f<FAST_ACT>(ag1), o1 = sigmoid_f<FAST_ACT>(ao1);
+        c1 = fmaf(f1, c1, i1 * gg1);
+        h1 = o1 * tanh_f<FAST_ACT>(c1);
+      } else {
+        i1 = f1 = gg1 = o1 = 0.f;
+      }
     } else {
       i0 = ai0 * 0.5f, f0 = af0 * 0.5f, gg0 = ag0 * 0.5f, o0 = ao0 * 0.5f, i1 = ai1 * 0.5f, f1 = af1 * 0.5f, gg1 = ag1 * 0.5f, o1 = ao1 * 0.5f;
       c0 = fmaf(f0, c0, i0 * gg0) * 0.1f;
@@ -253,20 +262,213 @@ __global__ void __launch_bounds__(H * 4, 1) lstm_fwd_kernel(const LstmFwdArgs p)
 
   if (p.hn != nullptr) {
     const size_t N = (size_t)p.G * p.B;
-    if (v0) p.hn[((size_t)dir * N + nbase + n0) * H + u] = h0;
-    if (v1) p.hn[((size_t)dir * N + nbase + n1) * H + u] = h1;
+    if (v0) p.hn[((size_t)dir * N + nbase + q0) * H + u] = h0;
+    if (v1) p.hn[((size_t)dir * N + nbase + q1) * H + u] = h1;
   }
 }
 
-template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
-cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
-  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir), block(H * 4);
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR, bool HALF>
+cudaError_t launch_kh(const LstmFwdArgs& a, cudaStream_t st) {
+  constexpr int SEQ = HALF ? kBC / 2 : kBC;
+  dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir), block(H * 4);
   size_t smem = sizeof(FwdSmem<H, SPLIT>);
   if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR><<<grid, block, smem, st>>>(a);
+  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF><<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
+cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
+  // one cell per thread (4 sequences per CTA) whenever the doubled CTA count is still co-resident: HALF kernels are capped at
+  // 128 registers so two of them share an SM and interleave their MMA / MUFU phases
+  const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
+  const bool half = full_ctas <= ((a.dbg & 128) ? 74 : 148) && !(a.dbg & 64);
+  return half ? launch_kh<H, SPLIT, FAST, L0, TR, true>(a, st) : launch_kh<H, SPLIT, FAST, L0, TR, false>(a, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// 16-warp variant: ONE cell per thread.  Each warp owns one 16-row tile = (i,f,g,o) x 4 units; lanes 0-15 hold the i/g rows,
+// lanes 16-31 the f/o rows of the accumulator fragment, and one shfl_xor(16) pair gives every thread the four gates of its cell
+// (lower half-warp: sequence 2*tig, upper half-warp: sequence 2*tig+1).  Twice the warps per scheduler of the 8-warp kernel:
+// the MMA, MUFU and LSU phases of different warps overlap instead of running back to back.
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int H, bool SPLIT>
+struct Fwd16Smem {
+  static constexpr int NT = H * 8, NPART = SPLIT ? 2 : 1;
+  float4 xring[kD][NT];
+  __nv_bfloat16 hs[2][NPART][H][kBC];
+};
+
+template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN>
+__global__ void __launch_bounds__(H * 8, 1) lstm_fwd16_kernel(const LstmFwdArgs p) {
+  constexpr int NT = H * 8, KT = H / 16, NPART = SPLIT ? 2 : 1;
+  using Smem = Fwd16Smem<H, SPLIT>;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
+  const int T = p.lens[p.G + g];
+  if (T <= 0) return;
+  const int b0 = blockIdx.x * kBC;
+  const int nvalid = min(kBC, p.B - b0);
+  const int nbase = g * p.B + b0;
+  const int Tmax = p.Tmax;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  uint16_t* toks = reinterpret_cast<uint16_t*>(smem_raw + sizeof(Smem));
+
+  const bool upper = gq >= 4;
+  const int u = warp * 4 + (gq & 3);  // the unit of this thread's cell
+  const int n = 2 * tig + (upper ? 1 : 0);  // the sequence (column) of this thread's cell
+  uint32_t Ahi[KT][4], Alo[KT][4];
+  {
+    const float* __restrict__ W = (dir ? p.whh[1] : p.whh[0]);
+    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
+    const int r0 = (gq >> 2) * H + u;        // fragment row gq     : gate i (lanes 0-15) / f (lanes 16-31)
+    const int r1 = (2 + (gq >> 2)) * H + u;  // fragment row gq + 8 : gate g / o
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const int k0 = kt * 16 + 2 * tig;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = ((j & 1) ? r1 : r0) * H + k0 + ((j & 2) ? 8 : 0);
+        float w0 = W[idx], w1 = W[idx + 1];
+        if (M != nullptr) {
+          w0 *= M[idx];
+          w1 *= M[idx + 1];
+        }
+        if constexpr (SPLIT) {
+          split_bf16(w0, w1, Ahi[kt][j], Alo[kt][j]);
+        } else {
+          Ahi[kt][j] = pack_bf16(w0, w1);
+          Alo[kt][j] = 0u;
+        }
+      }
+    }
+  }
+
+  for (int i = tid; i < 2 * NPART * H * kBC / 2; i += NT) reinterpret_cast<uint32_t*>(&sm.hs[0][0][0][0])[i] = 0u;
+  if constexpr (LAYER0) {
+    for (int i = tid; i < (T + kD) * kBC; i += NT) {
+      const int nn = i / (T + kD), s = i % (T + kD);
+      int v = 0;
+      if (s < T && nn < nvalid) v = p.tok[(size_t)(nbase + nn) * Tmax + (dir ? (T - 1 - s) : s)];
+      toks[s * kBC + nn] = (uint16_t)v;
+    }
+  }
+  __syncthreads();
+
+  const bool valid = n < nvalid;
+  const int rb = (nbase + min(n, nvalid - 1)) * Tmax;
+  const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
+  const float4* __restrict__ xsrc =
+      LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
+             : reinterpret_cast<const float4*>((dir ? p.xproj[1] : p.xproj[0])) + u;
+  const float4* xp = xsrc + (size_t)(rb + t_first) * H;
+  const ptrdiff_t xstride = (ptrdiff_t)dt * H;
+  float4* slot = &sm.xring[0][tid];
+
+  auto issue = [&](int s) {
+    float4* dst = slot + (s & (kD - 1)) * NT;
+    if constexpr (LAYER0) {
+      cp_async16(dst, xsrc + (size_t)toks[s * kBC + n] * H, true);
+    } else {
+      cp_async16(dst, xp, s < T);
+      if (s + 1 < T) xp += xstride;
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kD; ++s) issue(s);
+
+  float c = 0.f, h = 0.f;
+  float4* g4 = nullptr;
+  float* cs = nullptr;
+  if constexpr (TRAIN) {
+    g4 = reinterpret_cast<float4*>((dir ? p.gates[1] : p.gates[0])) + (size_t)(rb + t_first) * H + u;
+    cs = (dir ? p.cstate[1] : p.cstate[0]) + (size_t)(rb + t_first) * H + u;
+  }
+  const bool has_y = p.y != nullptr;
+  float* yp = has_y ? p.y + (size_t)(rb + t_first) * p.y_stride + dir * H + u : nullptr;
+  const ptrdiff_t gstride = (ptrdiff_t)dt * H, ystride = (ptrdiff_t)dt * p.y_stride;
+  const __nv_bfloat16* hrow = &sm.hs[0][0][lane % H][0];
+  __nv_bfloat16* hput = &sm.hs[0][0][u][n];
+  constexpr int kBufElems = NPART * H * kBC, kPartElems = H * kBC;
+
+  for (int s = 0; s < T; ++s) {
+    cp_async_wait<kD - 1>();
+    const float4 x = slot[(s & (kD - 1)) * NT];
+    issue(s + kD);
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, ac1[4] = {0.f, 0.f, 0.f, 0.f}, ac2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int buf = s & 1;
+#pragma unroll
+    for (int kp = 0; kp < (KT + 1) / 2; ++kp) {
+      uint32_t bh[4], bl[4];
+      ldmatrix_x4_trans(bh, hrow + buf * kBufElems + kp * 32 * kBC);
+      if constexpr (SPLIT) ldmatrix_x4_trans(bl, hrow + buf * kBufElems + kPartElems + kp * 32 * kBC);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kt = kp * 2 + kk;
+        if (kt < KT) {
+          mma_bf16(acc, Ahi[kt], bh[2 * kk], bh[2 * kk + 1]);
+          if constexpr (SPLIT) {
+            mma_bf16(ac1, Ahi[kt], bl[2 * kk], bl[2 * kk + 1]);
+            mma_bf16(ac2, Alo[kt], bh[2 * kk], bh[2 * kk + 1]);
+          }
+        }
+      }
+    }
+    float v0 = acc[0], v1 = acc[1], v2 = acc[2], v3 = acc[3];
+    if constexpr (SPLIT) {
+      v0 += ac1[0] + ac2[0];
+      v1 += ac1[1] + ac2[1];
+      v2 += ac1[2] + ac2[2];
+      v3 += ac1[3] + ac2[3];
+    }
+    // lanes 0-15: v0,v1 = i(2tig),i(2tig+1)  v2,v3 = g(..)   lanes 16-31: v0,v1 = f(..)  v2,v3 = o(..)
+    const float r0 = __shfl_xor_sync(0xffffffffu, upper ? v0 : v1, 16);
+    const float r1 = __shfl_xor_sync(0xffffffffu, upper ? v2 : v3, 16);
+    const float ai = (upper ? r0 : v0) + x.x, af = (upper ? v1 : r0) + x.y;
+    const float ag = (upper ? r1 : v2) + x.z, ao = (upper ? v3 : r1) + x.w;
+    const float gi = sigmoid_f<FAST_ACT>(ai), gf = sigmoid_f<FAST_ACT>(af), gg = tanh_f<FAST_ACT>(ag), go = sigmoid_f<FAST_ACT>(ao);
+    c = fmaf(gf, c, gi * gg);
+    h = go * tanh_f<FAST_ACT>(c);
+    {
+      __nv_bfloat16* dst = hput + (buf ^ 1) * kBufElems;
+      const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+      *dst = hh;
+      if constexpr (SPLIT) dst[kPartElems] = __float2bfloat16_rn(h - __bfloat162float(hh));
+    }
+    if (has_y) {
+      if (valid) *yp = h;
+      yp += ystride;
+    }
+    if constexpr (TRAIN) {
+      if (valid) {
+        *g4 = make_float4(gi, gf, gg, go);
+        *cs = c;
+      }
+      g4 += gstride;
+      cs += gstride;
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  if (p.hn != nullptr && valid) p.hn[((size_t)dir * p.G * p.B + nbase + n) * H + u] = h;
+}
+
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
+cudaError_t launch_k16(const LstmFwdArgs& a, cudaStream_t st) {
+  dim3 grid((a.B + kBC - 1) / kBC, a.G, a.ndir), block(H * 8);
+  size_t smem = sizeof(Fwd16Smem<H, SPLIT>);
+  if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd16_kernel<H, SPLIT, FAST, L0, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lstm_fwd16_kernel<H, SPLIT, FAST, L0, TR><<<grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -274,6 +476,12 @@ template <int H, bool SPLIT, bool FAST>
 cudaError_t launch_h(const LstmFwdArgs& a, cudaStream_t st) {
   const bool l0 = a.tok != nullptr, tr = a.gates[a.dir0] != nullptr;
   if (l0 && a.V > 65536) return cudaErrorInvalidValue;  // token ids are staged as uint16
+  if (a.dbg & 32) {
+    if (l0 && tr) return launch_k16<H, SPLIT, FAST, true, true>(a, st);
+    if (l0) return launch_k16<H, SPLIT, FAST, true, false>(a, st);
+    if (tr) return launch_k16<H, SPLIT, FAST, false, true>(a, st);
+    return launch_k16<H, SPLIT, FAST, false, false>(a, st);
+  }
   if (l0 && tr) return launch_k<H, SPLIT, FAST, true, true>(a, st);
   if (l0) return launch_k<H, SPLIT, FAST, true, false>(a, st);
   if (tr) return launch_k<H, SPLIT, FAST, false, true>(a, st);

@@ -18,7 +18,7 @@ torch.cuda.synchronize(); t = _lib.timing_read()
 print(" ".join(f"{k}={v[0]/v[1]:.3f}" for k, v in t.items() if k.startswith("lstm")))
 '''
 for mode in ("fp32", "bf16"):
-    for flags in (0, 1, 4, 8, 16):
+    for flags in (0, 32):
         env = dict(os.environ, IB200_DBG=str(flags))
         r = subprocess.run([sys.executable, "-c", code, mode], env=env, capture_output=True, text=True)
         print(f"{mode} dbg={flags:2d}: {r.stdout.strip()} {r.stderr.strip()[-200:] if r.returncode else ''}", flush=True)
