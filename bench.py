@@ -127,6 +127,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def make_net(variant, mode):
