@@ -339,23 +339,37 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       ta.G = p.G; ta.B = p.B; ta.Tmax = p.T; ta.lens = lens;
       ta.A = at<float>(ws, p.gates[l][d]); ta.KA = 4 * H;
       ta.partial = partial; ta.ctas_per_group = p.ctas_per_group;
+      const float* mask_hh = (l == 0 && d == 0) ? whh_l0_mask : nullptr;
+      if (l == 0 && H == 64 && use_tc() && getenv("IB200_FUSE_DW") != nullptr) {  // off by default: measured slower (gather latency)
+        // layer 0, tcgen05: ONE pass over dA gives dW_ih (B columns 0..H-1 = masked embedding rows gathered by token) and
+        // dW_hh + biases (B columns H..2H-1 = h of the previous scan position = Y_0 shifted by one step)
+        ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V;
+        ta.NB = 2 * H; ta.NB1 = H;
+        ta.Bsrc2 = at<float>(ws, p.Y[l]); ta.ldb2 = 2 * H; ta.col02 = d * H; ta.shift2 = d == 0 ? -1 : +1;
+        ta.colsum = 1;
+        TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_ih+dW_hh gemm");
+        DwReduceArgs rf{p.G, p.ctas_per_group, 4 * H, 2 * H, H, partial, 1, mask_hh, Gr->w_ih[l][d], H, Gr->w_hh[l][d],
+                        Gr->b_ih[l][d], Gr->b_hh[l][d]};
+        TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rf, st), "dW reduce");
+        continue;
+      }
       // dW_ih
       if (l == 0) {
         ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V; ta.NB = H;
       } else {
         ta.Bsrc = at<float>(ws, p.Y[l - 1]); ta.ldb = 2 * H; ta.col0 = 0; ta.shift = 0; ta.NB = 2 * H;
       }
+      ta.NB1 = ta.NB;
       ta.colsum = 0;
       TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_ih gemm");
-      DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], nullptr, nullptr};
+      DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], ta.NB, nullptr, nullptr, nullptr};
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW_ih reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
-      ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H;
+      ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H; ta.NB1 = H;
       ta.colsum = 1;
       TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_hh gemm");
-      DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, (l == 0 && d == 0) ? whh_l0_mask : nullptr,
-                      Gr->w_hh[l][d], Gr->b_ih[l][d], Gr->b_hh[l][d]};
+      DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, mask_hh, Gr->w_hh[l][d], H, nullptr, Gr->b_ih[l][d], Gr->b_hh[l][d]};
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rb, st), "dW_hh reduce");
     }
 
@@ -455,7 +469,7 @@ int ib200_dbg_gemm_tn(int32_t G, int32_t B, int32_t T, const int32_t* lens, cons
                       int32_t impl, void* stream) {
   GemmTNArgs a{};
   a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.A = A; a.KA = KA; a.Bsrc = Bsrc; a.ldb = ldb; a.col0 = col0; a.shift = shift;
-  a.tok = tok; a.emb = emb; a.emb_row_scale = emb_row_scale; a.V = V; a.NB = NB; a.partial = partial;
+  a.tok = tok; a.emb = emb; a.emb_row_scale = emb_row_scale; a.V = V; a.NB = NB; a.NB1 = NB; a.partial = partial;
   a.ctas_per_group = ctas_per_group; a.colsum = colsum;
   cudaStream_t st = (cudaStream_t)stream;
   CK(impl == 0 ? launch_gemm_tn(a, precision, st) : (impl == 1 ? launch_gemm_tn_tc(a, precision, st) : gemm_tn_auto(a, precision, st)),

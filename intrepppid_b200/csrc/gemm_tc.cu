@@ -47,10 +47,11 @@ __device__ __forceinline__ void store_split4(unsigned char* hi_plane, unsigned c
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
-// NT.  9 warps: 0-3 loaders (A tiles), 4-7 epilogue (TMEM -> HBM), 8 MMA issuer + TMEM owner.  W (all of K) is resident in smem.
+// NT.  13 warps: 0-7 loaders (two groups of four, group g owns stage g so two tiles are in flight), 8-11 epilogue (TMEM ->
+// smem transpose -> coalesced HBM stores), 12 MMA issuer + TMEM owner.  W (all of K) is resident in smem.
 // ------------------------------------------------------------------------------------------------------------------------------
 template <int NC, bool SPLIT>
-__global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) {
+__global__ void __launch_bounds__(416, 1) gemm_nt_tc_kernel(const GemmNTArgs p) {
   constexpr int NPART = SPLIT ? 2 : 1;
   constexpr uint32_t kWTile = NC * 128;  // one [NC x 64] bf16 plane of W
   constexpr uint32_t kTmemCols = 2 * NC < 32 ? 32 : 2 * NC;
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
   const int kslices = p.K / kBK, KC = p.nsrc * kslices;
   unsigned char* Wres = smem;                                    // [KC][NPART][NC x 128 B]
   unsigned char* Ast = Wres + (size_t)KC * NPART * kWTile;        // [stage][NPART][128 x 128 B]
-  NTBarriers* bars = reinterpret_cast<NTBarriers*>(Ast + (size_t)kStagesNT * NPART * kTileBytes);
+  float* Est = reinterpret_cast<float*>(Ast + (size_t)kStagesNT * NPART * kTileBytes);  // [4 warps][32 rows][36] epilogue transpose
+  NTBarriers* bars = reinterpret_cast<NTBarriers*>(Est + 4 * 32 * 36);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nrows = (long long)p.G * p.B * p.Tmax;
   const int ntiles = (int)((nrows + kBM - 1) / kBM);
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
     }
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&bars->tmem_base, kTmemCols);
+  if (warp == 12) tmem_alloc(&bars->tmem_base, kTmemCols);
   // resident W: all 256 loader+epilogue threads convert fp32 -> bf16 hi/lo, swizzled K-major
   if (warp < 8) {
     const int f4_per_row = p.K / 4;
@@ -96,9 +98,10 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== loaders =====================
-    const int f = tid & 15, rg = tid >> 4;  // float4 index within the 64-wide k slice, row group
+    const int grp = warp >> 2, tg = tid & 127;  // loader group (= the stage it fills), thread index inside the group
+    const int f = tg & 15, rg = tg >> 4;        // float4 index within the 64-wide k slice, row group
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * kBM;
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
       }
       for (int kc = 0; kc < KC; ++kc, ++it) {
         const int stage = it % kStagesNT;
+        if (stage != grp) continue;
         const float* __restrict__ A = (kc / kslices) ? p.A[1] : p.A[0];
         const int k0 = (kc % kslices) * kBK + f * 4;
         float4 v[16];
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
         mbar_arrive(&bars->full[stage]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_bf16(kBM, NC, false, false);
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* est = Est + q * 32 * 36;
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;  // transposed phase: 4 rows x 8 float4 per pass
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * kBM;
@@ -174,25 +180,27 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
       const uint32_t acc = tl & 1;
       mbar_wait(&bars->tfull[acc], (tl >> 1) & 1);
       fence_after_sync();
-      const long long row = row0 + q * 32 + lane;
-      bool ok = row < nrows;
-      if (ok) ok = (int)(row % p.Tmax) < p.lens[p.G + (int)(row / p.Tmax) / p.B];
-      float* crow = p.C + row * p.ldc;
+      const long long rbase = row0 + q * 32;
+      bool ok = rbase + lane < nrows;
+      if (ok) ok = (int)((rbase + lane) % p.Tmax) < p.lens[p.G + (int)((rbase + lane) / p.Tmax) / p.B];
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
 #pragma unroll 1
       for (int c = 0; c < NC / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC + c * 32, r);
-        if (ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                   __uint_as_float(r[4 * j + 3]));
-            const int col = c * 32 + 4 * j;
-            if (p.bias != nullptr) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            float4* dst = reinterpret_cast<float4*>(crow + col);
+        for (int j = 0; j < 8; ++j)  // thread = row: stage the 32 columns (row stride 36 floats: conflict-free both ways)
+          *reinterpret_cast<uint4*>(est + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + tc4));
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {  // 8 lanes cover one row's 32 columns: every store instruction writes 4 full 128-byte rows
+          const int rr = itr * 4 + tr;
+          if (okmask & (1u << rr)) {
+            float4 o = *reinterpret_cast<const float4*>(est + rr * 36 + tc4);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            float4* dst = reinterpret_cast<float4*>(p.C + (rbase + rr) * p.ldc + c * 32 + tc4);
             if (p.accumulate) {
               const float4 e = *dst;
               o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
             *dst = o;
           }
         }
+        __syncwarp();
       }
       fence_before_sync();
       mbar_arrive(&bars->tempty[acc]);
@@ -208,14 +217,15 @@ __global__ void __launch_bounds__(288, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 12) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <int NC>
 cudaError_t launch_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st) {
   const int npart = precision == 0 ? 2 : 1;
   const int KC = a.nsrc * (a.K / kBK);
-  const size_t smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + sizeof(NTBarriers) + 64;
+  const size_t smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + 4 * 32 * 36 * sizeof(float) +
+                      sizeof(NTBarriers) + 64;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back (one source per pass / legacy kernel)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -227,11 +237,11 @@ cudaError_t launch_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st) {
   if (precision == 0) {
     e = cudaFuncSetAttribute(gemm_nt_tc_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_nt_tc_kernel<NC, true><<<grid, 288, smem, st>>>(a);
+    gemm_nt_tc_kernel<NC, true><<<grid, 416, smem, st>>>(a);
   } else {
     e = cudaFuncSetAttribute(gemm_nt_tc_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_nt_tc_kernel<NC, false><<<grid, 288, smem, st>>>(a);
+    gemm_nt_tc_kernel<NC, false><<<grid, 416, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
@@ -305,14 +315,18 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const GemmTNArgs p) 
         const int t = t0 + rb + RPP * j;
         vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < T) {
-          if (gathered) {
+          const int col = fb * 4;
+          if (col >= p.NB1) {  // second dense source (h of the previous scan position)
+            const int ts = t + p.shift2;
+            if (ts >= 0 && ts < T) vb[j] = __ldg(reinterpret_cast<const float4*>(p.Bsrc2 + ((size_t)n * p.Tmax + ts) * p.ldb2 + p.col02 + (col - p.NB1)));
+          } else if (gathered) {
             const int tk = p.tok[(size_t)n * p.Tmax + t];
             const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + tk] : 1.0f;
-            const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB) + fb);
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * p.NB1 + col));
             vb[j] = make_float4(sc * e.x, sc * e.y, sc * e.z, sc * e.w);
           } else {
             const int ts = t + p.shift;
-            if (ts >= 0 && ts < T) vb[j] = __ldg(reinterpret_cast<const float4*>(p.Bsrc + ((size_t)n * p.Tmax + ts) * p.ldb + p.col0) + fb);
+            if (ts >= 0 && ts < T) vb[j] = __ldg(reinterpret_cast<const float4*>(p.Bsrc + ((size_t)n * p.Tmax + ts) * p.ldb + p.col0 + col));
           }
         }
       }
@@ -433,6 +447,7 @@ cudaError_t launch_gemm_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t s
 cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st) {
   if (a.KA != 256) return cudaErrorInvalidConfiguration;
   if (!a.tok && (a.ldb % 4 != 0 || a.col0 % 4 != 0)) return cudaErrorInvalidConfiguration;
+  if (a.NB1 != a.NB && (a.NB1 % 4 != 0 || a.ldb2 % 4 != 0 || a.col02 % 4 != 0 || a.Bsrc2 == nullptr)) return cudaErrorInvalidConfiguration;
   if (a.NB == 128) return launch_tn_tc<128>(a, precision, st);
   if (a.NB == 64) return launch_tn_tc<64>(a, precision, st);
   return cudaErrorInvalidConfiguration;

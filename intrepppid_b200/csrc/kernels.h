@@ -101,6 +101,10 @@ struct GemmTNArgs {
   const float* emb_row_scale;
   int V;
   int NB;
+  // optional second dense source for the columns [NB1, NB) (tcgen05 kernel only): fuses dW_ih and dW_hh into one pass over A
+  int NB1;                   // columns taken from the first source (== NB when there is no second source)
+  const float* Bsrc2;
+  int ldb2, col02, shift2;
   float* partial;            // [G][ctas_per_group][KA*NB (+ KA if colsum)]
   int ctas_per_group;
   int colsum;                // also produce column sums of A (bias gradient) after the KA*NB block
@@ -114,7 +118,9 @@ struct DwReduceArgs {
   const float* partial;
   int has_colsum;
   const float* mask;         // [G, KA, NB] in torch row order, or null
-  float* out;                // [KA, NB] torch row order
+  float* out;                // [KA, NB1] torch row order (NB1 == NB unless split)
+  int NB1;                   // columns [0,NB1) -> out (no mask); columns [NB1,NB) -> out2 (mask applies to these)
+  float* out2;               // [KA, NB-NB1] or null
   float* out_b1;             // [KA] or null (bias_ih grad)
   float* out_b2;             // [KA] or null (bias_hh grad, identical values)
 };

@@ -132,18 +132,29 @@ __global__ void pool_fc_bwd_dh_kernel(int N, int H, int mode, const float* __res
   }
 }
 
+// d_fc_w[e][k] = sum_n dz[n][e] pooled[n][k], d_fc_b[e] = sum_n dz[n][e].  One block per output row e; the N samples are
+// split over the warps and combined in a fixed order (deterministic).
 __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz, const float* __restrict__ pooled,
                                       float* __restrict__ d_fc_w, float* __restrict__ d_fc_b) {
-  const int e = blockIdx.x;
-  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+  extern __shared__ float part[];  // [nwarp][H+1]
+  const int e = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int k0 = 0; k0 < H; k0 += 32) {
+    const int k = k0 + lane;
     float s = 0.f, sb = 0.f;
-    for (int n = 0; n < N; ++n) {
+    for (int n = warp; n < N; n += nwarp) {
       const float d = dz[(size_t)n * H + e];
-      s = fmaf(d, pooled[(size_t)n * H + k], s);
+      if (k < H) s = fmaf(d, pooled[(size_t)n * H + k], s);
       sb += d;
     }
-    d_fc_w[(size_t)e * H + k] = s;
-    if (k == 0) d_fc_b[e] = sb;
+    if (k < H) part[warp * (H + 1) + k] = s;
+    if (k0 == 0 && lane == 0) part[warp * (H + 1) + H] = sb;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= H; k += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += part[w * (H + 1) + k];
+    if (k < H) d_fc_w[(size_t)e * H + k] = s;
+    else d_fc_b[e] = s;
   }
 }
 
@@ -174,7 +185,7 @@ cudaError_t launch_pool_fc_fwd(int N, int H, int mode, const float* hn, const fl
 cudaError_t launch_pool_fc_bwd(int N, int H, int mode, const float* dz, const float* pooled, const uint8_t* argmax,
                                const float* fc_w, float* d_hn, float* d_fc_w, float* d_fc_b, cudaStream_t st) {
   pool_fc_bwd_dh_kernel<<<N, 64, H * sizeof(float), st>>>(N, H, mode, dz, argmax, fc_w, d_hn);
-  pool_fc_bwd_dw_kernel<<<H, 64, 0, st>>>(N, H, dz, pooled, d_fc_w, d_fc_b);
+  pool_fc_bwd_dw_kernel<<<H, 512, 16 * (H + 1) * sizeof(float), st>>>(N, H, dz, pooled, d_fc_w, d_fc_b);
   return cudaGetLastError();
 }
 
