@@ -90,6 +90,7 @@ struct Plan {
   size_t gates[IB200_MAX_LAYERS][2], cst[IB200_MAX_LAYERS][2];
   size_t bwd_scratch;  // dY [R,2H] then dX0 [R,H]
   size_t partial;
+  size_t bias_partial;  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel
   int ctas_per_group;
   size_t total;
 };
@@ -138,17 +139,37 @@ Plan make_plan(const ib200_cfg* c) {
     p.bwd_scratch = p.L > 1 ? p.X[0] : take(sizeof(float) * p.R * 3 * H);  // X is dead once the forward is done
     p.ctas_per_group = std::max(1, 148 / p.G);
     p.partial = take(sizeof(float) * (size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 2 * H + 4 * H));
+    p.bias_partial = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
   }
   p.total = off;
   return p;
 }
 
 // GEMM dispatch: tcgen05 kernels where the shape is covered, legacy mma.sync otherwise (H=32 test shapes; IB200_GEMM=legacy)
-bool use_tc() {
-  static const bool v = [] { const char* e = getenv("IB200_GEMM"); return !(e && std::string(e) == "legacy"); }();
+// IB200_GEMM = "tma" (default: bf16 hi/lo planes + TMA-fed tcgen05), "threads" (fp32 storage, thread-staged tcgen05), "legacy" (mma.sync)
+int gemm_mode() {
+  static const int v = [] {
+    const char* e = getenv("IB200_GEMM");
+    if (e && std::string(e) == "legacy") return 0;
+    if (e && std::string(e) == "threads") return 1;
+    return 2;
+  }();
   return v;
 }
+bool use_tc() { return gemm_mode() >= 1; }
+bool use_planes(int H) { return H == 64 && gemm_mode() == 2; }
 cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st) {
+  if (a.plane_bytes > 0) {  // operands are bf16 planes: only the TMA kernels can read them
+    cudaError_t e = launch_gemm_nt_tma(a, prec, st);
+    if (e != cudaErrorInvalidConfiguration || a.nsrc != 2) return e;
+    (void)cudaGetLastError();
+    GemmNTArgs b = a;  // W of both sources does not fit: one source per pass, the second pass accumulates
+    b.nsrc = 1;
+    e = launch_gemm_nt_tma(b, prec, st);
+    if (e != cudaSuccess) return e;
+    b.A[0] = a.A[1]; b.W[0] = a.W[1]; b.accumulate = 1; b.bias = nullptr;
+    return launch_gemm_nt_tma(b, prec, st);
+  }
   if (use_tc()) {
     cudaError_t e = launch_gemm_nt_tc(a, prec, st);
     if (e != cudaErrorInvalidConfiguration) return e;
@@ -168,7 +189,8 @@ cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st) {
   return launch_gemm_nt(a, prec, st);
 }
 
-cudaError_t gemm_tn_auto(const GemmTNArgs& a, int prec, cudaStream_t st) {
+cudaError_t gemm_tn_auto(const GemmTNArgs& a, int prec, cudaStream_t st, bool planes = false) {
+  if (planes) return launch_gemm_tn_tma(a, prec, st);
   if (use_tc()) {
     cudaError_t e = launch_gemm_tn_tc(a, prec, st);
     if (e != cudaErrorInvalidConfiguration) return e;
@@ -233,6 +255,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       if (!P->w_ih[l][d] || !P->w_hh[l][d] || !P->b_ih[l][d] || !P->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_fwd: null LSTM parameter");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
+  const bool planes = use_planes(H);
 
   LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens)};
   TIMED(F_LENGTHS, 3, launch_lengths(la, st), "lengths");
@@ -263,6 +286,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
         ga.nsrc = 1; ga.A[0] = at<float>(ws, p.Y[l - 1]); ga.lda = 2 * H; ga.K = 2 * H;
         ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
         ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
+        ga.plane_bytes = planes ? 2 * H * 2 : 0;
         TIMED(F_GEMM_XPROJ, 1, gemm_nt_auto(ga, prec, st), "input projection gemm");
       }
     }
@@ -281,6 +305,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
     const bool need_y = p.train || l < p.L - 1;
     fa.y = need_y ? at<float>(ws, p.Y[l]) : nullptr;
     fa.y_stride = 2 * H;
+    fa.planes = planes ? 1 : 0;
     for (int d = 0; d < 2; ++d) {
       fa.gates[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.gates[l][d]) : nullptr;
       fa.cstate[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.cst[l][d]) : nullptr;
@@ -304,6 +329,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
   if (!Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
+  const bool planes = use_planes(H);
   const int* lens = at<int>(ws, p.lens);
   float* dY = at<float>(ws, p.bwd_scratch);
   float* dX0 = dY + p.R * 2 * H;
@@ -323,7 +349,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ba.dy_stride = 2 * H;
     ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
     { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
+    ba.planes = planes ? 1 : 0;
+    ba.bias_partial = planes ? at<float>(ws, p.bias_partial) : nullptr;
     TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
+    const int bwd_ctas = lstm_bwd_cta_count(ba, prec);  // CTAs per direction (= number of bias partials)
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
     for (int d = 0; d < 2; ++d) {
@@ -340,19 +369,6 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       ta.A = at<float>(ws, p.gates[l][d]); ta.KA = 4 * H;
       ta.partial = partial; ta.ctas_per_group = p.ctas_per_group;
       const float* mask_hh = (l == 0 && d == 0) ? whh_l0_mask : nullptr;
-      if (l == 0 && H == 64 && use_tc() && getenv("IB200_FUSE_DW") != nullptr) {  // off by default: measured slower (gather latency)
-        // layer 0, tcgen05: ONE pass over dA gives dW_ih (B columns 0..H-1 = masked embedding rows gathered by token) and
-        // dW_hh + biases (B columns H..2H-1 = h of the previous scan position = Y_0 shifted by one step)
-        ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V;
-        ta.NB = 2 * H; ta.NB1 = H;
-        ta.Bsrc2 = at<float>(ws, p.Y[l]); ta.ldb2 = 2 * H; ta.col02 = d * H; ta.shift2 = d == 0 ? -1 : +1;
-        ta.colsum = 1;
-        TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_ih+dW_hh gemm");
-        DwReduceArgs rf{p.G, p.ctas_per_group, 4 * H, 2 * H, H, partial, 1, mask_hh, Gr->w_ih[l][d], H, Gr->w_hh[l][d],
-                        Gr->b_ih[l][d], Gr->b_hh[l][d]};
-        TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rf, st), "dW reduce");
-        continue;
-      }
       // dW_ih
       if (l == 0) {
         ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V; ta.NB = H;
@@ -361,15 +377,24 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       }
       ta.NB1 = ta.NB;
       ta.colsum = 0;
-      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_ih gemm");
-      DwReduceArgs ra{p.G, p.ctas_per_group, 4 * H, ta.NB, H, partial, 0, nullptr, Gr->w_ih[l][d], ta.NB, nullptr, nullptr, nullptr};
+      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, planes), "dW_ih gemm");
+      DwReduceArgs ra{};
+      ra.G = p.G; ra.ctas_per_group = p.ctas_per_group; ra.KA = 4 * H; ra.NB = ta.NB; ra.H = H; ra.partial = partial;
+      ra.out = Gr->w_ih[l][d]; ra.NB1 = ta.NB;
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW_ih reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
       ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H; ta.NB1 = H;
-      ta.colsum = 1;
-      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st), "dW_hh gemm");
-      DwReduceArgs rb{p.G, p.ctas_per_group, 4 * H, H, H, partial, 1, mask_hh, Gr->w_hh[l][d], H, nullptr, Gr->b_ih[l][d], Gr->b_hh[l][d]};
+      ta.colsum = planes ? 0 : 1;
+      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, planes), "dW_hh gemm");
+      DwReduceArgs rb{};
+      rb.G = p.G; rb.ctas_per_group = p.ctas_per_group; rb.KA = 4 * H; rb.NB = H; rb.H = H; rb.partial = partial;
+      rb.has_colsum = planes ? 0 : 1; rb.mask = mask_hh; rb.out = Gr->w_hh[l][d]; rb.NB1 = H;
+      rb.out_b1 = Gr->b_ih[l][d]; rb.out_b2 = Gr->b_hh[l][d];
+      if (planes) {
+        rb.cs_ptr = at<float>(ws, p.bias_partial) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
+        rb.cs_count = bwd_ctas;
+      }
       TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rb, st), "dW_hh reduce");
     }
 
@@ -384,6 +409,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         ++ga.nsrc;
       }
     ga.lda = 4 * H; ga.K = 4 * H; ga.bias = nullptr; ga.accumulate = 0;
+    ga.plane_bytes = planes ? 4 * H * 2 : 0;
     if (l > 0) {
       ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
       TIMED(F_GEMM_DGRAD, 1, gemm_nt_auto(ga, prec, st), "dY gemm");

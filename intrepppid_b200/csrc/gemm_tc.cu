@@ -9,6 +9,7 @@
 
 #include "kernels.h"
 #include "tc05.cuh"
+#include "tma_host.h"
 
 namespace ib200 {
 namespace {
@@ -431,6 +432,397 @@ cudaError_t launch_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ==============================================================================================================================
+// TMA-fed variants.  The recurrent kernels store Y and the dgates as bf16 hi/lo PLANES (interleaved per row over the bytes of
+// the fp32 row), so the GEMM operands need no conversion: one thread issues cp.async.bulk.tensor loads straight into the
+// 128-byte-swizzled tiles, completion is counted on the stage's mbarrier (expect_tx), and the loader warps disappear.
+// ==============================================================================================================================
+struct NTTmaMaps {
+  CUtensorMap a[2][2];  // [source][plane]: 2D {K, rows}, box {64, 128}
+};
+
+template <int NC, bool SPLIT>
+__global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_constant__ NTTmaMaps maps, const GemmNTArgs p) {
+  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr uint32_t kWTile = NC * 128;
+  constexpr uint32_t kTmemCols = 2 * NC < 32 ? 32 : 2 * NC;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int kslices = p.K / kBK, KC = p.nsrc * kslices;
+  unsigned char* Wres = smem;
+  unsigned char* Ast = Wres + (size_t)KC * NPART * kWTile;
+  float* Est = reinterpret_cast<float*>(Ast + (size_t)kStagesNT * NPART * kTileBytes);
+  NTBarriers* bars = reinterpret_cast<NTBarriers*>(Est + 4 * 32 * 36);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nrows = (long long)p.G * p.B * p.Tmax;
+  const int ntiles = (int)((nrows + kBM - 1) / kBM);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesNT; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tfull[a], 1);
+      mbar_init(&bars->tempty[a], 128);
+    }
+    mbar_init_fence();
+    for (int sidx = 0; sidx < p.nsrc; ++sidx)
+      for (int pl = 0; pl < NPART; ++pl) tma_prefetch_desc(&maps.a[sidx][pl]);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  {  // resident W: fp32 -> bf16 hi/lo, swizzled K-major (tiny; every thread helps)
+    const int f4_per_row = p.K / 4;
+    for (int src = 0; src < p.nsrc; ++src) {
+      const float* __restrict__ W = src ? p.W[1] : p.W[0];
+      for (int i = tid; i < NC * f4_per_row; i += 192) {
+        const int n = i / f4_per_row, k4 = i % f4_per_row, k = k4 * 4;
+        const float4 v = *reinterpret_cast<const float4*>(W + (size_t)n * p.K + k);
+        const int kc = src * kslices + k / kBK, kk = k % kBK;
+        unsigned char* hi = Wres + (size_t)(kc * NPART) * kWTile;
+        store_split4<SPLIT>(hi, hi + kWTile, sw128_offset(n, kk >> 3) + ((kk >> 2) & 1) * 8, v);
+      }
+    }
+    fence_async_smem();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * kBM;
+        if (!nt_tile_live(p, row0, nrows)) continue;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int stage = it % kStagesNT, src = kc / kslices, k0 = (kc % kslices) * kBK;
+          mbar_wait(&bars->empty[stage], ((it / kStagesNT) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars->full[stage], NPART * kTileBytes);
+          unsigned char* dst = Ast + (size_t)(stage * NPART) * kTileBytes;
+          tma_load_2d(dst, &maps.a[src][0], &bars->full[stage], k0, (int)row0);
+          if constexpr (SPLIT) tma_load_2d(dst + kTileBytes, &maps.a[src][1], &bars->full[stage], k0, (int)row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kBM, NC, false, false);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (!nt_tile_live(p, (long long)tile * kBM, nrows)) continue;
+        const uint32_t acc = tl & 1;
+        mbar_wait(&bars->tempty[acc], ((tl >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * NC;
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int stage = it % kStagesNT;
+          mbar_wait(&bars->full[stage], (it / kStagesNT) & 1);
+          fence_after_sync();
+          const uint32_t a_hi = smem_u32(Ast + (size_t)(stage * NPART) * kTileBytes), a_lo = a_hi + kTileBytes;
+          const uint32_t b_hi = smem_u32(Wres + (size_t)(kc * NPART) * kWTile), b_lo = b_hi + kWTile;
+#pragma unroll
+          for (int k16 = 0; k16 < kBK / 16; ++k16) {
+            const uint32_t ko = k16 * 32;
+            const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, 0), bh = smem_desc_sw128(b_hi + ko, 1024, 0);
+            mma_bf16_ss(d_tmem, ah, bh, idesc, (kc | k16) != 0);
+            if constexpr (SPLIT) {
+              const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, 0), bl = smem_desc_sw128(b_lo + ko, 1024, 0);
+              mma_bf16_ss(d_tmem, ah, bl, idesc, true);
+              mma_bf16_ss(d_tmem, al, bh, idesc, true);
+            }
+          }
+          mma_commit(&bars->empty[stage]);
+        }
+        mma_commit(&bars->tfull[acc]);
+        ++tl;
+      }
+    }
+  } else {
+    // ===================== epilogue (TMEM -> smem transpose -> coalesced stores) =====================
+    const int q = warp & 3;
+    float* est = Est + q * 32 * 36;
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * kBM;
+      if (!nt_tile_live(p, row0, nrows)) continue;
+      const uint32_t acc = tl & 1;
+      mbar_wait(&bars->tfull[acc], (tl >> 1) & 1);
+      fence_after_sync();
+      const long long rbase = row0 + q * 32;
+      bool ok = rbase + lane < nrows;
+      if (ok) ok = (int)((rbase + lane) % p.Tmax) < p.lens[p.G + (int)((rbase + lane) / p.Tmax) / p.B];
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+#pragma unroll 1
+      for (int c = 0; c < NC / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC + c * 32, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(est + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + tc4));
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + tr;
+          if (okmask & (1u << rr)) {
+            float4 o = *reinterpret_cast<const float4*>(est + rr * 36 + tc4);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            float4* dst = reinterpret_cast<float4*>(p.C + (rbase + rr) * p.ldc + c * 32 + tc4);
+            if (p.accumulate) {
+              const float4 e = *dst;
+              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
+            *dst = o;
+          }
+        }
+        __syncwarp();
+      }
+      fence_before_sync();
+      mbar_arrive(&bars->tempty[acc]);
+      ++tl;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+struct TNTmaMaps {
+  CUtensorMap a[2];  // dgates planes: 3D {4H, Tmax, N}, box {64, 64, 1}
+  CUtensorMap b[2];  // B operand planes (unused when gathered)
+};
+
+template <int NB, bool SPLIT, bool GATHER>
+__global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_constant__ TNTmaMaps maps, const GemmTNArgs p) {
+  constexpr int KA = 256, NPART = SPLIT ? 2 : 1;
+  constexpr int kABytes = (KA / 64) * kBlkBytes, kBBytes = (NB / 64) * kBlkBytes;
+  constexpr int kStageBytes = NPART * (kABytes + kBBytes);
+  constexpr uint32_t kTmemCols = 2 * NB;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  TNBarriers* bars = reinterpret_cast<TNBarriers*>(smem + (size_t)kStagesTN * kStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y, cta = blockIdx.x;
+  const int T = p.lens[p.G + g];
+  const int tiles_per_seq = (T + 63) / 64;
+  const int items = p.B * tiles_per_seq;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesTN; ++s) {
+      mbar_init(&bars->full[s], GATHER ? 1 + 128 : 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->done, 1);
+    mbar_init_fence();
+    for (int pl = 0; pl < NPART; ++pl) {
+      tma_prefetch_desc(&maps.a[pl]);
+      if (!GATHER) tma_prefetch_desc(&maps.b[pl]);
+    }
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int my_items = cta < items ? (items - cta + p.ctas_per_group - 1) / p.ctas_per_group : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = cta; item < items; item += p.ctas_per_group, ++it) {
+        const int stage = it % kStagesTN;
+        const int n = g * p.B + item / tiles_per_seq, t0 = (item % tiles_per_seq) * 64;
+        mbar_wait(&bars->empty[stage], ((it / kStagesTN) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->full[stage], NPART * (kABytes + (GATHER ? 0 : kBBytes)));
+        unsigned char* a_dst = smem + (size_t)stage * kStageBytes;
+        unsigned char* b_dst = a_dst + NPART * kABytes;
+#pragma unroll
+        for (int pl = 0; pl < NPART; ++pl) {
+#pragma unroll
+          for (int blk = 0; blk < KA / 64; ++blk)
+            tma_load_3d(a_dst + pl * kABytes + blk * kBlkBytes, &maps.a[pl], &bars->full[stage], blk * 64, t0, n);
+          if constexpr (!GATHER) {
+#pragma unroll
+            for (int blk = 0; blk < NB / 64; ++blk)
+              tma_load_3d(b_dst + pl * kBBytes + blk * kBlkBytes, &maps.b[pl], &bars->full[stage], p.col0 + blk * 64, t0 + p.shift, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, NB, true, true);
+      for (int it = 0; it < my_items; ++it) {
+        const int stage = it % kStagesTN;
+        mbar_wait(&bars->full[stage], (it / kStagesTN) & 1);
+        fence_after_sync();
+        const uint32_t a_hi = smem_u32(smem + (size_t)stage * kStageBytes), a_lo = a_hi + kABytes;
+        const uint32_t b_hi = a_hi + NPART * kABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint32_t ko = k16 * 16 * 128;
+          const uint64_t bh = smem_desc_sw128(b_hi + ko, 1024, kBlkBytes), bl = smem_desc_sw128(b_lo + ko, 1024, kBlkBytes);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t mo = mt * 2 * kBlkBytes;
+            const uint64_t ah = smem_desc_sw128(a_hi + mo + ko, 1024, kBlkBytes);
+            const uint32_t d = tmem_base + mt * NB;
+            mma_bf16_ss(d, ah, bh, idesc, (it | k16) != 0);
+            if constexpr (SPLIT) {
+              const uint64_t al = smem_desc_sw128(a_lo + mo + ko, 1024, kBlkBytes);
+              mma_bf16_ss(d, ah, bl, idesc, true);
+              mma_bf16_ss(d, al, bh, idesc, true);
+            }
+          }
+        }
+        mma_commit(&bars->empty[stage]);
+      }
+      mma_commit(&bars->done);
+    }
+  } else if (GATHER) {
+    // ===================== B operand = scale[g][tok] * emb[tok] (layer-0 input), staged by 4 warps =====================
+    constexpr int FPR = NB / 4, RPP = 128 / FPR, BPASS = 64 / RPP;
+    const int tg = tid - 64, fb = tg % FPR, rb = tg / FPR;
+    const uint32_t b_off = (fb >> 4) * kBlkBytes + (fb & 1) * 8, b_chunk = (fb & 15) >> 1;
+    uint32_t it = 0;
+    for (int item = cta; item < items; item += p.ctas_per_group, ++it) {
+      const int stage = it % kStagesTN;
+      const int n = g * p.B + item / tiles_per_seq, t0 = (item % tiles_per_seq) * 64;
+      float4 vb[BPASS];
+#pragma unroll
+      for (int j = 0; j < BPASS; ++j) {
+        const int t = t0 + rb + RPP * j;
+        vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < T) {
+          const int tk = p.tok[(size_t)n * p.Tmax + t];
+          const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + tk] : 1.0f;
+          const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB) + fb);
+          vb[j] = make_float4(sc * e.x, sc * e.y, sc * e.z, sc * e.w);
+        }
+      }
+      mbar_wait(&bars->empty[stage], ((it / kStagesTN) & 1) ^ 1);
+      unsigned char* b_hi = smem + (size_t)stage * kStageBytes + NPART * kABytes;
+#pragma unroll
+      for (int j = 0; j < BPASS; ++j) store_split4<SPLIT>(b_hi, b_hi + kBBytes, b_off + sw128_offset(rb + RPP * j, b_chunk), vb[j]);
+      fence_async_smem();
+      mbar_arrive(&bars->full[stage]);
+    }
+  }
+  __syncthreads();
+
+  float* out = p.partial + ((size_t)g * p.ctas_per_group + cta) * ((size_t)KA * NB);
+  if (warp >= 2) {
+    const int q = warp & 3;
+    if (my_items > 0) {
+      mbar_wait(&bars->done, 0);
+      fence_after_sync();
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      float* orow = out + (size_t)(mt * 128 + q * 32 + lane) * NB;
+#pragma unroll 1
+      for (int c = 0; c < NB / 32; ++c) {
+        uint32_t r[32];
+        if (my_items > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mt * NB + c * 32, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(orow + c * 32 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+bool nt_maps(const GemmNTArgs& a, int npart, int row_floats, NTTmaMaps* m) {
+  // A_s points at the fp32-sized rows that hold the planes: hi at byte 0, lo at byte K*2; row pitch = lda floats
+  const long long nrows = (long long)a.G * a.B * a.Tmax;
+  (void)row_floats;
+  for (int s = 0; s < a.nsrc; ++s)
+    for (int pl = 0; pl < npart; ++pl) {
+      const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)nrows}, strides[1] = {(uint64_t)a.lda * 4};
+      const uint32_t box[2] = {64, 128};
+      if (!make_tmap_bf16_sw128(&m->a[s][pl], reinterpret_cast<const unsigned char*>(a.A[s]) + (size_t)pl * a.plane_bytes, 2, dims, strides, box))
+        return false;
+    }
+  return true;
+}
+
+template <int NC>
+cudaError_t launch_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st) {
+  const int npart = precision == 0 ? 2 : 1;
+  const int KC = a.nsrc * (a.K / kBK);
+  const size_t smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + 4 * 32 * 36 * sizeof(float) +
+                      sizeof(NTBarriers) + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  NTTmaMaps maps;
+  if (!nt_maps(a, npart, 0, &maps)) return cudaErrorInvalidConfiguration;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long nrows = (long long)a.G * a.B * a.Tmax;
+  const int ntiles = (int)((nrows + kBM - 1) / kBM);
+  const unsigned grid = (unsigned)std::min(ntiles, sms);
+  cudaError_t e;
+  if (precision == 0) {
+    e = cudaFuncSetAttribute(gemm_nt_tma_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_nt_tma_kernel<NC, true><<<grid, 192, smem, st>>>(maps, a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_nt_tma_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_nt_tma_kernel<NC, false><<<grid, 192, smem, st>>>(maps, a);
+  }
+  return cudaGetLastError();
+}
+
+template <int NB, bool GATHER>
+cudaError_t launch_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st) {
+  const int npart = precision == 0 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)kStagesTN * npart * ((256 / 64) + (NB / 64)) * kBlkBytes + sizeof(TNBarriers) + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  TNTmaMaps maps;
+  const uint32_t box[3] = {64, 64, 1};
+  for (int pl = 0; pl < npart; ++pl) {
+    const uint64_t da[3] = {256, (uint64_t)a.Tmax, (uint64_t)a.G * a.B}, sa[2] = {1024, (uint64_t)a.Tmax * 1024};
+    if (!make_tmap_bf16_sw128(&maps.a[pl], reinterpret_cast<const unsigned char*>(a.A) + (size_t)pl * 512, 3, da, sa, box))
+      return cudaErrorInvalidConfiguration;
+    if (!GATHER) {
+      const uint64_t db[3] = {(uint64_t)a.ldb, (uint64_t)a.Tmax, (uint64_t)a.G * a.B};
+      const uint64_t sb[2] = {(uint64_t)a.ldb * 4, (uint64_t)a.Tmax * a.ldb * 4};
+      if (!make_tmap_bf16_sw128(&maps.b[pl], reinterpret_cast<const unsigned char*>(a.Bsrc) + (size_t)pl * a.ldb * 2, 3, db, sb, box))
+        return cudaErrorInvalidConfiguration;
+    }
+  }
+  dim3 grid(a.ctas_per_group, a.G);
+  cudaError_t e;
+  if (precision == 0) {
+    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB, true, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tn_tma_kernel<NB, true, GATHER><<<grid, 192, smem, st>>>(maps, a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB, false, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tn_tma_kernel<NB, false, GATHER><<<grid, 192, smem, st>>>(maps, a);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 // returns cudaErrorInvalidConfiguration when the shape is not covered (caller uses the legacy mma.sync kernel)
@@ -450,6 +842,26 @@ cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t s
   if (a.NB1 != a.NB && (a.NB1 % 4 != 0 || a.ldb2 % 4 != 0 || a.col02 % 4 != 0 || a.Bsrc2 == nullptr)) return cudaErrorInvalidConfiguration;
   if (a.NB == 128) return launch_tn_tc<128>(a, precision, st);
   if (a.NB == 64) return launch_tn_tc<64>(a, precision, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+// TMA-fed versions: operands are bf16 hi/lo planes (see kernels.h: GemmNTArgs::plane_bytes, GemmTNArgs planes layout)
+cudaError_t launch_gemm_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st) {
+  if (a.K % kBK != 0 || a.lda % 4 != 0 || a.ldc % 4 != 0 || a.plane_bytes <= 0) return cudaErrorInvalidConfiguration;
+  switch (a.NC) {
+    case 256: return launch_nt_tma<256>(a, precision, st);
+    case 128: return launch_nt_tma<128>(a, precision, st);
+    case 64: return launch_nt_tma<64>(a, precision, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+cudaError_t launch_gemm_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st) {
+  if (a.KA != 256 || a.NB1 != a.NB || a.colsum) return cudaErrorInvalidConfiguration;
+  const bool gather = a.tok != nullptr;
+  if (!gather && (a.ldb % 4 != 0 || a.col0 % 8 != 0)) return cudaErrorInvalidConfiguration;
+  if (a.NB == 128 && !gather) return launch_tn_tma<128, false>(a, precision, st);
+  if (a.NB == 64 && !gather) return launch_tn_tma<64, false>(a, precision, st);
+  if (a.NB == 64 && gather) return launch_tn_tma<64, true>(a, precision, st);
   return cudaErrorInvalidConfiguration;
 }
 

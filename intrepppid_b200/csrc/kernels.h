@@ -44,6 +44,7 @@ struct LstmFwdArgs {
   const float* whh_mask;     // [G,4H,H] or null; direction 0 only
   float* y;                  // [N,Tmax,y_stride] (+dir*H) or null
   int y_stride;
+  int planes;                // 1: y rows hold bf16 [hi plane (y_stride) | lo plane (y_stride)] instead of y_stride floats (TMA GEMMs)
   float* gates[2];           // per direction [N,Tmax,H,4] (training) or null
   float* cstate[2];          // per direction [N,Tmax,H]
   float* hn;                 // [2,N,H] or null
@@ -63,9 +64,12 @@ struct LstmBwdArgs {
   const float* dy;           // [N,Tmax,dy_stride] (+dir*H) gradient w.r.t. this layer's output, or null
   int dy_stride;
   const float* dhn;          // [2,N,H] gradient w.r.t. the final hidden state, or null
+  int planes;                // 1: dgates rows are written as bf16 [hi plane (4H) | lo plane (4H)] over the 4H-float gate row
+  float* bias_partial;       // planes mode: [ndir][G*gridDim.x][4H] per-CTA column sums of the dgates (GI order)
   int dbg;                   // ablation flags (env IB200_DBG)
 };
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
+int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision);  // G * gridDim.x of the launch above (bias partials per direction)
 
 // ---- tensor-core GEMMs over token rows -------------------------------------------------------------------------------------
 // NT:  C[row, NC] (=|+=) sum_s A_s[row, K] * W_s[NC, K]^T (+ bias)   for rows (n,t), t < T_eff[group(n)]
@@ -82,10 +86,13 @@ struct GemmNTArgs {
   int ldc;
   int NC;
   int accumulate;            // C += instead of C =
+  int plane_bytes;           // TMA path: A rows hold bf16 planes; byte offset of the lo plane inside a row (= K*2); 0 = fp32 rows
 };
 cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st);      // legacy mma.sync (any supported H)
 // tcgen05 version (H=64 shapes); returns cudaErrorInvalidConfiguration when the shape / smem budget is not covered
 cudaError_t launch_gemm_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st);
+// tcgen05 + TMA version: A_s rows are bf16 hi/lo planes written by the recurrent kernels (plane_bytes > 0)
+cudaError_t launch_gemm_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st);
 
 // TN:  P[cta][KA, NB] = sum_{rows of cta} A[row, KA]^T * Bop[row, NB]   (partials; reduced by launch_dw_reduce)
 struct GemmTNArgs {
@@ -111,12 +118,17 @@ struct GemmTNArgs {
 };
 cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st);      // legacy mma.sync
 cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st);   // tcgen05 (KA=256, NB=128|64)
+// tcgen05 + TMA: A = dgates planes (row = [hi 4H bf16 | lo 4H bf16]); Bsrc = planes rows of ldb floats ([hi ldb bf16 | lo ldb bf16])
+// or gathered embeddings (tok != null); no colsum (the BPTT kernel produces the bias partials)
+cudaError_t launch_gemm_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st);
 
 // out[torch_row(gi)][c] = sum_g mask_g[torch_row][c] * sum_cta partial[g][cta][gi][c];  optional bias outputs
 struct DwReduceArgs {
   int G, ctas_per_group, KA, NB, H;
   const float* partial;
-  int has_colsum;
+  int has_colsum;            // 1: column sums follow each KA*NB block of `partial` (legacy / thread-loader GEMMs)
+  const float* cs_ptr;       // alternative column-sum partials [cs_count][KA] written by the BPTT kernel (TMA path), or null
+  int cs_count;
   const float* mask;         // [G, KA, NB] in torch row order, or null
   float* out;                // [KA, NB1] torch row order (NB1 == NB unless split)
   int NB1;                   // columns [0,NB1) -> out (no mask); columns [NB1,NB) -> out2 (mask applies to these)

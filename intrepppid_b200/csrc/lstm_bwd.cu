@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 namespace ib200 {
+static bool bwd_half(const LstmBwdArgs& a, bool split);
 namespace {
 
 constexpr int kD = 8;  // async prefetch depth in steps (power of two)
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   for (int i = tid; i < 2 * KTT * 32 * 2; i += NT) (&sm.dafrag[0][0][0][0])[i] = 0u;  // HALF: odd columns stay zero
   __syncthreads();
   float ccur[2], dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f};
+  float bsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // column sums of the dgates of my cells (bias gradient)
+  const bool planes = p.planes != 0;
   ccur[0] = cp0[0];
   ccur[1] = cp1[0];
   if (p.dhn != nullptr) {
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
     issue(s + kD);
 
     float4 sv[2];
+    uint4 pk[2];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const float gi = gin[c].x, gf = gin[c].y, gg = gin[c].z, go = gin[c].w;
@@ -171,6 +175,9 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       const float da_i = d_i * gi * (1.0f - gi), da_f = d_f * gf * (1.0f - gf);
       const float da_g = d_g * fmaf(-gg, gg, 1.0f), da_o = d_o * go * (1.0f - go);
       sv[c] = make_float4(da_i, da_f, da_g, da_o);
+      if (c == 0 ? v0 : v1) {
+        bsum[c][0] += da_i; bsum[c][1] += da_f; bsum[c][2] += da_g; bsum[c][3] += da_o;
+      }
       // B-fragment slot of this cell: k tile j/4, lane (col*4 + j%4)
       uint32_t hi0, hi1, lo0 = 0u, lo1 = 0u;
       if constexpr (SPLIT) {
@@ -182,12 +189,28 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       }
       *reinterpret_cast<uint2*>(dst_hi0 + c * 8) = make_uint2(hi0, hi1);
       if constexpr (SPLIT) *reinterpret_cast<uint2*>(dst_hi0 + c * 8 + kFragPart) = make_uint2(lo0, lo1);
+      pk[c] = make_uint4(hi0, hi1, lo0, lo1);
     }
     __syncthreads();  // (A) all da of this step are in smem
     // the in-place da store goes out right AFTER the barrier (bar.sync waits for outstanding global stores)
-    if (v0) *gs0 = sv[0];
-    if constexpr (!HALF) {
-      if (v1) *gs1 = sv[1];
+    if (planes) {  // bf16 planes over the same 4H-float row: [hi: 4H bf16 | lo: 4H bf16], gate-interleaved columns 4j..4j+3
+      if (v0) {
+        uint2* r0p = reinterpret_cast<uint2*>(gs0 - j) + j;  // row start, then 8-byte slot j
+        r0p[0] = make_uint2(pk[0].x, pk[0].y);
+        if constexpr (SPLIT) r0p[H] = make_uint2(pk[0].z, pk[0].w);
+      }
+      if constexpr (!HALF) {
+        if (v1) {
+          uint2* r1p = reinterpret_cast<uint2*>(gs1 - j) + j;
+          r1p[0] = make_uint2(pk[1].x, pk[1].y);
+          if constexpr (SPLIT) r1p[H] = make_uint2(pk[1].z, pk[1].w);
+        }
+      }
+    } else {
+      if (v0) *gs0 = sv[0];
+      if constexpr (!HALF) {
+        if (v1) *gs1 = sv[1];
+      }
     }
     gs0 += gstride;
     gs1 += gstride;
@@ -223,6 +246,29 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
     }
   }
   cp_async_wait<0>();
+
+  if (planes) {
+    // (1) bias-gradient partials of this CTA: sum my cells over the 8 columns held by the 4 lanes of a quad, lane tig==0 writes
+    if (p.bias_partial != nullptr) {
+      float4 b = make_float4(bsum[0][0] + bsum[1][0], bsum[0][1] + bsum[1][1], bsum[0][2] + bsum[1][2], bsum[0][3] + bsum[1][3]);
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        b.x += __shfl_xor_sync(0xffffffffu, b.x, o);
+        b.y += __shfl_xor_sync(0xffffffffu, b.y, o);
+        b.z += __shfl_xor_sync(0xffffffffu, b.z, o);
+        b.w += __shfl_xor_sync(0xffffffffu, b.w, o);
+      }
+      const size_t ncta = (size_t)p.G * gridDim.x, ci = (size_t)g * gridDim.x + blockIdx.x;
+      if (tig == 0) *reinterpret_cast<float4*>(p.bias_partial + ((size_t)blockIdx.z * ncta + ci) * 4 * H + 4 * j) = b;
+    }
+    // (2) zero tail rows [T, tail_end) of my sequences: the TN GEMM reads whole 64-row TMA boxes
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;  // +1: the row a shifted box touches
+    const int chunks = 4 * H * 4 / 16;  // 16-byte chunks per row (both planes)
+    for (int i = tid; i < nvalid * ntail * chunks; i += NT) {
+      const int c = i % chunks, r = (i / chunks) % ntail, q = i / (chunks * ntail);
+      reinterpret_cast<uint4*>(G4 + ((size_t)(nbase + q) * Tmax + T + r) * H)[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
 }
 
 template <int H, bool SPLIT, bool FAST, bool HAS_DY, bool HALF>
@@ -237,9 +283,8 @@ cudaError_t launch_kh(const LstmBwdArgs& a, cudaStream_t st) {
 }
 template <int H, bool SPLIT, bool FAST, bool HAS_DY>
 cudaError_t launch_k(const LstmBwdArgs& a, cudaStream_t st) {
-  const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
   // two co-resident HALF CTAs per SM pay off in the backward only when the MMA phase is short (bf16 mode); measured, DESIGN.md
-  const bool half = full_ctas <= (((a.dbg & 128) || SPLIT) ? 74 : 148) && !(a.dbg & 64);
+  const bool half = bwd_half(a, SPLIT);
   return half ? launch_kh<H, SPLIT, FAST, HAS_DY, true>(a, st) : launch_kh<H, SPLIT, FAST, HAS_DY, false>(a, st);
 }
 template <int H, bool SPLIT, bool FAST>
@@ -248,6 +293,15 @@ cudaError_t launch_b(const LstmBwdArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+static bool bwd_half(const LstmBwdArgs& a, bool split) {
+  const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
+  return full_ctas <= (((a.dbg & 128) || split) ? 74 : 148) && !(a.dbg & 64);
+}
+int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision) {
+  const int seq = bwd_half(a, precision == 0) ? kBC / 2 : kBC;
+  return a.G * ((a.B + seq - 1) / seq);
+}
 
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st) {
   if (H == 64) return precision == 0 ? launch_b<64, true, false>(a, st) : launch_b<64, false, true>(a, st);

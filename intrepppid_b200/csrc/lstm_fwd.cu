@@ -151,9 +151,12 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     cs0 = Cst + (size_t)(rb0 + t_first) * H + u;
     cs1 = Cst + (size_t)(rb1 + t_first) * H + u;
   }
-  const bool has_y = p.y != nullptr;
-  float* y0 = has_y ? p.y + (size_t)(rb0 + t_first) * p.y_stride + dir * H + u : nullptr;
-  float* y1 = has_y ? p.y + (size_t)(rb1 + t_first) * p.y_stride + dir * H + u : nullptr;
+  const bool has_y = p.y != nullptr, planes = p.planes != 0;
+  // fp32 layout: float at column dir*H+u.  planes layout: the same row bytes hold bf16 [hi | lo]; pointer kept in float units of
+  // the ROW START and the element is addressed as bf16 inside the row.
+  float* y0 = has_y ? p.y + (size_t)(rb0 + t_first) * p.y_stride + (planes ? 0 : dir * H + u) : nullptr;
+  float* y1 = has_y ? p.y + (size_t)(rb1 + t_first) * p.y_stride + (planes ? 0 : dir * H + u) : nullptr;
+  const int ycol = dir * H + u;
   const ptrdiff_t gstride = (ptrdiff_t)dt * H, ystride = (ptrdiff_t)dt * p.y_stride;
 
   const __nv_bfloat16* hrow = &sm.hs[0][0][lane % H][0];  // ldmatrix row address of this lane (k-pair block 0, buffer 0)
@@ -237,8 +240,29 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     }
     // stream out what later stages need (placement relative to the barrier makes no measurable difference: ablation in DESIGN.md)
     if (has_y && !(dbg & 4)) {
-      if (v0) *y0 = h0;
-      if (v1) *y1 = h1;
+      if (planes) {
+        // bf16 hi/lo of my two values as [hi | lo << 16] words; one shuffle with the neighbouring unit (lane ^ 4) lets every
+        // thread store a 2-unit bf16x2 word per plane (even gq: units (u,u+1) of column n0; odd gq: units (u-1,u) of column n1)
+        const __nv_bfloat162 a = __floats2bfloat162_rn(h0, h1);
+        const float2 af = __bfloat1622float2(a);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(h0 - af.x, h1 - af.y);
+        const uint32_t ab = *reinterpret_cast<const uint32_t*>(&a), lb = *reinterpret_cast<const uint32_t*>(&l);
+        const uint32_t w0 = (ab & 0xffffu) | (lb << 16), w1 = (ab >> 16) | (lb & 0xffff0000u);  // value n0 / value n1
+        const bool odd = gq & 1;
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, (odd || HALF) ? w0 : w1, 4);
+        const uint32_t mine = (odd && !HALF) ? w1 : w0;
+        const uint32_t first = odd ? recv : mine, second = odd ? mine : recv;
+        const uint32_t hiw = (first & 0xffffu) | (second << 16), low = (first >> 16) | (second & 0xffff0000u);
+        const bool st_ok = HALF ? (!odd && v0) : (odd ? v1 : v0);
+        if (st_ok) {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>((odd && !HALF) ? y1 : y0) + (ycol & ~1));
+          dst[0] = hiw;
+          if constexpr (SPLIT) dst[p.y_stride / 2] = low;
+        }
+      } else {
+        if (v0) *y0 = h0;
+        if (v1) *y1 = h1;
+      }
       y0 += ystride;
       y1 += ystride;
     }
@@ -259,6 +283,18 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     if (!(dbg & 16)) __syncthreads();
   }
   cp_async_wait<0>();
+
+  // planes mode: the weight-gradient GEMM reads 64-row TMA boxes (and the row after the last one for the shifted operand), so the
+  // rows [T, tail_end) of this CTA's sequences / this direction's columns must be finite zeros, not uninitialised memory
+  if (has_y && planes) {
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;  // +1: the row a shifted box touches
+    const int chunks = H * 2 / 16;  // 16-byte chunks per plane half-row of this direction
+    for (int i = tid; i < nvalid * ntail * chunks * 2; i += NT) {
+      const int c = i % chunks, pl = (i / chunks) & 1, r = (i / (2 * chunks)) % ntail, q = i / (2 * chunks * ntail);
+      unsigned char* row = reinterpret_cast<unsigned char*>(p.y + ((size_t)(nbase + q) * Tmax + T + r) * p.y_stride);
+      *reinterpret_cast<uint4*>(row + pl * p.y_stride * 2 + dir * H * 2 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
 
   if (p.hn != nullptr) {
     const size_t N = (size_t)p.G * p.B;
