@@ -30,10 +30,13 @@ struct BwdSmem {
   float2 xch[NW][32];              // partial dh handed to the partner warp
 };
 
-// HALF: 4 sequences per CTA on the even mma columns, one cell per thread (see lstm_fwd.cu).
+// HALF: 4 sequences per CTA, one cell per thread (see lstm_fwd.cu): bf16 mode on the even mma columns; fp32 mode ("HL") with
+// da_hi on columns 0-3 and da_lo on columns 4-7, so 2 MMAs per product (A_hi, A_lo) instead of 3 and one shfl_xor(2) to add the
+// hi-column and lo-column sums of a sequence.
 template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY, bool HALF>
 __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const LstmBwdArgs p) {
   constexpr int NT = H * 4, MT = H / 16, KTT = H / 4, KTH = KTT / 2;
+  constexpr bool HL = HALF && SPLIT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int mt = warp % MT, kh = warp / MT;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
@@ -79,8 +82,11 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
 
   // ---- the two cells this thread owns -----------------------------------------------------------------------------------------
   const int j = 16 * mt + gq + 8 * kh;
-  const int n0 = 2 * tig, n1 = n0 + 1;                   // mma columns (HALF: only n0 carries a sequence)
-  const int q0 = HALF ? tig : n0, q1 = HALF ? tig : n1;  // sequence index within the CTA
+  const int n0 = 2 * tig, n1 = n0 + 1;  // mma columns of this thread's accumulators
+  const bool low = tig < 2;
+  // sequence index within the CTA.  HALF/bf16: sequence tig on the even column.  HL: low lanes own sequence 2*tig (their even
+  // column carries its hi part), high lanes own sequence 2*(tig-2)+1 (their odd column carries its lo part).
+  const int q0 = HL ? (low ? 2 * tig : 2 * (tig - 2) + 1) : (HALF ? tig : n0), q1 = HALF ? q0 : n1;
   const bool v0 = q0 < nvalid, v1 = !HALF && q1 < nvalid;
   // columns beyond the batch read a valid sequence (clamped) and never store
   const int rb0 = (nbase + min(q0, nvalid - 1)) * Tmax, rb1 = (nbase + min(q1, nvalid - 1)) * Tmax;
@@ -97,7 +103,6 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + t_first) * p.dy_stride + dir * H + j : nullptr;
   const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + t_first) * p.dy_stride + dir * H + j : nullptr;
   const ptrdiff_t dstride = (ptrdiff_t)dt * p.dy_stride;
-  constexpr int kStage = 2 * NT;
 
   auto issue = [&](int s) {
     const int st = s & (kD - 1);
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
 
   float4* gs0 = G4 + (size_t)(rb0 + t_first) * H + j;  // da store pointers at t(s)
   float4* gs1 = G4 + (size_t)(rb1 + t_first) * H + j;
-  uint32_t* dst_hi0 = &sm.dafrag[0][j >> 2][n0 * 4 + (j & 3)][0];
+  uint32_t* dst_hi0 = &sm.dafrag[0][j >> 2][(HL ? q0 : n0) * 4 + (j & 3)][0];
   constexpr int kFragPart = KTT * 32 * 2;  // words per hi/lo part
   const uint32_t* bsrc = &sm.dafrag[0][kh * KTH][lane][0];
 
@@ -188,7 +193,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
         hi1 = pack_bf16(da_g, da_o);
       }
       *reinterpret_cast<uint2*>(dst_hi0 + c * 8) = make_uint2(hi0, hi1);
-      if constexpr (SPLIT) *reinterpret_cast<uint2*>(dst_hi0 + c * 8 + kFragPart) = make_uint2(lo0, lo1);
+      if constexpr (HL) *reinterpret_cast<uint2*>(dst_hi0 + (kBC / 2) * 4 * 2) = make_uint2(lo0, lo1);  // column q0 + 4
+      else if constexpr (SPLIT) *reinterpret_cast<uint2*>(dst_hi0 + c * 8 + kFragPart) = make_uint2(lo0, lo1);
       pk[c] = make_uint4(hi0, hi1, lo0, lo1);
     }
     __syncthreads();  // (A) all da of this step are in smem
@@ -223,7 +229,9 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       for (int ktl = 0; ktl < KTH; ++ktl) {
         const uint2 bh = *reinterpret_cast<const uint2*>(bsrc + ktl * 64);
         mma_bf16(acc[ktl & 1], Ahi[ktl], bh.x, bh.y);
-        if constexpr (SPLIT) {
+        if constexpr (HL) {
+          mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
+        } else if constexpr (SPLIT) {
           const uint2 bl = *reinterpret_cast<const uint2*>(bsrc + ktl * 64 + kFragPart);
           mma_bf16(ac1[ktl & 1], Ahi[ktl], bl.x, bl.y);
           mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
@@ -233,7 +241,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         r4[r] = acc[0][r] + acc[1][r];
-        if constexpr (SPLIT) r4[r] += (ac1[0][r] + ac1[1][r]) + (ac2[0][r] + ac2[1][r]);
+        if constexpr (HL) r4[r] += ac2[0][r] + ac2[1][r];
+        else if constexpr (SPLIT) r4[r] += (ac1[0][r] + ac1[1][r]) + (ac2[0][r] + ac2[1][r]);
       }
       // r4: [0]=(unit 16mt+gq, col n0) [1]=(.., n1) [2]=(unit 16mt+gq+8, n0) [3]=(.., n1).  Keep the rows of my unit, hand
       // the other two to the partner warp (same mt, other K half), which owns that unit.
@@ -241,8 +250,13 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       sm.xch[warp][lane] = kh ? make_float2(r4[0], r4[1]) : make_float2(r4[2], r4[3]);
       __syncthreads();  // (B)
       const float2 other = sm.xch[kh ? warp - MT : warp + MT][lane];
-      dhrec[0] = mine.x + other.x;
-      dhrec[1] = mine.y + other.y;
+      if constexpr (HL) {  // my column + the partner lane's column of the same sequence (hi part + lo part)
+        const float ev = mine.x + other.x, od = mine.y + other.y;
+        dhrec[0] = (low ? ev : od) + __shfl_xor_sync(0xffffffffu, low ? od : ev, 2);
+      } else {
+        dhrec[0] = mine.x + other.x;
+        dhrec[1] = mine.y + other.y;
+      }
     }
   }
   cp_async_wait<0>();
@@ -283,7 +297,7 @@ cudaError_t launch_kh(const LstmBwdArgs& a, cudaStream_t st) {
 }
 template <int H, bool SPLIT, bool FAST, bool HAS_DY>
 cudaError_t launch_k(const LstmBwdArgs& a, cudaStream_t st) {
-  // two co-resident HALF CTAs per SM pay off in the backward only when the MMA phase is short (bf16 mode); measured, DESIGN.md
+  // one cell per thread and two co-resident CTAs per SM whenever the full-width launch would leave SMs idle
   const bool half = bwd_half(a, SPLIT);
   return half ? launch_kh<H, SPLIT, FAST, HAS_DY, true>(a, st) : launch_kh<H, SPLIT, FAST, HAS_DY, false>(a, st);
 }
@@ -296,7 +310,8 @@ cudaError_t launch_b(const LstmBwdArgs& a, cudaStream_t st) {
 
 static bool bwd_half(const LstmBwdArgs& a, bool split) {
   const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
-  return full_ctas <= (((a.dbg & 128) || split) ? 74 : 148) && !(a.dbg & 64);
+  (void)split;  // fp32 mode too since the HL column layout cut its MMA phase by a third (bench: 1.14 -> 0.98 ms on layer 0)
+  return full_ctas <= ((a.dbg & 128) ? 74 : 148) && !(a.dbg & 64);
 }
 int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision) {
   const int seq = bwd_half(a, precision == 0) ? kBC / 2 : kBC;

@@ -1,8 +1,11 @@
+"""Print ms/step and the per-family kernel times of bench JSON lines: python tools/show_bench.py gpurun_out/bench12*.json"""
 import json, sys
-d = json.load(open(sys.argv[1]))
-print(f"value {d['value']:.0f} {d['unit']}  ms/step {d['ms_per_step']:.3f}  e2e {d['e2e']['value']:.0f} ({d['e2e']['ms_per_step']:.3f} ms)  launches {d['gpu_launches']}  clocks {d['clocks']}")
-for k, v in d["kernel_families"].items():
-    print(f"  {k:16s} {v['ms_per_step']:.3f} ms  x{v['launches_per_step']:.0f}  {100*v['share']:.1f}%")
-print(" other:", d.get("other_variants_1gpu"))
-r = d["roofline"]; print(" roofline:", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k != 'note'})
-if "cpu_baseline" in d: print(" cpu:", d["cpu_baseline"])
+for f in sys.argv[1:]:
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        print(f, "ERR", e)
+        continue
+    k = d.get("kernel_families", {})
+    print(f"{f}: {d['ms_per_step']:.3f} ms/step  {d['value']:.0f} {d['unit']}  e2e {d.get('e2e', {}).get('value', 0):.0f}")
+    print("   ", {n: round(v["ms_per_step"], 3) for n, v in k.items() if v["ms_per_step"] > 0.05})
