@@ -96,7 +96,7 @@ struct Plan {
 };
 
 bool cfg_ok(const ib200_cfg* c) {
-  return c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64) && c->L >= 1 &&
+  return c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64 || lstm_cluster_supports(c->H)) && c->L >= 1 &&
          c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1);
 }
 
@@ -156,9 +156,16 @@ int gemm_mode() {
   }();
   return v;
 }
+// recurrent kernels: register-resident W_hh for H = 32 / 64, thread-block clusters (lstm_cluster.cu) for every other supported H.
+// IB200_FORCE_CLUSTER=1 routes H = 32 / 64 through the cluster kernels too (cross-check of the two implementations in the tests).
+bool use_cluster(int H) {
+  static const bool force = [] { const char* e = getenv("IB200_FORCE_CLUSTER"); return e && atoi(e) != 0; }();
+  return force || (H != 32 && H != 64);
+}
 bool use_tc() { return gemm_mode() >= 1; }
-bool use_planes(int H) { return H == 64 && gemm_mode() == 2; }
-cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st) {
+bool use_planes(int H) { return H == 64 && gemm_mode() == 2 && !use_cluster(H); }
+cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st, bool wide = false) {
+  if (wide) return launch_gemm_nt(a, prec, st);  // H > 64: column-blocked legacy kernel
   if (a.plane_bytes > 0) {  // operands are bf16 planes: only the TMA kernels can read them
     cudaError_t e = launch_gemm_nt_tma(a, prec, st);
     if (e != cudaErrorInvalidConfiguration || a.nsrc != 2) return e;
@@ -197,6 +204,50 @@ cudaError_t gemm_tn_auto(const GemmTNArgs& a, int prec, cudaStream_t st, bool pl
     (void)cudaGetLastError();
   }
   return launch_gemm_tn(a, prec, st);
+}
+
+// dW block = dA^T * Bop over all token rows: per-CTA partials + deterministic reduction.  `wide` (H > 64): the [KA, NB] product is
+// cut into blocks the mma.sync kernel covers (KA 256|128 x NB 128|64|32); every block is reduced into its place of the result.
+cudaError_t tn_and_reduce(const GemmTNArgs& ta, const DwReduceArgs& ra, int prec, cudaStream_t st, bool planes, bool wide) {
+  if (!wide) {
+    cudaError_t e = gemm_tn_auto(ta, prec, st, planes);
+    if (e != cudaSuccess) return e;
+    return launch_dw_reduce(ra, st);
+  }
+  const int KA = ta.KA, NB = ta.NB;
+  for (int ka0 = 0; ka0 < KA;) {
+    const int kac = KA - ka0 >= 256 ? 256 : 128;
+    for (int nb0 = 0; nb0 < NB;) {
+      const int rem = NB - nb0, nbc = rem >= 128 ? 128 : (rem >= 64 ? 64 : 32);
+      GemmTNArgs t = ta;
+      t.KA = kac; t.lda = KA; t.a_col0 = ka0; t.NB = t.NB1 = nbc;
+      if (t.tok != nullptr) { t.emb_ld = NB; t.emb_col0 = nb0; } else { t.col0 = ta.col0 + nb0; }
+      t.colsum = (ta.colsum && nb0 == 0) ? 1 : 0;
+      cudaError_t e = launch_gemm_tn(t, prec, st);
+      if (e != cudaSuccess) return e;
+      DwReduceArgs r = ra;
+      r.KA = kac; r.NB = r.NB1 = nbc; r.gi0 = ka0; r.c0 = nb0; r.ldo = NB; r.has_colsum = t.colsum;
+      if (!t.colsum) r.out_b1 = r.out_b2 = nullptr;
+      e = launch_dw_reduce(r, st);
+      if (e != cudaSuccess) return e;
+      nb0 += nbc;
+    }
+    ka0 += kac;
+  }
+  return cudaSuccess;
+}
+int tn_launches(int KA, int NB, bool wide) {
+  if (!wide) return 2;
+  int n = 0;
+  for (int ka0 = 0; ka0 < KA; ka0 += (KA - ka0 >= 256 ? 256 : 128))
+    for (int nb0 = 0; nb0 < NB; nb0 += (NB - nb0 >= 128 ? 128 : (NB - nb0 >= 64 ? 64 : 32))) n += 2;
+  return n;
+}
+int nt_launches(int NC, bool wide) {
+  if (!wide) return 1;
+  int n = 0;
+  for (int c0 = 0; c0 < NC; c0 += (NC - c0 >= 256 ? 256 : (NC - c0 >= 128 ? 128 : (NC - c0 >= 64 ? 64 : 32)))) ++n;
+  return n;
 }
 
 template <typename T>
@@ -245,7 +296,7 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
 
 int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
                       const float* whh_l0_mask, int32_t* lengths_out, float* hn_top, void* ws, size_t ws_bytes, void* stream) {
-  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H must be 32 or 64, 1<=L<=4, bi_reduce in last/mean/max)");
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H must be a multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max)");
   if (!tokens || !P || !hn_top || !ws || !P->emb) return fail(IB200_E_NULL, "ib200_encoder_fwd: null pointer");
   const Plan p = make_plan(cfg);
   if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_fwd: workspace too small");
@@ -255,7 +306,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       if (!P->w_ih[l][d] || !P->w_hh[l][d] || !P->b_ih[l][d] || !P->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_fwd: null LSTM parameter");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
-  const bool planes = use_planes(H);
+  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
 
   LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens)};
   TIMED(F_LENGTHS, 3, launch_lengths(la, st), "lengths");
@@ -287,7 +338,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
         ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
         ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
         ga.plane_bytes = planes ? 2 * H * 2 : 0;
-        TIMED(F_GEMM_XPROJ, 1, gemm_nt_auto(ga, prec, st), "input projection gemm");
+        TIMED(F_GEMM_XPROJ, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "input projection gemm");
       }
     }
     LstmFwdArgs fa{};
@@ -312,7 +363,8 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
     }
     fa.hn = l == p.L - 1 ? hn_top : nullptr;
     { const char* e = getenv("IB200_DBG"); fa.dbg = e ? atoi(e) : 0; }
-    TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, launch_lstm_fwd(fa, H, prec, st), "lstm fwd");
+    TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, cluster ? launch_lstm_fwd_cluster(fa, H, prec, st) : launch_lstm_fwd(fa, H, prec, st),
+          "lstm fwd");
   }
   return 0;
 }
@@ -329,7 +381,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
   if (!Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
-  const bool planes = use_planes(H);
+  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
   const int* lens = at<int>(ws, p.lens);
   float* dY = at<float>(ws, p.bwd_scratch);
   float* dX0 = dY + p.R * 2 * H;
@@ -351,8 +403,9 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
     ba.planes = planes ? 1 : 0;
     ba.bias_partial = planes ? at<float>(ws, p.bias_partial) : nullptr;
-    TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, launch_lstm_bwd(ba, H, prec, st), "lstm bwd");
-    const int bwd_ctas = lstm_bwd_cta_count(ba, prec);  // CTAs per direction (= number of bias partials)
+    TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st),
+          "lstm bwd");
+    const int bwd_ctas = planes ? lstm_bwd_cta_count(ba, prec) : 0;  // CTAs per direction (= number of bias partials)
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
     for (int d = 0; d < 2; ++d) {
@@ -377,16 +430,14 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       }
       ta.NB1 = ta.NB;
       ta.colsum = 0;
-      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, planes), "dW_ih gemm");
       DwReduceArgs ra{};
       ra.G = p.G; ra.ctas_per_group = p.ctas_per_group; ra.KA = 4 * H; ra.NB = ta.NB; ra.H = H; ra.partial = partial;
       ra.out = Gr->w_ih[l][d]; ra.NB1 = ta.NB;
-      TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW_ih reduce");
+      TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, ra, prec, st, planes, wide), "dW_ih gemm + reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
       ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H; ta.NB1 = H;
       ta.colsum = planes ? 0 : 1;
-      TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, planes), "dW_hh gemm");
       DwReduceArgs rb{};
       rb.G = p.G; rb.ctas_per_group = p.ctas_per_group; rb.KA = 4 * H; rb.NB = H; rb.H = H; rb.partial = partial;
       rb.has_colsum = planes ? 0 : 1; rb.mask = mask_hh; rb.out = Gr->w_hh[l][d]; rb.NB1 = H;
@@ -395,7 +446,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         rb.cs_ptr = at<float>(ws, p.bias_partial) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
         rb.cs_count = bwd_ctas;
       }
-      TIMED(F_DW_REDUCE, 1, launch_dw_reduce(rb, st), "dW_hh reduce");
+      TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, rb, prec, st, planes, wide), "dW_hh gemm + reduce");
     }
 
     // input gradient of this layer
@@ -412,10 +463,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ga.plane_bytes = planes ? 4 * H * 2 : 0;
     if (l > 0) {
       ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
-      TIMED(F_GEMM_DGRAD, 1, gemm_nt_auto(ga, prec, st), "dY gemm");
+      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "dY gemm");
     } else {
       ga.C = dX0; ga.ldc = H; ga.NC = H;
-      TIMED(F_GEMM_DGRAD, 1, gemm_nt_auto(ga, prec, st), "dX0 gemm");
+      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "dX0 gemm");
       EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
       TIMED(F_EMB_GRAD, 2, launch_emb_grad(ea, st), "embedding grad");
     }

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTNArgs p) {
   const int tiles_per_seq = (T + kBK - 1) / kBK;
   const int items = p.B * tiles_per_seq;
   const bool gathered = p.tok != nullptr;
+  const int lda = p.lda > 0 ? p.lda : KA, a_col0 = p.lda > 0 ? p.a_col0 : 0;
+  const int emb_ld = p.emb_ld > 0 ? p.emb_ld : NB, emb_col0 = p.emb_ld > 0 ? p.emb_col0 : 0;
 
   float acc[MTW][NTW][4];
 #pragma unroll
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTNArgs p) {
     for (int c = tid; c < kBK * (KA / 4); c += 256) {
       const int r = c / (KA / 4), q = c % (KA / 4);
       const bool valid = t0 + r < T;
-      cp_async16(at + r * SA + q * 4, p.A + ((size_t)n * p.Tmax + (valid ? t0 + r : 0)) * KA + q * 4, valid);
+      cp_async16(at + r * SA + q * 4, p.A + ((size_t)n * p.Tmax + (valid ? t0 + r : 0)) * lda + a_col0 + q * 4, valid);
     }
     if (!gathered) {
       float* bt = Bt + buf * kBK * SB;
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTNArgs p) {
         if (t0 + r < T) {
           const int tk = p.tok[(size_t)n * p.Tmax + t0 + r];
           const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + tk] : 1.0f;
-          float4 e = *reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB + q * 4);
+          float4 e = *reinterpret_cast<const float4*>(p.emb + (size_t)tk * emb_ld + emb_col0 + q * 4);
           breg[i] = make_float4(sc * e.x, sc * e.y, sc * e.z, sc * e.w);
         }
       }
@@ -372,6 +374,7 @@ __global__ void dw_reduce_kernel(const DwReduceArgs p) {
   const bool is_mat = w < nmat4;
   const int idx = w * 4;  // element offset inside a partial block (matrix part first, then the column sums)
   const int gi = is_mat ? idx / p.NB : (idx - p.KA * p.NB), c = is_mat ? idx % p.NB : 0;
+  const int ldo = p.ldo > 0 ? p.ldo : p.NB;  // chunked GEMMs: this block is rows [gi0, gi0+KA) x columns [c0, c0+NB) of [4H, ldo]
   float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!is_mat && p.cs_ptr != nullptr) {
     // bias partials written by the BPTT kernel: [cs_count][KA]
@@ -389,8 +392,8 @@ __global__ void dw_reduce_kernel(const DwReduceArgs p) {
       }
       s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z); s.w = warp_sum(s.w);
       if (is_mat && p.mask != nullptr && c >= (p.out2 != nullptr ? p.NB1 : 0)) {
-        const int mc = p.out2 != nullptr ? c - p.NB1 : c, mld = p.out2 != nullptr ? p.NB - p.NB1 : p.NB;
-        const float4 m = *reinterpret_cast<const float4*>(p.mask + ((size_t)g * p.KA + gi_to_torch_row(gi, p.H)) * mld + mc);
+        const int mc = p.out2 != nullptr ? c - p.NB1 : p.c0 + c, mld = p.out2 != nullptr ? p.NB - p.NB1 : ldo;
+        const float4 m = *reinterpret_cast<const float4*>(p.mask + ((size_t)g * 4 * p.H + gi_to_torch_row(p.gi0 + gi, p.H)) * mld + mc);
         s.x *= m.x; s.y *= m.y; s.z *= m.z; s.w *= m.w;
       }
       tot.x += s.x; tot.y += s.y; tot.z += s.z; tot.w += s.w;
@@ -398,15 +401,15 @@ __global__ void dw_reduce_kernel(const DwReduceArgs p) {
   }
   if (lane != 0) return;
   if (is_mat) {
-    const int row = gi_to_torch_row(gi, p.H);
-    if (p.out2 == nullptr) *reinterpret_cast<float4*>(p.out + (size_t)row * p.NB + c) = tot;
+    const int row = gi_to_torch_row(p.gi0 + gi, p.H);
+    if (p.out2 == nullptr) *reinterpret_cast<float4*>(p.out + (size_t)row * ldo + p.c0 + c) = tot;
     else if (c < p.NB1) *reinterpret_cast<float4*>(p.out + (size_t)row * p.NB1 + c) = tot;
     else *reinterpret_cast<float4*>(p.out2 + (size_t)row * (p.NB - p.NB1) + (c - p.NB1)) = tot;
   } else {
     const float t4[4] = {tot.x, tot.y, tot.z, tot.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // gi+j are the 4 gates of one unit: rows q*H + u
-      const int row = gi_to_torch_row(gi + j, p.H);
+      const int row = gi_to_torch_row(p.gi0 + gi + j, p.H);
       if (p.out_b1 != nullptr) p.out_b1[row] = t4[j];
       if (p.out_b2 != nullptr) p.out_b2[row] = t4[j];
     }
@@ -466,20 +469,34 @@ __global__ void fill_zero_kernel(float* p, size_t n) {
 }  // namespace
 
 cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st) {
-  if (a.K % kBK != 0 || a.lda % 4 != 0 || a.ldc % 2 != 0) return cudaErrorInvalidValue;
-  switch (a.NC) {
-    case 256: return launch_nt<256, 2, 4>(a, precision, st);
-    case 128: return launch_nt<128, 4, 2>(a, precision, st);
-    case 64: return launch_nt<64, 8, 1>(a, precision, st);
-    case 32: return launch_nt<32, 8, 1>(a, precision, st);
-    default: return cudaErrorInvalidValue;
+  if (a.K % kBK != 0 || a.lda % 4 != 0 || a.ldc % 2 != 0 || a.NC % 32 != 0) return cudaErrorInvalidValue;
+  // wide outputs (NC = 4H, 2H for H > 64) are produced in column blocks of 256 / 128 / 64 / 32: W rows, bias and C shift together
+  for (int c0 = 0; c0 < a.NC;) {
+    const int rem = a.NC - c0, nc = rem >= 256 ? 256 : (rem >= 128 ? 128 : (rem >= 64 ? 64 : 32));
+    GemmNTArgs b = a;
+    b.NC = nc;
+    b.C = a.C + c0;
+    b.bias = a.bias != nullptr ? a.bias + c0 : nullptr;
+    for (int s = 0; s < a.nsrc; ++s) b.W[s] = a.W[s] + (size_t)c0 * a.K;
+    cudaError_t e;
+    switch (nc) {
+      case 256: e = launch_nt<256, 2, 4>(b, precision, st); break;
+      case 128: e = launch_nt<128, 4, 2>(b, precision, st); break;
+      case 64: e = launch_nt<64, 8, 1>(b, precision, st); break;
+      default: e = launch_nt<32, 8, 1>(b, precision, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    c0 += nc;
   }
+  return cudaSuccess;
 }
 
 cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st) {
   if (a.NB1 != a.NB) return cudaErrorInvalidValue;  // the two-source B operand exists in the tcgen05 kernel only
   if (a.KA == 256 && a.NB == 128) return launch_tn<256, 128>(a, precision, st);
   if (a.KA == 256 && a.NB == 64) return launch_tn<256, 64>(a, precision, st);
+  if (a.KA == 256 && a.NB == 32) return launch_tn<256, 32>(a, precision, st);
+  if (a.KA == 128 && a.NB == 128) return launch_tn<128, 128>(a, precision, st);
   if (a.KA == 128 && a.NB == 64) return launch_tn<128, 64>(a, precision, st);
   if (a.KA == 128 && a.NB == 32) return launch_tn<128, 32>(a, precision, st);
   return cudaErrorInvalidValue;

@@ -71,6 +71,12 @@ struct LstmBwdArgs {
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision);  // G * gridDim.x of the launch above (bias partials per direction)
 
+// ---- K2c / K3c: cluster versions for H = 32k, 32 <= H <= 256 (lstm_cluster.cu): W_hh sliced over H/32 CTAs, h exchanged over DSMEM.
+// fp32 y / gates / dgates layouts only (planes must be 0); bias gradients come from the TN GEMM's column sums.
+bool lstm_cluster_supports(int H);
+cudaError_t launch_lstm_fwd_cluster(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
+cudaError_t launch_lstm_bwd_cluster(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
+
 // ---- tensor-core GEMMs over token rows -------------------------------------------------------------------------------------
 // NT:  C[row, NC] (=|+=) sum_s A_s[row, K] * W_s[NC, K]^T (+ bias)   for rows (n,t), t < T_eff[group(n)]
 struct GemmNTArgs {
@@ -98,8 +104,9 @@ cudaError_t launch_gemm_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t 
 struct GemmTNArgs {
   int G, B, Tmax;
   const int* lens;
-  const float* A;            // dgates [N*Tmax, KA] (GI)
-  int KA;                    // 4H
+  const float* A;            // dgates [N*Tmax, lda] (GI); the GEMM uses columns [a_col0, a_col0 + KA)
+  int KA;                    // 4H, or a column chunk of it (legacy kernel: lda / a_col0 select the chunk)
+  int lda, a_col0;           // legacy kernel only; lda == 0 means lda = KA, a_col0 = 0
   // B operand: either dense rows Bsrc[(n, t+shift), col0 .. col0+NB) with zero outside [0,T_eff), or gathered embeddings
   const float* Bsrc;
   int ldb, col0, shift;
@@ -107,6 +114,7 @@ struct GemmTNArgs {
   const float* emb;
   const float* emb_row_scale;
   int V;
+  int emb_ld, emb_col0;      // legacy kernel only: embedding row pitch and first column (emb_ld == 0 means NB, 0)
   int NB;
   // optional second dense source for the columns [NB1, NB) (tcgen05 kernel only): fuses dW_ih and dW_hh into one pass over A
   int NB1;                   // columns taken from the first source (== NB when there is no second source)
@@ -125,6 +133,7 @@ cudaError_t launch_gemm_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t 
 // out[torch_row(gi)][c] = sum_g mask_g[torch_row][c] * sum_cta partial[g][cta][gi][c];  optional bias outputs
 struct DwReduceArgs {
   int G, ctas_per_group, KA, NB, H;
+  int gi0, c0, ldo;          // chunked GEMMs: first GI row / first column of this block inside the full [4H, ldo] result (ldo == 0: NB)
   const float* partial;
   int has_colsum;            // 1: column sums follow each KA*NB block of `partial` (legacy / thread-loader GEMMs)
   const float* cs_ptr;       // alternative column-sum partials [cs_count][KA] written by the BPTT kernel (TMA path), or null

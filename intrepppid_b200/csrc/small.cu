@@ -88,6 +88,28 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int 
   }
 }
 
+// any H (used for H > 64, where the weight row no longer fits the register file): same summation order, weights from L2
+__global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p, int v_per_block) {
+  extern __shared__ float xs[];  // [H]
+  const int H = p.H, g = blockIdx.y >> 1, d = blockIdx.y & 1;
+  const int vend = min(p.V, (int)(blockIdx.x + 1) * v_per_block);
+  for (int v = blockIdx.x * v_per_block; v < vend; ++v) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < H; e += blockDim.x) {
+      const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
+      xs[e] = sc * p.emb[(size_t)v * H + e];
+    }
+    __syncthreads();
+    for (int gi = threadIdx.x; gi < 4 * H; gi += blockDim.x) {
+      const int row = gi_to_torch_row(gi, H);
+      const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
+      float s = 0.f;
+      for (int k = 0; k < H; ++k) s = fmaf(xs[k], wr[k], s);
+      p.table[(((size_t)(g * 2 + d)) * p.V + v) * 4 * H + gi] = s + (p.b_ih[d][row] + p.b_hh[d][row]);
+    }
+  }
+}
+
 // ---- K4: bi_reduce on h_n[-2:] + fc (encoders/awd_lstm.py:58-71) -----------------------------------------------------------------
 __global__ void pool_fc_fwd_kernel(int N, int H, int mode, const float* __restrict__ hn, const float* __restrict__ fc_w,
                                    const float* __restrict__ fc_b, float* __restrict__ z, float* __restrict__ pooled_out,
@@ -172,7 +194,7 @@ cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
   dim3 grid((a.V + vpb - 1) / vpb, a.G * 2);
   if (a.H == 64) l0_table_kernel<64><<<grid, 256, 0, st>>>(a, vpb);
   else if (a.H == 32) l0_table_kernel<32><<<grid, 128, 0, st>>>(a, vpb);
-  else return cudaErrorInvalidValue;
+  else l0_table_generic_kernel<<<grid, 256, a.H * sizeof(float), st>>>(a, vpb);
   return cudaGetLastError();
 }
 

@@ -93,7 +93,7 @@ class _EncodeHidden(torch.autograd.Function):
         cfg = econf.cfg(G, B, T, V, H, training)
         nbytes = lib().ib200_workspace_bytes(cfg)
         if nbytes == 0:
-            raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (32 or 64), L={L} (1..4)")
+            raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), L={L} (1..4)")
         dev = tokens.device
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         lens = torch.empty(2, G, dtype=torch.int32, device=dev)
