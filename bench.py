@@ -113,6 +113,20 @@ def algorithmic_bytes(family: str, tokens_per_chain: float, H: int) -> float:
     return per_token * tokens_per_chain
 
 
+def ncu_traffic(family: str, tokens_per_chain: float, mode: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `family`, from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json: bytes per token measured on the same workload, scaled to this run's token count).  None when no
+    capture exists for this precision mode."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if mode != "fp32" or not os.path.exists(path):
+        return None
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["kernels"][family]["dram_bytes_per_token"]) * tokens_per_chain
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -242,7 +256,8 @@ def run_b200(args):
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
     chains_steps = float(teff.max())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "traffic": ncu_traffic(dom, tokens_per_chain, args.mode), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes,
                 "avg_launch_ms": dom_ms, "tau_us_per_cell_step": dom_ms * 1e3 / chains_steps,
                 "note": "recurrent kernels are bound by the dependent chain (tau per cell step), not by HBM; see DESIGN.md"}
 

@@ -497,7 +497,7 @@ int ib200_loss_head_fwd(int32_t B, int32_t H, float beta, const float* z, const 
                         const ib200_head_masks* hm, float* losses_out, float* y_hat_out, void* stream) {
   if (!z || !y || !hp || !losses_out || !y_hat_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b)
     return fail(IB200_E_NULL, "ib200_loss_head_fwd: null pointer");
-  if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_fwd: bad shape");
+  if (B < 1 || !head_supports(H) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_fwd: bad shape (H must be a multiple of 32 in [32, 256])");
   ib200_head_masks none{};
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_LOSS_HEAD, 1, launch_loss_head_fwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, losses_out, y_hat_out, st), "loss_head fwd");
@@ -509,7 +509,7 @@ int ib200_loss_head_bwd(int32_t B, int32_t H, float beta, const float* z, const 
                         void* stream) {
   if (!z || !y || !hp || !d_loss || !dz_out || !hg || !hg->fc1_w || !hg->fc1_b || !hg->fc2_w || !hg->fc2_b)
     return fail(IB200_E_NULL, "ib200_loss_head_bwd: null pointer");
-  if (B < 1 || (H != 32 && H != 64) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_bwd: bad shape");
+  if (B < 1 || !head_supports(H) || !(beta > 0.f)) return fail(IB200_E_SHAPE, "ib200_loss_head_bwd: bad shape (H must be a multiple of 32 in [32, 256])");
   ib200_head_masks none{};
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_LOSS_HEAD, 1, launch_loss_head_bwd(B, H, beta, z, (const long long*)y, *hp, hm ? *hm : none, d_loss, d_y_hat, dz_out, *hg, st), "loss_head bwd");
@@ -520,7 +520,7 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
                      const ib200_head_params* hp, float* prob_out, void* stream) {
   if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score: null pointer");
   if ((idx_a == nullptr) != (idx_b == nullptr)) return fail(IB200_E_NULL, "ib200_pair_score: idx_a and idx_b must both be given or both be null");
-  if (M < 1 || (H != 32 && H != 64) || P < 0) return fail(IB200_E_SHAPE, "ib200_pair_score: bad shape");
+  if (M < 1 || !head_supports(H) || P < 0) return fail(IB200_E_SHAPE, "ib200_pair_score: bad shape (H must be a multiple of 32 in [32, 256])");
   if (!idx_a && P != (int64_t)M * (M + 1) / 2) return fail(IB200_E_SHAPE, "ib200_pair_score: P must be M(M+1)/2 for the implicit upper triangle");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, st), "pair_score");

@@ -19,22 +19,38 @@ __device__ __forceinline__ float mish_grad_acc(float x) {
 }
 
 constexpr int kHeadWarps = 8;
-constexpr int kChunk = 32;  // samples per backward chunk
 constexpr float kEps = 1e-6f;  // nn.TripletMarginLoss eps (pairwise_distance adds it to the difference)
+// samples per backward chunk; the wide variants (H > 64) keep the per-chunk vectors small enough for shared memory
+template <int H>
+constexpr int chunk_of() { return H <= 64 ? 32 : 8; }
 
+// H <= 64: both weight matrices are staged in shared memory (masked fc1 weight, projection weight).  H > 64 (up to 256): they no
+// longer fit, the kernels read them from global memory / L2 (a few hundred KB, read by one CTA) through the same accessors.
 template <int H>
 struct HeadSmem {
   static constexpr int HH = H / 2;
-  float w1[HH][H + 1];           // fc1 weight * mask
-  float wp[H][H + 1];            // projection weight
-  float scratch[kHeadWarps][H];  // per-warp broadcast vector
+  static constexpr bool kStaged = H <= 64;
+  float w1[kStaged ? HH : 1][H + 1];  // fc1 weight * mask
+  float wp[kStaged ? H : 1][H + 1];   // projection weight
+  float scratch[kHeadWarps][H];       // per-warp broadcast vector
   float red[kHeadWarps][4];
 };
+template <int H>
+__device__ __forceinline__ float w1_at(const HeadSmem<H>& sm, const ib200_head_params& hp, const ib200_head_masks& hm, int j, int k) {
+  if constexpr (HeadSmem<H>::kStaged) return sm.w1[j][k];
+  else return hp.fc1_w[j * H + k] * (hm.fc1_w != nullptr ? hm.fc1_w[j * H + k] : 1.0f);
+}
+template <int H>
+__device__ __forceinline__ float wp_at(const HeadSmem<H>& sm, const ib200_head_params& hp, int e, int k) {
+  if constexpr (HeadSmem<H>::kStaged) return sm.wp[e][k];
+  else return hp.proj_w[e * H + k];
+}
 
 // projection a' = Wp mish(z) + bp for one sample held as z[e = lane + 32 i]
 template <int H>
-__device__ __forceinline__ void project(HeadSmem<H>& sm, int warp, int lane, const float* __restrict__ bp, float (&z)[H / 32],
+__device__ __forceinline__ void project(HeadSmem<H>& sm, const ib200_head_params& hp, int warp, int lane, float (&z)[H / 32],
                                         float (&out)[H / 32]) {
+  const float* __restrict__ bp = hp.proj_b;
   constexpr int FPL = H / 32;
 #pragma unroll
   for (int i = 0; i < FPL; ++i) sm.scratch[warp][lane + 32 * i] = mish_acc(z[i]);
@@ -43,7 +59,7 @@ __device__ __forceinline__ void project(HeadSmem<H>& sm, int warp, int lane, con
   for (int i = 0; i < FPL; ++i) {
     const int e = lane + 32 * i;
     float s = bp[e];
-    for (int k = 0; k < H; ++k) s = fmaf(sm.wp[e][k], sm.scratch[warp][k], s);
+    for (int k = 0; k < H; ++k) s = fmaf(wp_at<H>(sm, hp, e, k), sm.scratch[warp][k], s);
     out[i] = s;
   }
   __syncwarp();
@@ -52,6 +68,7 @@ __device__ __forceinline__ void project(HeadSmem<H>& sm, int warp, int lane, con
 template <int H>
 __device__ __forceinline__ void load_head_weights(HeadSmem<H>& sm, const ib200_head_params& hp, const ib200_head_masks& hm) {
   constexpr int HH = H / 2;
+  if constexpr (!HeadSmem<H>::kStaged) return;
   for (int i = threadIdx.x; i < HH * H; i += blockDim.x) {
     const float m = hm.fc1_w != nullptr ? hm.fc1_w[i] : 1.0f;
     sm.w1[i / H][i % H] = hp.fc1_w[i] * m;  // WeightDrop on fc1.weight (mlp.py:38-46, weightdrop.py:100-102)
@@ -63,9 +80,10 @@ __device__ __forceinline__ void load_head_weights(HeadSmem<H>& sm, const ib200_h
 // forward pieces of the head for one sample; returns the logit (valid in all lanes) and keeps intermediates for backward
 template <int H>
 struct HeadFwd {
-  float x[H / 32];   // (z1+z2)/2
-  float a1, d1;      // lane j < H/2: fc1 pre-activation, dropout-1 output
-  float d2;          // dropout-2 output
+  static constexpr int JPL = (H / 2 + 31) / 32;  // fc1 outputs per lane: j = lane + 32 m
+  float x[H / 32];       // (z1+z2)/2
+  float a1[JPL], d1[JPL];  // fc1 pre-activation, dropout-1 output
+  float d2[JPL];         // dropout-2 output
   float logit;
 };
 
@@ -82,17 +100,21 @@ __device__ __forceinline__ void head_forward(HeadSmem<H>& sm, int warp, int lane
   }
   __syncwarp();
   float contrib = 0.f;
-  o.a1 = o.d1 = o.d2 = 0.f;
-  if (lane < HH) {
-    float s = hp.fc1_b[lane];
-    for (int k = 0; k < H; ++k) s = fmaf(sm.w1[lane][k], sm.scratch[warp][k], s);
-    o.a1 = s;
-    const float m1 = mish_acc(s);                                                    // nl1
-    o.d1 = m1 * (hm.do1 != nullptr ? hm.do1[(size_t)b * HH + lane] : 1.0f);           // do1
-    const float m2 = mish_acc(o.d1);                                                 // nl2
-    o.d2 = m2 * (hm.do2 != nullptr ? hm.do2[(size_t)b * HH + lane] : 1.0f);           // do2
-    const float w2 = hp.fc2_w[lane] * (hm.fc2_w != nullptr ? hm.fc2_w[lane] : 1.0f);  // WeightDrop on fc2.weight
-    contrib = w2 * o.d2;
+#pragma unroll
+  for (int m = 0; m < HeadFwd<H>::JPL; ++m) {
+    const int j = lane + 32 * m;
+    o.a1[m] = o.d1[m] = o.d2[m] = 0.f;
+    if (j < HH) {
+      float s = hp.fc1_b[j];
+      for (int k = 0; k < H; ++k) s = fmaf(w1_at<H>(sm, hp, hm, j, k), sm.scratch[warp][k], s);
+      o.a1[m] = s;
+      const float m1 = mish_acc(s);                                                 // nl1
+      o.d1[m] = m1 * (hm.do1 != nullptr ? hm.do1[(size_t)b * HH + j] : 1.0f);        // do1
+      const float m2 = mish_acc(o.d1[m]);                                           // nl2
+      o.d2[m] = m2 * (hm.do2 != nullptr ? hm.do2[(size_t)b * HH + j] : 1.0f);        // do2
+      const float w2 = hp.fc2_w[j] * (hm.fc2_w != nullptr ? hm.fc2_w[j] : 1.0f);     // WeightDrop on fc2.weight
+      contrib += w2 * o.d2[m];
+    }
   }
   __syncwarp();
   o.logit = warp_sum(contrib) + hp.fc2_b[0];
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_fwd_kernel(int B, f
       float zr[FPL];
 #pragma unroll
       for (int i = 0; i < FPL; ++i) zr[i] = z[((size_t)r * B + b) * H + lane + 32 * i];
-      if (proj) project<H>(sm, warp, lane, hp.proj_b, zr, v[r]);
+      if (proj) project<H>(sm, hp, warp, lane, zr, v[r]);
       else {
 #pragma unroll
         for (int i = 0; i < FPL; ++i) v[r][i] = zr[i];
@@ -163,6 +185,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_fwd_kernel(int B, f
 template <int H>
 struct HeadBwdSmem {
   static constexpr int HH = H / 2;
+  static constexpr int kChunk = chunk_of<H>();
   HeadSmem<H> f;
   float dlt1[kChunk][HH];        // delta at fc1 pre-activation
   float m0s[kChunk][H];          // mish((z1+z2)/2)
@@ -177,7 +200,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
                                                                          ib200_head_masks hm, const float* __restrict__ d_loss,
                                                                          const float* __restrict__ d_y_hat, float* __restrict__ dz,
                                                                          ib200_head_grads hg) {
-  constexpr int FPL = H / 32, HH = H / 2;
+  constexpr int FPL = H / 32, HH = H / 2, kChunk = chunk_of<H>(), JPL = HeadFwd<H>::JPL;
+  constexpr bool kRegAcc = H <= 64;  // matrix-gradient accumulators in registers; wider heads accumulate in the output buffers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HeadBwdSmem<H>& sm = *reinterpret_cast<HeadBwdSmem<H>*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -189,13 +213,15 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
   const float w_t = dL * (1.0f / beta) / (float)B, w_c = dL * (1.0f - 1.0f / beta) / (float)B;
 
   // matrix-gradient accumulators owned by this thread: fc1 [HH*H/256], proj [H*H/256]
-  constexpr int N1 = (HH * H + 255) / 256, NP = (H * H + 255) / 256;
+  constexpr int N1 = kRegAcc ? (HH * H + 255) / 256 : 1, NP = kRegAcc ? (H * H + 255) / 256 : 1;
   float acc1[N1], accp[NP];
 #pragma unroll
   for (int i = 0; i < N1; ++i) acc1[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < NP; ++i) accp[i] = 0.f;
-  float db1 = 0.f, dw2 = 0.f, db2 = 0.f, dbp[FPL];
+  float db1[JPL], dw2[JPL], db2 = 0.f, dbp[FPL];
+#pragma unroll
+  for (int m = 0; m < JPL; ++m) db1[m] = dw2[m] = 0.f;
 #pragma unroll
   for (int i = 0; i < FPL; ++i) dbp[i] = 0.f;
 
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
 #pragma unroll
         for (int i = 0; i < FPL; ++i) zr[r][i] = z[((size_t)r * B + b) * H + lane + 32 * i];
         if (proj) {
-          project<H>(sm.f, warp, lane, hp.proj_b, zr[r], v[r]);
+          project<H>(sm.f, hp, warp, lane, zr[r], v[r]);
 #pragma unroll
           for (int i = 0; i < FPL; ++i) sm.mzs[r][c][lane + 32 * i] = mish_acc(zr[r][i]);
         } else {
@@ -251,7 +277,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
           for (int i = 0; i < FPL; ++i) {
             const int k = lane + 32 * i;
             float s = 0.f;
-            for (int e = 0; e < H; ++e) s = fmaf(sm.f.wp[e][k], sm.dltp[r][c][e], s);
+            for (int e = 0; e < H; ++e) s = fmaf(wp_at<H>(sm.f, hp, e, k), sm.dltp[r][c][e], s);
             dz[((size_t)r * B + b) * H + k] = s * mish_grad_acc(zr[r][i]);
           }
         }
@@ -267,17 +293,20 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
 #pragma unroll
       for (int i = 0; i < FPL; ++i) sm.m0s[c][lane + 32 * i] = sm.f.scratch[warp][lane + 32 * i];
       const float dlogit = w_c * (1.0f / (1.0f + expf(-hf.logit)) - (float)y[b]) + (d_y_hat != nullptr ? d_y_hat[b] : 0.0f);
-      float delta1 = 0.f;
-      if (lane < HH) {
-        const float m2mask = hm.fc2_w != nullptr ? hm.fc2_w[lane] : 1.0f;
-        const float dd2 = dlogit * hp.fc2_w[lane] * m2mask;
-        dw2 += dlogit * hf.d2 * m2mask;
-        const float dm2 = dd2 * (hm.do2 != nullptr ? hm.do2[(size_t)b * HH + lane] : 1.0f);
-        const float dd1 = dm2 * mish_grad_acc(hf.d1);
-        const float dm1 = dd1 * (hm.do1 != nullptr ? hm.do1[(size_t)b * HH + lane] : 1.0f);
-        delta1 = dm1 * mish_grad_acc(hf.a1);
-        db1 += delta1;
-        sm.dlt1[c][lane] = delta1;
+#pragma unroll
+      for (int m = 0; m < JPL; ++m) {
+        const int j = lane + 32 * m;
+        if (j < HH) {
+          const float m2mask = hm.fc2_w != nullptr ? hm.fc2_w[j] : 1.0f;
+          const float dd2 = dlogit * hp.fc2_w[j] * m2mask;
+          dw2[m] += dlogit * hf.d2[m] * m2mask;
+          const float dm2 = dd2 * (hm.do2 != nullptr ? hm.do2[(size_t)b * HH + j] : 1.0f);
+          const float dd1 = dm2 * mish_grad_acc(hf.d1[m]);
+          const float dm1 = dd1 * (hm.do1 != nullptr ? hm.do1[(size_t)b * HH + j] : 1.0f);
+          const float delta1 = dm1 * mish_grad_acc(hf.a1[m]);
+          db1[m] += delta1;
+          sm.dlt1[c][j] = delta1;
+        }
       }
       if (lane == 0) db2 += dlogit;
       __syncwarp();
@@ -285,7 +314,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
       for (int i = 0; i < FPL; ++i) {
         const int k = lane + 32 * i;
         float s = 0.f;
-        for (int jj = 0; jj < HH; ++jj) s = fmaf(sm.f.w1[jj][k], sm.dlt1[c][jj], s);
+        for (int jj = 0; jj < HH; ++jj) s = fmaf(w1_at<H>(sm.f, hp, hm, jj, k), sm.dlt1[c][jj], s);
         const float dx = s * mish_grad_acc(hf.x[i]) * 0.5f;
         dz[((size_t)3 * B + b) * H + k] = dx;
         dz[((size_t)4 * B + b) * H + k] = dx;
@@ -294,26 +323,45 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
     }
     __syncthreads();
     // ---- phase B: every thread reduces its matrix entries over the chunk (fixed order => deterministic) ----------------------
+    if constexpr (kRegAcc) {
 #pragma unroll
-    for (int i = 0; i < N1; ++i) {
-      const int idx = tid + 256 * i;
-      if (idx < HH * H) {
-        const int jj = idx / H, k = idx % H;
-        float s = acc1[i];
-        for (int c = 0; c < cn; ++c) s = fmaf(sm.dlt1[c][jj], sm.m0s[c][k], s);
-        acc1[i] = s;
-      }
-    }
-    if (proj) {
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
+      for (int i = 0; i < N1; ++i) {
         const int idx = tid + 256 * i;
-        if (idx < H * H) {
+        if (idx < HH * H) {
+          const int jj = idx / H, k = idx % H;
+          float s = acc1[i];
+          for (int c = 0; c < cn; ++c) s = fmaf(sm.dlt1[c][jj], sm.m0s[c][k], s);
+          acc1[i] = s;
+        }
+      }
+      if (proj) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const int idx = tid + 256 * i;
+          if (idx < H * H) {
+            const int e = idx / H, k = idx % H;
+            float s = accp[i];
+            for (int r = 0; r < 3; ++r)
+              for (int c = 0; c < cn; ++c) s = fmaf(sm.dltp[r][c][e], sm.mzs[r][c][k], s);
+            accp[i] = s;
+          }
+        }
+      }
+    } else {
+      // wide head: every matrix entry is owned by one thread of this single CTA and accumulated in the output buffer itself
+      for (int idx = tid; idx < HH * H; idx += 256) {
+        const int jj = idx / H, k = idx % H;
+        float s = c0 == 0 ? 0.f : hg.fc1_w[idx];
+        for (int c = 0; c < cn; ++c) s = fmaf(sm.dlt1[c][jj], sm.m0s[c][k], s);
+        hg.fc1_w[idx] = s;
+      }
+      if (proj && hg.proj_w != nullptr) {
+        for (int idx = tid; idx < H * H; idx += 256) {
           const int e = idx / H, k = idx % H;
-          float s = accp[i];
+          float s = c0 == 0 ? 0.f : hg.proj_w[idx];
           for (int r = 0; r < 3; ++r)
             for (int c = 0; c < cn; ++c) s = fmaf(sm.dltp[r][c][e], sm.mzs[r][c][k], s);
-          accp[i] = s;
+          hg.proj_w[idx] = s;
         }
       }
     }
@@ -321,21 +369,29 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
   }
 
   // ---- write parameter gradients -------------------------------------------------------------------------------------------
+  if constexpr (kRegAcc) {
 #pragma unroll
-  for (int i = 0; i < N1; ++i) {
-    const int idx = tid + 256 * i;
-    if (idx < HH * H) hg.fc1_w[idx] = acc1[i] * (hm.fc1_w != nullptr ? hm.fc1_w[idx] : 1.0f);  // grad of weight_raw
-  }
-  if (proj && hg.proj_w != nullptr) {
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
+    for (int i = 0; i < N1; ++i) {
       const int idx = tid + 256 * i;
-      if (idx < H * H) hg.proj_w[idx] = accp[i];
+      if (idx < HH * H) hg.fc1_w[idx] = acc1[i] * (hm.fc1_w != nullptr ? hm.fc1_w[idx] : 1.0f);  // grad of weight_raw
     }
+    if (proj && hg.proj_w != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int idx = tid + 256 * i;
+        if (idx < H * H) hg.proj_w[idx] = accp[i];
+      }
+    }
+  } else if (hm.fc1_w != nullptr) {
+    for (int idx = tid; idx < HH * H; idx += 256) hg.fc1_w[idx] *= hm.fc1_w[idx];  // same owner thread as the accumulation
   }
-  if (lane < HH) {
-    sm.vec[warp][lane] = db1;
-    sm.vec[warp][HH + lane] = dw2;
+#pragma unroll
+  for (int m = 0; m < JPL; ++m) {
+    const int j = lane + 32 * m;
+    if (j < HH) {
+      sm.vec[warp][j] = db1[m];
+      sm.vec[warp][HH + j] = dw2[m];
+    }
   }
 #pragma unroll
   for (int i = 0; i < FPL; ++i) sm.vec[warp][H + lane + 32 * i] = dbp[i];
@@ -416,46 +472,139 @@ __global__ void __launch_bounds__(128) pair_score_kernel(int M, const float* __r
   }
 }
 
+// wide variant (H > 64): one WARP per pair; the fc1 weight sits transposed in shared memory ([k][j], conflict-free across lanes),
+// the warp stages mish((z_a+z_b)/2) in its smem slot and every lane owns the fc1 outputs j = lane + 32 m.
+template <int H>
+__global__ void __launch_bounds__(256) pair_score_wide_kernel(int M, const float* __restrict__ z, const int* __restrict__ ia,
+                                                               const int* __restrict__ ib, long long P, ib200_head_params hp,
+                                                               float* __restrict__ prob) {
+  constexpr int HH = H / 2, JPL = (HH + 31) / 32, FPL = H / 32;
+  extern __shared__ __align__(16) float smw[];
+  float* w1t = smw;                  // [H][HH]
+  float* m0 = smw + H * HH;          // [8 warps][H]
+  for (int i = threadIdx.x; i < HH * H; i += blockDim.x) w1t[(i % H) * HH + i / H] = hp.fc1_w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* mine = m0 + warp * H;
+  float b1[JPL], w2[JPL];
+#pragma unroll
+  for (int m = 0; m < JPL; ++m) {
+    const int j = lane + 32 * m;
+    b1[m] = j < HH ? hp.fc1_b[j] : 0.f;
+    w2[m] = j < HH ? hp.fc2_w[j] : 0.f;
+  }
+  const float b2 = hp.fc2_b[0];
+  const long long nw = (long long)gridDim.x * 8;
+  for (long long pidx = (long long)blockIdx.x * 8 + warp; pidx < P; pidx += nw) {
+    int i, j;
+    if (ia != nullptr) {
+      i = ia[pidx];
+      j = ib[pidx];
+    } else {
+      const double Md = (double)M;
+      long long r = (long long)floor(((2.0 * Md + 1.0) - sqrt((2.0 * Md + 1.0) * (2.0 * Md + 1.0) - 8.0 * (double)pidx)) * 0.5);
+      if (r < 0) r = 0;
+      while (r * M - r * (r - 1) / 2 > pidx) --r;
+      while ((r + 1) * M - (r + 1) * r / 2 <= pidx) ++r;
+      i = (int)r;
+      j = (int)(pidx - (r * M - r * (r - 1) / 2)) + i;
+    }
+#pragma unroll
+    for (int f = 0; f < FPL; ++f) {
+      const int k = lane + 32 * f;
+      mine[k] = mish_fast((z[(size_t)i * H + k] + z[(size_t)j * H + k]) * 0.5f);
+    }
+    __syncwarp();
+    float s[JPL];
+#pragma unroll
+    for (int m = 0; m < JPL; ++m) s[m] = b1[m];
+    for (int k = 0; k < H; ++k) {
+      const float x = mine[k];
+#pragma unroll
+      for (int m = 0; m < JPL; ++m)
+        if (lane + 32 * m < HH) s[m] = fmaf(w1t[k * HH + lane + 32 * m], x, s[m]);
+    }
+    float contrib = 0.f;
+#pragma unroll
+    for (int m = 0; m < JPL; ++m)
+      if (lane + 32 * m < HH) contrib = fmaf(w2[m], mish_fast(mish_fast(s[m])), contrib);
+    const float logit = warp_sum(contrib) + b2;
+    if (lane == 0) prob[pidx] = __fdividef(1.0f, 1.0f + __expf(-logit));
+    __syncwarp();
+  }
+}
+
+template <int H>
+cudaError_t head_fwd_h(int B, float beta, const float* z, const long long* y, const ib200_head_params& hp, const ib200_head_masks& hm,
+                       float* losses, float* y_hat, cudaStream_t st) {
+  const size_t smem = sizeof(HeadSmem<H>);
+  cudaError_t e = cudaFuncSetAttribute(loss_head_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  loss_head_fwd_kernel<H><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, losses, y_hat);
+  return cudaGetLastError();
+}
+template <int H>
+cudaError_t head_bwd_h(int B, float beta, const float* z, const long long* y, const ib200_head_params& hp, const ib200_head_masks& hm,
+                       const float* d_loss, const float* d_y_hat, float* dz, const ib200_head_grads& hg, cudaStream_t st) {
+  const size_t smem = sizeof(HeadBwdSmem<H>);
+  cudaError_t e = cudaFuncSetAttribute(loss_head_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  loss_head_bwd_kernel<H><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, d_loss, d_y_hat, dz, hg);
+  return cudaGetLastError();
+}
+template <int H>
+cudaError_t pair_wide_h(int M, const float* z, const int* idx_a, const int* idx_b, long long P, const ib200_head_params& hp,
+                        float* prob, cudaStream_t st) {
+  const size_t smem = ((size_t)H * (H / 2) + 8 * H) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(pair_score_wide_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)std::min<long long>((P + 7) / 8, 148LL * 8);
+  pair_score_wide_kernel<H><<<grid, 256, smem, st>>>(M, z, idx_a, idx_b, P, hp, prob);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+bool head_supports(int H) { return H % 32 == 0 && H >= 32 && H <= 256; }
+
+#define IB200_HEAD_DISPATCH(FN, ...)                 \
+  switch (H) {                                       \
+    case 32: return FN<32>(__VA_ARGS__);             \
+    case 64: return FN<64>(__VA_ARGS__);             \
+    case 96: return FN<96>(__VA_ARGS__);             \
+    case 128: return FN<128>(__VA_ARGS__);           \
+    case 160: return FN<160>(__VA_ARGS__);           \
+    case 192: return FN<192>(__VA_ARGS__);           \
+    case 224: return FN<224>(__VA_ARGS__);           \
+    case 256: return FN<256>(__VA_ARGS__);           \
+    default: return cudaErrorInvalidValue;           \
+  }
 
 cudaError_t launch_loss_head_fwd(int B, int H, float beta, const float* z, const long long* y, const ib200_head_params& hp,
                                  const ib200_head_masks& hm, float* losses, float* y_hat, cudaStream_t st) {
-  if (H == 64) {
-    const size_t smem = sizeof(HeadSmem<64>);
-    cudaError_t e = cudaFuncSetAttribute(loss_head_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    loss_head_fwd_kernel<64><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, losses, y_hat);
-  } else if (H == 32) {
-    const size_t smem = sizeof(HeadSmem<32>);
-    loss_head_fwd_kernel<32><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, losses, y_hat);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  IB200_HEAD_DISPATCH(head_fwd_h, B, beta, z, y, hp, hm, losses, y_hat, st)
 }
 
 cudaError_t launch_loss_head_bwd(int B, int H, float beta, const float* z, const long long* y, const ib200_head_params& hp,
                                  const ib200_head_masks& hm, const float* d_loss, const float* d_y_hat, float* dz,
                                  const ib200_head_grads& hg, cudaStream_t st) {
-  if (H == 64) {
-    const size_t smem = sizeof(HeadBwdSmem<64>);
-    cudaError_t e = cudaFuncSetAttribute(loss_head_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    loss_head_bwd_kernel<64><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, d_loss, d_y_hat, dz, hg);
-  } else if (H == 32) {
-    const size_t smem = sizeof(HeadBwdSmem<32>);
-    cudaError_t e = cudaFuncSetAttribute(loss_head_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    loss_head_bwd_kernel<32><<<1, kHeadWarps * 32, smem, st>>>(B, beta, z, y, hp, hm, d_loss, d_y_hat, dz, hg);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  IB200_HEAD_DISPATCH(head_bwd_h, B, beta, z, y, hp, hm, d_loss, d_y_hat, dz, hg, st)
 }
 
 cudaError_t launch_pair_score(int M, int H, const float* z, const int* idx_a, const int* idx_b, long long P,
                               const ib200_head_params& hp, float* prob, cudaStream_t st) {
   if (P <= 0) return cudaSuccess;
+  if (H > 64) {
+    switch (H) {
+      case 96: return pair_wide_h<96>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 128: return pair_wide_h<128>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 160: return pair_wide_h<160>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 192: return pair_wide_h<192>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 224: return pair_wide_h<224>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 256: return pair_wide_h<256>(M, z, idx_a, idx_b, P, hp, prob, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   const unsigned grid = (unsigned)std::min<long long>((P + 127) / 128, 148LL * 16);
   if (H == 64) pair_score_kernel<64><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, hp, prob);
   else if (H == 32) pair_score_kernel<32><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, hp, prob);
