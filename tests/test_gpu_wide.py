@@ -72,3 +72,33 @@ def test_cluster_kernels_match_register_kernels_at_64():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                         "-k", "golden or fp64_oracle or seeded"], env=env, capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("E,L,bi,proj,B", [(128, 2, "last", False, 11), (256, 2, "mean", True, 19), (96, 1, "last", True, 8)])
+def test_wide_training_step_vs_fp64_oracle(E, L, bi, proj, B):
+    """The whole e2e_rnn_triplet step (5 encoder calls, triplet (+projection), head, BCE, beta mix, backward) at embedding sizes
+    above 64: cluster encoder kernels + the wide loss/head kernels (weights read through L2, several backward chunks)."""
+    from helpers import run_oracle_step, run_product_step
+    from test_gpu_parity import _check
+
+    V, T = 97, 36
+    P = R.init_params(vocab=V, E=E, L=L, seed=41, use_projection=proj)
+    batch = list(R.synthetic_batch(B, T, V, seed=42, padded=True))
+    masks = R.draw_step_masks(B, V, E, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=43)
+    kw = dict(L=L, bi=bi, beta=4.0, use_projection=proj, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+    ref = run_oracle_step(P, batch, masks, **kw)
+    _check(got, ref, 1e-4)
+
+
+def test_wide_pair_score_vs_oracle():
+    P = R.init_params(E=128, L=1, seed=5)
+    net = build_product(P, L=1, bi="last").eval()
+    z = torch.randn(70, 128)
+    ia, ib = torch.triu_indices(70, 70)
+    with torch.no_grad():
+        ref = torch.sigmoid(R.mlp_head(z[ia], z[ib], P).squeeze(1))
+    got_tri = net.score_pairs(z.cuda()).cpu()
+    got_idx = net.score_pairs(z.cuda(), ia.cuda(), ib.cuda()).cpu()
+    assert float((got_tri - ref).abs().max()) < 1e-5
+    assert float((got_idx - ref).abs().max()) < 1e-5
