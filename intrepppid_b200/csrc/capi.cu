@@ -138,7 +138,7 @@ Plan make_plan(const ib200_cfg* c) {
         }
     p.bwd_scratch = p.L > 1 ? p.X[0] : take(sizeof(float) * p.R * 3 * H);  // X is dead once the forward is done
     p.ctas_per_group = std::max(1, 148 / p.G);
-    p.partial = take(sizeof(float) * (size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 2 * H + 4 * H));
+    p.partial = take(sizeof(float) * (size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H));  // up to [dW_ih | dW_hh] fused
     p.bias_partial = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
   }
   p.total = off;
@@ -422,7 +422,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       ta.A = at<float>(ws, p.gates[l][d]); ta.KA = 4 * H;
       ta.partial = partial; ta.ctas_per_group = p.ctas_per_group;
       const float* mask_hh = (l == 0 && d == 0) ? whh_l0_mask : nullptr;
-      // dW_ih
+      // first B source: the layer input (dW_ih)
       if (l == 0) {
         ta.tok = at<int>(ws, p.tok32); ta.emb = P->emb; ta.emb_row_scale = emb_row_scale; ta.V = p.V; ta.NB = H;
       } else {
@@ -433,19 +433,28 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       DwReduceArgs ra{};
       ra.G = p.G; ra.ctas_per_group = p.ctas_per_group; ra.KA = 4 * H; ra.NB = ta.NB; ra.H = H; ra.partial = partial;
       ra.out = Gr->w_ih[l][d]; ra.NB1 = ta.NB;
+      if (planes) {
+        // TMA path: ONE pass over the dgates produces [dW_ih | dW_hh]: second B source = h of the previous scan position = Y_l
+        // shifted by one step; the bias gradients come from the column sums the BPTT kernel left behind
+        ta.Bsrc2 = at<float>(ws, p.Y[l]); ta.ldb2 = 2 * H; ta.col02 = d * H; ta.shift2 = d == 0 ? -1 : +1;
+        ta.NB = ta.NB1 + H;
+        ra.NB = ta.NB; ra.out2 = Gr->w_hh[l][d]; ra.mask = mask_hh;
+        ra.out_b1 = Gr->b_ih[l][d]; ra.out_b2 = Gr->b_hh[l][d];
+        ra.cs_ptr = at<float>(ws, p.bias_partial) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
+        ra.cs_count = bwd_ctas;
+        TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, true), "dW_ih|dW_hh gemm");
+        TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
+        continue;
+      }
       TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, ra, prec, st, planes, wide), "dW_ih gemm + reduce");
       // dW_hh (+ bias gradients): B operand = h of the previous scan position = Y_l shifted by one step
       ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
       ta.Bsrc = at<float>(ws, p.Y[l]); ta.ldb = 2 * H; ta.col0 = d * H; ta.shift = d == 0 ? -1 : +1; ta.NB = H; ta.NB1 = H;
-      ta.colsum = planes ? 0 : 1;
+      ta.colsum = 1;
       DwReduceArgs rb{};
       rb.G = p.G; rb.ctas_per_group = p.ctas_per_group; rb.KA = 4 * H; rb.NB = H; rb.H = H; rb.partial = partial;
-      rb.has_colsum = planes ? 0 : 1; rb.mask = mask_hh; rb.out = Gr->w_hh[l][d]; rb.NB1 = H;
+      rb.has_colsum = 1; rb.mask = mask_hh; rb.out = Gr->w_hh[l][d]; rb.NB1 = H;
       rb.out_b1 = Gr->b_ih[l][d]; rb.out_b2 = Gr->b_hh[l][d];
-      if (planes) {
-        rb.cs_ptr = at<float>(ws, p.bias_partial) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
-        rb.cs_count = bwd_ctas;
-      }
       TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, rb, prec, st, planes, wide), "dW_hh gemm + reduce");
     }
 

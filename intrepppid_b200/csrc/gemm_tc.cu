@@ -594,16 +594,18 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
 }
 
 struct TNTmaMaps {
-  CUtensorMap a[2];  // dgates planes: 3D {4H, Tmax, N}, box {64, 64, 1}
-  CUtensorMap b[2];  // B operand planes (unused when gathered)
+  CUtensorMap a[2];   // dgates planes: 3D {4H, Tmax, N}, box {64, 64, 1}
+  CUtensorMap b[2];   // first B source planes (unused when gathered)
+  CUtensorMap b2[2];  // second B source planes (NB2 > 0): fuses dW_ih and dW_hh into one pass over the dgates
 };
 
-template <int NB, bool SPLIT, bool GATHER>
+// B operand = [first source: NB1 columns (dense planes, or gathered masked embeddings) | second source: NB2 columns (dense planes)]
+template <int NB1, int NB2, bool SPLIT, bool GATHER>
 __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_constant__ TNTmaMaps maps, const GemmTNArgs p) {
-  constexpr int KA = 256, NPART = SPLIT ? 2 : 1;
-  constexpr int kABytes = (KA / 64) * kBlkBytes, kBBytes = (NB / 64) * kBlkBytes;
+  constexpr int KA = 256, NPART = SPLIT ? 2 : 1, NB = NB1 + NB2;
+  constexpr int kABytes = (KA / 64) * kBlkBytes, kBBytes = (NB / 64) * kBlkBytes, kB2Bytes = (NB2 / 64) * kBlkBytes;
   constexpr int kStageBytes = NPART * (kABytes + kBBytes);
-  constexpr uint32_t kTmemCols = 2 * NB;
+  constexpr uint32_t kTmemCols = 2 * NB <= 256 ? 2 * NB : 512;  // power of two
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   TNBarriers* bars = reinterpret_cast<TNBarriers*>(smem + (size_t)kStagesTN * kStageBytes);
@@ -623,6 +625,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
     for (int pl = 0; pl < NPART; ++pl) {
       tma_prefetch_desc(&maps.a[pl]);
       if (!GATHER) tma_prefetch_desc(&maps.b[pl]);
+      if (NB2 > 0) tma_prefetch_desc(&maps.b2[pl]);
     }
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
         const int stage = it % kStagesTN;
         const int n = g * p.B + item / tiles_per_seq, t0 = (item % tiles_per_seq) * 64;
         mbar_wait(&bars->empty[stage], ((it / kStagesTN) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->full[stage], NPART * (kABytes + (GATHER ? 0 : kBBytes)));
+        mbar_arrive_expect_tx(&bars->full[stage], NPART * (kABytes + (GATHER ? kB2Bytes : kBBytes)));
         unsigned char* a_dst = smem + (size_t)stage * kStageBytes;
         unsigned char* b_dst = a_dst + NPART * kABytes;
 #pragma unroll
@@ -650,9 +653,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
             tma_load_3d(a_dst + pl * kABytes + blk * kBlkBytes, &maps.a[pl], &bars->full[stage], blk * 64, t0, n);
           if constexpr (!GATHER) {
 #pragma unroll
-            for (int blk = 0; blk < NB / 64; ++blk)
+            for (int blk = 0; blk < NB1 / 64; ++blk)
               tma_load_3d(b_dst + pl * kBBytes + blk * kBlkBytes, &maps.b[pl], &bars->full[stage], p.col0 + blk * 64, t0 + p.shift, n);
           }
+#pragma unroll
+          for (int blk = 0; blk < NB2 / 64; ++blk)
+            tma_load_3d(b_dst + pl * kBBytes + (NB1 / 64 + blk) * kBlkBytes, &maps.b2[pl], &bars->full[stage], p.col02 + blk * 64,
+                        t0 + p.shift2, n);
         }
       }
     }
@@ -689,7 +696,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
     }
   } else if (GATHER) {
     // ===================== B operand = scale[g][tok] * emb[tok] (layer-0 input), staged by 4 warps =====================
-    constexpr int FPR = NB / 4, RPP = 128 / FPR, BPASS = 64 / RPP;
+    constexpr int FPR = NB1 / 4, RPP = 128 / FPR, BPASS = 64 / RPP;
     const int tg = tid - 64, fb = tg % FPR, rb = tg / FPR;
     const uint32_t b_off = (fb >> 4) * kBlkBytes + (fb & 1) * 8, b_chunk = (fb & 15) >> 1;
     uint32_t it = 0;
@@ -704,7 +711,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
         if (t < T) {
           const int tk = p.tok[(size_t)n * p.Tmax + t];
           const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + tk] : 1.0f;
-          const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB) + fb);
+          const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)tk * NB1) + fb);
           vb[j] = make_float4(sc * e.x, sc * e.y, sc * e.z, sc * e.w);
         }
       }
@@ -791,8 +798,9 @@ cudaError_t launch_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int NB, bool GATHER>
+template <int NB1, int NB2, bool GATHER>
 cudaError_t launch_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st) {
+  constexpr int NB = NB1 + NB2;
   const int npart = precision == 0 ? 2 : 1;
   const size_t smem = 1024 + (size_t)kStagesTN * npart * ((256 / 64) + (NB / 64)) * kBlkBytes + sizeof(TNBarriers) + 64;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
@@ -808,17 +816,23 @@ cudaError_t launch_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st) {
       if (!make_tmap_bf16_sw128(&maps.b[pl], reinterpret_cast<const unsigned char*>(a.Bsrc) + (size_t)pl * a.ldb * 2, 3, db, sb, box))
         return cudaErrorInvalidConfiguration;
     }
+    if (NB2 > 0) {
+      const uint64_t db[3] = {(uint64_t)a.ldb2, (uint64_t)a.Tmax, (uint64_t)a.G * a.B};
+      const uint64_t sb[2] = {(uint64_t)a.ldb2 * 4, (uint64_t)a.Tmax * a.ldb2 * 4};
+      if (!make_tmap_bf16_sw128(&maps.b2[pl], reinterpret_cast<const unsigned char*>(a.Bsrc2) + (size_t)pl * a.ldb2 * 2, 3, db, sb, box))
+        return cudaErrorInvalidConfiguration;
+    }
   }
   dim3 grid(a.ctas_per_group, a.G);
   cudaError_t e;
   if (precision == 0) {
-    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB, true, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB1, NB2, true, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_tn_tma_kernel<NB, true, GATHER><<<grid, 192, smem, st>>>(maps, a);
+    gemm_tn_tma_kernel<NB1, NB2, true, GATHER><<<grid, 192, smem, st>>>(maps, a);
   } else {
-    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB, false, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(gemm_tn_tma_kernel<NB1, NB2, false, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_tn_tma_kernel<NB, false, GATHER><<<grid, 192, smem, st>>>(maps, a);
+    gemm_tn_tma_kernel<NB1, NB2, false, GATHER><<<grid, 192, smem, st>>>(maps, a);
   }
   return cudaGetLastError();
 }
@@ -856,12 +870,19 @@ cudaError_t launch_gemm_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t 
   }
 }
 cudaError_t launch_gemm_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st) {
-  if (a.KA != 256 || a.NB1 != a.NB || a.colsum) return cudaErrorInvalidConfiguration;
+  if (a.KA != 256 || a.colsum) return cudaErrorInvalidConfiguration;
   const bool gather = a.tok != nullptr;
+  const int nb2 = a.NB - a.NB1;
   if (!gather && (a.ldb % 4 != 0 || a.col0 % 8 != 0)) return cudaErrorInvalidConfiguration;
-  if (a.NB == 128 && !gather) return launch_tn_tma<128, false>(a, precision, st);
-  if (a.NB == 64 && !gather) return launch_tn_tma<64, false>(a, precision, st);
-  if (a.NB == 64 && gather) return launch_tn_tma<64, true>(a, precision, st);
+  if (nb2 != 0 && (a.Bsrc2 == nullptr || a.ldb2 % 4 != 0 || a.col02 % 8 != 0)) return cudaErrorInvalidConfiguration;
+  if (nb2 == 0) {
+    if (a.NB == 128 && !gather) return launch_tn_tma<128, 0, false>(a, precision, st);
+    if (a.NB == 64 && !gather) return launch_tn_tma<64, 0, false>(a, precision, st);
+    if (a.NB == 64 && gather) return launch_tn_tma<64, 0, true>(a, precision, st);
+  } else if (nb2 == 64) {  // dW_ih | dW_hh in one pass over the dgates
+    if (a.NB1 == 128 && !gather) return launch_tn_tma<128, 64, false>(a, precision, st);
+    if (a.NB1 == 64 && gather) return launch_tn_tma<64, 64, true>(a, precision, st);
+  }
   return cudaErrorInvalidConfiguration;
 }
 
