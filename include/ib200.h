@@ -18,7 +18,8 @@
  *
  * Conventions
  *   - weights are in PyTorch layout: weight_ih [4H,in], weight_hh [4H,H], gate row-blocks in order (i,f,g,o); two biases.
- *   - E == H (nn.LSTM(embedding_size, embedding_size, ...), awd_lstm.py:35-41).  Supported H: 32, 64.
+ *   - E == H (nn.LSTM(embedding_size, embedding_size, ...), awd_lstm.py:35-41).  Supported H: multiples of 32 in [32, 256]
+ *     (32 / 64: register-resident recurrent kernels + tcgen05/TMA GEMMs; 96..256: thread-block-cluster recurrent kernels).
  *   - "group" = one encoder call of the reference.  A training step fuses G=5 calls (anchor, positive, negative, p1, p2 --
  *     e2e_triplet.py:116-129) into one launch set; every group has its own masks and its own truncation lengths.
  *   - masks are INPUTS (nullptr = no drop).  emb_row_scale[g][v] = keep/(1-p) per vocabulary row; whh_l0_mask[g] = scaled
