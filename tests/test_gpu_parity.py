@@ -169,3 +169,24 @@ def test_headline_shape_determinism_and_group_fusion():
             assert torch.equal(net.encoder.last_lengths[:, 0], lens[:, g])
             assert float((zg - z_fused[g]).abs().max()) == 0.0
     assert int(lens[1].max()) <= 1500 and int(lens[1].min()) > 900
+
+
+_HEADLINE_REF = {}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_headline_shape_step_vs_oracle(precision):
+    """BASELINE.json's full configuration (batch 80 x 5 sequences, trunc_len 1500, E=64, 2 layers, `last`, rates 0.3) against the
+    CPU oracle with the same 14 masks: T1/T_eff bit-exact, embeddings, the three losses and all 23 live gradients inside the gate.
+    The oracle runs in fp32 here (6 s of host time at this size; its own distance to fp64 is <= 5e-6) and is shared by
+    the two precision modes."""
+    P = R.init_params(vocab=250, E=64, L=2, seed=0)
+    batch = list(R.synthetic_batch(80, 1500, 250, seed=1234))
+    masks = R.draw_step_masks(80, 250, 64, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=5)
+    kw = dict(L=2, bi="last", beta=2.0, use_projection=False, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, precision=precision, **kw)
+    if "ref" not in _HEADLINE_REF:
+        _HEADLINE_REF["ref"] = run_oracle_step(P, batch, masks, dtype=torch.float32, **kw)
+    ref = _HEADLINE_REF["ref"]
+    assert int(ref["lengths"][1].min()) > 900  # the quirk-Q2 truncation is active (T_eff ~ 1100 of 1500)
+    _check(got, ref, TOL[precision])
