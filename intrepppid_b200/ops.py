@@ -1,6 +1,10 @@
-"""torch.autograd wiring over the C ABI (include/ib200.h).  Torch is plumbing here: device memory, streams, autograd graph.
+"""torch custom ops + autograd wiring over the C ABI (include/ib200.h).  Torch is plumbing here: device memory, streams, the
+dispatcher and the autograd graph.
 
-Three differentiable ops:
+The raw launchers are registered with the PyTorch dispatcher as `torch.ops.intrepppid_b200.*` (schemas below, CUDA kernels only:
+there is no CPU / Meta implementation, a CPU tensor fails in the dispatcher or earlier with IB200Error):
+  encoder_fwd, encoder_bwd, pool_fc_fwd, pool_fc_bwd, loss_head_fwd, loss_head_bwd, pair_score
+On top of them, three differentiable ops:
   encode_hidden   tokens[G,B,T] -> top-layer final hidden states hn[2,G*B,H]   (ib200_encoder_fwd / _bwd)
   pool_fc         hn -> z[G*B,H]                                               (ib200_pool_fc_fwd / _bwd)
   loss_head       z[5,B,H], y -> (loss, classifier_loss, triplet_loss, y_hat)  (ib200_loss_head_fwd / _bwd)
@@ -70,6 +74,140 @@ def _fill_encoder_struct(emb, lstm: Sequence[torch.Tensor], L: int) -> EncoderPa
     return s
 
 
+# ------------------------------------------------------------------------------------------------------------------------------
+# dispatcher registration: torch.ops.intrepppid_b200.*  (CUDA only)
+# ------------------------------------------------------------------------------------------------------------------------------
+_TORCH_LIB = torch.library.Library("intrepppid_b200", "DEF")
+_TORCH_LIB.define("encoder_fwd(Tensor tokens, Tensor emb, Tensor[] lstm, Tensor? emb_row_scale, Tensor? whh_mask, int num_layers, "
+                  "int bi_reduce, int precision, bool training) -> (Tensor, Tensor, Tensor)")
+_TORCH_LIB.define("encoder_bwd(Tensor(a!) ws, Tensor d_hn, Tensor emb, Tensor[] lstm, Tensor? emb_row_scale, Tensor? whh_mask, int G, "
+                  "int B, int T, int num_layers, int bi_reduce, int precision) -> Tensor")
+_TORCH_LIB.define("pool_fc_fwd(Tensor hn, Tensor fc_w, Tensor fc_b, int bi_reduce) -> (Tensor, Tensor, Tensor)")
+_TORCH_LIB.define("pool_fc_bwd(Tensor dz, Tensor pooled, Tensor? argmax, Tensor fc_w, int bi_reduce) -> (Tensor, Tensor)")
+_TORCH_LIB.define("loss_head_fwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta) -> (Tensor, Tensor)")
+_TORCH_LIB.define("loss_head_bwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta, Tensor d_loss, Tensor? d_y_hat) "
+                  "-> (Tensor, Tensor)")
+_TORCH_LIB.define("pair_score(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, Tensor? idx_a, Tensor? idx_b) -> Tensor")
+
+
+def _cfg(G, B, T, V, H, L, bi_reduce, precision, training) -> Cfg:
+    return Cfg(G, B, T, V, H, L, bi_reduce, precision, 1 if training else 0, 0)
+
+
+def _encoder_fwd_cuda(tokens, emb, lstm, emb_row_scale, whh_mask, num_layers, bi_reduce, precision, training):
+    """-> (hn_top [2,G*B,H], lengths int32 [2,G], workspace uint8).  ib200_encoder_fwd."""
+    G, B, T = tokens.shape
+    V, H = emb.shape
+    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, training)
+    nbytes = lib().ib200_workspace_bytes(cfg)
+    if nbytes == 0:
+        raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), "
+                              f"L={num_layers} (1..4)")
+    dev = tokens.device
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    lens = torch.empty(2, G, dtype=torch.int32, device=dev)
+    hn = torch.empty(2, G * B, H, dtype=torch.float32, device=dev)
+    P = _fill_encoder_struct(emb, lstm, num_layers)
+    check(lib().ib200_encoder_fwd(cfg, ptr(tokens), P, ptr(emb_row_scale), ptr(whh_mask), ptr(lens), ptr(hn), ptr(ws), nbytes,
+                                  _stream()), "ib200_encoder_fwd")
+    return hn, lens, ws
+
+
+def _encoder_bwd_cuda(ws, d_hn, emb, lstm, emb_row_scale, whh_mask, G, B, T, num_layers, bi_reduce, precision):
+    """-> one flat fp32 gradient buffer: [d_emb | d_lstm tensors in `lstm` order] (a single allreduce bucket).  ib200_encoder_bwd."""
+    V, H = emb.shape
+    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, True)
+    sizes = [emb.numel()] + [p.numel() for p in lstm]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=emb.device)
+    views, off = [], 0
+    for n, ref in zip(sizes, [emb] + list(lstm)):
+        views.append(flat[off:off + n].view(ref.shape))
+        off += n
+    Gs = _fill_encoder_struct(views[0], views[1:], num_layers)
+    P = _fill_encoder_struct(emb, lstm, num_layers)
+    check(lib().ib200_encoder_bwd(cfg, P, ptr(emb_row_scale), ptr(whh_mask), ptr(d_hn), Gs, ptr(ws), ws.numel(), _stream()),
+          "ib200_encoder_bwd")
+    return flat
+
+
+def _pool_fc_fwd_cuda(hn, fc_w, fc_b, mode):
+    _, N, H = hn.shape
+    z = torch.empty(N, H, dtype=torch.float32, device=hn.device)
+    pooled = torch.empty(N, H, dtype=torch.float32, device=hn.device)
+    argmax = torch.empty((N, H) if mode == 2 else (0,), dtype=torch.uint8, device=hn.device)
+    check(lib().ib200_pool_fc_fwd(N, H, mode, ptr(hn), ptr(fc_w), ptr(fc_b), ptr(z), ptr(pooled), ptr(argmax) if mode == 2 else None,
+                                  _stream()), "ib200_pool_fc_fwd")
+    return z, pooled, argmax
+
+
+def _pool_fc_bwd_cuda(dz, pooled, argmax, fc_w, mode):
+    N, H = dz.shape
+    d_hn = torch.empty(2, N, H, dtype=torch.float32, device=dz.device)
+    flat = torch.empty(H * H + H, dtype=torch.float32, device=dz.device)
+    d_w, d_b = flat[:H * H].view(H, H), flat[H * H:]
+    check(lib().ib200_pool_fc_bwd(N, H, mode, ptr(dz), ptr(pooled), ptr(argmax) if mode == 2 else None, ptr(fc_w), ptr(d_hn), ptr(d_w),
+                                  ptr(d_b), _stream()), "ib200_pool_fc_bwd")
+    return d_hn, flat
+
+
+def _head_structs(params, masks):
+    params = list(params) + [None] * (6 - len(params))
+    hp = HeadParams(*(ptr(t) for t in params))
+    hm = HeadMasks(*(ptr(m) for m in masks))
+    return hp, hm
+
+
+def _loss_head_fwd_cuda(z, y, params, masks, beta):
+    """params = [fc1_w, fc1_b, fc2_w, fc2_b (, proj_w, proj_b)], masks = [fc1_w, do1, do2, fc2_w] (None = no drop)."""
+    _, B, H = z.shape
+    hp, hm = _head_structs(params, masks)
+    losses = torch.empty(3, dtype=torch.float32, device=z.device)
+    y_hat = torch.empty(B, dtype=torch.float32, device=z.device)
+    check(lib().ib200_loss_head_fwd(B, H, float(beta), ptr(z), ptr(y), hp, hm, ptr(losses), ptr(y_hat), _stream()),
+          "ib200_loss_head_fwd")
+    return losses, y_hat
+
+
+def _loss_head_bwd_cuda(z, y, params, masks, beta, d_loss, d_y_hat):
+    """-> (dz [5,B,H], flat gradient buffer [fc1_w | fc1_b | fc2_w | fc2_b (| proj_w | proj_b)])."""
+    _, B, H = z.shape
+    has_proj = len(params) == 6
+    hp, hm = _head_structs(params, masks)
+    dz = torch.empty_like(z)
+    HH = H // 2
+    n_flat = HH * H + HH + HH + 1 + (H * H + H if has_proj else 0)
+    flat = torch.empty(n_flat, dtype=torch.float32, device=z.device)
+    o = 0
+    g_fc1_w = flat[o:o + HH * H]; o += HH * H
+    g_fc1_b = flat[o:o + HH]; o += HH
+    g_fc2_w = flat[o:o + HH]; o += HH
+    g_fc2_b = flat[o:o + 1]; o += 1
+    g_pw = g_pb = None
+    if has_proj:
+        g_pw = flat[o:o + H * H]; o += H * H
+        g_pb = flat[o:o + H]
+    hg = HeadParams(ptr(g_fc1_w), ptr(g_fc1_b), ptr(g_fc2_w), ptr(g_fc2_b), ptr(g_pw), ptr(g_pb))
+    check(lib().ib200_loss_head_bwd(B, H, float(beta), ptr(z), ptr(y), hp, hm, ptr(d_loss), ptr(d_y_hat), ptr(dz), hg, _stream()),
+          "ib200_loss_head_bwd")
+    return dz, flat
+
+
+def _pair_score_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a, idx_b):
+    M, H = z.shape
+    P = idx_a.numel() if idx_a is not None else M * (M + 1) // 2
+    out = torch.empty(P, dtype=torch.float32, device=z.device)
+    hp = HeadParams(ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), None, None)
+    check(lib().ib200_pair_score(M, H, ptr(z), ptr(idx_a), ptr(idx_b), P, hp, ptr(out), _stream()), "ib200_pair_score")
+    return out
+
+
+for _name, _fn in (("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
+                   ("pool_fc_bwd", _pool_fc_bwd_cuda), ("loss_head_fwd", _loss_head_fwd_cuda), ("loss_head_bwd", _loss_head_bwd_cuda),
+                   ("pair_score", _pair_score_cuda)):
+    _TORCH_LIB.impl(_name, _fn, "CUDA")
+_OPS = torch.ops.intrepppid_b200
+
+
 class _EncodeHidden(torch.autograd.Function):
     """tokens, masks, emb, 8L LSTM tensors -> hn_top [2,N,H].  Saved activations live in one workspace tensor."""
 
@@ -90,43 +228,26 @@ class _EncodeHidden(torch.autograd.Function):
             raise ValueError(f"emb_row_scale must be [G={G}, V={V}], got {tuple(ers.shape)}")
         if whm is not None and tuple(whm.shape) != (G, 4 * H, H):
             raise ValueError(f"whh_l0_mask must be [G={G}, {4 * H}, {H}], got {tuple(whm.shape)}")
-        cfg = econf.cfg(G, B, T, V, H, training)
-        nbytes = lib().ib200_workspace_bytes(cfg)
-        if nbytes == 0:
-            raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), L={L} (1..4)")
-        dev = tokens.device
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        lens = torch.empty(2, G, dtype=torch.int32, device=dev)
-        hn = torch.empty(2, G * B, H, dtype=torch.float32, device=dev)
-        P = _fill_encoder_struct(emb_c, lstm_c, L)
-        check(lib().ib200_encoder_fwd(cfg, ptr(tokens), P, ptr(ers), ptr(whm), ptr(lens), ptr(hn), ptr(ws), nbytes, _stream()),
-              "ib200_encoder_fwd")
+        cfg = econf.cfg(G, B, T, V, H, training)  # validates bi_reduce (concat raises like the reference)
+        hn, lens, ws = _OPS.encoder_fwd(tokens, emb_c, lstm_c, ers, whm, L, cfg.bi_reduce, cfg.precision, training)
         if lengths_holder is not None:
             lengths_holder.append(lens)
         if check_lengths:
             if int(lens[1].min()) <= 0:  # one host sync; the reference does two per encoder call (awd_lstm.py:53-54,149-150)
                 raise RuntimeError("Expected sequence length to be larger than 0 in RNN")
         if training:
-            ctx.econf, ctx.cfg, ctx.nbytes, ctx.L = econf, cfg, nbytes, L
+            ctx.dims = (G, B, T, L, cfg.bi_reduce, cfg.precision)
             ctx.save_for_backward(ws, emb_c, ers, whm, *lstm_c)
         return hn
 
     @staticmethod
     def backward(ctx, d_hn):
         ws, emb, ers, whm, *lstm = ctx.saved_tensors
-        L = ctx.L
-        d_hn = _f32c(d_hn)
-        # one flat gradient buffer (a single allreduce bucket for data parallelism)
-        sizes = [emb.numel()] + [p.numel() for p in lstm]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=emb.device)
+        flat = _OPS.encoder_bwd(ws, _f32c(d_hn), emb, lstm, ers, whm, *ctx.dims)
         views, off = [], 0
-        for n, ref in zip(sizes, [emb] + list(lstm)):
-            views.append(flat[off:off + n].view(ref.shape))
-            off += n
-        Gs = _fill_encoder_struct(views[0], views[1:], L)
-        P = _fill_encoder_struct(emb, lstm, L)
-        check(lib().ib200_encoder_bwd(ctx.cfg, P, ptr(ers), ptr(whm), ptr(d_hn), Gs, ptr(ws), ctx.nbytes, _stream()),
-              "ib200_encoder_bwd")
+        for ref in [emb] + list(lstm):
+            views.append(flat[off:off + ref.numel()].view(ref.shape))
+            off += ref.numel()
         return (None, None, None, None, None, None, *views)
 
 
@@ -140,13 +261,8 @@ class _PoolFc(torch.autograd.Function):
     def forward(ctx, bi_reduce: str, hn, fc_w, fc_b):
         _need_cuda(hn, fc_w, fc_b)
         hn, fc_w, fc_b = _f32c(hn), _f32c(fc_w), _f32c(fc_b)
-        _, N, H = hn.shape
         mode = _lib.REDUCE[bi_reduce]
-        z = torch.empty(N, H, dtype=torch.float32, device=hn.device)
-        pooled = torch.empty(N, H, dtype=torch.float32, device=hn.device)
-        argmax = torch.empty(N, H, dtype=torch.uint8, device=hn.device) if mode == 2 else None
-        check(lib().ib200_pool_fc_fwd(N, H, mode, ptr(hn), ptr(fc_w), ptr(fc_b), ptr(z), ptr(pooled), ptr(argmax), _stream()),
-              "ib200_pool_fc_fwd")
+        z, pooled, argmax = _OPS.pool_fc_fwd(hn, fc_w, fc_b, mode)
         ctx.mode = mode
         ctx.save_for_backward(pooled, argmax, fc_w)
         return z
@@ -154,24 +270,13 @@ class _PoolFc(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         pooled, argmax, fc_w = ctx.saved_tensors
-        dz = _f32c(dz)
-        N, H = dz.shape
-        d_hn = torch.empty(2, N, H, dtype=torch.float32, device=dz.device)
-        flat = torch.empty(H * H + H, dtype=torch.float32, device=dz.device)
-        d_w, d_b = flat[:H * H].view(H, H), flat[H * H:]
-        check(lib().ib200_pool_fc_bwd(N, H, ctx.mode, ptr(dz), ptr(pooled), ptr(argmax), ptr(fc_w), ptr(d_hn), ptr(d_w), ptr(d_b),
-                                      _stream()), "ib200_pool_fc_bwd")
-        return None, d_hn, d_w, d_b
+        H = fc_w.shape[0]
+        d_hn, flat = _OPS.pool_fc_bwd(_f32c(dz), pooled, argmax if ctx.mode == 2 else None, fc_w, ctx.mode)
+        return None, d_hn, flat[:H * H].view(H, H), flat[H * H:]
 
 
 def pool_fc(bi_reduce: str, hn, fc_w, fc_b):
     return _PoolFc.apply(bi_reduce, hn, fc_w, fc_b)
-
-
-def _head_structs(fc1_w, fc1_b, fc2_w, fc2_b, proj_w, proj_b, masks):
-    hp = HeadParams(ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), ptr(proj_w), ptr(proj_b))
-    hm = HeadMasks(*(ptr(m) for m in masks))
-    return hp, hm
 
 
 class _LossHead(torch.autograd.Function):
@@ -185,15 +290,11 @@ class _LossHead(torch.autograd.Function):
         if G5 != 5:
             raise ValueError("loss_head expects z of shape [5,B,H] in group order (anchor, positive, negative, p1, p2)")
         y = y.long().contiguous()
-        params = [_f32c(t) for t in (fc1_w, fc1_b, fc2_w, fc2_b, proj_w, proj_b)]
+        params = [_f32c(t) for t in (fc1_w, fc1_b, fc2_w, fc2_b)] + ([_f32c(proj_w), _f32c(proj_b)] if proj_w is not None else [])
         masks = [_f32c(t) for t in (m_fc1, m_do1, m_do2, m_fc2)]
-        hp, hm = _head_structs(*params, masks)
-        losses = torch.empty(3, dtype=torch.float32, device=z.device)
-        y_hat = torch.empty(B, dtype=torch.float32, device=z.device)
-        check(lib().ib200_loss_head_fwd(B, H, float(beta), ptr(z), ptr(y), hp, hm, ptr(losses), ptr(y_hat), _stream()),
-              "ib200_loss_head_fwd")
-        ctx.beta, ctx.has_proj = float(beta), proj_w is not None
-        ctx.save_for_backward(z, y, *[t for t in params if t is not None], *[t for t in masks if t is not None])
+        losses, y_hat = _OPS.loss_head_fwd(z, y, params, masks, float(beta))
+        ctx.beta, ctx.npar = float(beta), len(params)
+        ctx.save_for_backward(z, y, *params, *[t for t in masks if t is not None])
         ctx.mask_present = [m is not None for m in masks]
         return losses, y_hat
 
@@ -201,36 +302,25 @@ class _LossHead(torch.autograd.Function):
     def backward(ctx, d_losses, d_y_hat):
         saved = list(ctx.saved_tensors)
         z, y = saved[0], saved[1]
-        npar = 6 if ctx.has_proj else 4
-        params = saved[2:2 + npar] + [None] * (6 - npar)
-        rest = saved[2 + npar:]
-        masks = []
-        for present in ctx.mask_present:
-            masks.append(rest.pop(0) if present else None)
+        params = saved[2:2 + ctx.npar]
+        rest = saved[2 + ctx.npar:]
+        masks = [rest.pop(0) if present else None for present in ctx.mask_present]
         _, B, H = z.shape
-        hp, hm = _head_structs(*params, masks)
-        dev = z.device
         if d_losses is None:
-            d_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            d_loss = torch.zeros(1, dtype=torch.float32, device=z.device)
         else:
             # only `loss` (element 0) is an optimisation target; classifier/triplet losses are logged detached by the reference
             d_loss = _f32c(d_losses)[0:1].contiguous()
-        dz = torch.empty_like(z)
-        HH = H // 2
-        n_flat = HH * H + HH + HH + 1 + (H * H + H if ctx.has_proj else 0)
-        flat = torch.empty(n_flat, dtype=torch.float32, device=dev)
-        o = 0
+        dz, flat = _OPS.loss_head_bwd(z, y, params, masks, ctx.beta, d_loss, _f32c(d_y_hat))
+        HH, o = H // 2, 0
         g_fc1_w = flat[o:o + HH * H].view(HH, H); o += HH * H
         g_fc1_b = flat[o:o + HH]; o += HH
         g_fc2_w = flat[o:o + HH].view(1, HH); o += HH
         g_fc2_b = flat[o:o + 1]; o += 1
         g_pw = g_pb = None
-        if ctx.has_proj:
+        if ctx.npar == 6:
             g_pw = flat[o:o + H * H].view(H, H); o += H * H
             g_pb = flat[o:o + H]
-        hg = HeadParams(ptr(g_fc1_w), ptr(g_fc1_b), ptr(g_fc2_w), ptr(g_fc2_b), ptr(g_pw), ptr(g_pb))
-        check(lib().ib200_loss_head_bwd(B, H, ctx.beta, ptr(z), ptr(y), hp, hm, ptr(d_loss), ptr(_f32c(d_y_hat)), ptr(dz), hg,
-                                        _stream()), "ib200_loss_head_bwd")
         return None, dz, None, None, None, None, None, g_fc1_w, g_fc1_b, g_fc2_w, g_fc2_b, g_pw, g_pb
 
 
@@ -242,14 +332,6 @@ def loss_head(beta, z, y, fc1_w, fc1_b, fc2_w, fc2_b, proj_w=None, proj_b=None, 
 def pair_score(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a=None, idx_b=None):
     """sigmoid(head(z[i], z[j])) in eval mode for explicit pairs, or for the whole upper triangle (i<=j) when no indices are given."""
     _need_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a, idx_b)
-    z = _f32c(z)
-    M, H = z.shape
     if idx_a is not None:
         idx_a, idx_b = idx_a.to(torch.int32).contiguous(), idx_b.to(torch.int32).contiguous()
-        P = idx_a.numel()
-    else:
-        P = M * (M + 1) // 2
-    out = torch.empty(P, dtype=torch.float32, device=z.device)
-    hp = HeadParams(ptr(_f32c(fc1_w)), ptr(_f32c(fc1_b)), ptr(_f32c(fc2_w)), ptr(_f32c(fc2_b)), None, None)
-    check(lib().ib200_pair_score(M, H, ptr(z), ptr(idx_a), ptr(idx_b), P, hp, ptr(out), _stream()), "ib200_pair_score")
-    return out
+    return _OPS.pair_score(_f32c(z), _f32c(fc1_w), _f32c(fc1_b), _f32c(fc2_w), _f32c(fc2_b), idx_a, idx_b)

@@ -132,3 +132,20 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", ""), f
+
+
+def test_torch_custom_ops_are_registered_cuda_only():
+    """The launchers are torch custom ops (torch.ops.intrepppid_b200.*) with a CUDA kernel only: the dispatcher has nothing to run
+    for CPU tensors, so there is no silent fallback."""
+    import torch
+
+    import intrepppid_b200  # noqa: F401  (registers the ops)
+
+    ops = torch.ops.intrepppid_b200
+    for name in ("encoder_fwd", "encoder_bwd", "pool_fc_fwd", "pool_fc_bwd", "loss_head_fwd", "loss_head_bwd", "pair_score"):
+        schema = str(getattr(ops, name).default._schema)
+        assert schema.startswith(f"intrepppid_b200::{name}("), schema
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "CUDA")
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "CPU")
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.pool_fc_fwd(torch.zeros(2, 3, 32), torch.zeros(32, 32), torch.zeros(32), 0)
