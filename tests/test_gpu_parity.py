@@ -190,3 +190,44 @@ def test_headline_shape_step_vs_oracle(precision):
     ref = _HEADLINE_REF["ref"]
     assert int(ref["lengths"][1].min()) > 900  # the quirk-Q2 truncation is active (T_eff ~ 1100 of 1500)
     _check(got, ref, TOL[precision])
+
+
+def test_quirks_interior_zeros_zero_weights_and_grad_sparsity():
+    """Q1: an interior id 0 counts as a pad for T1 (a COUNT of non-zero ids, so the slice is shorter than the last non-zero
+    position).  Q2 with exact zeros in the embedding matrix: T_eff counts non-zero VALUES per embedding column.  Q14: the embedding
+    gradient is exactly zero on row 0, on rows dropped by the row mask and on ids that occur only in the truncated tail."""
+    V, E, L, B, T = 61, 32, 2, 6, 48
+    P = R.init_params(vocab=V, E=E, L=L, seed=7)
+    P["emb"][5] = 0.0          # a whole row of exact zeros (besides the padding row)
+    P["emb"][9, ::2] = 0.0     # and a row that is zero in every other column
+    g = torch.Generator().manual_seed(8)
+    batch = [torch.randint(1, V, (B, T), generator=g) for _ in range(5)] + [torch.randint(0, 2, (B,), generator=g)]
+    for t in batch[:5]:
+        t[2, :] = 5            # a sequence made only of the all-zero-embedding id
+        t[:, 10:14] = 0        # interior zeros in every sequence
+        t[1, 30:] = 0          # plus an ordinary padded tail
+        t[:, 40:] = torch.where(t[:, 40:] != 0, torch.full_like(t[:, 40:], 17), t[:, 40:])  # id 17 lives in the tail
+        t[:, :40][t[:, :40] == 17] = 18
+    masks = R.draw_step_masks(B, V, E, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=9)
+    kw = dict(L=L, bi="last", beta=2.0, use_projection=False, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+    ref = run_oracle_step(P, batch, masks, **kw)
+    assert int(ref["lengths"][0].max()) <= T - 4          # the interior zeros shortened T1
+    assert int(ref["lengths"][1].max()) < int(ref["lengths"][0].min())  # and the row mask shortened it again
+    _check(got, ref, 1e-4)
+    zero_rows = (ref["grads"]["emb"].abs().sum(1) == 0)
+    assert bool(zero_rows[0]) and bool(zero_rows[17])  # padding row; the id that occurs only beyond T_eff
+    assert torch.equal(got["grads"]["emb"].abs().sum(1) == 0, zero_rows), "sparsity pattern of the embedding gradient"
+
+
+def test_single_step_and_single_sequence():
+    """Smallest shapes: one time step, one sequence per group."""
+    for B, T in ((1, 1), (1, 9), (3, 1)):
+        P = R.init_params(vocab=40, E=32, L=2, seed=3)
+        batch = list(R.synthetic_batch(B, T, 40, seed=4))
+        masks = R.draw_step_masks(B, 40, 32, emb_droprate=0.0, rnn_droprate=0.3, do_rate=0.3, seed=5)
+        masks.emb_row_keep = None
+        kw = dict(L=2, bi="mean", beta=2.0, use_projection=False, p_emb=0.0)
+        got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+        ref = run_oracle_step(P, batch, masks, **kw)
+        _check(got, ref, 1e-4)
