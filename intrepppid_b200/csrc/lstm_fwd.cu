@@ -27,6 +27,22 @@ namespace {
 
 constexpr int kD = 4;  // async prefetch depth in steps (power of two)
 
+// predicated global stores as volatile asm: they keep their place BETWEEN the (volatile) mma instructions, so the scheduler issues
+// them in the gaps the tensor pipe leaves between the HMMAs of one warp instead of after the last one
+__device__ __forceinline__ void stg_v4_if(void* ptr, const float4& v, bool pred) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q st.global.v4.f32 [%0], {%1,%2,%3,%4};\n}\n" ::"l"(ptr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void stg_f32_if(void* ptr, float v, bool pred) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q st.global.f32 [%0], %1;\n}\n" ::"l"(ptr), "f"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void stg_bf16_if(void* ptr, __nv_bfloat16 v, bool pred) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q st.global.u16 [%0], %1;\n}\n" ::"l"(ptr),
+               "h"(*reinterpret_cast<const unsigned short*>(&v)), "r"((int)pred)
+               : "memory");
+}
+
 // In-kernel ablation switches (tools/ablate_fwd.py) exist only in -DIB200_ABLATE builds: the production loop carries no flag tests.
 #ifdef IB200_ABLATE
 #define IB200_DBGBITS(p) ((p).dbg)
@@ -49,8 +65,12 @@ struct FwdSmem {
 //     yields hi*hi + hi*lo (A_hi) and lo*hi + lo*lo (A_lo): 2 MMAs per product instead of 3.  The hi-column and lo-column
 //     partial sums of a sequence live in lanes tig and tig^2: one shfl_xor(2) per gate hands every lane one complete cell
 //     (lanes tig<2 keep their even column = sequence 2*tig, lanes tig>=2 keep their odd column = sequence 2*(tig-2)+1).
-template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN, bool HALF>
+// DEFER (HALF modes, launches with at most one CTA per SM): the global stores of a step and the input-projection read are moved
+// into the NEXT step's MMA phase, interleaved with the HMMAs.  With two co-resident CTAs per SM the other CTA already fills
+// those issue gaps and the deferral only costs registers (measured: -13 % alone on an SM, +3 % when sharing it).
+template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN, bool HALF, bool DEFER>
 __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const LstmFwdArgs p) {
+  static_assert(!DEFER || HALF, "DEFER is a HALF-mode variant");
   constexpr int NT = H * 4, KT = H / 16;
   constexpr bool HL = HALF && SPLIT;
   constexpr int NPART = (SPLIT && !HL) ? 2 : 1;
@@ -171,14 +191,42 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   constexpr int kBufElems = NPART * H * kBC, kPartElems = H * kBC;
 
   const int dbg = IB200_DBGBITS(p);
+
+  // HALF modes: the global stores of a step (one cell per thread) are DEFERRED into the MMA shadow of the next step, off the
+  // chain  STS h -> barrier -> LDSM -> HMMA  that bounds the step time; the last step is flushed after the loop.
+  auto emit_half = [&](int row, const float4& gt, float cc, float hv, __nv_bfloat16 hhx, __nv_bfloat16 hlx) {
+    if (!v0 || (dbg & 4)) return;
+    if (has_y) {
+      float* yr = p.y + (size_t)row * ystr;
+      if (planes) {  // the row bytes hold bf16 [hi plane: y_stride values | lo plane: y_stride values]
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(yr) + ycol;
+        d[0] = hhx;
+        if constexpr (SPLIT) d[ystr] = hlx;
+      } else {
+        yr[ycol] = hv;
+      }
+    }
+    if constexpr (TRAIN) {
+      G4[(size_t)row * H] = gt;
+      Cst[(size_t)row * H] = cc;
+    }
+  };
+  float4 pgt = make_float4(0.f, 0.f, 0.f, 0.f);
+  float pcc = 0.f, phv = 0.f;
+  __nv_bfloat16 phh = __float2bfloat16_rn(0.f), phl = phh;
+  int prow = row0;
+
   for (int s = 0; s < T; ++s) {
     float4 x0 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), x1 = x0;
-    if (!(dbg & 8)) {
+    auto fetch_x = [&]() {
       cp_async_wait<kD - 1>();  // this thread's copies for step s have landed
       const float4* cur = slot + (s & (kD - 1)) * kStage;
       x0 = cur[0];
       if constexpr (!HALF) x1 = cur[NT];
       issue(s + kD);
+    };
+    if constexpr (!(HL && DEFER)) {  // (HL + DEFER fetches x between the HMMAs; it is only added after them)
+      if (!(dbg & 8)) fetch_x();
     }
 
     const int buf = s & 1;
@@ -186,7 +234,29 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     if constexpr (HL) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float ac2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      if (!(dbg & 1))
+      // work that is off the dependent chain is interleaved with the HMMAs (slot i after the i-th group of four): the previous
+      // step's global stores, this step's input projection read, the prefetch kD steps ahead
+      const bool st_ok = v0 && s > 0 && !(dbg & 4);
+      auto shadow = [&](int slot_i) {
+        if constexpr (!DEFER) return;
+        if (slot_i == 0) {
+          if constexpr (TRAIN) stg_v4_if(G4 + (size_t)prow * H, pgt, st_ok);
+        } else if (slot_i == 1) {
+          if constexpr (TRAIN) stg_f32_if(Cst + (size_t)prow * H, pcc, st_ok);
+          if (has_y) {
+            float* yr = p.y + (size_t)prow * ystr;
+            if (planes) {
+              __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(yr) + ycol;
+              stg_bf16_if(d, phh, st_ok);
+              stg_bf16_if(d + ystr, phl, st_ok);
+            } else {
+              stg_f32_if(yr + ycol, phv, st_ok);
+            }
+          }
+        } else if (slot_i == 2) {
+          if (!(dbg & 8)) fetch_x();
+        }
+      };
 #pragma unroll
       for (int kp = 0; kp < (KT + 1) / 2; ++kp) {
         uint32_t b[4];
@@ -195,14 +265,19 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
         for (int kk = 0; kk < 2; ++kk) {
           const int kt = kp * 2 + kk;
           if (kt < KT) {
+            if (!(dbg & 1)) {
 #pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-              mma_bf16(acc[tile], Ahi[tile][kt], b[2 * kk], b[2 * kk + 1]);
-              mma_bf16(ac2[tile], Alo[tile][kt], b[2 * kk], b[2 * kk + 1]);
+              for (int tile = 0; tile < 2; ++tile) {
+                mma_bf16(acc[tile], Ahi[tile][kt], b[2 * kk], b[2 * kk + 1]);
+                mma_bf16(ac2[tile], Alo[tile][kt], b[2 * kk], b[2 * kk + 1]);
+              }
             }
+            shadow(kt);
           }
         }
       }
+#pragma unroll
+      for (int i = KT; i < 3; ++i) shadow(i);
       // [0]=(row gq, col n0) [1]=(row gq, col n1) [2]=(row gq+8, n0) [3]=(row gq+8, n1); tile 0 rows: i,f ; tile 1 rows: g,o.
       // Keep my column (low lanes: even = hi part of my sequence; high lanes: odd = lo part), send the other one to lane^2.
       float keep[4], send[4];
@@ -244,6 +319,9 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
             }
           }
         }
+      }
+      if constexpr (DEFER) {
+        if (s > 0) emit_half(prow, pgt, pcc, phv, phh, phl);  // after the HMMAs have been issued
       }
       ai0 = acc[0][0], af0 = acc[0][2], ag0 = acc[1][0], ao0 = acc[1][2];
       ai1 = acc[0][1], af1 = acc[0][3], ag1 = acc[1][1], ao1 = acc[1][3];
@@ -291,18 +369,22 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
         if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat162*>(dst + kPartElems) = hl;
       }
     }
-    // stream out what later stages need (placement relative to the barrier makes no measurable difference: ablation in DESIGN.md)
-    if (has_y && !(dbg & 4)) {
+    if constexpr (DEFER) {  // remember this step's outputs; they are stored in the next step's MMA phase
+      pgt = make_float4(i0, f0, gg0, o0);
+      pcc = c0;
+      phv = h0;
+      phh = hh.x;
+      phl = hl.x;
+      prow = row0;
+    } else if constexpr (HALF) {
+      emit_half(row0, make_float4(i0, f0, gg0, o0), c0, h0, hh.x, hl.x);
+    }
+    // FULL mode: stream out what later stages need right away
+    if (!HALF && has_y && !(dbg & 4)) {
       float* yr0 = p.y + (size_t)row0 * ystr;
       if (planes) {
         // planes layout: the row bytes hold bf16 [hi plane: y_stride values | lo plane: y_stride values]
-        if constexpr (HALF) {
-          if (v0) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(yr0) + ycol;
-            d[0] = hh.x;
-            if constexpr (SPLIT) d[ystr] = hl.x;
-          }
-        } else {
+        {
           // one shuffle with the neighbouring unit (lane ^ 4) lets every thread store a 2-unit bf16x2 word per plane
           // (even gq: units (u,u+1) of column n0; odd gq: units (u-1,u) of column n1)
           const uint32_t ab = *reinterpret_cast<const uint32_t*>(&hh), lb = *reinterpret_cast<const uint32_t*>(&hl);
@@ -324,7 +406,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
         if (v1) p.y[(size_t)row1 * ystr + ycol] = h1;
       }
     }
-    if (TRAIN && !(dbg & 4)) {
+    if (!HALF && TRAIN && !(dbg & 4)) {
       if (v0) {
         G4[(size_t)row0 * H] = make_float4(i0, f0, gg0, o0);
         Cst[(size_t)row0 * H] = c0;
@@ -338,6 +420,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     row1 += dt;
     if (!(dbg & 16)) __syncthreads();
   }
+  if constexpr (DEFER) emit_half(prow, pgt, pcc, phv, phh, phl);  // flush the last step
   cp_async_wait<0>();
 
   // planes mode: the weight-gradient GEMM reads 64-row TMA boxes (and the row after the last one for the shifted operand), so the
@@ -359,16 +442,16 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   }
 }
 
-template <int H, bool SPLIT, bool FAST, bool L0, bool TR, bool HALF>
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR, bool HALF, bool DEFER = false>
 cudaError_t launch_kh(const LstmFwdArgs& a, cudaStream_t st) {
   constexpr int SEQ = HALF ? kBC / 2 : kBC;
   dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir), block(H * 4);
   size_t smem = sizeof(FwdSmem<H, (SPLIT && !HALF) ? 2 : 1>);
   if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF><<<grid, block, smem, st>>>(a);
+  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER><<<grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
@@ -377,7 +460,10 @@ cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
   // 128 registers so two of them share an SM and interleave their MMA / MUFU phases
   const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
   const bool half = full_ctas <= ((a.dbg & 128) ? 74 : 148) && !(a.dbg & 64);
-  return half ? launch_kh<H, SPLIT, FAST, L0, TR, true>(a, st) : launch_kh<H, SPLIT, FAST, L0, TR, false>(a, st);
+  if (!half) return launch_kh<H, SPLIT, FAST, L0, TR, false>(a, st);
+  const int half_ctas = ((a.B + kBC / 2 - 1) / (kBC / 2)) * a.G * a.ndir;
+  const bool defer = (half_ctas <= 148 || (a.dbg & 512)) && !(a.dbg & 1024);  // at most one CTA per SM
+  return defer ? launch_kh<H, SPLIT, FAST, L0, TR, true, true>(a, st) : launch_kh<H, SPLIT, FAST, L0, TR, true, false>(a, st);
 }
 
 
