@@ -20,6 +20,17 @@ namespace {
 
 constexpr int kD = 8;  // async prefetch depth in steps (power of two)
 
+__device__ __forceinline__ void stg_v4_if(void* ptr, const float4& v, bool pred) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q st.global.v4.f32 [%0], {%1,%2,%3,%4};\n}\n" ::"l"(ptr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void stg_v2_if(void* ptr, uint32_t a, uint32_t b, bool pred) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n @q st.global.v2.u32 [%0], {%1,%2};\n}\n" ::"l"(ptr), "r"(a), "r"(b),
+               "r"((int)pred)
+               : "memory");
+}
+
 template <int H>
 struct BwdSmem {
   static constexpr int NT = H * 4, NW = H / 8, KTT = H / 4;
@@ -150,35 +161,47 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   constexpr int kFragPart = KTT * 32 * 2;  // words per hi/lo part
   const uint32_t* bsrc = &sm.dafrag[0][kh * KTH][lane][0];
 
-  for (int s = 0; s < T; ++s) {
-    cp_async_wait<kD - 1>();
+  // The factors of step s that do not depend on the recurrent gradient are computed one step EARLY, inside the MMA phase of
+  // step s-1 (ring read, tanh(c), gate-derivative products), so the dependent chain of a step is only
+  //   dh = dhrec + dy ; dct = dh*Ac + dc ; da = (dct*Ai, dct*Af, dct*Ag, dh*Ao) ; dc = dct*gf
+  // followed by the pack, STS, barrier and the MMAs.   Ao = tanh(c) o(1-o), Ac = o (1-tanh(c)^2), Ai = g i(1-i), Ag = i (1-g^2),
+  // Af = c_prev f(1-f).
+  struct Coef {
+    float Ao, Ac, Ai, Ag, Af, gf, dy;
+  };
+  Coef K[2];
+  auto load_coef = [&](int s) {
     const int st = s & (kD - 1);
-    float4 gin[2];
-    float cprev[2], dyin[2] = {0.f, 0.f};
-    gin[0] = sm.rg[st][0][tid];
-    cprev[0] = sm.rc[st][0][tid];
-    if constexpr (HAS_DY) dyin[0] = sm.rdy[st][0][tid];
-    if constexpr (!HALF) {
-      gin[1] = sm.rg[st][1][tid];
-      cprev[1] = sm.rc[st][1][tid];
-      if constexpr (HAS_DY) dyin[1] = sm.rdy[st][1][tid];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 g = sm.rg[st][c][tid];
+      const float cprev = sm.rc[st][c][tid];
+      const float gi = g.x, gf = g.y, gg = g.z, go = g.w;
+      const float tc = tanh_f<FAST_ACT>(ccur[c]);
+      K[c].Ao = tc * (go * (1.0f - go));
+      K[c].Ac = go * fmaf(-tc, tc, 1.0f);
+      K[c].Ai = gg * (gi * (1.0f - gi));
+      K[c].Ag = gi * fmaf(-gg, gg, 1.0f);
+      K[c].Af = cprev * (gf * (1.0f - gf));
+      K[c].gf = gf;
+      K[c].dy = 0.f;
+      if constexpr (HAS_DY) K[c].dy = sm.rdy[st][c][tid];
+      ccur[c] = cprev;
     }
-    issue(s + kD);
+  };
+  cp_async_wait<kD - 1>();
+  load_coef(0);
+  issue(kD);
 
+  for (int s = 0; s < T; ++s) {
     float4 sv[2];
     uint4 pk[2];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const float gi = gin[c].x, gf = gin[c].y, gg = gin[c].z, go = gin[c].w;
-      const float dh = dhrec[c] + dyin[c];
-      const float tc = tanh_f<FAST_ACT>(ccur[c]);
-      const float d_o = dh * tc;
-      const float dct = fmaf(dh * go, fmaf(-tc, tc, 1.0f), dc[c]);
-      const float d_i = dct * gg, d_g = dct * gi, d_f = dct * cprev[c];
-      dc[c] = dct * gf;
-      ccur[c] = cprev[c];
-      const float da_i = d_i * gi * (1.0f - gi), da_f = d_f * gf * (1.0f - gf);
-      const float da_g = d_g * fmaf(-gg, gg, 1.0f), da_o = d_o * go * (1.0f - go);
+      const float dh = dhrec[c] + K[c].dy;
+      const float dct = fmaf(dh, K[c].Ac, dc[c]);
+      const float da_i = dct * K[c].Ai, da_f = dct * K[c].Af, da_g = dct * K[c].Ag, da_o = dh * K[c].Ao;
+      dc[c] = dct * K[c].gf;
       sv[c] = make_float4(da_i, da_f, da_g, da_o);
       if (c == 0 ? v0 : v1) {
         bsum[c][0] += da_i; bsum[c][1] += da_f; bsum[c][2] += da_g; bsum[c][3] += da_o;
@@ -198,28 +221,25 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       pk[c] = make_uint4(hi0, hi1, lo0, lo1);
     }
     __syncthreads();  // (A) all da of this step are in smem
-    // the in-place da store goes out right AFTER the barrier (bar.sync waits for outstanding global stores)
-    if (planes) {  // bf16 planes over the same 4H-float row: [hi: 4H bf16 | lo: 4H bf16], gate-interleaved columns 4j..4j+3
-      if (v0) {
+
+    // the in-place da store (volatile asm: it keeps its place among the HMMAs below and issues in the gaps between them)
+    auto store_da = [&]() {
+      if (planes) {  // bf16 planes over the same 4H-float row: [hi: 4H bf16 | lo: 4H bf16], gate-interleaved columns 4j..4j+3
         uint2* r0p = reinterpret_cast<uint2*>(gs0 - j) + j;  // row start, then 8-byte slot j
-        r0p[0] = make_uint2(pk[0].x, pk[0].y);
-        if constexpr (SPLIT) r0p[H] = make_uint2(pk[0].z, pk[0].w);
-      }
-      if constexpr (!HALF) {
-        if (v1) {
+        stg_v2_if(r0p, pk[0].x, pk[0].y, v0);
+        if constexpr (SPLIT) stg_v2_if(r0p + H, pk[0].z, pk[0].w, v0);
+        if constexpr (!HALF) {
           uint2* r1p = reinterpret_cast<uint2*>(gs1 - j) + j;
-          r1p[0] = make_uint2(pk[1].x, pk[1].y);
-          if constexpr (SPLIT) r1p[H] = make_uint2(pk[1].z, pk[1].w);
+          stg_v2_if(r1p, pk[1].x, pk[1].y, v1);
+          if constexpr (SPLIT) stg_v2_if(r1p + H, pk[1].z, pk[1].w, v1);
         }
+      } else {
+        stg_v4_if(gs0, sv[0], v0);
+        if constexpr (!HALF) stg_v4_if(gs1, sv[1], v1);
       }
-    } else {
-      if (v0) *gs0 = sv[0];
-      if constexpr (!HALF) {
-        if (v1) *gs1 = sv[1];
-      }
-    }
-    gs0 += gstride;
-    gs1 += gstride;
+      gs0 += gstride;
+      gs1 += gstride;
+    };
 
     if (s + 1 < T) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -235,6 +255,12 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
           const uint2 bl = *reinterpret_cast<const uint2*>(bsrc + ktl * 64 + kFragPart);
           mma_bf16(ac1[ktl & 1], Ahi[ktl], bl.x, bl.y);
           mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
+        }
+        if (ktl == (KTH > 2 ? 1 : 0)) store_da();
+        if (ktl == (KTH > 2 ? KTH / 2 : KTH - 1)) {  // next step's factors + the prefetch kD steps ahead
+          cp_async_wait<kD - 1>();
+          load_coef(s + 1);
+          issue(s + 1 + kD);
         }
       }
       float r4[4];
@@ -257,6 +283,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
         dhrec[0] = mine.x + other.x;
         dhrec[1] = mine.y + other.y;
       }
+    } else {
+      store_da();
     }
   }
   cp_async_wait<0>();
