@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   const float4* gp1 = G4 + (size_t)(rb1 + t_first) * H + j;
   const float* cp0 = C + (size_t)(rb0 + t_first) * H + j;  // advanced BEFORE use: first use is t(1)
   const float* cp1 = C + (size_t)(rb1 + t_first) * H + j;
-  const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + t_first) * p.dy_stride + dir * H + j : nullptr;
-  const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + t_first) * p.dy_stride + dir * H + j : nullptr;
-  const ptrdiff_t dstride = (ptrdiff_t)dt * p.dy_stride;
+  const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + t_first) * (2 * H) + dir * H + j : nullptr;
+  const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + t_first) * (2 * H) + dir * H + j : nullptr;
+  const ptrdiff_t dstride = (ptrdiff_t)dt * (2 * H);  // == p.dy_stride (checked by the launcher)
 
   auto issue = [&](int s) {
     const int st = s & (kD - 1);
@@ -248,10 +248,13 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
 #pragma unroll
       for (int ktl = 0; ktl < KTH; ++ktl) {
         const uint2 bh = *reinterpret_cast<const uint2*>(bsrc + ktl * 64);
-        mma_bf16(acc[ktl & 1], Ahi[ktl], bh.x, bh.y);
-        if constexpr (HL) {
-          mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
-        } else if constexpr (SPLIT) {
+        if constexpr (HL) {  // two chains of depth KTH are enough to keep the tensor pipe busy: fewer adds afterwards
+          mma_bf16(acc[0], Ahi[ktl], bh.x, bh.y);
+          mma_bf16(ac2[0], Alo[ktl], bh.x, bh.y);
+        } else {
+          mma_bf16(acc[ktl & 1], Ahi[ktl], bh.x, bh.y);
+        }
+        if constexpr (SPLIT && !HL) {
           const uint2 bl = *reinterpret_cast<const uint2*>(bsrc + ktl * 64 + kFragPart);
           mma_bf16(ac1[ktl & 1], Ahi[ktl], bl.x, bl.y);
           mma_bf16(ac2[ktl & 1], Alo[ktl], bh.x, bh.y);
@@ -266,9 +269,9 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
       float r4[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        r4[r] = acc[0][r] + acc[1][r];
-        if constexpr (HL) r4[r] += ac2[0][r] + ac2[1][r];
-        else if constexpr (SPLIT) r4[r] += (ac1[0][r] + ac1[1][r]) + (ac2[0][r] + ac2[1][r]);
+        if constexpr (HL) r4[r] = acc[0][r] + ac2[0][r];
+        else if constexpr (SPLIT) r4[r] = (acc[0][r] + acc[1][r]) + ((ac1[0][r] + ac1[1][r]) + (ac2[0][r] + ac2[1][r]));
+        else r4[r] = acc[0][r] + acc[1][r];
       }
       // r4: [0]=(unit 16mt+gq, col n0) [1]=(.., n1) [2]=(unit 16mt+gq+8, n0) [3]=(.., n1).  Keep the rows of my unit, hand
       // the other two to the partner warp (same mt, other K half), which owns that unit.
@@ -318,6 +321,7 @@ cudaError_t launch_kh(const LstmBwdArgs& a, cudaStream_t st) {
   constexpr int SEQ = HALF ? kBC / 2 : kBC;
   dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir);
   const size_t smem = sizeof(BwdSmem<H>);
+  if (a.dy != nullptr && a.dy_stride != 2 * H) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF><<<grid, H * 4, smem, st>>>(a);

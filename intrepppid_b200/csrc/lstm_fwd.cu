@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   float4* const G4 = TRAIN ? reinterpret_cast<float4*>((dir ? p.gates[1] : p.gates[0])) + u : nullptr;
   float* const Cst = TRAIN ? (dir ? p.cstate[1] : p.cstate[0]) + u : nullptr;
   const bool has_y = p.y != nullptr, planes = p.planes != 0;
-  const int ycol = dir * H + u, ystr = p.y_stride;
+  const int ycol = dir * H + u;
+  constexpr int ystr = 2 * H;  // == p.y_stride (checked by the launcher): a compile-time row pitch keeps the address math short
   int row0 = rb0 + t_first, row1 = rb1 + t_first;
 
   const __nv_bfloat16* hrow = &sm.hs[0][0][lane % H][0];  // ldmatrix row address of this lane (k-pair block 0, buffer 0)
@@ -449,6 +450,7 @@ cudaError_t launch_kh(const LstmFwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(FwdSmem<H, (SPLIT && !HALF) ? 2 : 1>);
   if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  if (a.y != nullptr && a.y_stride != 2 * H) return cudaErrorInvalidValue;  // the kernel addresses y rows with a fixed pitch of 2H
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER><<<grid, block, smem, st>>>(a);
