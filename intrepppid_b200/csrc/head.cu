@@ -18,7 +18,8 @@ __device__ __forceinline__ float mish_grad_acc(float x) {
   return n / d + x * 4.0f * e * (e + 1.0f) / (d * d);
 }
 
-constexpr int kHeadWarps = 8;
+constexpr int kHeadWarps = 16;  // one warp per sample: 16 samples in flight in the single CTA
+constexpr int kHeadThreads = kHeadWarps * 32;
 constexpr float kEps = 1e-6f;  // nn.TripletMarginLoss eps (pairwise_distance adds it to the difference)
 // samples per backward chunk; the wide variants (H > 64) keep the per-chunk vectors small enough for shared memory
 template <int H>
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
   const float dL = d_loss[0];
   const float w_t = dL * (1.0f / beta) / (float)B, w_c = dL * (1.0f - 1.0f / beta) / (float)B;
 
-  // matrix-gradient accumulators owned by this thread: fc1 [HH*H/256], proj [H*H/256]
-  constexpr int N1 = kRegAcc ? (HH * H + 255) / 256 : 1, NP = kRegAcc ? (H * H + 255) / 256 : 1;
+  // matrix-gradient accumulators owned by this thread: fc1 [HH*H/threads], proj [H*H/threads]
+  constexpr int N1 = kRegAcc ? (HH * H + kHeadThreads - 1) / kHeadThreads : 1, NP = kRegAcc ? (H * H + kHeadThreads - 1) / kHeadThreads : 1;
   float acc1[N1], accp[NP];
 #pragma unroll
   for (int i = 0; i < N1; ++i) acc1[i] = 0.f;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
     if constexpr (kRegAcc) {
 #pragma unroll
       for (int i = 0; i < N1; ++i) {
-        const int idx = tid + 256 * i;
+        const int idx = tid + kHeadThreads * i;
         if (idx < HH * H) {
           const int jj = idx / H, k = idx % H;
           float s = acc1[i];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
       if (proj) {
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          const int idx = tid + 256 * i;
+          const int idx = tid + kHeadThreads * i;
           if (idx < H * H) {
             const int e = idx / H, k = idx % H;
             float s = accp[i];
@@ -349,14 +350,14 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
       }
     } else {
       // wide head: every matrix entry is owned by one thread of this single CTA and accumulated in the output buffer itself
-      for (int idx = tid; idx < HH * H; idx += 256) {
+      for (int idx = tid; idx < HH * H; idx += kHeadThreads) {
         const int jj = idx / H, k = idx % H;
         float s = c0 == 0 ? 0.f : hg.fc1_w[idx];
         for (int c = 0; c < cn; ++c) s = fmaf(sm.dlt1[c][jj], sm.m0s[c][k], s);
         hg.fc1_w[idx] = s;
       }
       if (proj && hg.proj_w != nullptr) {
-        for (int idx = tid; idx < H * H; idx += 256) {
+        for (int idx = tid; idx < H * H; idx += kHeadThreads) {
           const int e = idx / H, k = idx % H;
           float s = c0 == 0 ? 0.f : hg.proj_w[idx];
           for (int r = 0; r < 3; ++r)
@@ -372,18 +373,18 @@ __global__ void __launch_bounds__(kHeadWarps * 32) loss_head_bwd_kernel(int B, f
   if constexpr (kRegAcc) {
 #pragma unroll
     for (int i = 0; i < N1; ++i) {
-      const int idx = tid + 256 * i;
+      const int idx = tid + kHeadThreads * i;
       if (idx < HH * H) hg.fc1_w[idx] = acc1[i] * (hm.fc1_w != nullptr ? hm.fc1_w[idx] : 1.0f);  // grad of weight_raw
     }
     if (proj && hg.proj_w != nullptr) {
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const int idx = tid + 256 * i;
+        const int idx = tid + kHeadThreads * i;
         if (idx < H * H) hg.proj_w[idx] = accp[i];
       }
     }
   } else if (hm.fc1_w != nullptr) {
-    for (int idx = tid; idx < HH * H; idx += 256) hg.fc1_w[idx] *= hm.fc1_w[idx];  // same owner thread as the accumulation
+    for (int idx = tid; idx < HH * H; idx += kHeadThreads) hg.fc1_w[idx] *= hm.fc1_w[idx];  // same owner thread as the accumulation
   }
 #pragma unroll
   for (int m = 0; m < JPL; ++m) {

@@ -41,15 +41,15 @@ __global__ void len2_kernel(const LengthArgs p) {
     if (v >= 0 && v < p.V) atomicAdd(&hist[v], 1);
   }
   __syncthreads();
+  // fold the row mask into the histogram once (a dropped row contributes to no column), then a branch-free scan per column
+  for (int v = threadIdx.x; v < p.V; v += blockDim.x)
+    if (p.emb_row_scale != nullptr && p.emb_row_scale[(size_t)g * p.V + v] == 0.0f) hist[v] = 0;
+  __syncthreads();
   int best = 0;
   for (int e = threadIdx.x; e < p.H; e += blockDim.x) {
     int cnt = 0;
-    for (int v = 0; v < p.V; ++v) {
-      const int hv = hist[v];
-      if (hv == 0) continue;
-      const bool keep = p.emb_row_scale == nullptr || p.emb_row_scale[(size_t)g * p.V + v] != 0.0f;
-      if (keep && p.emb[(size_t)v * p.H + e] != 0.0f) cnt += hv;
-    }
+#pragma unroll 8
+    for (int v = 0; v < p.V; ++v) cnt += (p.emb[(size_t)v * p.H + e] != 0.0f) ? hist[v] : 0;
     best = max(best, cnt);
   }
   best = __reduce_max_sync(0xffffffffu, best);
