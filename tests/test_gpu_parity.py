@@ -231,3 +231,33 @@ def test_single_step_and_single_sequence():
         got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
         ref = run_oracle_step(P, batch, masks, **kw)
         _check(got, ref, 1e-4)
+
+
+def test_config4_full_size_proteome_and_all_pairs():
+    """BASELINE.json config 4 at FULL size: 20 000 synthetic proteins x 1500 tokens embedded in batches of 512 (eval mode), then all
+    200 010 000 pairs (i <= j) scored.  Rows of the embedding matrix and a random sample of the pair scores are compared with the
+    CPU oracle; the triangle enumeration is checked at its corners and against explicit-index scoring."""
+    M, T = 20000, 1500
+    P = R.init_params(vocab=250, E=64, L=2, seed=0)
+    net = build_product(P, L=2, bi="last").eval()
+    x = torch.randint(1, 250, (M, T), generator=torch.Generator().manual_seed(4321))
+    with torch.no_grad():
+        z = net.embed(x.cuda(), 512)
+        prob = net.score_pairs(z)
+    assert z.shape == (M, 64) and prob.numel() == M * (M + 1) // 2
+    rows = [0, 511, 512, 9999, M - 1]  # batch boundaries included
+    with torch.no_grad():
+        zr, _ = R.encoder_forward(x[rows], {k: v.double() for k, v in P.items()}, num_layers=2, bi_reduce="last", training=False)
+    assert rel_l2(z[rows].cpu(), zr.float()) < 1e-4
+    g = torch.Generator().manual_seed(1)
+    ia = torch.randint(0, M, (2000,), generator=g)
+    ib = torch.randint(0, M, (2000,), generator=g)
+    ia, ib = torch.minimum(ia, ib), torch.maximum(ia, ib)
+    ia[:3], ib[:3] = torch.tensor([0, 0, M - 1]), torch.tensor([0, M - 1, M - 1])  # corners of the triangle
+    flat = ia * M - ia * (ia - 1) // 2 + (ib - ia)  # row-major index of (i, j), i <= j
+    zc = z.cpu()
+    with torch.no_grad():
+        ref = torch.sigmoid(R.mlp_head(zc[ia], zc[ib], P).squeeze(1))
+    got = prob[flat.cuda()].cpu()
+    assert float((got - ref).abs().max()) < 1e-5
+    assert torch.equal(net.score_pairs(z, ia.cuda(), ib.cuda()).cpu(), got)

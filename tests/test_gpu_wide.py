@@ -102,3 +102,22 @@ def test_wide_pair_score_vs_oracle():
     got_idx = net.score_pairs(z.cuda(), ia.cuda(), ib.cuda()).cpu()
     assert float((got_tri - ref).abs().max()) < 1e-5
     assert float((got_idx - ref).abs().max()) < 1e-5
+
+
+def test_config5_full_size_inference_rows_vs_oracle():
+    """BASELINE.json config 5 at FULL size (E=256, 3 layers, mean pooling, T=4000, batch 256, eval mode): sequences are independent
+    in eval mode, so three rows of the 256-sequence launch are compared with the CPU oracle run on those rows alone (fp32 and bf16
+    modes), plus run-to-run determinism of the whole batch."""
+    E, L, B, T = 256, 3, 256, 4000
+    P = R.init_params(vocab=250, E=E, L=L, seed=0)
+    x = torch.randint(1, 250, (B, T), generator=torch.Generator().manual_seed(777))
+    rows = [0, 131, 255]
+    with torch.no_grad():
+        zr, _ = R.encoder_forward(x[rows], {k: v.double() for k, v in P.items()}, num_layers=L, bi_reduce="mean", training=False)
+    for precision in ("fp32", "bf16"):
+        net = build_product(P, L=L, bi="mean", precision=precision).eval()
+        with torch.no_grad():
+            z1 = net.encoder(x.cuda())
+            z2 = net.encoder(x.cuda())
+        assert torch.equal(z1, z2), "deterministic"
+        assert rel_l2(z1[rows].cpu(), zr.float()) < TOL[precision], precision
