@@ -160,6 +160,12 @@ int ib200_loss_head_bwd(int32_t B, int32_t H, float beta_classifier, const float
 int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a, const int32_t* idx_b, int64_t P,
                      const ib200_head_params* params, float* prob_out, void* stream);
 
+/* The same over a contiguous range [p_begin, p_begin + p_count) of the row-major upper triangle: prob_out[k] is the score of flat
+ * pair index p_begin + k.  A rank of a multi-GPU inference job scores its block of triangle rows with this (shard the
+ * proteins, all-gather the [M,H] embeddings, split the pair matrix by rows). */
+int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin, int64_t p_count,
+                           const ib200_head_params* params, float* prob_out, void* stream);
+
 /* Test hook (tests/test_gpu_gemm.py): the token-row NT GEMM in isolation.  impl: 0 legacy mma.sync, 1 tcgen05, 2 auto.
  * C[row,NC] (=|+=) sum_s A_s[row,K] W_s[NC,K]^T (+bias) for rows (n,t) with t < lens[G + n/B] of the [G*B, T] row space. */
 int ib200_dbg_gemm_nt(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,

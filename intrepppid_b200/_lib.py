@@ -35,7 +35,7 @@ class HeadMasks(C.Structure):
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_bwd",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn")
 
 _lib = None
@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     L.ib200_loss_head_bwd.argtypes = [C.c_int32, C.c_int32, C.c_float, vp, vp, C.POINTER(HeadParams), C.POINTER(HeadMasks), vp,
                                       vp, vp, C.POINTER(HeadParams), vp]
     L.ib200_pair_score.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.POINTER(HeadParams), vp, vp]
+    L.ib200_pair_score_range.argtypes = [C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64, C.POINTER(HeadParams), vp, vp]
     L.ib200_dbg_gemm_nt.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.ib200_dbg_gemm_tn.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp,

@@ -532,7 +532,19 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
   if (M < 1 || !head_supports(H) || P < 0) return fail(IB200_E_SHAPE, "ib200_pair_score: bad shape (H must be a multiple of 32 in [32, 256])");
   if (!idx_a && P != (int64_t)M * (M + 1) / 2) return fail(IB200_E_SHAPE, "ib200_pair_score: P must be M(M+1)/2 for the implicit upper triangle");
   cudaStream_t st = (cudaStream_t)stream;
-  TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, *hp, prob_out, st), "pair_score");
+  TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, idx_a, idx_b, (long long)P, 0, *hp, prob_out, st), "pair_score");
+  return 0;
+}
+
+int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin, int64_t p_count, const ib200_head_params* hp,
+                           float* prob_out, void* stream) {
+  if (M < 1 || !head_supports(H)) return fail(IB200_E_SHAPE, "ib200_pair_score_range: bad shape (H must be a multiple of 32 in [32, 256])");
+  const int64_t total = (int64_t)M * (M + 1) / 2;
+  if (p_begin < 0 || p_count < 0 || p_begin + p_count > total) return fail(IB200_E_SHAPE, "ib200_pair_score_range: range outside the M(M+1)/2 triangle");
+  if (p_count == 0) return 0;
+  if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score_range: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, nullptr, nullptr, (long long)p_count, (long long)p_begin, *hp, prob_out, st), "pair_score_range");
   return 0;
 }
 

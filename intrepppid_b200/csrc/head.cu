@@ -417,8 +417,8 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 template <int H>
 __global__ void __launch_bounds__(128) pair_score_kernel(int M, const float* __restrict__ z, const int* __restrict__ ia,
-                                                          const int* __restrict__ ib, long long P, ib200_head_params hp,
-                                                          float* __restrict__ prob) {
+                                                          const int* __restrict__ ib, long long P, long long p0,
+                                                          ib200_head_params hp, float* __restrict__ prob) {
   constexpr int HH = H / 2;
   __shared__ __align__(16) float w1[HH][H];
   __shared__ float b1[HH], w2[HH];
@@ -437,12 +437,13 @@ __global__ void __launch_bounds__(128) pair_score_kernel(int M, const float* __r
     } else {
       // upper triangle, row-major: row i holds M-i pairs (i,i) .. (i,M-1); first index of row i = i*M - i(i-1)/2
       const double Md = (double)M;
-      long long r = (long long)floor(((2.0 * Md + 1.0) - sqrt((2.0 * Md + 1.0) * (2.0 * Md + 1.0) - 8.0 * (double)pidx)) * 0.5);
+      const long long pg = p0 + pidx;  // flat index inside the whole triangle
+      long long r = (long long)floor(((2.0 * Md + 1.0) - sqrt((2.0 * Md + 1.0) * (2.0 * Md + 1.0) - 8.0 * (double)pg)) * 0.5);
       if (r < 0) r = 0;
-      while (r * M - r * (r - 1) / 2 > pidx) --r;
-      while ((r + 1) * M - (r + 1) * r / 2 <= pidx) ++r;
+      while (r * M - r * (r - 1) / 2 > pg) --r;
+      while ((r + 1) * M - (r + 1) * r / 2 <= pg) ++r;
       i = (int)r;
-      j = (int)(pidx - (r * M - r * (r - 1) / 2)) + i;
+      j = (int)(pg - (r * M - r * (r - 1) / 2)) + i;
     }
     float m0[H];
     const float4* za = reinterpret_cast<const float4*>(z + (size_t)i * H);
@@ -477,8 +478,8 @@ __global__ void __launch_bounds__(128) pair_score_kernel(int M, const float* __r
 // the warp stages mish((z_a+z_b)/2) in its smem slot and every lane owns the fc1 outputs j = lane + 32 m.
 template <int H>
 __global__ void __launch_bounds__(256) pair_score_wide_kernel(int M, const float* __restrict__ z, const int* __restrict__ ia,
-                                                               const int* __restrict__ ib, long long P, ib200_head_params hp,
-                                                               float* __restrict__ prob) {
+                                                               const int* __restrict__ ib, long long P, long long p0,
+                                                               ib200_head_params hp, float* __restrict__ prob) {
   constexpr int HH = H / 2, JPL = (HH + 31) / 32, FPL = H / 32;
   extern __shared__ __align__(16) float smw[];
   float* w1t = smw;                  // [H][HH]
@@ -503,12 +504,13 @@ __global__ void __launch_bounds__(256) pair_score_wide_kernel(int M, const float
       j = ib[pidx];
     } else {
       const double Md = (double)M;
-      long long r = (long long)floor(((2.0 * Md + 1.0) - sqrt((2.0 * Md + 1.0) * (2.0 * Md + 1.0) - 8.0 * (double)pidx)) * 0.5);
+      const long long pg = p0 + pidx;
+      long long r = (long long)floor(((2.0 * Md + 1.0) - sqrt((2.0 * Md + 1.0) * (2.0 * Md + 1.0) - 8.0 * (double)pg)) * 0.5);
       if (r < 0) r = 0;
-      while (r * M - r * (r - 1) / 2 > pidx) --r;
-      while ((r + 1) * M - (r + 1) * r / 2 <= pidx) ++r;
+      while (r * M - r * (r - 1) / 2 > pg) --r;
+      while ((r + 1) * M - (r + 1) * r / 2 <= pg) ++r;
       i = (int)r;
-      j = (int)(pidx - (r * M - r * (r - 1) / 2)) + i;
+      j = (int)(pg - (r * M - r * (r - 1) / 2)) + i;
     }
 #pragma unroll
     for (int f = 0; f < FPL; ++f) {
@@ -554,13 +556,13 @@ cudaError_t head_bwd_h(int B, float beta, const float* z, const long long* y, co
   return cudaGetLastError();
 }
 template <int H>
-cudaError_t pair_wide_h(int M, const float* z, const int* idx_a, const int* idx_b, long long P, const ib200_head_params& hp,
-                        float* prob, cudaStream_t st) {
+cudaError_t pair_wide_h(int M, const float* z, const int* idx_a, const int* idx_b, long long P, long long p0,
+                        const ib200_head_params& hp, float* prob, cudaStream_t st) {
   const size_t smem = ((size_t)H * (H / 2) + 8 * H) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(pair_score_wide_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)std::min<long long>((P + 7) / 8, 148LL * 8);
-  pair_score_wide_kernel<H><<<grid, 256, smem, st>>>(M, z, idx_a, idx_b, P, hp, prob);
+  pair_score_wide_kernel<H><<<grid, 256, smem, st>>>(M, z, idx_a, idx_b, P, p0, hp, prob);
   return cudaGetLastError();
 }
 
@@ -592,23 +594,23 @@ cudaError_t launch_loss_head_bwd(int B, int H, float beta, const float* z, const
   IB200_HEAD_DISPATCH(head_bwd_h, B, beta, z, y, hp, hm, d_loss, d_y_hat, dz, hg, st)
 }
 
-cudaError_t launch_pair_score(int M, int H, const float* z, const int* idx_a, const int* idx_b, long long P,
+cudaError_t launch_pair_score(int M, int H, const float* z, const int* idx_a, const int* idx_b, long long P, long long p0,
                               const ib200_head_params& hp, float* prob, cudaStream_t st) {
   if (P <= 0) return cudaSuccess;
   if (H > 64) {
     switch (H) {
-      case 96: return pair_wide_h<96>(M, z, idx_a, idx_b, P, hp, prob, st);
-      case 128: return pair_wide_h<128>(M, z, idx_a, idx_b, P, hp, prob, st);
-      case 160: return pair_wide_h<160>(M, z, idx_a, idx_b, P, hp, prob, st);
-      case 192: return pair_wide_h<192>(M, z, idx_a, idx_b, P, hp, prob, st);
-      case 224: return pair_wide_h<224>(M, z, idx_a, idx_b, P, hp, prob, st);
-      case 256: return pair_wide_h<256>(M, z, idx_a, idx_b, P, hp, prob, st);
+      case 96: return pair_wide_h<96>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
+      case 128: return pair_wide_h<128>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
+      case 160: return pair_wide_h<160>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
+      case 192: return pair_wide_h<192>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
+      case 224: return pair_wide_h<224>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
+      case 256: return pair_wide_h<256>(M, z, idx_a, idx_b, P, p0, hp, prob, st);
       default: return cudaErrorInvalidValue;
     }
   }
   const unsigned grid = (unsigned)std::min<long long>((P + 127) / 128, 148LL * 16);
-  if (H == 64) pair_score_kernel<64><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, hp, prob);
-  else if (H == 32) pair_score_kernel<32><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, hp, prob);
+  if (H == 64) pair_score_kernel<64><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, p0, hp, prob);
+  else if (H == 32) pair_score_kernel<32><<<grid, 128, 0, st>>>(M, z, idx_a, idx_b, P, p0, hp, prob);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -16,6 +16,7 @@ cudaError_t launch_loss_head_bwd(int B, int H, float beta, const float* z, const
                                  const ib200_head_grads& hg,
                                  cudaStream_t st);
 bool head_supports(int H);  // loss/head/pair kernels: H multiple of 32 in [32, 256]
-cudaError_t launch_pair_score(int M, int H, const float* z, const int* idx_a, const int* idx_b, long long P,
+// P pairs: explicit (idx_a, idx_b), or -- both null -- the flat upper-triangle indices [p0, p0 + P)
+cudaError_t launch_pair_score(int M, int H, const float* z, const int* idx_a, const int* idx_b, long long P, long long p0,
                               const ib200_head_params& hp, float* prob, cudaStream_t st);
 }  // namespace ib200

@@ -86,6 +86,12 @@ class TripletE2ENet(_Base):
         """sigmoid(head(z[i], z[j])) for explicit pairs or the whole upper triangle (eval mode)."""
         return ops.pair_score(z, *self.head.tensors(), idx_a, idx_b)
 
+    @torch.no_grad()
+    def score_pairs_range(self, z, p_begin: int, p_count: int):
+        """The slice [p_begin, p_begin + p_count) of `score_pairs(z)` (flat row-major upper triangle) -- one rank's block in
+        multi-GPU inference (intrepppid_b200.parallel.sharded_proteome_scores)."""
+        return ops.pair_score_range(z, *self.head.tensors(), p_begin, p_count)
+
     # -- training step (e2e_triplet.py:113-187) ---------------------------------------------------------------------------------
     def step(self, batch, stage, masks: Optional[StepMasks] = None):
         p1_seq, p2_seq, omid_anchor_seq, omid_positive_seq, omid_negative_seq, y = batch

@@ -88,6 +88,7 @@ _TORCH_LIB.define("loss_head_fwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] 
 _TORCH_LIB.define("loss_head_bwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta, Tensor d_loss, Tensor? d_y_hat) "
                   "-> (Tensor, Tensor)")
 _TORCH_LIB.define("pair_score(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, Tensor? idx_a, Tensor? idx_b) -> Tensor")
+_TORCH_LIB.define("pair_score_range(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int p_begin, int p_count) -> Tensor")
 
 
 def _cfg(G, B, T, V, H, L, bi_reduce, precision, training) -> Cfg:
@@ -201,7 +202,15 @@ def _pair_score_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a, idx_b):
     return out
 
 
-for _name, _fn in (("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
+def _pair_score_range_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin, p_count):
+    M, H = z.shape
+    out = torch.empty(p_count, dtype=torch.float32, device=z.device)
+    hp = HeadParams(ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), None, None)
+    check(lib().ib200_pair_score_range(M, H, ptr(z), int(p_begin), int(p_count), hp, ptr(out), _stream()), "ib200_pair_score_range")
+    return out
+
+
+for _name, _fn in (("pair_score_range", _pair_score_range_cuda), ("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
                    ("pool_fc_bwd", _pool_fc_bwd_cuda), ("loss_head_fwd", _loss_head_fwd_cuda), ("loss_head_bwd", _loss_head_bwd_cuda),
                    ("pair_score", _pair_score_cuda)):
     _TORCH_LIB.impl(_name, _fn, "CUDA")
@@ -335,3 +344,10 @@ def pair_score(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a=None, idx_b=None):
     if idx_a is not None:
         idx_a, idx_b = idx_a.to(torch.int32).contiguous(), idx_b.to(torch.int32).contiguous()
     return _OPS.pair_score(_f32c(z), _f32c(fc1_w), _f32c(fc1_b), _f32c(fc2_w), _f32c(fc2_b), idx_a, idx_b)
+
+
+@torch.no_grad()
+def pair_score_range(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin: int, p_count: int):
+    """Scores of the flat upper-triangle pair indices [p_begin, p_begin + p_count) (row-major, i <= j) of the M embeddings in z."""
+    _need_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b)
+    return _OPS.pair_score_range(_f32c(z), _f32c(fc1_w), _f32c(fc1_b), _f32c(fc2_w), _f32c(fc2_b), int(p_begin), int(p_count))

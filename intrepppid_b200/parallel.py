@@ -86,3 +86,53 @@ def shard_range(n_items: int, rank: int, world: int):
     per, rem = divmod(n_items, world)
     lo = rank * per + min(rank, rem)
     return lo, lo + per + (1 if rank < rem else 0)
+
+
+def triangle_row_start(M: int, i: int) -> int:
+    """Flat index of pair (i, i) in the row-major upper triangle of an M x M pair matrix (row i holds M - i pairs)."""
+    return i * M - i * (i - 1) // 2
+
+
+def pair_block(M: int, rank: int, world: int):
+    """(row_lo, row_hi, p_begin, p_count): the block of whole triangle ROWS scored by `rank`, balanced by pair count (row i has
+    M - i pairs, so equal row counts would give rank 0 almost twice the average).  Blocks are contiguous in the flat index."""
+    total = M * (M + 1) // 2
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        lo, hi = bounds[-1], M
+        while lo < hi:  # first row whose start index reaches the target
+            mid = (lo + hi) // 2
+            if triangle_row_start(M, mid) < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        bounds.append(lo)
+    bounds.append(M)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    p0 = triangle_row_start(M, r0)
+    return r0, r1, p0, triangle_row_start(M, r1) - p0
+
+
+@torch.no_grad()
+def sharded_proteome_scores(net, tokens: torch.Tensor, batch_size: int = 512, process_group=None):
+    """Multi-GPU inference of BASELINE config 4: every rank embeds its contiguous shard of the M proteins, the [M,E]
+    embedding matrix is all-gathered (M*E*4 bytes, 5 MB at M=20k), and each rank scores its block of triangle rows.
+    tokens: the FULL [M, trunc_len] id matrix (every rank indexes its own shard).  Returns (z_all [M,E], p_begin, probs_of_block)."""
+    world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+    rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+    M = tokens.shape[0]
+    lo, hi = shard_range(M, rank, world)
+    dev = next(net.parameters()).device
+    z_local = net.embed(tokens[lo:hi].to(dev), batch_size) if hi > lo else torch.empty(0, net.encoder.encoder.embedding_size, device=dev)
+    if world > 1:
+        per = (M + world - 1) // world  # equal-size slots for all_gather_into_tensor; the tail of a short shard is padding
+        slot = torch.zeros(per, z_local.shape[1], dtype=z_local.dtype, device=dev)
+        slot[: hi - lo] = z_local
+        gathered = torch.empty(world * per, z_local.shape[1], dtype=z_local.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, slot, group=process_group)
+        z_all = torch.cat([gathered[r * per: r * per + (shard_range(M, r, world)[1] - shard_range(M, r, world)[0])] for r in range(world)])
+    else:
+        z_all = z_local
+    _, _, p0, pc = pair_block(M, rank, world)
+    return z_all, p0, net.score_pairs_range(z_all, p0, pc)

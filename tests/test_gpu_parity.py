@@ -261,3 +261,25 @@ def test_config4_full_size_proteome_and_all_pairs():
     got = prob[flat.cuda()].cpu()
     assert float((got - ref).abs().max()) < 1e-5
     assert torch.equal(net.score_pairs(z, ia.cuda(), ib.cuda()).cpu(), got)
+
+
+def test_pair_score_ranges_tile_the_triangle():
+    """ib200_pair_score_range: the blocks three ranks would score (parallel.pair_block) concatenate to the full triangle, bit for bit;
+    sharded_proteome_scores on one process equals embed + score_pairs."""
+    from intrepppid_b200.parallel import pair_block, sharded_proteome_scores
+
+    P = R.init_params(E=64, L=2, seed=5)
+    net = build_product(P, L=2, bi="last").eval()
+    M = 301
+    z = torch.randn(M, 64).cuda()
+    full = net.score_pairs(z)
+    parts = [net.score_pairs_range(z, *pair_block(M, r, 3)[2:]) for r in range(3)]
+    assert torch.equal(torch.cat(parts), full)
+    assert net.score_pairs_range(z, 17, 0).numel() == 0
+    with pytest.raises(RuntimeError):
+        net.score_pairs_range(z, M * (M + 1) // 2 - 3, 4)  # past the end of the triangle
+    x = torch.randint(1, 250, (40, 64))
+    z_all, p0, probs = sharded_proteome_scores(net, x, batch_size=16)
+    with torch.no_grad():
+        assert torch.equal(z_all, net.embed(x.cuda(), 16)) and p0 == 0
+        assert torch.equal(probs, net.score_pairs(z_all))

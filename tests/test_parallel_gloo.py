@@ -85,3 +85,20 @@ def test_shard_range_partitions_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_pair_block_partitions_the_triangle_and_balances_pairs():
+    """Multi-GPU inference: blocks of whole triangle rows, contiguous in the flat pair index, balanced by pair count."""
+    from intrepppid_b200.parallel import pair_block, triangle_row_start
+
+    for M in (1, 2, 7, 513, 20000):
+        total = M * (M + 1) // 2
+        assert triangle_row_start(M, M) == total
+        for w in (1, 2, 3, 8):
+            blocks = [pair_block(M, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == M and blocks[0][2] == 0
+            assert sum(b[3] for b in blocks) == total
+            for a, b in zip(blocks, blocks[1:]):
+                assert a[1] == b[0] and a[2] + a[3] == b[2]
+            if M >= 513:  # no rank is more than one row of pairs away from the ideal share
+                assert max(b[3] for b in blocks) - total // w <= M
