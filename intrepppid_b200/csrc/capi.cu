@@ -96,8 +96,14 @@ struct Plan {
 };
 
 bool cfg_ok(const ib200_cfg* c) {
-  return c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64 || lstm_cluster_supports(c->H)) && c->L >= 1 &&
-         c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1);
+  if (!(c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64 || lstm_cluster_supports(c->H)) && c->L >= 1 &&
+        c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1)))
+    return false;
+  // token rows are indexed with 32-bit integers inside the kernels; ids are staged as uint16 by the H <= 64 layer-0 kernel, whose
+  // per-CTA token stage ((T + 4) x 16 bytes of shared memory) bounds trunc_len
+  if ((long long)c->G * c->B * c->T >= (1LL << 31)) return false;
+  if ((c->H == 32 || c->H == 64) && (c->V > 65536 || c->T > 11000)) return false;
+  return true;
 }
 
 Plan make_plan(const ib200_cfg* c) {
@@ -296,7 +302,7 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
 
 int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
                       const float* whh_l0_mask, int32_t* lengths_out, float* hn_top, void* ws, size_t ws_bytes, void* stream) {
-  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H must be a multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max)");
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max, G*B*T < 2^31; for H <= 64 also V <= 65536 and T <= 11000)");
   if (!tokens || !P || !hn_top || !ws || !P->emb) return fail(IB200_E_NULL, "ib200_encoder_fwd: null pointer");
   const Plan p = make_plan(cfg);
   if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_fwd: workspace too small");

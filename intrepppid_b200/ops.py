@@ -103,7 +103,7 @@ def _encoder_fwd_cuda(tokens, emb, lstm, emb_row_scale, whh_mask, num_layers, bi
     nbytes = lib().ib200_workspace_bytes(cfg)
     if nbytes == 0:
         raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), "
-                              f"L={num_layers} (1..4)")
+                              f"L={num_layers} (1..4), G*B*T={G * B * T} (< 2^31), T={T} (<= 11000 when H <= 64), V={V}")
     dev = tokens.device
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     lens = torch.empty(2, G, dtype=torch.int32, device=dev)
