@@ -22,7 +22,9 @@ namespace {
 
 constexpr int kUS = 32;          // hidden units per CTA
 constexpr int kRows = 4 * kUS;   // gate rows per CTA
-constexpr int kClThreads = 128;  // 4 warps: warp w owns local units 8w .. 8w+7
+constexpr int kUnitWarps = 4;     // warps along the units: warp group ug owns local units 8ug .. 8ug+7
+// NWG warp groups along the sequences (1 or 2): with 32 sequences per cluster, 8 warps (two per scheduler) keep the tensor pipe fed,
+// one warp per scheduler is limited by its own HMMA issue interval; warp (ug, nh) owns units 8ug.. and n-tiles [nh*NTW, (nh+1)*NTW)
 constexpr int kWPad = 8;         // bf16 padding of a W slice row (16 bytes): conflict-free ldmatrix
 constexpr int kNPad = 8;         // bf16 padding of an h / da tile row
 
@@ -65,7 +67,7 @@ template <bool SPLIT>
 __device__ __forceinline__ void load_w_slice(__nv_bfloat16* Wsm, const float* __restrict__ W, const float* __restrict__ M, int H,
                                              int rank) {
   const int ldw = H + kWPad;
-  for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += kClThreads) {
+  for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += blockDim.x) {
     const int lr = idx / (H / 2), k = (idx % (H / 2)) * 2;
     int ul, gate;
     local_row(lr, ul, gate);
@@ -86,12 +88,16 @@ __device__ __forceinline__ void load_w_slice(__nv_bfloat16* Wsm, const float* __
 // =================================================================================================================================
 // forward
 // =================================================================================================================================
-template <int NTILE, bool SPLIT>
-__global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFwdArgs p, const int H) {
-  constexpr int NS = 8 * NTILE, NSP = NS + kNPad, NPART = SPLIT ? 2 : 1, NCELL = 2 * NTILE;
+template <int NTILE, bool SPLIT, int NWG>
+__global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(const LstmFwdArgs p, const int H) {
+  static_assert(NTILE % NWG == 0, "n-tiles split evenly over the warp groups");
+  constexpr int NS = 8 * NTILE, NSP = NS + kNPad, NPART = SPLIT ? 2 : 1, NTW = NTILE / NWG, NCELL = 2 * NTW;
+  constexpr int kClThreads = 32 * kUnitWarps * NWG;
   constexpr bool FAST = !SPLIT;
   const int C = H / kUS, KT = H / 16, ldw = H + kWPad;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int warp = (tid >> 5) & (kUnitWarps - 1), nh = (tid >> 5) / kUnitWarps;  // unit group, sequence group
+  const int ncol0 = nh * NTW * 8;  // first mma column (sequence) of this warp
   const int rank = (int)cluster_ctarank(), tile = blockIdx.x / C;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
   bool valid[NCELL];
 #pragma unroll
   for (int c = 0; c < NCELL; ++c) {
-    const int q = 8 * (c >> 1) + 2 * tig + (c & 1);  // sequence (= mma column) of cell c
+    const int q = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);  // sequence (= mma column) of cell c
     valid[c] = q < nvalid;
     rb[c] = (nbase + min(q, nvalid - 1)) * Tmax;  // columns beyond the batch read a valid sequence and never store
   }
@@ -149,12 +155,12 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
   // remote addresses of my h slot (unit u, column 2*tig) in every CTA of the cluster
   uint32_t hdst[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) hdst[r] = r < C ? map_to_rank(hs + (size_t)u * NSP + 2 * tig, (uint32_t)r) : 0u;
+  for (int r = 0; r < 8; ++r) hdst[r] = r < C ? map_to_rank(hs + (size_t)u * NSP + ncol0 + 2 * tig, (uint32_t)r) : 0u;
 
   // ldmatrix lane addresses: A (non transposed) row = tile*16 + (lane&7) + (lane&8), k offset (lane&16 ? 8 : 0)
   const __nv_bfloat16* a_lane = Wsm + (size_t)((2 * warp) * 16 + (lane & 7) + (lane & 8)) * ldw + ((lane & 16) ? 8 : 0);
   // B (transposed): k row = lane & 15, n-tile offset (lane & 16 ? 8 : 0) (clamped to the last n-tile for NTILE == 1)
-  const __nv_bfloat16* b_lane = hs + (size_t)(lane & 15) * NSP + ((NTILE > 1 && (lane & 16)) ? 8 : 0);
+  const __nv_bfloat16* b_lane = hs + (size_t)(lane & 15) * NSP + ncol0 + ((NTW > 1 && (lane & 16)) ? 8 : 0);
 
   float cst[NCELL], hv[NCELL];
 #pragma unroll
@@ -168,9 +174,9 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
     const int buf = s & 1;
 
     // acc[t2][j]: [0]=(row gq, col n0) [1]=(row gq, col n1) [2]=(row gq+8, n0) [3]=(row gq+8, n1); t2=0: rows i,f ; t2=1: rows g,o
-    float acc[2][NTILE][4];
+    float acc[2][NTW][4];
 #pragma unroll
-    for (int j = 0; j < NTILE; ++j) {
+    for (int j = 0; j < NTW; ++j) {
       acc[0][j][0] = x[2 * j].x; acc[0][j][1] = x[2 * j + 1].x; acc[0][j][2] = x[2 * j].y; acc[0][j][3] = x[2 * j + 1].y;
       acc[1][j][0] = x[2 * j].z; acc[1][j][1] = x[2 * j + 1].z; acc[1][j][2] = x[2 * j].w; acc[1][j][3] = x[2 * j + 1].w;
     }
@@ -184,14 +190,14 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
         if constexpr (SPLIT) ldmatrix_x4(al[t2], a_lane + (size_t)(kRows + t2 * 16) * ldw + kt * 16);
       }
 #pragma unroll
-      for (int jp = 0; jp < (NTILE + 1) / 2; ++jp) {
+      for (int jp = 0; jp < (NTW + 1) / 2; ++jp) {
         uint32_t bh[4], bl[4];
         ldmatrix_x4_trans(bh, hb + (size_t)kt * 16 * NSP + jp * 16);
         if constexpr (SPLIT) ldmatrix_x4_trans(bl, hb + kPartElems + (size_t)kt * 16 * NSP + jp * 16);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * jp + jj;
-          if (j < NTILE) {
+          if (j < NTW) {
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2) {
               mma_bf16(acc[t2][j], ah[t2], bh[2 * jj], bh[2 * jj + 1]);
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
     // publish my slice of h_t to every CTA of the cluster (buffer buf^1)
     const uint32_t boff = (uint32_t)((buf ^ 1) * kBufElems) * 2u;
 #pragma unroll
-    for (int j = 0; j < NTILE; ++j) {
+    for (int j = 0; j < NTW; ++j) {
       uint32_t hi, lo = 0u;
       if constexpr (SPLIT) split_bf16(hv[2 * j], hv[2 * j + 1], hi, lo);
       else hi = pack_bf16(hv[2 * j], hv[2 * j + 1]);
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
     const size_t N = (size_t)p.G * p.B;
 #pragma unroll
     for (int c = 0; c < NCELL; ++c) {
-      const int q = 8 * (c >> 1) + 2 * tig + (c & 1);
+      const int q = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);
       if (valid[c]) p.hn[((size_t)dir * N + nbase + q) * H + u] = hv[c];
     }
   }
@@ -253,12 +259,16 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cl_kernel(const LstmFw
 // =================================================================================================================================
 // backward
 // =================================================================================================================================
-template <int NTILE, bool SPLIT>
-__global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBwdArgs p, const int H) {
-  constexpr int NS = 8 * NTILE, NSP = NS + kNPad, NPART = SPLIT ? 2 : 1, NCELL = 2 * NTILE;
+template <int NTILE, bool SPLIT, int NWG>
+__global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(const LstmBwdArgs p, const int H) {
+  static_assert(NTILE % NWG == 0, "n-tiles split evenly over the warp groups");
+  constexpr int NS = 8 * NTILE, NSP = NS + kNPad, NPART = SPLIT ? 2 : 1, NTW = NTILE / NWG, NCELL = 2 * NTW;
+  constexpr int kWarps = kUnitWarps * NWG;
   constexpr bool FAST = !SPLIT;
   const int C = H / kUS, MT = H / 16, ldw = H + kWPad;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int warp = wid & (kUnitWarps - 1), nh = wid / kUnitWarps;  // unit group (cells), sequence group (cells)
+  const int ncol0 = nh * NTW * 8;
   const int rank = (int)cluster_ctarank(), tile = blockIdx.x / C;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBw
   bool valid[NCELL];
 #pragma unroll
   for (int c = 0; c < NCELL; ++c) {
-    const int q = 8 * (c >> 1) + 2 * tig + (c & 1);
+    const int q = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);
     valid[c] = q < nvalid;
     rb[c] = (nbase + min(q, nvalid - 1)) * Tmax;
   }
@@ -317,14 +327,14 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBw
   float ccur[NCELL], dc[NCELL], dhrec[NCELL];
 #pragma unroll
   for (int c = 0; c < NCELL; ++c) {
-    const int q = 8 * (c >> 1) + 2 * tig + (c & 1);
+    const int q = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);
     ccur[c] = Cst[(size_t)(rb[c] + t_first) * H];
     dc[c] = 0.f;
     dhrec[c] = p.dhn != nullptr ? p.dhn[((size_t)dir * N + nbase + min(q, nvalid - 1)) * H + u] : 0.f;
   }
 
   // my da rows in the K order of the resident slice: i -> (2w)*16+gq, f -> +8, g -> (2w+1)*16+gq, o -> +8
-  __nv_bfloat16* da_i = das + (size_t)((2 * warp) * 16 + gq) * NSP + 2 * tig;
+  __nv_bfloat16* da_i = das + (size_t)((2 * warp) * 16 + gq) * NSP + ncol0 + 2 * tig;
   const int kDaPart = kRows * NSP;
   // A = W slice read transposed: m = unit j (columns of the slice), k = local gate row.  matrix l/8: k + (l&16 ? 8:0), m + (l&8 ? 8:0)
   const __nv_bfloat16* a_lane = Wsm + (size_t)((lane & 7) + ((lane & 16) ? 8 : 0)) * ldw + ((lane & 8) ? 8 : 0);
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBw
     if (s + 1 == T) break;
     // da -> smem B tile (bf16 hi / lo), packed pairs of columns (n0, n1)
 #pragma unroll
-    for (int j = 0; j < NTILE; ++j) {
+    for (int j = 0; j < NTW; ++j) {
       const float4 a = in.g[2 * j], b = in.g[2 * j + 1];
       const float v0[4] = {a.x, a.y, a.z, a.w}, v1[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBw
 
     // partial dh^T[H, NS] = Wslice^T[H, 128] * da[128, NS]; warp w takes the unit tiles mt = w, w+4, ...
     const uint32_t xoff = (uint32_t)(((s + 1) & 1) * kXBuf) * 4u;
-    for (int mt = warp; mt < MT; mt += 4) {
+    for (int mt = wid; mt < MT; mt += kWarps) {
       float acc[NTILE][4];
 #pragma unroll
       for (int j = 0; j < NTILE; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
@@ -414,7 +424,7 @@ __global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cl_kernel(const LstmBw
     const float* xb = xbuf + (size_t)((s + 1) & 1) * kXBuf + (size_t)ul * NS;
 #pragma unroll
     for (int c = 0; c < NCELL; ++c) {
-      const int col = 8 * (c >> 1) + 2 * tig + (c & 1);
+      const int col = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);
       float sum = 0.f;
       for (int r = 0; r < C; ++r) sum += xb[(size_t)r * kUS * NS + col];
       dhrec[c] = sum;
@@ -431,7 +441,7 @@ size_t bwd_smem(int H, int ntile, bool split) {
   return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)npart * kRows * nsp * 2 + (size_t)2 * (H / kUS) * kUS * ns * 4;
 }
 
-// sequences per cluster: as many n-tiles as the batch fills and shared memory allows
+// sequences per cluster: as many n-tiles as the batch fills and shared memory allows (4 n-tiles run with two warp groups)
 int pick_ntile(int B, int H, bool split, bool bwd) {
   int nt = B >= 24 ? 4 : (B >= 12 ? 2 : 1);
   while (nt > 1 && (bwd ? bwd_smem(H, nt, split) : fwd_smem(H, nt, split)) > 220 * 1024) nt >>= 1;
@@ -439,13 +449,13 @@ int pick_ntile(int B, int H, bool split, bool bwd) {
 }
 
 template <typename Kern, typename Args>
-cudaError_t launch_cluster(Kern kern, const Args& a, int H, int ntile, size_t smem, int ndir, cudaStream_t st) {
+cudaError_t launch_cluster(Kern kern, const Args& a, int H, int ntile, int nwg, size_t smem, int ndir, cudaStream_t st) {
   const int C = H / kUS, NS = 8 * ntile;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(C * ((a.B + NS - 1) / NS)), (unsigned)a.G, (unsigned)ndir);
-  cfg.blockDim = dim3(kClThreads);
+  cfg.blockDim = dim3(32 * kUnitWarps * nwg);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -468,15 +478,15 @@ cudaError_t launch_lstm_fwd_cluster(const LstmFwdArgs& a, int H, int precision, 
   const int nt = pick_ntile(a.B, H, split, false);
   const size_t smem = fwd_smem(H, nt, split);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-#define IB200_FWD_CL(NT_, SP_) return launch_cluster(lstm_fwd_cl_kernel<NT_, SP_>, a, H, NT_, smem, a.ndir, st)
+#define IB200_FWD_CL(NT_, SP_, NWG_) return launch_cluster(lstm_fwd_cl_kernel<NT_, SP_, NWG_>, a, H, NT_, NWG_, smem, a.ndir, st)
   if (split) {
-    if (nt == 4) IB200_FWD_CL(4, true);
-    if (nt == 2) IB200_FWD_CL(2, true);
-    IB200_FWD_CL(1, true);
+    if (nt == 4) IB200_FWD_CL(4, true, 2);
+    if (nt == 2) IB200_FWD_CL(2, true, 1);
+    IB200_FWD_CL(1, true, 1);
   }
-  if (nt == 4) IB200_FWD_CL(4, false);
-  if (nt == 2) IB200_FWD_CL(2, false);
-  IB200_FWD_CL(1, false);
+  if (nt == 4) IB200_FWD_CL(4, false, 2);
+  if (nt == 2) IB200_FWD_CL(2, false, 1);
+  IB200_FWD_CL(1, false, 1);
 #undef IB200_FWD_CL
 }
 
@@ -486,15 +496,15 @@ cudaError_t launch_lstm_bwd_cluster(const LstmBwdArgs& a, int H, int precision, 
   const int nt = pick_ntile(a.B, H, split, true);
   const size_t smem = bwd_smem(H, nt, split);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-#define IB200_BWD_CL(NT_, SP_) return launch_cluster(lstm_bwd_cl_kernel<NT_, SP_>, a, H, NT_, smem, a.ndir, st)
+#define IB200_BWD_CL(NT_, SP_, NWG_) return launch_cluster(lstm_bwd_cl_kernel<NT_, SP_, NWG_>, a, H, NT_, NWG_, smem, a.ndir, st)
   if (split) {
-    if (nt == 4) IB200_BWD_CL(4, true);
-    if (nt == 2) IB200_BWD_CL(2, true);
-    IB200_BWD_CL(1, true);
+    if (nt == 4) IB200_BWD_CL(4, true, 2);
+    if (nt == 2) IB200_BWD_CL(2, true, 1);
+    IB200_BWD_CL(1, true, 1);
   }
-  if (nt == 4) IB200_BWD_CL(4, false);
-  if (nt == 2) IB200_BWD_CL(2, false);
-  IB200_BWD_CL(1, false);
+  if (nt == 4) IB200_BWD_CL(4, false, 2);
+  if (nt == 2) IB200_BWD_CL(2, false, 1);
+  IB200_BWD_CL(1, false, 1);
 #undef IB200_BWD_CL
 }
 

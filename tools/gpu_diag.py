@@ -1,7 +1,7 @@
-"""Stage-by-stage GPU-vs-oracle diagnostic (development aid; run on the GPU box: python tools_gpu_diag.py)."""
+"""Stage-by-stage GPU-vs-oracle diagnostic (development aid; run on the GPU box from the repo root: python tools/gpu_diag.py)."""
 import sys, time, traceback
 import torch
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from helpers import run_product_step, run_oracle_step
 from oracle import restatement as R
 from conftest import rel_l2
