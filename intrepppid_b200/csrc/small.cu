@@ -12,9 +12,12 @@ __global__ void len1_kernel(const LengthArgs p) {
   int* __restrict__ dst = p.tok32 + (size_t)n * p.Tin;
   int cnt = 0;
   for (int t = threadIdx.x; t < p.Tin; t += blockDim.x) {
-    const int v = (int)src[t];
+    const long long v64 = src[t];
+    // ids outside [0, V) make F.embedding raise in the reference (the Python layer checks that when check_lengths is on); here
+    // they are clamped so that no kernel can index outside the [V, .] tables
+    const int v = v64 < 0 ? 0 : (v64 >= p.V ? p.V - 1 : (int)v64);
     dst[t] = v;
-    cnt += (v != 0);
+    cnt += (v64 != 0);
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   __shared__ int ws[32];

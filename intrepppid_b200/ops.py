@@ -242,6 +242,9 @@ class _EncodeHidden(torch.autograd.Function):
         if lengths_holder is not None:
             lengths_holder.append(lens)
         if check_lengths:
+            lo, hi = int(tokens.min()), int(tokens.max())
+            if lo < 0 or hi >= V:  # F.embedding raises on such ids; the kernels clamp them for memory safety only
+                raise IndexError(f"token id out of range: ids must lie in [0, {V}), got [{lo}, {hi}]")
             if int(lens[1].min()) <= 0:  # one host sync; the reference does two per encoder call (awd_lstm.py:53-54,149-150)
                 raise RuntimeError("Expected sequence length to be larger than 0 in RNN")
         if training:

@@ -283,3 +283,42 @@ def test_pair_score_ranges_tile_the_triangle():
     with torch.no_grad():
         assert torch.equal(z_all, net.embed(x.cuda(), 16)) and p0 == 0
         assert torch.equal(probs, net.score_pairs(z_all))
+
+
+def test_out_of_range_token_ids_raise_like_f_embedding():
+    P = R.init_params(vocab=40, E=32, L=1)
+    net = build_product(P, L=1, bi="last").eval()
+    x = torch.randint(1, 40, (3, 12))
+    x[1, 5] = 40
+    with pytest.raises(IndexError):
+        net.encoder(x.cuda())
+    x[1, 5] = -1
+    with pytest.raises(IndexError):
+        net.encoder(x.cuda())
+    net.encoder.check_lengths = False  # no host-side check: the ids are clamped, nothing faults
+    with torch.no_grad():
+        z = net.encoder(x.cuda())
+    assert bool(torch.isfinite(z).all())
+
+
+def test_variational_dropout_row_mask_also_in_eval():
+    """Q8: variational_dropout=True draws a ROW mask [4H,1] for weight_hh_l0 and -- as the reference does (`training=True` at
+    utils/weightdrop.py:94) -- applies it in eval mode too; DropConnect (the default) is the identity in eval."""
+    import intrepppid_b200 as ib
+
+    V, E, L = 50, 32, 2
+    P = R.init_params(vocab=V, E=E, L=L, seed=11)
+    x = torch.randint(1, V, (5, 20), generator=torch.Generator().manual_seed(12))
+    row = (torch.rand(4 * E, 1, generator=torch.Generator().manual_seed(13)) >= 0.3).float() / 0.7
+    net = build_product(P, L=L, bi="last").eval()
+    with torch.no_grad():
+        z = net.encoder(x.cuda(), None, row.expand(4 * E, E).contiguous().cuda()).cpu()
+        zr, _ = R.encoder_forward(x, P, num_layers=L, bi_reduce="last", training=False, whh_mask=row.expand(4 * E, E))
+        assert rel_l2(z, zr) < 1e-4
+        assert torch.equal(net.encoder(x.cuda()), net.encoder(x.cuda()))  # DropConnect: no mask in eval, deterministic
+    torch.manual_seed(0)
+    vnet = ib.intrepppid_network(1, vocab_size=V, embedding_size=E, rnn_num_layers=L, variational_dropout=True).cuda().eval()
+    m = vnet.encoder.encoder.rnn_dp.sample_mask("weight_hh_l0", 3)
+    assert m.shape == (3, 4 * E, E) and bool((m == m[:, :, :1]).all())  # one value per row, per group
+    with torch.no_grad():
+        assert not torch.equal(vnet.encoder(x.cuda()), vnet.encoder(x.cuda()))  # a fresh row mask per call, even in eval
