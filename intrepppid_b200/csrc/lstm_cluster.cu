@@ -20,6 +20,14 @@
 namespace ib200 {
 namespace {
 
+// timing experiments only (IB200_ABLATE=1 builds, env IB200_DBG): 1 no remote h stores, 2 CTA barrier instead of the cluster barrier,
+// 4 no global stores, 8 no MMAs.  Production builds compile the switches out.
+#ifdef IB200_ABLATE
+#define IB200_CL_DBG(p) ((p).dbg)
+#else
+#define IB200_CL_DBG(p) 0
+#endif
+
 constexpr int kUS = 32;          // hidden units per CTA
 constexpr int kRows = 4 * kUS;   // gate rows per CTA
 constexpr int kUnitWarps = 4;     // warps along the units: warp group ug owns local units 8ug .. 8ug+7
@@ -165,6 +173,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
   float cst[NCELL], hv[NCELL];
 #pragma unroll
   for (int c = 0; c < NCELL; ++c) cst[c] = hv[c] = 0.f;
+  const int dbg = IB200_CL_DBG(p);
 
   for (int s = 0; s < T; ++s) {
     float4 x[NCELL];
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     }
     const __nv_bfloat16* hb = b_lane + (size_t)buf * kBufElems;
 #pragma unroll 2
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kt = 0; kt < ((dbg & 8) ? 0 : KT); ++kt) {
       uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int t2 = 0; t2 < 2; ++t2) {
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
       const float gg = tanh_f<FAST>(acc[1][j][o]), go = sigmoid_f<FAST>(acc[1][j][2 + o]);
       cst[c] = fmaf(gf, cst[c], gi * gg);
       hv[c] = go * tanh_f<FAST>(cst[c]);
-      if (valid[c]) {
+      if (valid[c] && !(dbg & 4)) {
         const size_t row = (size_t)(rb[c] + t);
         if (train) {
           G4[row * H] = make_float4(gi, gf, gg, go);
@@ -237,13 +246,17 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
       else hi = pack_bf16(hv[2 * j], hv[2 * j + 1]);
 #pragma unroll
       for (int r = 0; r < 8; ++r)
-        if (r < C) {
+        if (r < C && !((dbg & 1) && r != rank)) {
           st_cluster_u32(hdst[r] + boff + j * 16, hi);
           if constexpr (SPLIT) st_cluster_u32(hdst[r] + boff + (uint32_t)kPartElems * 2u + j * 16, lo);
         }
     }
-    cluster_arrive();
-    cluster_wait();
+    if (dbg & 2) {
+      __syncthreads();
+    } else {
+      cluster_arrive();
+      cluster_wait();
+    }
   }
 
   if (p.hn != nullptr) {
