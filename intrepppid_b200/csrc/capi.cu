@@ -91,6 +91,7 @@ struct Plan {
   size_t bwd_scratch;  // dY [R,2H] then dX0 [R,H]
   size_t partial;
   size_t bias_partial;  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel
+  size_t ph_state, ph_sched;  // two-phase rebalancing (common.cuh): [2][N][H][2] floats; sm_load[256] + resume_list[1 + CTAs] ints
   int ctas_per_group;
   size_t total;
 };
@@ -131,6 +132,8 @@ Plan make_plan(const ib200_cfg* c) {
       }
       if (p.train) p.wihT_gi[l][d] = take(sizeof(float) * 4 * H * K);
     }
+  p.ph_state = take(sizeof(float) * 2 * (size_t)p.N * H * 2);
+  p.ph_sched = take(sizeof(int) * (256 + 1 + 2 * (size_t)p.G * ((p.B + 3) / 4)));
   for (int l = 0; l < p.L; ++l)
     if (p.train || l < p.L - 1) p.Y[l] = take(sizeof(float) * p.R * 2 * H);
   if (p.L > 1)
@@ -259,6 +262,27 @@ int nt_launches(int NC, bool wide) {
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
 
+// split point of the two-phase rebalancing = (step time of a CTA alone on its SM) / (step time of two co-resident CTAs): the shared
+// SMs and the exclusive SMs then finish phase 1 together.  Measured on B200; IB200_SPLIT_FWD / IB200_SPLIT_BWD override.
+float split_frac(bool bwd) {
+  static const float f[2] = {[] { const char* e = getenv("IB200_SPLIT_FWD"); return e ? (float)atof(e) : 0.69f; }(),
+                             [] { const char* e = getenv("IB200_SPLIT_BWD"); return e ? (float)atof(e) : 0.65f; }()};
+  return f[bwd ? 1 : 0];
+}
+// the launchers rebalance in two phases exactly when a HALF launch has between one and two CTAs per SM (lstm_fwd.cu / lstm_bwd.cu)
+bool wants_phases(const Plan& p, int ndir) {
+  const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir;
+  return full_ctas <= 148 && half_ctas > 148 && half_ctas < 2 * 148 && p.T >= 128;
+}
+PhaseArgs phase_args(void* ws, const Plan& p, bool bwd) {
+  PhaseArgs a{};
+  a.state = at<float>(ws, p.ph_state);
+  a.sm_load = at<int>(ws, p.ph_sched);
+  a.resume_list = a.sm_load + 256;
+  a.split_frac = split_frac(bwd);
+  return a;
+}
+
 }  // namespace
 
 extern "C" {
@@ -369,6 +393,10 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
     }
     fa.hn = l == p.L - 1 ? hn_top : nullptr;
     { const char* e = getenv("IB200_DBG"); fa.dbg = e ? atoi(e) : 0; }
+    if (!cluster && wants_phases(p, ndir)) {  // scheduling state of the two-phase rebalancing
+      fa.ph = phase_args(ws, p, false);
+      TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(fa.ph.sm_load), 257, st), "phase counters");
+    }
     TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, cluster ? launch_lstm_fwd_cluster(fa, H, prec, st) : launch_lstm_fwd(fa, H, prec, st),
           "lstm fwd");
   }
@@ -409,6 +437,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
     ba.planes = planes ? 1 : 0;
     ba.bias_partial = planes ? at<float>(ws, p.bias_partial) : nullptr;
+    if (!cluster && wants_phases(p, ndir)) {
+      ba.ph = phase_args(ws, p, true);
+      TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(ba.ph.sm_load), 257, st), "phase counters");
+    }
     TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st),
           "lstm bwd");
     const int bwd_ctas = planes ? lstm_bwd_cta_count(ba, prec) : 0;  // CTAs per direction (= number of bias partials)

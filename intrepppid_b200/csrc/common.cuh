@@ -113,6 +113,43 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-phase rebalancing of a recurrent launch whose CTAs do not divide over the SMs (e.g. 200 CTAs, two resident per SM at most,
+// on 148 SMs: 52 SMs hold two CTAs and set the kernel time while 96 hold one and idle 40 % of it).
+//   phase 1: the whole grid starts.  Every CTA registers on its SM (atomic counter per %smid); a CTA that finds a second resident
+//            on its SM stops after `split` steps, saves its recurrent state and appends its id to `resume_list`.
+//   phase 2: a 1-D grid (at most one CTA per SM) resumes the listed CTAs from the saved state to the end of the chain.
+// The split point is chosen so that the shared SMs and the exclusive SMs finish phase 1 together.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PhaseArgs {
+  float* state;       // [ndir][N][H][2] recurrent state carried from phase 1 to phase 2 (forward: c, h; backward: dc, dh)
+  int* sm_load;       // [256] resident-CTA counters per SM id, zeroed before phase 1
+  int* resume_list;   // [0] = number of stopped CTAs (zeroed before phase 1), [1..] = their linear ids (x + grid_x*(g + G*dz))
+  int phase;          // 0: one launch runs the whole chain (default)
+  float split_frac;   // fraction of the chain a shared CTA runs in phase 1
+  int grid_x;         // blockIdx.x extent of the phase-1 grid (tiles per group)
+};
+constexpr int kPhaseCheck = 16;  // step at which a phase-1 CTA looks at its SM's counter (all CTAs of the launch have started by then)
+
+__device__ __forceinline__ int sm_id() {
+  unsigned id;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+  return (int)id;
+}
+// which (tile, group, direction slot) this CTA works on; false: nothing to do (phase 2 CTA beyond the list)
+__device__ __forceinline__ bool phase_cta(const PhaseArgs& ph, int G, int& bx, int& g, int& dz) {
+  bx = blockIdx.x; g = blockIdx.y; dz = blockIdx.z;
+  if (ph.phase != 2) return true;
+  if ((int)blockIdx.x >= ph.resume_list[0]) return false;
+  const int id = ph.resume_list[1 + blockIdx.x];
+  bx = id % ph.grid_x; g = (id / ph.grid_x) % G; dz = id / (ph.grid_x * G);
+  return true;
+}
+__device__ __forceinline__ int phase_split(const PhaseArgs& ph, int T) {
+  const int s = max((int)(ph.split_frac * (float)T), kPhaseCheck + 2);
+  return s < T ? s : T;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

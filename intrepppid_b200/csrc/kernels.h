@@ -49,6 +49,7 @@ struct LstmFwdArgs {
   float* cstate[2];          // per direction [N,Tmax,H]
   float* hn;                 // [2,N,H] or null
   int dbg;                   // ablation flags for timing experiments (env IB200_DBG; 0 in production)
+  PhaseArgs ph;              // two-phase rebalancing (common.cuh); buffers null => always one phase
 };
 cudaError_t launch_lstm_fwd(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
 
@@ -67,6 +68,7 @@ struct LstmBwdArgs {
   int planes;                // 1: dgates rows are written as bf16 [hi plane (4H) | lo plane (4H)] over the 4H-float gate row
   float* bias_partial;       // planes mode: [ndir][G*gridDim.x][4H] per-CTA column sums of the dgates (GI order)
   int dbg;                   // ablation flags (env IB200_DBG)
+  PhaseArgs ph;              // two-phase rebalancing (common.cuh); buffers null => always one phase
 };
 cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision);  // G * gridDim.x of the launch above (bias partials per direction)

@@ -39,22 +39,33 @@ struct BwdSmem {
   float rdy[kD][2][NT];            // upstream gradient of h_t
   uint32_t dafrag[2][KTT][32][2];  // da as mma B fragments: [hi/lo][k tile][lane][2 words]
   float2 xch[NW][32];              // partial dh handed to the partner warp
+  int shared_sm;                   // phase 1 (two-phase rebalancing, common.cuh): 1 when a second CTA is resident on this SM
 };
 
 // HALF: 4 sequences per CTA, one cell per thread (see lstm_fwd.cu): bf16 mode on the even mma columns; fp32 mode ("HL") with
 // da_hi on columns 0-3 and da_lo on columns 4-7, so 2 MMAs per product (A_hi, A_lo) instead of 3 and one shfl_xor(2) to add the
 // hi-column and lo-column sums of a sequence.
-template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY, bool HALF>
+// PHASED: takes part in the two-phase rebalancing of common.cuh (window of steps, state save / restore); plain variants carry none of it.
+template <int H, bool SPLIT, bool FAST_ACT, bool HAS_DY, bool HALF, bool PHASED>
 __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const LstmBwdArgs p) {
+  static_assert(!PHASED || HALF, "PHASED is a HALF-mode variant");
   constexpr int NT = H * 4, MT = H / 16, KTT = H / 4, KTH = KTT / 2;
   constexpr bool HL = HALF && SPLIT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const int mt = warp % MT, kh = warp / MT;
-  const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
+  int bx = blockIdx.x, g = blockIdx.y, dz = blockIdx.z;
+  if constexpr (PHASED) {
+    if (!phase_cta(p.ph, p.G, bx, g, dz)) return;
+  }
+  const int dir = p.dir0 + dz;
   const int T = p.lens[p.G + g];
   if (T <= 0) return;
+  // scan steps [s_begin, s_end) of the chain run in this launch (two-phase rebalancing, common.cuh)
+  const int split = PHASED ? phase_split(p.ph, T) : T;
+  const int s_begin = (PHASED && p.ph.phase == 2) ? split : 0;
+  int s_end = T;
   constexpr int SEQ = HALF ? kBC / 2 : kBC, NC = HALF ? 1 : 2;  // sequences per CTA, cells per thread
-  const int b0 = blockIdx.x * SEQ;
+  const int b0 = bx * SEQ;
   const int nvalid = min(SEQ, p.B - b0);
   const int nbase = g * p.B + b0;
   const int Tmax = p.Tmax;
@@ -107,12 +118,13 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   const float* __restrict__ C = (dir ? p.cstate[1] : p.cstate[0]);
   const ptrdiff_t gstride = (ptrdiff_t)dt * H;
   // running pointers of the prefetch (kD steps ahead): gates at t(s), c of the scan predecessor = c at t(s+1), dy at t(s)
-  const float4* gp0 = G4 + (size_t)(rb0 + t_first) * H + j;
-  const float4* gp1 = G4 + (size_t)(rb1 + t_first) * H + j;
-  const float* cp0 = C + (size_t)(rb0 + t_first) * H + j;  // advanced BEFORE use: first use is t(1)
-  const float* cp1 = C + (size_t)(rb1 + t_first) * H + j;
-  const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + t_first) * (2 * H) + dir * H + j : nullptr;
-  const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + t_first) * (2 * H) + dir * H + j : nullptr;
+  const int tb = t_first + s_begin * dt;  // time index of the first step of this launch
+  const float4* gp0 = G4 + (size_t)(rb0 + tb) * H + j;
+  const float4* gp1 = G4 + (size_t)(rb1 + tb) * H + j;
+  const float* cp0 = C + (size_t)(rb0 + tb) * H + j;  // advanced BEFORE use: first use is the step after
+  const float* cp1 = C + (size_t)(rb1 + tb) * H + j;
+  const float* dp0 = HAS_DY ? p.dy + (size_t)(rb0 + tb) * (2 * H) + dir * H + j : nullptr;
+  const float* dp1 = HAS_DY ? p.dy + (size_t)(rb1 + tb) * (2 * H) + dir * H + j : nullptr;
   const ptrdiff_t dstride = (ptrdiff_t)dt * (2 * H);  // == p.dy_stride (checked by the launcher)
 
   auto issue = [&](int s) {
@@ -142,21 +154,42 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   };
 
   for (int i = tid; i < 2 * KTT * 32 * 2; i += NT) (&sm.dafrag[0][0][0][0])[i] = 0u;  // HALF: odd columns stay zero
+  if constexpr (PHASED) {
+    if (tid == 0) {
+      sm.shared_sm = 0;
+      if (p.ph.phase == 1) atomicAdd(p.ph.sm_load + sm_id(), 1);
+    }
+  }
   __syncthreads();
   float ccur[2], dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f};
   float bsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // column sums of the dgates of my cells (bias gradient)
   const bool planes = p.planes != 0;
   ccur[0] = cp0[0];
   ccur[1] = cp1[0];
-  if (p.dhn != nullptr) {
+  // two-phase rebalancing: recurrent state of my cell(s), [dir slot][sequence][unit][dc, dh]
+  auto state_slot = [&](int q) {
+    return reinterpret_cast<float2*>(p.ph.state) + ((size_t)dz * N + nbase + min(q, nvalid - 1)) * H + j;
+  };
+  if (PHASED && s_begin > 0) {  // phase 2: resume
+    float2* st0 = state_slot(q0);
+    float2* st1 = state_slot(q1);
+    const float2 a = *st0;
+    dc[0] = a.x;
+    dhrec[0] = a.y;
+    if constexpr (!HALF) {
+      const float2 b = *st1;
+      dc[1] = b.x;
+      dhrec[1] = b.y;
+    }
+  } else if (p.dhn != nullptr) {
     dhrec[0] = p.dhn[((size_t)dir * N + nbase + min(q0, nvalid - 1)) * H + j];
     dhrec[1] = p.dhn[((size_t)dir * N + nbase + min(q1, nvalid - 1)) * H + j];
   }
 #pragma unroll
-  for (int s = 0; s < kD; ++s) issue(s);
+  for (int s = 0; s < kD; ++s) issue(s_begin + s);
 
-  float4* gs0 = G4 + (size_t)(rb0 + t_first) * H + j;  // da store pointers at t(s)
-  float4* gs1 = G4 + (size_t)(rb1 + t_first) * H + j;
+  float4* gs0 = G4 + (size_t)(rb0 + tb) * H + j;  // da store pointers at t(s)
+  float4* gs1 = G4 + (size_t)(rb1 + tb) * H + j;
   uint32_t* dst_hi0 = &sm.dafrag[0][j >> 2][(HL ? q0 : n0) * 4 + (j & 3)][0];
   constexpr int kFragPart = KTT * 32 * 2;  // words per hi/lo part
   const uint32_t* bsrc = &sm.dafrag[0][kh * KTH][lane][0];
@@ -190,10 +223,19 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
     }
   };
   cp_async_wait<kD - 1>();
-  load_coef(0);
-  issue(kD);
+  load_coef(s_begin);
+  issue(s_begin + kD);
 
-  for (int s = 0; s < T; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
+    if constexpr (PHASED) {
+      if (p.ph.phase == 1) {  // (uniform; two compares per step)
+        if (s == kPhaseCheck) {
+          if (tid == 0) sm.shared_sm = *reinterpret_cast<volatile int*>(p.ph.sm_load + sm_id()) >= 2;  // visible after this step's barriers
+        } else if (s == kPhaseCheck + 1) {
+          if (sm.shared_sm) s_end = split;
+        }
+      }
+    }
     float4 sv[2];
     uint4 pk[2];
 #pragma unroll
@@ -292,6 +334,16 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   }
   cp_async_wait<0>();
 
+  const bool stopped = PHASED && s_end < T;  // phase 1 on a shared SM: park the state, ask for a phase-2 CTA
+  if (stopped) {
+    if (v0) *state_slot(q0) = make_float2(dc[0], dhrec[0]);
+    if (v1) *state_slot(q1) = make_float2(dc[1], dhrec[1]);
+    if (tid == 0) {
+      const int lin = bx + p.ph.grid_x * (g + p.G * dz);
+      p.ph.resume_list[1 + atomicAdd(p.ph.resume_list, 1)] = lin;
+    }
+  }
+
   if (planes) {
     // (1) bias-gradient partials of this CTA: sum my cells over the 8 columns held by the 4 lanes of a quad, lane tig==0 writes
     if (p.bias_partial != nullptr) {
@@ -303,9 +355,18 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
         b.z += __shfl_xor_sync(0xffffffffu, b.z, o);
         b.w += __shfl_xor_sync(0xffffffffu, b.w, o);
       }
-      const size_t ncta = (size_t)p.G * gridDim.x, ci = (size_t)g * gridDim.x + blockIdx.x;
-      if (tig == 0) *reinterpret_cast<float4*>(p.bias_partial + ((size_t)blockIdx.z * ncta + ci) * 4 * H + 4 * j) = b;
+      const int tiles_x = (PHASED && p.ph.phase == 2) ? p.ph.grid_x : (int)gridDim.x;
+      const size_t ncta = (size_t)p.G * tiles_x, ci = (size_t)g * tiles_x + bx;
+      if (tig == 0) {
+        float4* slot = reinterpret_cast<float4*>(p.bias_partial + ((size_t)dz * ncta + ci) * 4 * H + 4 * j);
+        if (s_begin > 0) {  // phase 2 adds to what the same logical CTA summed in phase 1
+          const float4 o = *slot;
+          b.x += o.x; b.y += o.y; b.z += o.z; b.w += o.w;
+        }
+        *slot = b;
+      }
     }
+    if (stopped) return;
     // (2) zero tail rows [T, tail_end) of my sequences: the TN GEMM reads whole 64-row TMA boxes
     const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;  // +1: the row a shifted box touches
     const int chunks = 4 * H * 4 / 16;  // 16-byte chunks per row (both planes)
@@ -316,22 +377,37 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_bwd_kernel(const Lst
   }
 }
 
-template <int H, bool SPLIT, bool FAST, bool HAS_DY, bool HALF>
+template <int H, bool SPLIT, bool FAST, bool HAS_DY, bool HALF, bool PHASED = false>
 cudaError_t launch_kh(const LstmBwdArgs& a, cudaStream_t st) {
   constexpr int SEQ = HALF ? kBC / 2 : kBC;
   dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir);
+  if (PHASED && a.ph.phase == 2) grid = dim3(grid.x * grid.y * grid.z, 1, 1);  // 1-D: CTA i resumes resume_list[i], the rest exit at once
   const size_t smem = sizeof(BwdSmem<H>);
   if (a.dy != nullptr && a.dy_stride != 2 * H) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF><<<grid, H * 4, smem, st>>>(a);
+  lstm_bwd_kernel<H, SPLIT, FAST, HAS_DY, HALF, PHASED><<<grid, H * 4, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <int H, bool SPLIT, bool FAST, bool HAS_DY>
 cudaError_t launch_k(const LstmBwdArgs& a, cudaStream_t st) {
   // one cell per thread and two co-resident CTAs per SM whenever the full-width launch would leave SMs idle
   const bool half = bwd_half(a, SPLIT);
-  return half ? launch_kh<H, SPLIT, FAST, HAS_DY, true>(a, st) : launch_kh<H, SPLIT, FAST, HAS_DY, false>(a, st);
+  LstmBwdArgs b = a;
+  b.ph = PhaseArgs{};
+  if (!half) return launch_kh<H, SPLIT, FAST, HAS_DY, false>(b, st);
+  const int tiles = (a.B + kBC / 2 - 1) / (kBC / 2), half_ctas = tiles * a.G * a.ndir;
+  if (a.ph.state != nullptr && half_ctas > 148 && half_ctas < 2 * 148 && a.Tmax >= 8 * kPhaseCheck && !(a.dbg & 2048)) {
+    // between one and two CTAs per SM: two-phase rebalancing (common.cuh)
+    b.ph = a.ph;
+    b.ph.phase = 1;
+    b.ph.grid_x = tiles;
+    cudaError_t e = launch_kh<H, SPLIT, FAST, HAS_DY, true, true>(b, st);
+    if (e != cudaSuccess) return e;
+    b.ph.phase = 2;
+    return launch_kh<H, SPLIT, FAST, HAS_DY, true, true>(b, st);
+  }
+  return launch_kh<H, SPLIT, FAST, HAS_DY, true>(b, st);
 }
 template <int H, bool SPLIT, bool FAST>
 cudaError_t launch_b(const LstmBwdArgs& a, cudaStream_t st) {

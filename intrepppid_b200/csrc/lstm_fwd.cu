@@ -55,6 +55,7 @@ struct FwdSmem {
   static constexpr int NT = H * 4;
   float4 xring[kD][2][NT];                 // per-thread slots of the input projection
   __nv_bfloat16 hs[2][NPART][H][kBC];      // h_{t-1}: [buffer][part][unit][mma column]
+  int shared_sm;                           // phase 1: 1 when a second CTA is resident on this SM
   // followed by uint16 toks[T + kD][kBC] (layer 0)
 };
 
@@ -68,19 +69,30 @@ struct FwdSmem {
 // DEFER (HALF modes, launches with at most one CTA per SM): the global stores of a step and the input-projection read are moved
 // into the NEXT step's MMA phase, interleaved with the HMMAs.  With two co-resident CTAs per SM the other CTA already fills
 // those issue gaps and the deferral only costs registers (measured: -13 % alone on an SM, +3 % when sharing it).
-template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN, bool HALF, bool DEFER>
+// PHASED: the kernel takes part in the two-phase rebalancing of common.cuh (window of steps, state save / restore); the plain
+// variants carry none of that code.
+template <int H, bool SPLIT, bool FAST_ACT, bool LAYER0, bool TRAIN, bool HALF, bool DEFER, bool PHASED>
 __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const LstmFwdArgs p) {
   static_assert(!DEFER || HALF, "DEFER is a HALF-mode variant");
+  static_assert(!PHASED || HALF, "PHASED is a HALF-mode variant");
   constexpr int NT = H * 4, KT = H / 16;
   constexpr bool HL = HALF && SPLIT;
   constexpr int NPART = (SPLIT && !HL) ? 2 : 1;
   using Smem = FwdSmem<H, NPART>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
-  const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
+  int bx = blockIdx.x, g = blockIdx.y, dz = blockIdx.z;
+  if constexpr (PHASED) {
+    if (!phase_cta(p.ph, p.G, bx, g, dz)) return;
+  }
+  const int dir = p.dir0 + dz;
   const int T = p.lens[p.G + g];  // T_eff of this group
   if (T <= 0) return;
+  // steps [s_begin, s_end) of the chain run in this launch (two-phase rebalancing, common.cuh)
+  const int split = PHASED ? phase_split(p.ph, T) : T;
+  const int s_begin = (PHASED && p.ph.phase == 2) ? split : 0;
+  int s_end = T;
   constexpr int SEQ = HALF ? kBC / 2 : kBC;  // sequences per CTA
-  const int b0 = blockIdx.x * SEQ;
+  const int b0 = bx * SEQ;
   const int nvalid = min(SEQ, p.B - b0);
   const int nbase = g * p.B + b0;  // first global sequence index of this CTA
   const int Tmax = p.Tmax;
@@ -129,6 +141,12 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   const bool v0 = q0 < nvalid, v1 = !HALF && q1 < nvalid;
 
   // ---- init h = 0 (both buffers); stage this CTA's token ids in scan order (layer 0) ------------------------------------------
+  if constexpr (PHASED) {
+    if (tid == 0) {
+      sm.shared_sm = 0;
+      if (p.ph.phase == 1) atomicAdd(p.ph.sm_load + sm_id(), 1);
+    }
+  }
   for (int i = tid; i < 2 * NPART * H * kBC / 2; i += NT) reinterpret_cast<uint32_t*>(&sm.hs[0][0][0][0])[i] = 0u;
   if constexpr (LAYER0) {
     for (int i = tid; i < (T + kD) * SEQ; i += NT) {
@@ -147,8 +165,8 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
       LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
              : reinterpret_cast<const float4*>((dir ? p.xproj[1] : p.xproj[0])) + u;
   // layer >= 1: running source pointers of the prefetch (kD steps ahead of the compute), advanced by one row per step
-  const float4* xp0 = xsrc + (size_t)(rb0 + t_first) * H;
-  const float4* xp1 = xsrc + (size_t)(rb1 + t_first) * H;
+  const float4* xp0 = xsrc + (size_t)(rb0 + t_first + s_begin * dt) * H;
+  const float4* xp1 = xsrc + (size_t)(rb1 + t_first + s_begin * dt) * H;
   const ptrdiff_t xstride = (ptrdiff_t)dt * H;
   float4* slot = &sm.xring[0][0][tid];
   constexpr int kStage = 2 * NT;  // float4 per ring stage
@@ -176,7 +194,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
     cp_async_commit();
   };
 #pragma unroll
-  for (int s = 0; s < kD; ++s) issue(s);
+  for (int s = 0; s < kD; ++s) issue(s_begin + s);
 
   float c0 = 0.f, c1 = 0.f, h0 = 0.f, h1 = 0.f;
   // output bases; the token row of my cells at the current step is (row0, row1), advanced by dt per step
@@ -185,13 +203,43 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   const bool has_y = p.y != nullptr, planes = p.planes != 0;
   const int ycol = dir * H + u;
   constexpr int ystr = 2 * H;  // == p.y_stride (checked by the launcher): a compile-time row pitch keeps the address math short
-  int row0 = rb0 + t_first, row1 = rb1 + t_first;
+  int row0 = rb0 + t_first + s_begin * dt, row1 = rb1 + t_first + s_begin * dt;
 
   const __nv_bfloat16* hrow = &sm.hs[0][0][lane % H][0];  // ldmatrix row address of this lane (k-pair block 0, buffer 0)
   __nv_bfloat16* hput = &sm.hs[0][0][u][HL ? q0 : n0];
   constexpr int kBufElems = NPART * H * kBC, kPartElems = H * kBC;
 
   const int dbg = IB200_DBGBITS(p);
+
+  // two-phase rebalancing: recurrent state of my cell(s), [dir slot][sequence][unit][c, h]
+  auto state_slot = [&](int q) {
+    return reinterpret_cast<float2*>(p.ph.state) + ((size_t)dz * p.G * p.B + nbase + min(q, nvalid - 1)) * H + u;
+  };
+  if (PHASED && s_begin > 0) {
+    float2* st0 = state_slot(q0);
+    float2* st1 = state_slot(q1);  // phase 2: resume.  h re-enters the MMA exactly as it left: the same bf16 hi (+ lo) split of the fp32 value
+    const float2 a = *st0;
+    c0 = a.x;
+    h0 = a.y;
+    if constexpr (!HALF) {
+      const float2 b = *st1;
+      c1 = b.x;
+      h1 = b.y;
+    }
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
+    __nv_bfloat16* dst = hput + (s_begin & 1) * kBufElems;
+    if constexpr (HL) {
+      dst[0] = hh.x;
+      dst[kBC / 2] = __float2bfloat16_rn(h0 - __bfloat162float(hh.x));
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(dst) = hh;
+      if constexpr (SPLIT) {
+        const float2 hf = __bfloat1622float2(hh);
+        *reinterpret_cast<__nv_bfloat162*>(dst + kPartElems) = __floats2bfloat162_rn(h0 - hf.x, h1 - hf.y);
+      }
+    }
+    __syncthreads();
+  }
 
   // HALF modes: the global stores of a step (one cell per thread) are DEFERRED into the MMA shadow of the next step, off the
   // chain  STS h -> barrier -> LDSM -> HMMA  that bounds the step time; the last step is flushed after the loop.
@@ -217,7 +265,16 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   __nv_bfloat16 phh = __float2bfloat16_rn(0.f), phl = phh;
   int prow = row0;
 
-  for (int s = 0; s < T; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
+    if constexpr (PHASED) {
+      if (p.ph.phase == 1) {  // (uniform; two compares per step)
+        if (s == kPhaseCheck) {
+          if (tid == 0) sm.shared_sm = *reinterpret_cast<volatile int*>(p.ph.sm_load + sm_id()) >= 2;  // visible after this step's barrier
+        } else if (s == kPhaseCheck + 1) {
+          if (sm.shared_sm) s_end = split;
+        }
+      }
+    }
     float4 x0 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), x1 = x0;
     auto fetch_x = [&]() {
       cp_async_wait<kD - 1>();  // this thread's copies for step s have landed
@@ -237,7 +294,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
       float ac2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       // work that is off the dependent chain is interleaved with the HMMAs (slot i after the i-th group of four): the previous
       // step's global stores, this step's input projection read, the prefetch kD steps ahead
-      const bool st_ok = v0 && s > 0 && !(dbg & 4);
+      const bool st_ok = v0 && s > s_begin && !(dbg & 4);
       auto shadow = [&](int slot_i) {
         if constexpr (!DEFER) return;
         if (slot_i == 0) {
@@ -322,7 +379,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
         }
       }
       if constexpr (DEFER) {
-        if (s > 0) emit_half(prow, pgt, pcc, phv, phh, phl);  // after the HMMAs have been issued
+        if (s > s_begin) emit_half(prow, pgt, pcc, phv, phh, phl);  // after the HMMAs have been issued
       }
       ai0 = acc[0][0], af0 = acc[0][2], ag0 = acc[1][0], ao0 = acc[1][2];
       ai1 = acc[0][1], af1 = acc[0][3], ag1 = acc[1][1], ao1 = acc[1][3];
@@ -424,6 +481,16 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   if constexpr (DEFER) emit_half(prow, pgt, pcc, phv, phh, phl);  // flush the last step
   cp_async_wait<0>();
 
+  if (PHASED && s_end < T) {  // phase 1, shared SM: park the state and ask for a phase-2 CTA
+    if (v0) *state_slot(q0) = make_float2(c0, h0);
+    if (v1) *state_slot(q1) = make_float2(c1, h1);
+    if (tid == 0) {
+      const int lin = bx + p.ph.grid_x * (g + p.G * dz);
+      p.ph.resume_list[1 + atomicAdd(p.ph.resume_list, 1)] = lin;
+    }
+    return;
+  }
+
   // planes mode: the weight-gradient GEMM reads 64-row TMA boxes (and the row after the last one for the shifted operand), so the
   // rows [T, tail_end) of this CTA's sequences / this direction's columns must be finite zeros, not uninitialised memory
   if (has_y && planes) {
@@ -443,17 +510,18 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   }
 }
 
-template <int H, bool SPLIT, bool FAST, bool L0, bool TR, bool HALF, bool DEFER = false>
+template <int H, bool SPLIT, bool FAST, bool L0, bool TR, bool HALF, bool DEFER = false, bool PHASED = false>
 cudaError_t launch_kh(const LstmFwdArgs& a, cudaStream_t st) {
   constexpr int SEQ = HALF ? kBC / 2 : kBC;
   dim3 grid((a.B + SEQ - 1) / SEQ, a.G, a.ndir), block(H * 4);
+  if (PHASED && a.ph.phase == 2) grid = dim3(grid.x * grid.y * grid.z, 1, 1);  // 1-D: CTA i resumes resume_list[i], the rest exit at once
   size_t smem = sizeof(FwdSmem<H, (SPLIT && !HALF) ? 2 : 1>);
   if (L0) smem += (size_t)(a.Tmax + kD) * kBC * sizeof(uint16_t);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   if (a.y != nullptr && a.y_stride != 2 * H) return cudaErrorInvalidValue;  // the kernel addresses y rows with a fixed pitch of 2H
-  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER><<<grid, block, smem, st>>>(a);
+  lstm_fwd_kernel<H, SPLIT, FAST, L0, TR, HALF, DEFER, PHASED><<<grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <int H, bool SPLIT, bool FAST, bool L0, bool TR>
@@ -462,10 +530,31 @@ cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
   // 128 registers so two of them share an SM and interleave their MMA / MUFU phases
   const int full_ctas = ((a.B + kBC - 1) / kBC) * a.G * a.ndir;
   const bool half = full_ctas <= ((a.dbg & 128) ? 74 : 148) && !(a.dbg & 64);
-  if (!half) return launch_kh<H, SPLIT, FAST, L0, TR, false>(a, st);
-  const int half_ctas = ((a.B + kBC / 2 - 1) / (kBC / 2)) * a.G * a.ndir;
+  if (!half) {
+    LstmFwdArgs b = a;
+    b.ph = PhaseArgs{};
+    return launch_kh<H, SPLIT, FAST, L0, TR, false>(b, st);
+  }
+  const int tiles = (a.B + kBC / 2 - 1) / (kBC / 2), half_ctas = tiles * a.G * a.ndir;
   const bool defer = (half_ctas <= 148 || (a.dbg & 512)) && !(a.dbg & 1024);  // at most one CTA per SM
-  return defer ? launch_kh<H, SPLIT, FAST, L0, TR, true, true>(a, st) : launch_kh<H, SPLIT, FAST, L0, TR, true, false>(a, st);
+  if (defer) {
+    LstmFwdArgs b = a;
+    b.ph = PhaseArgs{};
+    return launch_kh<H, SPLIT, FAST, L0, TR, true, true>(b, st);
+  }
+  if (a.ph.state != nullptr && half_ctas < 2 * 148 && a.Tmax >= 8 * kPhaseCheck && !(a.dbg & 2048)) {
+    // between one and two CTAs per SM: two-phase rebalancing (common.cuh).  Phase 2 has at most one CTA per SM => DEFER variant.
+    LstmFwdArgs b = a;
+    b.ph.phase = 1;
+    b.ph.grid_x = tiles;
+    cudaError_t e = launch_kh<H, SPLIT, FAST, L0, TR, true, false, true>(b, st);
+    if (e != cudaSuccess) return e;
+    b.ph.phase = 2;
+    return launch_kh<H, SPLIT, FAST, L0, TR, true, true, true>(b, st);
+  }
+  LstmFwdArgs b = a;
+  b.ph = PhaseArgs{};
+  return launch_kh<H, SPLIT, FAST, L0, TR, true, false>(b, st);
 }
 
 
