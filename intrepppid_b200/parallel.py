@@ -37,6 +37,7 @@ class GradientAllReducer:
         self._pending = [len(b) for b in self.buckets]
         self._flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
         self._work = [None] * len(self.buckets)
+        self._inplace = [False] * len(self.buckets)
         self._hooks = []
         for b in self.buckets:
             for p in b:
@@ -49,8 +50,22 @@ class GradientAllReducer:
         if self._pending[i] == 0:
             self._launch(i)
 
+    @staticmethod
+    def _shared_flat(grads):
+        """The kernels hand back the gradients of one op as views of ONE flat buffer (ops.py): when a bucket is exactly such a
+        buffer it is reduced in place -- no torch.cat before and no copy back after the collective."""
+        st = grads[0].untyped_storage()
+        if any(g.untyped_storage().data_ptr() != st.data_ptr() or not g.is_contiguous() or g.dtype != torch.float32 for g in grads):
+            return None
+        if sum(g.numel() for g in grads) * 4 != st.nbytes():
+            return None
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, 0, (st.nbytes() // 4,))
+
     def _launch(self, i):
-        flat = torch.cat([p.grad.reshape(-1) for p in self.buckets[i]])
+        grads = [p.grad for p in self.buckets[i]]
+        base = self._shared_flat(grads)
+        self._inplace[i] = base is not None
+        flat = base if base is not None else torch.cat([g.reshape(-1) for g in grads])
         self._flat[i] = flat
         if self.world > 1:
             self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -67,11 +82,12 @@ class GradientAllReducer:
             flat = self._flat[i]
             if self.world > 1:
                 flat.div_(self.world)
-            off = 0
-            for p in b:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            if not self._inplace[i]:  # (in-place buckets: the gradients ARE views of `flat`)
+                off = 0
+                for p in b:
+                    n = p.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
             self._flat[i], self._work[i] = None, None
             self._pending[i] = len(b)
 
