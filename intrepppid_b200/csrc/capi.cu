@@ -449,10 +449,16 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     for (int d = 0; d < 2; ++d) {
       const int K = l == 0 ? H : 2 * H;
       if (!p.live[l][d]) {  // dead chain: exact zeros
-        TIMED(F_FILL, 1, launch_fill_zero(Gr->w_ih[l][d], (size_t)4 * H * K, st), "zero");
-        TIMED(F_FILL, 1, launch_fill_zero(Gr->w_hh[l][d], (size_t)4 * H * H, st), "zero");
-        TIMED(F_FILL, 1, launch_fill_zero(Gr->b_ih[l][d], (size_t)4 * H, st), "zero");
-        TIMED(F_FILL, 1, launch_fill_zero(Gr->b_hh[l][d], (size_t)4 * H, st), "zero");
+        const size_t n_ih = (size_t)4 * H * K, n_hh = (size_t)4 * H * H, n_b = (size_t)4 * H;
+        if (Gr->w_hh[l][d] == Gr->w_ih[l][d] + n_ih && Gr->b_ih[l][d] == Gr->w_hh[l][d] + n_hh && Gr->b_hh[l][d] == Gr->b_ih[l][d] + n_b) {
+          // the four tensors are consecutive slices of one flat gradient buffer (the layout ops.py hands in): one fill
+          TIMED(F_FILL, 1, launch_fill_zero(Gr->w_ih[l][d], n_ih + n_hh + 2 * n_b, st), "zero");
+        } else {
+          TIMED(F_FILL, 1, launch_fill_zero(Gr->w_ih[l][d], n_ih, st), "zero");
+          TIMED(F_FILL, 1, launch_fill_zero(Gr->w_hh[l][d], n_hh, st), "zero");
+          TIMED(F_FILL, 1, launch_fill_zero(Gr->b_ih[l][d], n_b, st), "zero");
+          TIMED(F_FILL, 1, launch_fill_zero(Gr->b_hh[l][d], n_b, st), "zero");
+        }
         continue;
       }
       GemmTNArgs ta{};

@@ -66,6 +66,8 @@ __global__ void zero_int_kernel(int* p, int n) {
 
 // ---- K1a: P[g][d][v][gi] = (scale[g][v] * emb[v]) . w_ih_d[row(gi)] + b_ih_d[row] + b_hh_d[row] -----------------------------------
 // (utils/embedding_do.py:26-43 folded with the layer-0 x W_ih^T of nn.LSTM: the lookup-table identity)
+constexpr int kTableVpb = 8;  // vocabulary rows per block
+
 template <int H>
 __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int v_per_block) {
   const int gi = threadIdx.x, row = gi_to_torch_row(gi, H);
@@ -75,19 +77,20 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int 
 #pragma unroll
   for (int k = 0; k < H; ++k) w[k] = wr[k];
   const float bias = p.b_ih[d][row] + p.b_hh[d][row];
-  __shared__ float x[H];
-  const int vend = min(p.V, (int)(blockIdx.x + 1) * v_per_block);
-  for (int v = blockIdx.x * v_per_block; v < vend; ++v) {
-    __syncthreads();
-    if (gi < H) {
-      const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
-      x[gi] = sc * p.emb[(size_t)v * H + gi];  // the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
-    }
-    __syncthreads();
+  __shared__ float x[kTableVpb][H];
+  const int v0 = blockIdx.x * v_per_block, nv = min(p.V - v0, v_per_block);
+  // stage all rows of this block at once: the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
+  for (int i = gi; i < nv * H; i += 4 * H) {
+    const int v = v0 + i / H, k = i % H;
+    const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
+    x[i / H][k] = sc * p.emb[(size_t)v * H + k];
+  }
+  __syncthreads();
+  for (int j = 0; j < nv; ++j) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < H; ++k) s = fmaf(x[k], w[k], s);
-    p.table[(((size_t)(g * 2 + d)) * p.V + v) * 4 * H + gi] = s + bias;
+    for (int k = 0; k < H; ++k) s = fmaf(x[j][k], w[k], s);
+    p.table[(((size_t)(g * 2 + d)) * p.V + v0 + j) * 4 * H + gi] = s + bias;
   }
 }
 
@@ -193,7 +196,7 @@ cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
-  const int vpb = 8;
+  const int vpb = kTableVpb;
   dim3 grid((a.V + vpb - 1) / vpb, a.G * 2);
   if (a.H == 64) l0_table_kernel<64><<<grid, 256, 0, st>>>(a, vpb);
   else if (a.H == 32) l0_table_kernel<32><<<grid, 128, 0, st>>>(a, vpb);
