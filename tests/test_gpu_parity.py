@@ -322,3 +322,17 @@ def test_variational_dropout_row_mask_also_in_eval():
     assert m.shape == (3, 4 * E, E) and bool((m == m[:, :, :1]).all())  # one value per row, per group
     with torch.no_grad():
         assert not torch.equal(vnet.encoder(x.cuda()), vnet.encoder(x.cuda()))  # a fresh row mask per call, even in eval
+
+
+def test_long_sequences_t4000():
+    """trunc_len 4000 (the stress configuration's length) on the register-resident kernels: token staging, ring prefetch and the
+    error growth over 4000 recurrent steps stay inside the fp32 gate."""
+    V, E, L, B, T = 250, 64, 2, 6, 4000
+    P = R.init_params(vocab=V, E=E, L=L, seed=2)
+    batch = list(R.synthetic_batch(B, T, V, seed=3, padded=True))
+    masks = R.draw_step_masks(B, V, E, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=4)
+    kw = dict(L=L, bi="mean", beta=2.0, use_projection=False, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+    ref = run_oracle_step(P, batch, masks, **kw)
+    assert int(ref["lengths"][1].max()) > 2500
+    _check(got, ref, 1e-4)
