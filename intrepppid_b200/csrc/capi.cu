@@ -91,6 +91,7 @@ struct Plan {
   size_t bwd_scratch;  // dY [R,2H] then dX0 [R,H]
   size_t partial;
   size_t bias_partial;  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel
+  size_t l0_scratch;  // R of gemm_l0.cu
   size_t ph_state, ph_sched;  // two-phase rebalancing (common.cuh): [2][N][H][2] floats; sm_load[256] + resume_list[1 + CTAs] ints
   int ctas_per_group;
   size_t total;
@@ -147,7 +148,9 @@ Plan make_plan(const ib200_cfg* c) {
         }
     p.bwd_scratch = p.L > 1 ? p.X[0] : take(sizeof(float) * p.R * 3 * H);  // X is dead once the forward is done
     p.ctas_per_group = std::max(1, 148 / p.G);
-    p.partial = take(sizeof(float) * (size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H));  // up to [dW_ih | dW_hh] fused
+    p.partial = take(sizeof(float) * std::max((size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H),  // up to [dW_ih | dW_hh] fused
+                                              l0_grad_partial_floats(p.G, 2)));
+    p.l0_scratch = take(sizeof(float) * l0_grad_scratch_floats(p.G, 2));
     p.bias_partial = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
   }
   p.total = off;
@@ -445,6 +448,29 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
           "lstm bwd");
     const int bwd_ctas = planes ? lstm_bwd_cta_count(ba, prec) : 0;  // CTAs per direction (= number of bias partials)
 
+    // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates
+    // (gemm_l0.cu: the token-indexed sums S = dA^T onehot(tok) replace the gathered dW GEMM, the dX_0 GEMM and the atomic scatter)
+    bool l0_done = false;
+    if (l == 0 && planes && !getenv("IB200_NO_L0_FUSED")) {
+      L0GradArgs la{};
+      la.G = p.G; la.B = p.B; la.Tmax = p.T; la.V = p.V; la.H = H; la.dir0 = dir0; la.ndir = ndir;
+      la.lens = lens; la.tok = at<int>(ws, p.tok32);
+      for (int d = 0; d < 2; ++d) {
+        la.dA[d] = p.live[0][d] ? at<float>(ws, p.gates[0][d]) : nullptr;
+        la.w_ih[d] = P->w_ih[0][d];
+        la.d_wih[d] = Gr->w_ih[0][d]; la.d_whh[d] = Gr->w_hh[0][d]; la.d_bih[d] = Gr->b_ih[0][d]; la.d_bhh[d] = Gr->b_hh[0][d];
+      }
+      la.Y0 = at<float>(ws, p.Y[0]);
+      la.emb = P->emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_l0_mask;
+      la.bias_partial = at<float>(ws, p.bias_partial); la.bias_count = bwd_ctas;
+      la.partial = partial; la.R = at<float>(ws, p.l0_scratch); la.d_emb = Gr->emb;
+      TimedScope ts(F_GEMM_DW, 4, st);
+      const cudaError_t e = launch_l0_grads(la, prec, st);
+      if (e == cudaSuccess) l0_done = true;
+      else if (e != cudaErrorInvalidConfiguration) return cuda_fail(e, "layer-0 gradient gemm");
+      else (void)cudaGetLastError();
+    }
+
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
     for (int d = 0; d < 2; ++d) {
       const int K = l == 0 ? H : 2 * H;
@@ -461,6 +487,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         }
         continue;
       }
+      if (l0_done) continue;
       GemmTNArgs ta{};
       ta.G = p.G; ta.B = p.B; ta.Tmax = p.T; ta.lens = lens;
       ta.A = at<float>(ws, p.gates[l][d]); ta.KA = 4 * H;
@@ -503,6 +530,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     }
 
     // input gradient of this layer
+    if (l0_done) continue;
     GemmNTArgs ga{};
     ga.G = p.G; ga.B = p.B; ga.Tmax = p.T; ga.lens = lens;
     ga.nsrc = 0;

@@ -160,6 +160,34 @@ struct EmbGradArgs {
 };
 cudaError_t launch_emb_grad(const EmbGradArgs& a, cudaStream_t st);
 
+// ---- layer-0 parameter gradients of the H = 64 planes path in one pass over the layer-0 dgates (gemm_l0.cu) --------------------------
+struct L0GradArgs {
+  int G, B, Tmax, V, H;
+  int dir0, ndir;              // live directions of layer 0: dir0 .. dir0 + ndir - 1
+  const int* lens;
+  const int* tok;              // [N, Tmax]
+  const float* dA[2];          // per direction: dgates planes (rows of 4H floats holding [hi 4H bf16 | lo 4H bf16])
+  const float* Y0;             // layer-0 output planes (rows of 2H floats holding [hi 2H bf16 | lo 2H bf16])
+  const float* emb;            // [V, H]
+  const float* emb_row_scale;  // [G, V] or null
+  const float* whh_mask;       // [G, 4H, H] or null (forward direction)
+  const float* w_ih[2];        // [4H, H]
+  const float* bias_partial;   // [ndir][bias_count][4H] column sums of the dgates left by the BPTT kernel
+  int bias_count;
+  float* partial;              // l0_grad_partial_floats() floats
+  float* R;                    // l0_grad_scratch_floats() floats
+  int ctas_per_group;          // (set by the launcher)
+  float* d_wih[2];
+  float* d_whh[2];
+  float* d_bih[2];
+  float* d_bhh[2];
+  float* d_emb;                // [V, H] (overwritten)
+};
+size_t l0_grad_scratch_floats(int G, int ndir);
+size_t l0_grad_partial_floats(int G, int ndir);
+// cudaErrorInvalidConfiguration when the shape is not covered (H != 64 or V > 256): the caller keeps the general path
+cudaError_t launch_l0_grads(const L0GradArgs& a, int precision, cudaStream_t st);
+
 cudaError_t launch_fill_zero(float* p, size_t n, cudaStream_t st);
 
 }  // namespace ib200
