@@ -363,10 +363,10 @@ cudaError_t launch_tn(const GemmTNArgs& a, int precision, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------------------------------
-// one warp per 4 consecutive output elements: lanes stride over the (group, cta) partials (independent coalesced float4 loads),
-// the per-group mask is applied before the cross-group sum, then a fixed-order shuffle tree => deterministic
-__global__ void dw_reduce_kernel(const DwReduceArgs p) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// one thread per 4 consecutive output elements: adjacent threads read adjacent float4 of every (group, cta) partial (coalesced),
+// sum them in a fixed order (deterministic); the per-group mask is applied before the cross-group sum
+__global__ void __launch_bounds__(128) dw_reduce_kernel(const DwReduceArgs p) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
   const bool any_cs = p.has_colsum || p.cs_ptr != nullptr;
   const int nmat4 = p.KA * p.NB / 4, ncs4 = any_cs ? p.KA / 4 : 0;
   if (w >= nmat4 + ncs4) return;
@@ -378,19 +378,17 @@ __global__ void dw_reduce_kernel(const DwReduceArgs p) {
   float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!is_mat && p.cs_ptr != nullptr) {
     // bias partials written by the BPTT kernel: [cs_count][KA]
-    for (int k = lane; k < p.cs_count; k += 32) {
+    for (int k = 0; k < p.cs_count; ++k) {
       const float4 v = *reinterpret_cast<const float4*>(p.cs_ptr + (size_t)k * p.KA + gi);
       tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
     }
-    tot.x = warp_sum(tot.x); tot.y = warp_sum(tot.y); tot.z = warp_sum(tot.z); tot.w = warp_sum(tot.w);
   } else {
     for (int g = 0; g < p.G; ++g) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = lane; k < p.ctas_per_group; k += 32) {
+      for (int k = 0; k < p.ctas_per_group; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(p.partial + ((size_t)g * p.ctas_per_group + k) * blk + idx);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
-      s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z); s.w = warp_sum(s.w);
       if (is_mat && p.mask != nullptr && c >= (p.out2 != nullptr ? p.NB1 : 0)) {
         const int mc = p.out2 != nullptr ? c - p.NB1 : p.c0 + c, mld = p.out2 != nullptr ? p.NB - p.NB1 : ldo;
         const float4 m = *reinterpret_cast<const float4*>(p.mask + ((size_t)g * 4 * p.H + gi_to_torch_row(p.gi0 + gi, p.H)) * mld + mc);
@@ -399,7 +397,6 @@ __global__ void dw_reduce_kernel(const DwReduceArgs p) {
       tot.x += s.x; tot.y += s.y; tot.z += s.z; tot.w += s.w;
     }
   }
-  if (lane != 0) return;
   if (is_mat) {
     const int row = gi_to_torch_row(p.gi0 + gi, p.H);
     if (p.out2 == nullptr) *reinterpret_cast<float4*>(p.out + (size_t)row * ldo + p.c0 + c) = tot;
@@ -503,8 +500,8 @@ cudaError_t launch_gemm_tn(const GemmTNArgs& a, int precision, cudaStream_t st) 
 }
 
 cudaError_t launch_dw_reduce(const DwReduceArgs& a, cudaStream_t st) {
-  const int warps = (a.KA * a.NB + ((a.has_colsum || a.cs_ptr != nullptr) ? a.KA : 0)) / 4;
-  dw_reduce_kernel<<<(warps + 7) / 8, 256, 0, st>>>(a);
+  const int quads = (a.KA * a.NB + ((a.has_colsum || a.cs_ptr != nullptr) ? a.KA : 0)) / 4;
+  dw_reduce_kernel<<<(quads + 127) / 128, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 

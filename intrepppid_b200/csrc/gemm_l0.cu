@@ -198,40 +198,51 @@ __global__ void __launch_bounds__(kNOut) l0_reduce_kernel(const float* __restric
   R[blk * kNOut + c] = s;
 }
 
-// dW_hh (per-group DropConnect mask on the forward direction), dW_ih, both bias gradients; one block per (direction slot, gate row k)
-__global__ void __launch_bounds__(64) l0_finish_w_kernel(const L0GradArgs p, const float* __restrict__ R) {
+// dW_hh (per-group DropConnect mask on the forward direction), dW_ih, both bias gradients; one block per (direction slot, gate row k).
+// 256 threads = 64 output columns x 4 slices of the vocabulary; the slices are added in a fixed order.
+__global__ void __launch_bounds__(256) l0_finish_w_kernel(const L0GradArgs p, const float* __restrict__ R) {
   constexpr int H = 64;
-  const int ds = blockIdx.y, d = p.dir0 + ds, k = blockIdx.x, h = threadIdx.x;
+  __shared__ float sr[kNS];        // S_gd[k][v] * scale_g[v]
+  __shared__ float part[4][H];
+  const int ds = blockIdx.y, d = p.dir0 + ds, k = blockIdx.x, h = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int row = gi_to_torch_row(k, H);
   float whh = 0.f, wih = 0.f;
   for (int g = 0; g < p.G; ++g) {
     const float* __restrict__ Rk = R + (((size_t)ds * p.G + g) * 256 + k) * kNOut;
-    float m = 1.0f;
-    if (d == 0 && p.whh_mask != nullptr) m = p.whh_mask[((size_t)g * 4 * H + row) * H + h];
-    whh = fmaf(m, Rk[h], whh);
-    float acc = 0.f;
-    for (int v = 0; v < p.V; ++v) {
-      const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
-      acc = fmaf(Rk[64 + v] * sc, p.emb[(size_t)v * H + h], acc);
+    __syncthreads();
+    for (int v = threadIdx.x; v < p.V; v += 256)
+      sr[v] = Rk[64 + v] * (p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f);
+    __syncthreads();
+    if (q == 0) {
+      float m = 1.0f;
+      if (d == 0 && p.whh_mask != nullptr) m = p.whh_mask[((size_t)g * 4 * H + row) * H + h];
+      whh = fmaf(m, Rk[h], whh);
     }
+    float acc = 0.f;
+    for (int v = q; v < p.V; v += 4) acc = fmaf(sr[v], p.emb[(size_t)v * H + h], acc);
     wih += acc;
   }
-  p.d_whh[d][(size_t)row * H + h] = whh;
-  p.d_wih[d][(size_t)row * H + h] = wih;
-  if (h == 0) {  // bias gradient = column sum of the dgates: per-CTA partials left by the BPTT kernel
-    float b = 0.f;
+  part[q][h] = wih;
+  __syncthreads();
+  if (q == 0) {
+    p.d_whh[d][(size_t)row * H + h] = whh;
+    p.d_wih[d][(size_t)row * H + h] = (part[0][h] + part[1][h]) + (part[2][h] + part[3][h]);
+  }
+  if (threadIdx.x == 64) {  // bias gradient = column sum of the dgates: per-CTA partials left by the BPTT kernel
+    float bsum = 0.f;
     const float* cs = p.bias_partial + (size_t)ds * p.bias_count * 4 * H;
-    for (int i = 0; i < p.bias_count; ++i) b += cs[(size_t)i * 4 * H + k];
-    p.d_bih[d][row] = b;
-    p.d_bhh[d][row] = b;
+    for (int i = 0; i < p.bias_count; ++i) bsum += cs[(size_t)i * 4 * H + k];
+    p.d_bih[d][row] = bsum;
+    p.d_bhh[d][row] = bsum;
   }
 }
 
-// dEmb[v] = sum_g scale_g[v] * sum_d sum_k S_gd[k][v] W_ih,d[row(k)]; one block per vocabulary row
-__global__ void __launch_bounds__(64) l0_finish_emb_kernel(const L0GradArgs p, const float* __restrict__ R) {
+// dEmb[v] = sum_g scale_g[v] * sum_d sum_k S_gd[k][v] W_ih,d[row(k)]; one block per vocabulary row, 64 columns x 4 slices of k
+__global__ void __launch_bounds__(256) l0_finish_emb_kernel(const L0GradArgs p, const float* __restrict__ R) {
   constexpr int H = 64;
   __shared__ float col[256];
-  const int v = blockIdx.x, h = threadIdx.x;
+  __shared__ float part[4][H];
+  const int v = blockIdx.x, h = threadIdx.x & 63, q = threadIdx.x >> 6;
   float tot = 0.f;
   if (v != 0) {  // padding_idx = 0 receives no gradient (nn.Embedding(..., padding_idx=0), e2e_triplet.py:345)
     for (int g = 0; g < p.G; ++g) {
@@ -239,17 +250,18 @@ __global__ void __launch_bounds__(64) l0_finish_emb_kernel(const L0GradArgs p, c
       if (sc == 0.0f) continue;  // (uniform over the block)
       float acc = 0.f;
       for (int ds = 0; ds < p.ndir; ++ds) {
-        const float* __restrict__ Rg = R + (((size_t)ds * p.G + g) * 256) * kNOut + 64 + v;
         __syncthreads();
-        for (int k = h; k < 256; k += 64) col[k] = Rg[(size_t)k * kNOut];
+        col[threadIdx.x] = R[(((size_t)ds * p.G + g) * 256 + threadIdx.x) * kNOut + 64 + v];
         __syncthreads();
         const float* __restrict__ W = p.w_ih[p.dir0 + ds];
-        for (int k = 0; k < 256; ++k) acc = fmaf(col[k], W[(size_t)gi_to_torch_row(k, H) * H + h], acc);
+        for (int k = 64 * q; k < 64 * q + 64; ++k) acc = fmaf(col[k], W[(size_t)gi_to_torch_row(k, H) * H + h], acc);
       }
       tot = fmaf(sc, acc, tot);
     }
   }
-  p.d_emb[(size_t)v * H + h] = tot;
+  part[q][h] = tot;
+  __syncthreads();
+  if (q == 0) p.d_emb[(size_t)v * H + h] = (part[0][h] + part[1][h]) + (part[2][h] + part[3][h]);
 }
 
 }  // namespace
@@ -292,8 +304,8 @@ cudaError_t launch_l0_grads(const L0GradArgs& a0, int precision, cudaStream_t st
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   l0_reduce_kernel<<<(unsigned)(a.ndir * a.G * 256), kNOut, 0, st>>>(a.partial, a.R, a.ctas_per_group);
-  l0_finish_w_kernel<<<dim3(256, a.ndir), 64, 0, st>>>(a, a.R);
-  l0_finish_emb_kernel<<<a.V, 64, 0, st>>>(a, a.R);
+  l0_finish_w_kernel<<<dim3(256, a.ndir), 256, 0, st>>>(a, a.R);
+  l0_finish_emb_kernel<<<a.V, 256, 0, st>>>(a, a.R);
   return cudaGetLastError();
 }
 
