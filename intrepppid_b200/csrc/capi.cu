@@ -83,7 +83,7 @@ struct Plan {
   size_t R;  // token rows = N*T
   bool train;
   bool live[IB200_MAX_LAYERS][2];
-  size_t lens, tok32, table;
+  size_t lens, tok32, table, row_kind;
   size_t wih_gi[IB200_MAX_LAYERS][2], b_gi[IB200_MAX_LAYERS][2], wihT_gi[IB200_MAX_LAYERS][2];
   size_t Y[IB200_MAX_LAYERS];
   size_t X[2];
@@ -123,6 +123,7 @@ Plan make_plan(const ib200_cfg* c) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   p.lens = take(sizeof(int) * 2 * p.G);
   p.tok32 = take(sizeof(int) * p.R);
+  p.row_kind = take(sizeof(int) * (size_t)p.G * p.V);
   p.table = take(sizeof(float) * (size_t)p.G * 2 * p.V * 4 * H);
   for (int l = 0; l < p.L; ++l)
     for (int d = 0; d < 2; ++d) {
@@ -265,6 +266,9 @@ int nt_launches(int NC, bool wide) {
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
 
+// gemm_l0.cu covers layer 0 of the TMA path when the vocabulary fits its one-hot tile (the decision must be the same in _fwd and _bwd)
+bool l0_fused_ok(const Plan& p, bool planes) { return planes && p.H == 64 && p.V <= 256 && !getenv("IB200_NO_L0_FUSED"); }
+
 // split point of the two-phase rebalancing = (step time of a CTA alone on its SM) / (step time of two co-resident CTAs): the shared
 // SMs and the exclusive SMs then finish phase 1 together.  Measured on B200; IB200_SPLIT_FWD / IB200_SPLIT_BWD override.
 float split_frac(bool bwd) {
@@ -341,8 +345,9 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
   const int H = p.H, prec = cfg->precision;
   const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
 
-  LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens)};
-  TIMED(F_LENGTHS, 3, launch_lengths(la, st), "lengths");
+  LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens),
+                at<int>(ws, p.row_kind)};
+  TIMED(F_LENGTHS, 4, launch_lengths(la, st), "lengths");
   if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
 
   TableArgs ta{p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
@@ -356,6 +361,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
       float* w = l > 0 ? at<float>(ws, p.wih_gi[l][d]) : nullptr;
       float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
       float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
+      if (l == 0 && l0_fused_ok(p, planes)) wT = nullptr;  // W_ih^T of layer 0 only feeds the dX_0 GEMM, which the fused path replaces
       if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
     }
 
@@ -451,7 +457,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates
     // (gemm_l0.cu: the token-indexed sums S = dA^T onehot(tok) replace the gathered dW GEMM, the dX_0 GEMM and the atomic scatter)
     bool l0_done = false;
-    if (l == 0 && planes && !getenv("IB200_NO_L0_FUSED")) {
+    if (l == 0 && l0_fused_ok(p, planes)) {
       L0GradArgs la{};
       la.G = p.G; la.B = p.B; la.Tmax = p.T; la.V = p.V; la.H = H; la.dir0 = dir0; la.ndir = ndir;
       la.lens = lens; la.tok = at<int>(ws, p.tok32);

@@ -12,6 +12,7 @@ struct LengthArgs {
   const float* emb_row_scale;  // [G,V] or null
   int* tok32;                  // [G*B, Tin]
   int* lens;                   // [2,G]: T1 then T_eff (zeroed by the launcher)
+  int* row_kind;               // scratch [G,V]
 };
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st);
 

@@ -31,31 +31,54 @@ __global__ void len1_kernel(const LengthArgs p) {
 }
 
 // ---- A3: T_eff[g] = max_{b,e} #{t < T1 : (scale[g][tok] * emb[tok][e]) != 0} (encoders/awd_lstm.py:53-54, quirk Q2) -----------
-// count[b][e] = sum_v hist_b[v] * [scale[g][v] != 0 && emb[v][e] != 0]   (scale >= 1 when non-zero, so no underflow to 0)
-__global__ void len2_kernel(const LengthArgs p) {
-  extern __shared__ int hist[];  // [V]
+// count[b][e] = sum_v hist_b[v] * [scale[g][v] != 0 && emb[v][e] != 0]   (scale >= 1 when non-zero, so no underflow to 0).
+// A vocabulary row is "full" when it is kept and has no zero entry: it adds hist_b[v] to EVERY column.  Rows that are kept but
+// contain zeros (normally only the zero-initialised padding row) are listed per group and handled column by column.
+__global__ void nz_rows_kernel(const LengthArgs p, int* __restrict__ row_kind) {  // row_kind[g][v]: 0 contributes nothing, 1 full, 2 partial
+  const int g = blockIdx.y, v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= p.V) return;
+  int nz = 0;
+  for (int e = lane; e < p.H; e += 32) nz += p.emb[(size_t)v * p.H + e] != 0.0f;
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  const bool keep = p.emb_row_scale == nullptr || p.emb_row_scale[(size_t)g * p.V + v] != 0.0f;
+  if (lane == 0) row_kind[(size_t)g * p.V + v] = (!keep || nz == 0) ? 0 : (nz == p.H ? 1 : 2);
+}
+
+__global__ void len2_kernel(const LengthArgs p, const int* __restrict__ row_kind) {
+  extern __shared__ int hist[];  // [V] histogram, then [V] list of partial rows
+  int* partial = hist + p.V;
+  __shared__ int n_partial, full_sum;
   const int n = blockIdx.x, g = n / p.B;
   const int T1 = p.lens[g];
   for (int v = threadIdx.x; v < p.V; v += blockDim.x) hist[v] = 0;
+  if (threadIdx.x == 0) n_partial = full_sum = 0;
   __syncthreads();
   const int* __restrict__ tk = p.tok32 + (size_t)n * p.Tin;
-  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
-    const int v = tk[t];
-    if (v >= 0 && v < p.V) atomicAdd(&hist[v], 1);
-  }
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) atomicAdd(&hist[tk[t]], 1);  // ids were clamped to [0, V) by len1_kernel
   __syncthreads();
-  // fold the row mask into the histogram once (a dropped row contributes to no column), then a branch-free scan per column
-  for (int v = threadIdx.x; v < p.V; v += blockDim.x)
-    if (p.emb_row_scale != nullptr && p.emb_row_scale[(size_t)g * p.V + v] == 0.0f) hist[v] = 0;
+  int mine = 0;
+  for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
+    const int kind = row_kind[(size_t)g * p.V + v], hv = hist[v];
+    if (kind == 1) mine += hv;
+    else if (kind == 2 && hv != 0) partial[atomicAdd(&n_partial, 1)] = v;
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine != 0) atomicAdd(&full_sum, mine);
   __syncthreads();
   int best = 0;
-  for (int e = threadIdx.x; e < p.H; e += blockDim.x) {
-    int cnt = 0;
-#pragma unroll 8
-    for (int v = 0; v < p.V; ++v) cnt += (p.emb[(size_t)v * p.H + e] != 0.0f) ? hist[v] : 0;
-    best = max(best, cnt);
+  if (n_partial == 0) {
+    best = full_sum;
+  } else {
+    for (int e = threadIdx.x; e < p.H; e += blockDim.x) {
+      int cnt = full_sum;
+      for (int i = 0; i < n_partial; ++i) {
+        const int v = partial[i];
+        cnt += (p.emb[(size_t)v * p.H + e] != 0.0f) ? hist[v] : 0;
+      }
+      best = max(best, cnt);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
   }
-  best = __reduce_max_sync(0xffffffffu, best);
   if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(p.lens + p.G + g, best);
 }
 
@@ -191,7 +214,8 @@ __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
   zero_int_kernel<<<1, 64, 0, st>>>(a.lens, 2 * a.G);
   len1_kernel<<<a.G * a.B, 256, 0, st>>>(a);
-  len2_kernel<<<a.G * a.B, 128, a.V * sizeof(int), st>>>(a);
+  nz_rows_kernel<<<dim3((a.V + 7) / 8, a.G), 256, 0, st>>>(a, a.row_kind);
+  len2_kernel<<<a.G * a.B, 128, 2 * a.V * sizeof(int), st>>>(a, a.row_kind);
   return cudaGetLastError();
 }
 

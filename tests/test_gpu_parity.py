@@ -336,3 +336,17 @@ def test_long_sequences_t4000():
     ref = run_oracle_step(P, batch, masks, **kw)
     assert int(ref["lengths"][1].max()) > 2500
     _check(got, ref, 1e-4)
+
+
+def test_vocabulary_larger_than_the_one_hot_tile():
+    """vocab_size > 256 does not fit the one-hot tile of the fused layer-0 gradient kernel: the general path (gathered dW GEMM,
+    dX_0 GEMM, scatter) must take over transparently."""
+    V, E, L, B, T = 300, 64, 2, 7, 90
+    P = R.init_params(vocab=V, E=E, L=L, seed=17)
+    batch = list(R.synthetic_batch(B, T, V, seed=18, padded=True))
+    masks = R.draw_step_masks(B, V, E, emb_droprate=0.3, rnn_droprate=0.3, do_rate=0.3, seed=19)
+    kw = dict(L=L, bi="last", beta=2.0, use_projection=False, p_emb=0.3)
+    got = run_product_step(P, batch, masks, p_rnn=0.3, p_do=0.3, **kw)
+    ref = run_oracle_step(P, batch, masks, **kw)
+    assert int(torch.stack(batch[:5]).max()) > 256
+    _check(got, ref, 1e-4)
