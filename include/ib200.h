@@ -14,6 +14,7 @@
  *   ib200_pool_fc_fwd / _bwd    encoders/awd_lstm.py:58-71   (bi_reduce on h_n[-2:], fc Linear)
  *   ib200_loss_head_fwd / _bwd  e2e/e2e_triplet.py:113-136   (TripletE2ENet.step: triplet projection, TripletMarginLoss,
  *                               classifier/head/mlp.py:35-68  MLPHead, BCEWithLogitsLoss, beta mix)
+ *   ib200_adamw_step            e2e/e2e_triplet.py:231-255   (configure_optimizers: torch.optim.AdamW over self.parameters())
  *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
  *
  * Conventions
@@ -43,6 +44,11 @@ enum { IB200_REDUCE_LAST = 0, IB200_REDUCE_MEAN = 1, IB200_REDUCE_MAX = 2 };
 /* IB200_PREC_FP32: bf16 hi/lo split operands (3 tensor-core MMAs per product, ~2^-16 operand error), fp32 state, exact-ish
  * exp/rcp activations, fp32 activation storage.  IB200_PREC_BF16: single bf16 MMA, tanh.approx, bf16 activation storage. */
 enum { IB200_PREC_FP32 = 0, IB200_PREC_BF16 = 1 };
+/* Token id storage.  The reference ships int64 ids (data/ppi_oma.py:388-390, 8 B/token over PCIe); ids < V <= 256 fit a byte.
+ * Narrow types are read as they are by the lengths kernel (which also makes the int32 working copy), so a caller that feeds
+ * uint8 / int16 / int32 ids cuts the per-step H2D traffic 8x / 4x / 2x (SURVEY 8f "input feeding").  Values outside [0, V) are
+ * clamped exactly as for int64 (negative int16/int32 -> 0). */
+enum { IB200_TOK_I64 = 0, IB200_TOK_I32 = 1, IB200_TOK_I16 = 2, IB200_TOK_U8 = 3 };
 enum {
   IB200_E_NULL = -1, IB200_E_SHAPE = -2, IB200_E_UNSUPPORTED = -3, IB200_E_WORKSPACE = -4, IB200_E_ALIGN = -5
 };
@@ -57,7 +63,7 @@ typedef struct ib200_cfg {
   int32_t bi_reduce;  /* IB200_REDUCE_* ("concat" is not functional in the reference either) */
   int32_t precision;  /* IB200_PREC_* */
   int32_t training;   /* 1: keep activations for ib200_encoder_bwd in the workspace */
-  int32_t reserved;
+  int32_t token_dtype; /* IB200_TOK_*: element type of `tokens` (0 = int64, the reference's dataloader format) */
 } ib200_cfg;
 
 /* Parameters of the encoder, PyTorch layout (state_dict names in comments; d=0 forward, d=1 "_reverse"). */
@@ -97,7 +103,7 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg);
 
 /*
  * Encoder forward for G groups.
- *   tokens          int64 [G*B, T] row-major, pad id 0, ids in [0,V)                         (data/ppi_oma.py:388-390)
+ *   tokens          [G*B, T] row-major of cfg.token_dtype (int64 by default), pad id 0, ids in [0,V)  (data/ppi_oma.py:388-390)
  *   emb_row_scale   float [G,V] or NULL
  *   whh_l0_mask     float [G,4H,H] or NULL
  *   lengths_out     int32 [2,G]: row 0 = T1 (awd_lstm.py:149-150), row 1 = T_eff (awd_lstm.py:53-54); exact integers.
@@ -105,7 +111,7 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg);
  *   hn_top          float [2, G*B, H]: final hidden state of the top layer, [0]=forward dir, [1]=reverse dir.  Under
  *                   bi_reduce=last only [1] is produced ([0] is zero-filled: the dead chain is skipped, Q16).
  */
-int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* params,
+int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_encoder_params* params,
                       const float* emb_row_scale, const float* whh_l0_mask, int32_t* lengths_out, float* hn_top,
                       void* workspace, size_t workspace_bytes, void* stream);
 
@@ -165,6 +171,24 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
  * proteins, all-gather the [M,H] embeddings, split the pair matrix by rows). */
 int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin, int64_t p_count,
                            const ib200_head_params* params, float* prob_out, void* stream);
+
+/*
+ * Multi-tensor AdamW: the optimizer step right after the hot path (e2e/e2e_triplet.py:231-255 -- torch.optim.AdamW(self.parameters(), lr)
+ * with torch defaults betas (0.9, 0.999), eps 1e-8, weight_decay 1e-2).  One launch per 32 tensors instead of
+ * torch's per-tensor / foreach kernels; arithmetic follows torch's `_single_tensor_adamw` (decoupled decay, no amsgrad) in fp32.
+ *   params / grads / exp_avg / exp_avg_sq   HOST arrays of n_tensors DEVICE pointers (fp32, numel[k] elements each); a tensor whose
+ *                                           grads[k] is NULL is skipped (p.grad is None)
+ *   hyper.step                              1-based step count of this update (host integer: no device sync)
+ *   hyper.grad_scale                        multiplied into every gradient first (1/world_size folds the data-parallel mean into
+ *                                           the step when the all-reduce was a SUM; 1.0 otherwise)
+ */
+typedef struct ib200_adamw_hyper {
+  double lr, beta1, beta2, eps, weight_decay, grad_scale; /* doubles: torch derives 1-beta, lr*wd and the bias corrections from Python floats */
+  int32_t step;
+  int32_t maximize;
+} ib200_adamw_hyper;
+int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* numel, const ib200_adamw_hyper* hyper, void* stream);
 
 /* Test hook (tests/test_gpu_gemm.py): the token-row NT GEMM in isolation.  impl: 0 legacy mma.sync, 1 tcgen05, 2 auto.
  * C[row,NC] (=|+=) sum_s A_s[row,K] W_s[NC,K]^T (+bias) for rows (n,t) with t < lens[G + n/B] of the [G*B, T] row space. */

@@ -11,13 +11,14 @@ LIB_PATH = os.path.join(PKG, "libib200.so")
 MAX_LAYERS = 4
 REDUCE = {"last": 0, "mean": 1, "max": 2}
 PRECISION = {"fp32": 0, "bf16": 1}
+TOKEN_DTYPE = {"int64": 0, "int32": 1, "int16": 2, "uint8": 3}  # IB200_TOK_*
 
 F = C.POINTER(C.c_float)
 vp = C.c_void_p
 
 
 class Cfg(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("G", "B", "T", "V", "H", "L", "bi_reduce", "precision", "training", "reserved")]
+    _fields_ = [(n, C.c_int32) for n in ("G", "B", "T", "V", "H", "L", "bi_reduce", "precision", "training", "token_dtype")]
 
 
 class EncoderParams(C.Structure):
@@ -29,13 +30,18 @@ class HeadParams(C.Structure):
     _fields_ = [(n, vp) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b", "proj_w", "proj_b")]
 
 
+class AdamWHyper(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("lr", "beta1", "beta2", "eps", "weight_decay", "grad_scale")] + [("step", C.c_int32),
+                                                                                                            ("maximize", C.c_int32)]
+
+
 class HeadMasks(C.Structure):
     _fields_ = [(n, vp) for n in ("fc1_w", "do1", "do2", "fc2_w")]
 
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_bwd",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn")
 
 _lib = None
@@ -68,6 +74,8 @@ def lib() -> C.CDLL:
                                       vp, vp, C.POINTER(HeadParams), vp]
     L.ib200_pair_score.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.POINTER(HeadParams), vp, vp]
     L.ib200_pair_score_range.argtypes = [C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64, C.POINTER(HeadParams), vp, vp]
+    L.ib200_adamw_step.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64),
+                                   C.POINTER(AdamWHyper), vp]
     L.ib200_dbg_gemm_nt.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.ib200_dbg_gemm_tn.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp,

@@ -1,5 +1,6 @@
 // C ABI of libib200.so (see include/ib200.h): argument validation, workspace carve-up and the launch sequences.
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -35,10 +36,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -99,12 +100,13 @@ struct Plan {
 
 bool cfg_ok(const ib200_cfg* c) {
   if (!(c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64 || lstm_cluster_supports(c->H)) && c->L >= 1 &&
-        c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1)))
+        c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1) &&
+        c->token_dtype >= IB200_TOK_I64 && c->token_dtype <= IB200_TOK_U8))
     return false;
   // token rows are indexed with 32-bit integers inside the kernels; ids are staged as uint16 by the H <= 64 layer-0 kernel, whose
   // per-CTA token stage ((T + 4) x 16 bytes of shared memory) bounds trunc_len
   if ((long long)c->G * c->B * c->T >= (1LL << 31)) return false;
-  if ((c->H == 32 || c->H == 64) && (c->V > 65536 || c->T > 11000)) return false;
+  if ((c->H == 32 || c->H == 64) && (c->V + kPadRows > 65536 || c->T > 11000)) return false;
   return true;
 }
 
@@ -124,7 +126,7 @@ Plan make_plan(const ib200_cfg* c) {
   p.lens = take(sizeof(int) * 2 * p.G);
   p.tok32 = take(sizeof(int) * p.R);
   p.row_kind = take(sizeof(int) * (size_t)p.G * p.V);
-  p.table = take(sizeof(float) * (size_t)p.G * 2 * p.V * 4 * H);
+  p.table = take(sizeof(float) * (size_t)p.G * 2 * (p.V + kPadRows) * 4 * H);
   for (int l = 0; l < p.L; ++l)
     for (int d = 0; d < 2; ++d) {
       const size_t K = l == 0 ? H : 2 * H;
@@ -331,9 +333,9 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
   return make_plan(cfg).total;
 }
 
-int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
+int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
                       const float* whh_l0_mask, int32_t* lengths_out, float* hn_top, void* ws, size_t ws_bytes, void* stream) {
-  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max, G*B*T < 2^31; for H <= 64 also V <= 65536 and T <= 11000)");
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max, token_dtype in IB200_TOK_*, G*B*T < 2^31; for H <= 64 also V <= 65472 and T <= 11000)");
   if (!tokens || !P || !hn_top || !ws || !P->emb) return fail(IB200_E_NULL, "ib200_encoder_fwd: null pointer");
   const Plan p = make_plan(cfg);
   if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_fwd: workspace too small");
@@ -345,12 +347,14 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
   const int H = p.H, prec = cfg->precision;
   const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
 
-  LengthArgs la{p.G, p.B, p.T, p.V, H, (const long long*)tokens, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens),
+  LengthArgs la{p.G, p.B, p.T, p.V, H, tokens, cfg->token_dtype, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens),
                 at<int>(ws, p.row_kind)};
   TIMED(F_LENGTHS, 4, launch_lengths(la, st), "lengths");
   if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
 
-  TableArgs ta{p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
+  // without a row scale every group has the same table: build it once (inference launches fuse up to hundreds of groups)
+  const bool table_shared = emb_row_scale == nullptr;
+  TableArgs ta{table_shared ? 1 : p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
                {P->b_hh[0][0], P->b_hh[0][1]}, at<float>(ws, p.table)};
   TIMED(F_L0_TABLE, 1, launch_l0_table(ta, st), "l0 table");
 
@@ -386,6 +390,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const int64_t* tokens, const ib200_e
     if (l == 0) {
       fa.tok = at<int>(ws, p.tok32);
       fa.table = at<float>(ws, p.table);
+      fa.table_shared = table_shared ? 1 : 0;
     } else {
       fa.xproj[0] = at<float>(ws, p.X[0]);
       fa.xproj[1] = at<float>(ws, p.X[1]);
@@ -623,6 +628,38 @@ int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin
   if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score_range: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, nullptr, nullptr, (long long)p_count, (long long)p_begin, *hp, prob_out, st), "pair_score_range");
+  return 0;
+}
+
+int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* numel, const ib200_adamw_hyper* h, void* stream) {
+  if (n_tensors < 0) return fail(IB200_E_SHAPE, "ib200_adamw_step: negative tensor count");
+  if (n_tensors == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !h) return fail(IB200_E_NULL, "ib200_adamw_step: null pointer");
+  if (h->step < 1) return fail(IB200_E_SHAPE, "ib200_adamw_step: step counts from 1");
+  if (!(h->beta1 >= 0. && h->beta1 < 1. && h->beta2 >= 0. && h->beta2 < 1. && h->eps >= 0. && h->lr >= 0. && h->weight_decay >= 0.))
+    return fail(IB200_E_SHAPE, "ib200_adamw_step: hyper-parameters out of range (torch.optim.AdamW raises on these too)");
+  for (int k = 0; k < n_tensors; ++k)
+    if (numel[k] > 0 && grads[k] && (!params[k] || !exp_avg[k] || !exp_avg_sq[k])) return fail(IB200_E_NULL, "ib200_adamw_step: null tensor pointer");
+  // every scalar is derived in double on the host and rounded once, as torch does with Python floats (torch/optim/adamw.py)
+  const double bc1 = 1.0 - std::pow(h->beta1, (double)h->step), bc2 = 1.0 - std::pow(h->beta2, (double)h->step);
+  AdamScalars s;
+  s.grad_scale = (float)(h->maximize ? -h->grad_scale : h->grad_scale);
+  s.decay = (float)(1.0 - h->lr * h->weight_decay);
+  s.one_minus_b1 = (float)(1.0 - h->beta1);
+  s.b2 = (float)h->beta2;
+  s.one_minus_b2 = (float)(1.0 - h->beta2);
+  s.bc2_sqrt = (float)std::sqrt(bc2);
+  s.eps = (float)h->eps;
+  s.step_size = (float)(h->lr / bc1);
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  {
+    TimedScope ts__(F_ADAMW, 0, st);
+    const cudaError_t e = launch_adamw(n_tensors, params, grads, exp_avg, exp_avg_sq, (const long long*)numel, s, st, &launches);
+    g_launches.fetch_add((unsigned long long)launches);
+    if (e != cudaSuccess) return cuda_fail(e, "adamw");
+  }
   return 0;
 }
 

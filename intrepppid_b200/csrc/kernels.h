@@ -7,7 +7,8 @@ namespace ib200 {
 // ---- K0: truncation lengths + int32 token copy (A1/A3) ------------------------------------------------------------------
 struct LengthArgs {
   int G, B, Tin, V, H;
-  const long long* tokens;     // [G*B, Tin] int64
+  const void* tokens;          // [G*B, Tin] of token_dtype (IB200_TOK_*)
+  int token_dtype;
   const float* emb;            // [V,H]
   const float* emb_row_scale;  // [G,V] or null
   int* tok32;                  // [G*B, Tin]
@@ -17,6 +18,10 @@ struct LengthArgs {
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st);
 
 // ---- K1a: layer-0 input-projection table P[g][d][v][4H] (GI order) --------------------------------------------------------
+// Pad replicas: a padded batch makes every short sequence read vocabulary row 0 at the same step (all of them at once at the start
+// of the reverse scan), i.e. hundreds of requests per step for the same few L2 lines.  The table therefore carries kPadRows extra
+// copies of row 0 (rows V .. V+kPadRows-1) and every CTA of the recurrent kernel redirects its pad ids to "its" copy.
+constexpr int kPadRows = 64;
 struct TableArgs {
   int G, V, H;
   const float* emb;            // [V,H]
@@ -24,7 +29,7 @@ struct TableArgs {
   const float* w_ih[2];        // [4H,H]
   const float* b_ih[2];
   const float* b_hh[2];
-  float* table;                // [G,2,V,4H]
+  float* table;                // [G,2,V+kPadRows,4H]
 };
 cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st);
 
@@ -39,7 +44,8 @@ struct LstmFwdArgs {
   int dir0, ndir;            // directions run: dir0 .. dir0+ndir-1 (grid.z)
   const int* lens;           // [2,G]
   const int* tok;            // [N,Tmax] (layer 0) or null
-  const float* table;        // layer 0: [G,2,V,4H]
+  const float* table;        // layer 0: [G,2,V+kPadRows,4H] (rows >= V are copies of row 0)
+  int table_shared;          // 1: no per-group row scale (eval / p = 0) -- all groups read the table of group 0
   const float* xproj[2];     // layer >= 1: per direction [N,Tmax,4H] (GI)
   const float* whh[2];       // [4H,H] per direction
   const float* whh_mask;     // [G,4H,H] or null; direction 0 only
@@ -190,5 +196,14 @@ size_t l0_grad_partial_floats(int G, int ndir);
 cudaError_t launch_l0_grads(const L0GradArgs& a, int precision, cudaStream_t st);
 
 cudaError_t launch_fill_zero(float* p, size_t n, cudaStream_t st);
+
+// ---- multi-tensor AdamW (optim.cu) -------------------------------------------------------------------------------------------
+constexpr int kAdamMaxTensors = 32;  // tensors per launch (pointer table travels in the kernel parameters)
+struct AdamScalars {
+  float grad_scale, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, step_size;
+};
+// pointer arrays are HOST arrays of device pointers; *launches = kernels launched
+cudaError_t launch_adamw(int n, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                         const long long* numel, const AdamScalars& s, cudaStream_t st, int* launches);
 
 }  // namespace ib200

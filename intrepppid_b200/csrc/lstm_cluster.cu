@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     rb[c] = (nbase + min(q, nvalid - 1)) * Tmax;  // columns beyond the batch read a valid sequence and never store
   }
   const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
-  const float4* __restrict__ xsrc = layer0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
+  const int pad_row = p.V + (int)((tile + gridDim.x / C * (blockIdx.y + gridDim.y * blockIdx.z)) % kPadRows);
+  const float4* __restrict__ xsrc = layer0 ? reinterpret_cast<const float4*>(p.table) + (size_t)((p.table_shared ? 0 : g) * 2 + dir) * (p.V + kPadRows) * H + u
                                            : reinterpret_cast<const float4*>(dir ? p.xproj[1] : p.xproj[0]) + u;
   auto load_x = [&](int s, float4 (&x)[NCELL]) {
     const int t = t_first + s * dt;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     for (int c = 0; c < NCELL; ++c) {
       if (layer0) {
         const int tk = p.tok[(size_t)rb[c] + t];
-        x[c] = __ldg(xsrc + (size_t)tk * H);
+        x[c] = __ldg(xsrc + (size_t)(tk == 0 ? pad_row : tk) * H);  // pads read this cluster's copy of row 0 (kernels.h)
       } else {
         x[c] = __ldg(xsrc + (size_t)(rb[c] + t) * H);
       }

@@ -149,10 +149,12 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   }
   for (int i = tid; i < 2 * NPART * H * kBC / 2; i += NT) reinterpret_cast<uint32_t*>(&sm.hs[0][0][0][0])[i] = 0u;
   if constexpr (LAYER0) {
+    const int pad_slot = (int)((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) % kPadRows);
     for (int i = tid; i < (T + kD) * SEQ; i += NT) {
       const int n = i / (T + kD), s = i % (T + kD);  // consecutive threads read consecutive time steps (coalesced)
       int v = 0;
       if (s < T && n < nvalid) v = p.tok[(size_t)(nbase + n) * Tmax + (dir ? (T - 1 - s) : s)];
+      if (v == 0) v = p.V + pad_slot;  // this CTA's copy of row 0 (kernels.h: pad replicas)
       toks[s * kBC + ((HALF && !HL) ? 2 * n : n)] = (uint16_t)v;
     }
   }
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(H * 4, HALF ? 2 : 1) lstm_fwd_kernel(const Lst
   const int rb0 = (nbase + min(q0, nvalid - 1)) * Tmax, rb1 = (nbase + min(q1, nvalid - 1)) * Tmax;
   const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
   const float4* __restrict__ xsrc =
-      LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)(g * 2 + dir) * p.V * H + u
+      LAYER0 ? reinterpret_cast<const float4*>(p.table) + (size_t)((p.table_shared ? 0 : g) * 2 + dir) * (p.V + kPadRows) * H + u
              : reinterpret_cast<const float4*>((dir ? p.xproj[1] : p.xproj[0])) + u;
   // layer >= 1: running source pointers of the prefetch (kD steps ahead of the compute), advanced by one row per step
   const float4* xp0 = xsrc + (size_t)(rb0 + t_first + s_begin * dt) * H;
@@ -561,7 +563,7 @@ cudaError_t launch_k(const LstmFwdArgs& a, cudaStream_t st) {
 template <int H, bool SPLIT, bool FAST>
 cudaError_t launch_h(const LstmFwdArgs& a, cudaStream_t st) {
   const bool l0 = a.tok != nullptr, tr = a.gates[a.dir0] != nullptr;
-  if (l0 && a.V > 65536) return cudaErrorInvalidValue;  // token ids are staged as uint16
+  if (l0 && a.V + kPadRows > 65536) return cudaErrorInvalidValue;  // token ids are staged as uint16
   if (l0 && tr) return launch_k<H, SPLIT, FAST, true, true>(a, st);
   if (l0) return launch_k<H, SPLIT, FAST, true, false>(a, st);
   if (tr) return launch_k<H, SPLIT, FAST, false, true>(a, st);

@@ -6,13 +6,16 @@ namespace ib200 {
 namespace {
 
 // ---- A1: T1[g] = max_b #{t : tok != 0} (a COUNT, encoders/awd_lstm.py:149-150) + int32 copy of the ids ---------------------
+// TOK = the caller's id type: int64 as the reference's dataloader ships them (data/ppi_oma.py:388-390), or the narrowed
+// int32 / int16 / uint8 ids of the input-feeding path (V = 250 fits a byte -> 8x less H2D traffic).
+template <typename TOK>
 __global__ void len1_kernel(const LengthArgs p) {
   const int n = blockIdx.x, g = n / p.B;
-  const long long* __restrict__ src = p.tokens + (size_t)n * p.Tin;
+  const TOK* __restrict__ src = (const TOK*)p.tokens + (size_t)n * p.Tin;
   int* __restrict__ dst = p.tok32 + (size_t)n * p.Tin;
   int cnt = 0;
   for (int t = threadIdx.x; t < p.Tin; t += blockDim.x) {
-    const long long v64 = src[t];
+    const long long v64 = (long long)src[t];
     // ids outside [0, V) make F.embedding raise in the reference (the Python layer checks that when check_lengths is on); here
     // they are clamped so that no kernel can index outside the [V, .] tables
     const int v = v64 < 0 ? 0 : (v64 >= p.V ? p.V - 1 : (int)v64);
@@ -101,10 +104,11 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int 
   for (int k = 0; k < H; ++k) w[k] = wr[k];
   const float bias = p.b_ih[d][row] + p.b_hh[d][row];
   __shared__ float x[kTableVpb][H];
-  const int v0 = blockIdx.x * v_per_block, nv = min(p.V - v0, v_per_block);
+  const int VT = p.V + kPadRows;  // rows >= V replicate row 0 (pad replicas, kernels.h)
+  const int v0 = blockIdx.x * v_per_block, nv = min(VT - v0, v_per_block);
   // stage all rows of this block at once: the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
   for (int i = gi; i < nv * H; i += 4 * H) {
-    const int v = v0 + i / H, k = i % H;
+    const int vt = v0 + i / H, v = vt < p.V ? vt : 0, k = i % H;
     const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
     x[i / H][k] = sc * p.emb[(size_t)v * H + k];
   }
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int 
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < H; ++k) s = fmaf(x[j][k], w[k], s);
-    p.table[(((size_t)(g * 2 + d)) * p.V + v0 + j) * 4 * H + gi] = s + bias;
+    p.table[(((size_t)(g * 2 + d)) * VT + v0 + j) * 4 * H + gi] = s + bias;
   }
 }
 
@@ -121,8 +125,10 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int 
 __global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p, int v_per_block) {
   extern __shared__ float xs[];  // [H]
   const int H = p.H, g = blockIdx.y >> 1, d = blockIdx.y & 1;
-  const int vend = min(p.V, (int)(blockIdx.x + 1) * v_per_block);
-  for (int v = blockIdx.x * v_per_block; v < vend; ++v) {
+  const int VT = p.V + kPadRows;
+  const int vend = min(VT, (int)(blockIdx.x + 1) * v_per_block);
+  for (int vt = blockIdx.x * v_per_block; vt < vend; ++vt) {
+    const int v = vt < p.V ? vt : 0;
     __syncthreads();
     for (int e = threadIdx.x; e < H; e += blockDim.x) {
       const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p
       const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
       float s = 0.f;
       for (int k = 0; k < H; ++k) s = fmaf(xs[k], wr[k], s);
-      p.table[(((size_t)(g * 2 + d)) * p.V + v) * 4 * H + gi] = s + (p.b_ih[d][row] + p.b_hh[d][row]);
+      p.table[(((size_t)(g * 2 + d)) * VT + vt) * 4 * H + gi] = s + (p.b_ih[d][row] + p.b_hh[d][row]);
     }
   }
 }
@@ -212,8 +218,14 @@ __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz
 }  // namespace
 
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
-  zero_int_kernel<<<1, 64, 0, st>>>(a.lens, 2 * a.G);
-  len1_kernel<<<a.G * a.B, 256, 0, st>>>(a);
+  zero_int_kernel<<<(2 * a.G + 63) / 64, 64, 0, st>>>(a.lens, 2 * a.G);
+  switch (a.token_dtype) {
+    case IB200_TOK_I64: len1_kernel<long long><<<a.G * a.B, 256, 0, st>>>(a); break;
+    case IB200_TOK_I32: len1_kernel<int><<<a.G * a.B, 256, 0, st>>>(a); break;
+    case IB200_TOK_I16: len1_kernel<short><<<a.G * a.B, 256, 0, st>>>(a); break;
+    case IB200_TOK_U8: len1_kernel<unsigned char><<<a.G * a.B, 256, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
   nz_rows_kernel<<<dim3((a.V + 7) / 8, a.G), 256, 0, st>>>(a, a.row_kind);
   len2_kernel<<<a.G * a.B, 128, 2 * a.V * sizeof(int), st>>>(a, a.row_kind);
   return cudaGetLastError();
@@ -221,7 +233,7 @@ cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
 
 cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
   const int vpb = kTableVpb;
-  dim3 grid((a.V + vpb - 1) / vpb, a.G * 2);
+  dim3 grid((a.V + kPadRows + vpb - 1) / vpb, a.G * 2);
   if (a.H == 64) l0_table_kernel<64><<<grid, 256, 0, st>>>(a, vpb);
   else if (a.H == 32) l0_table_kernel<32><<<grid, 128, 0, st>>>(a, vpb);
   else l0_table_generic_kernel<<<grid, 256, a.H * sizeof(float), st>>>(a, vpb);

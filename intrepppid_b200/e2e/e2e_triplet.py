@@ -12,10 +12,10 @@ from typing import Optional
 
 import torch
 from torch import nn
-from torch.optim import AdamW
 from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts, OneCycleLR
 
 from .. import ops
+from ..optim import FusedAdamW as AdamW  # torch.optim.AdamW's arguments / state layout on the multi-tensor CUDA kernel
 
 try:  # optional orchestration dependencies (absent in the build image)
     import pytorch_lightning as pl
@@ -137,7 +137,7 @@ class TripletE2ENet(_Base):
     def test_step(self, batch, batch_idx):
         return self.step(batch, "test")
 
-    # -- optimizers (e2e_triplet.py:198-255; the step after the hot path, unchanged) -----------------------------------------------
+    # -- optimizers (e2e_triplet.py:198-255; the AdamW variants step through ib200_adamw_step, Ranger21 stays third-party) ---------
     def configure_optimizers(self):
         if self.optimizer_type in ("ranger21", "ranger21_xx"):
             from ranger21 import Ranger21  # third-party, same pin as the reference; imported lazily

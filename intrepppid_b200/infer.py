@@ -1,0 +1,167 @@
+"""Batched inference with an embedding cache -- the caller either side of the hot path that SURVEY 8f ranks first.
+
+The reference's `infer from_csv` (cli/infer.py:181-227) re-encodes BOTH proteins of every CSV row with a batch of one
+(`net(embed_a.unsqueeze(0), embed_b.unsqueeze(0))`, :216-222, "TODO: Batch inference").  Here every distinct protein is encoded
+once on the sm_100a encoder kernels and every row is scored by `ib200_pair_score` from the cached embeddings.
+
+Batch-of-one semantics are kept EXACTLY: the reference truncates each encoder call to the longest sequence OF THAT CALL
+(encoders/awd_lstm.py:149-150 and :53-54) and does not pack, so a protein embedded inside a mixed-length batch steps through pad
+positions and gets a different embedding than at batch 1.  `embed_batch1` therefore buckets the proteins by their own truncation
+lengths (T1, T_eff): proteins of one bucket form encoder groups (the C ABI's "group" = one encoder call with its own lengths) of
+8 / 4 / 2 / 1 sequences, and up to `max_groups` groups -- of different lengths -- share one launch set.  Every sequence is scanned
+over exactly the steps a batch-of-one call would scan.
+"""
+from __future__ import annotations
+
+import csv
+import gzip
+from typing import Dict, Iterable, List, Mapping, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+GROUP_SIZES = (8, 4, 2, 1)  # sequences per encoder group; 8 = one full tile of the recurrent kernels
+
+
+def batch1_lengths(tokens: torch.Tensor, emb_weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-sequence (T1, T_eff) of a batch-of-one encoder call in eval mode, as int64 tensors [M] on tokens.device.
+    T1 = number of non-zero ids (awd_lstm.py:149-150); T_eff = max_e #{t < T1 : emb[x_t, e] != 0} (awd_lstm.py:53-54).
+    Integer bookkeeping for the bucketing only -- the kernels recompute both lengths per group (K0)."""
+    M, T = tokens.shape
+    V = emb_weight.shape[0]
+    tok = tokens.long().clamp(0, V - 1)
+    t1 = (tokens != 0).sum(dim=1)
+    inside = torch.arange(T, device=tokens.device).unsqueeze(0) < t1.unsqueeze(1)
+    hist = torch.zeros(M, V, dtype=torch.float64, device=tokens.device)
+    hist.scatter_add_(1, tok, inside.to(torch.float64))
+    nz = (emb_weight.detach().to(tokens.device) != 0).to(torch.float64)  # [V,E]
+    t_eff = (hist @ nz).max(dim=1).values.round().long()
+    return t1, t_eff
+
+
+def plan_buckets(keys: Sequence[Tuple[int, int]], group_sizes: Sequence[int] = GROUP_SIZES,
+                 max_groups: int = 128) -> List[Tuple[int, List[List[int]]]]:
+    """Partition sequence indices into launch sets.  keys[m] = (T1, T_eff) of sequence m.  Returns [(B, groups)] where every
+    group is a list of B indices sharing one key; a launch set holds at most `max_groups` groups of the same B, ordered by
+    decreasing length so that the CTAs of one launch finish together.  Pure host logic (tested on CPU)."""
+    if sorted(group_sizes, reverse=True) != list(group_sizes) or group_sizes[-1] != 1:
+        raise ValueError("group_sizes must be decreasing and end with 1")
+    by_key: Dict[Tuple[int, int], List[int]] = {}
+    for m, k in enumerate(keys):
+        by_key.setdefault((int(k[0]), int(k[1])), []).append(m)
+    per_size: Dict[int, List[List[int]]] = {b: [] for b in group_sizes}
+    for key in sorted(by_key, key=lambda k: (-k[1], -k[0])):
+        members, pos = by_key[key], 0
+        for b in group_sizes:
+            while len(members) - pos >= b:
+                per_size[b].append(members[pos:pos + b])
+                pos += b
+    plan = []
+    for b in group_sizes:
+        groups = per_size[b]
+        for i in range(0, len(groups), max_groups):
+            plan.append((b, groups[i:i + max_groups]))
+    return plan
+
+
+@torch.no_grad()
+def embed_batch1(net, tokens: torch.Tensor, max_groups: int = 128) -> torch.Tensor:
+    """Eval-mode embeddings z [M,E] of M token rows, each EXACTLY as `net.encoder(tokens[m:m+1])` (the reference's batch-of-one
+    call) would give, computed in a few large launch sets.  tokens: [M, trunc_len] integer ids on the CUDA device."""
+    enc = net.encoder
+    if enc.training:
+        raise RuntimeError("embed_batch1 is an inference API: call net.eval() first (cli/infer.py:171)")
+    if not tokens.is_cuda:
+        raise ops._lib.IB200Error("embed_batch1 needs CUDA tokens (no CPU fallback)")
+    M = tokens.shape[0]
+    E = enc.embedder.weight.shape[1]
+    t1, t_eff = batch1_lengths(tokens, enc.embedder.weight)
+    keys = torch.stack((t1, t_eff), dim=1).cpu().tolist()  # the one host sync of the whole call
+    empty = [m for m, k in enumerate(keys) if k[1] <= 0]
+    if empty:  # nn.LSTM raises on a zero-length batch-of-one call
+        raise RuntimeError(f"Expected sequence length to be larger than 0 in RNN (sequences {empty[:8]} have no usable token)")
+    out = torch.empty(M, E, dtype=torch.float32, device=tokens.device)
+    saved = enc.check_lengths
+    enc.check_lengths = False  # lengths were validated above: no per-launch host sync
+    try:
+        for b, groups in plan_buckets(keys, max_groups=max_groups):
+            idx = torch.tensor(groups, dtype=torch.long, device=tokens.device)  # [G,b]
+            z = enc.forward_groups(tokens[idx.reshape(-1)].view(len(groups), b, -1), draw=False)
+            out[idx.reshape(-1)] = z.reshape(-1, E)
+    finally:
+        enc.check_lengths = saved
+    return out
+
+
+class EmbeddingCache:
+    """name -> row of a [M,E] embedding matrix; proteins are encoded once (batch-of-one semantics) when first needed."""
+
+    def __init__(self, net, max_groups: int = 128):
+        self.net, self.max_groups = net, max_groups
+        self.rows: Dict[str, int] = {}
+        self.z = None
+
+    def add(self, tokens_by_name: Mapping[str, torch.Tensor]) -> None:
+        new = [n for n in tokens_by_name if n not in self.rows]
+        if not new:
+            return
+        dev = self.net.encoder.embedder.weight.device
+        tok = torch.stack([torch.as_tensor(tokens_by_name[n]) for n in new]).to(dev)
+        z = embed_batch1(self.net, tok, self.max_groups)
+        base = 0 if self.z is None else self.z.shape[0]
+        self.z = z if self.z is None else torch.cat((self.z, z), dim=0)
+        for i, n in enumerate(new):
+            self.rows[n] = base + i
+
+    @torch.no_grad()
+    def score(self, pairs: Sequence[Tuple[str, str]]) -> torch.Tensor:
+        """sigmoid(head(z_a, z_b)) for named pairs -> float32 [P] on the device (TripletE2ENet.forward + sigmoid, infer.py:222-224)."""
+        dev = self.z.device
+        ia = torch.tensor([self.rows[a] for a, _ in pairs], dtype=torch.int32, device=dev)
+        ib = torch.tensor([self.rows[b] for _, b in pairs], dtype=torch.int32, device=dev)
+        return self.net.score_pairs(self.z, ia, ib)
+
+
+@torch.no_grad()
+def infer_pairs(net, tokens_by_name: Mapping[str, torch.Tensor], rows: Iterable[Tuple[str, str, str]],
+                on_missing=None) -> List[Tuple[str, float]]:
+    """The row loop of `infer from_csv` (cli/infer.py:196-225) without re-encoding: rows = (itx_id, id_a, id_b); rows naming an
+    unknown id are skipped (reported through `on_missing(itx_id, id_a, id_b)`, the reference prints and continues, :203-213).
+    Returns [(itx_id, probability)] in input order."""
+    rows = list(rows)
+    known = [(i, a, b) for i, a, b in rows if a in tokens_by_name and b in tokens_by_name]
+    if on_missing is not None:
+        for i, a, b in rows:
+            if a not in tokens_by_name or b not in tokens_by_name:
+                on_missing(i, a, b)
+    if not known:
+        return []
+    cache = EmbeddingCache(net)
+    needed = {}
+    for _, a, b in known:
+        needed.setdefault(a, tokens_by_name[a])
+        needed.setdefault(b, tokens_by_name[b])
+    cache.add(needed)
+    prob = cache.score([(a, b) for _, a, b in known]).cpu().tolist()
+    return [(i, p) for (i, _, _), p in zip(known, prob)]
+
+
+def from_csv(net, tokens_by_name: Mapping[str, torch.Tensor], interactions_path: str, out_path: str) -> int:
+    """File-level mirror of cli/infer.py:181-227: read `itx_id,id_a,id_b` rows (optionally .gz), write `itx_id,probability`
+    rows (no header line in either file, as in the reference).  `tokens_by_name` maps a protein id to its SentencePiece ids padded to trunc_len (what
+    IntrepppidDataset.static_encode returns, data/ppi_oma.py:347-392 -- tokenisation itself is outside the hot path).
+    Returns the number of scored interactions."""
+    opener, mode = (gzip.open, "rt") if interactions_path.endswith(".gz") else (open, "r")
+    with opener(interactions_path, mode) as f_in:
+        rows = [(r["itx_id"], r["id_a"], r["id_b"]) for r in csv.DictReader(f_in, fieldnames=["itx_id", "id_a", "id_b"])]
+
+    def report(itx_id, a, b):
+        print(f"Can't compute pair id: {itx_id} (\"{a}\", \"{b}\"): missing sequence")
+
+    scored = infer_pairs(net, tokens_by_name, rows, on_missing=report)
+    with open(out_path, "w") as f_out:
+        w = csv.DictWriter(f_out, fieldnames=["itx_id", "probability"])
+        for itx_id, p in scored:
+            w.writerow({"itx_id": itx_id, "probability": p})
+    return len(scored)

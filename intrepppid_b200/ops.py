@@ -91,15 +91,21 @@ _TORCH_LIB.define("pair_score(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w
 _TORCH_LIB.define("pair_score_range(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int p_begin, int p_count) -> Tensor")
 
 
-def _cfg(G, B, T, V, H, L, bi_reduce, precision, training) -> Cfg:
-    return Cfg(G, B, T, V, H, L, bi_reduce, precision, 1 if training else 0, 0)
+_TOKEN_DTYPES = {torch.int64: _lib.TOKEN_DTYPE["int64"], torch.int32: _lib.TOKEN_DTYPE["int32"],
+                 torch.int16: _lib.TOKEN_DTYPE["int16"], torch.uint8: _lib.TOKEN_DTYPE["uint8"]}
+
+
+def _cfg(G, B, T, V, H, L, bi_reduce, precision, training, token_dtype=0) -> Cfg:
+    return Cfg(G, B, T, V, H, L, bi_reduce, precision, 1 if training else 0, token_dtype)
 
 
 def _encoder_fwd_cuda(tokens, emb, lstm, emb_row_scale, whh_mask, num_layers, bi_reduce, precision, training):
     """-> (hn_top [2,G*B,H], lengths int32 [2,G], workspace uint8).  ib200_encoder_fwd."""
     G, B, T = tokens.shape
     V, H = emb.shape
-    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, training)
+    if tokens.dtype not in _TOKEN_DTYPES:
+        raise _lib.IB200Error(f"token ids must be int64 / int32 / int16 / uint8, got {tokens.dtype}")
+    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, training, _TOKEN_DTYPES[tokens.dtype])
     nbytes = lib().ib200_workspace_bytes(cfg)
     if nbytes == 0:
         raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), "
@@ -227,7 +233,7 @@ class _EncodeHidden(torch.autograd.Function):
         L = econf.num_layers
         training = any(ctx.needs_input_grad[6:])  # (grad mode is off inside Function.forward; this is the reliable signal)
         _need_cuda(tokens, emb, emb_row_scale, whh_mask, *lstm)
-        if tokens.dtype != torch.int64:
+        if tokens.dtype not in _TOKEN_DTYPES:  # int64 as the reference ships them, or narrowed ids (SURVEY 8f input feeding)
             tokens = tokens.long()
         tokens = tokens.contiguous()
         emb_c = _f32c(emb)

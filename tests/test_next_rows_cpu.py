@@ -1,0 +1,130 @@
+"""CPU-side checks for the SURVEY 8f rows built around the hot path: the AdamW restatement against torch.optim.AdamW (the
+reference's optimizer, e2e_triplet.py:231-255), FusedAdamW's host-side contract, and the batch-of-one bucketing of the
+inference path (cli/infer.py:196-225).  No CUDA compute here."""
+import copy
+
+import pytest
+import torch
+
+from oracle import restatement as R
+
+
+def _rand_problem(seed, n=7, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(1,), (7,), (33, 5), (256, 64), (2049,), (64,), (3, 3, 3)][:n]
+    params = [torch.randn(s, generator=g, dtype=dtype) for s in shapes]
+    grads = [[torch.randn(s, generator=g, dtype=dtype) * 0.1 for s in shapes] for _ in range(6)]
+    return params, grads
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-7), (torch.float64, 1e-14)])
+def test_adamw_restatement_matches_torch_adamw(dtype, tol):
+    params, grads = _rand_problem(3, dtype=dtype)
+    ref = [torch.nn.Parameter(p.clone()) for p in params]
+    opt = torch.optim.AdamW(ref, lr=1e-2, foreach=False)  # the reference's call: AdamW(self.parameters(), lr=self.lr)
+    mine = [p.clone() for p in params]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    for t, gs in enumerate(grads, start=1):
+        for p, g in zip(ref, gs):
+            p.grad = g.clone()
+        opt.step()
+        R.adamw_step(mine, gs, m, v, step=t, lr=1e-2)
+        for a, b in zip(mine, ref):
+            assert float((a - b.detach()).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+    st = opt.state[ref[3]]
+    assert torch.allclose(st["exp_avg"], m[3], rtol=1e-6, atol=1e-9) and torch.allclose(st["exp_avg_sq"], v[3], rtol=1e-6, atol=1e-12)
+
+
+def test_fused_adamw_host_contract():
+    from intrepppid_b200 import FusedAdamW
+    from intrepppid_b200._lib import IB200Error
+
+    params = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt = FusedAdamW(params, lr=1e-2)
+    tref = torch.optim.AdamW([torch.nn.Parameter(torch.randn(1))], lr=1e-2)
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):  # same defaults as the reference's optimizer
+        assert opt.param_groups[0][k] == tref.param_groups[0][k], k
+    with pytest.raises(ValueError):
+        FusedAdamW(params, lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdamW(params, betas=(1.0, 0.999))
+    with pytest.raises(ValueError):
+        FusedAdamW(params, amsgrad=True)
+    opt.step()  # no gradients yet: nothing to do, no state created (torch skips p.grad is None)
+    assert len(opt.state) == 0
+    params[0].grad = torch.zeros(4, 3)
+    with pytest.raises(IB200Error):  # CPU parameters: there is no fallback
+        opt.step()
+    # schedulers used by the reference drive it like any torch optimizer (e2e_triplet.py:239-253)
+    sched = torch.optim.lr_scheduler.OneCycleLR(FusedAdamW(params, lr=1e-2), 1e-2, epochs=2, steps_per_epoch=3)
+    assert sched.get_last_lr()[0] < 1e-2
+
+
+def test_configure_optimizers_uses_the_fused_kernel_for_adamw_types():
+    import intrepppid_b200 as ib
+
+    for kind in ("adamw", "adamw_1cycle", "adamw_cosine"):
+        net = ib.intrepppid_network(3, optimizer_type=kind, num_epochs=2)
+        got = net.configure_optimizers()
+        opt = got if isinstance(got, torch.optim.Optimizer) else got[0][0]
+        assert isinstance(opt, ib.FusedAdamW) and opt.param_groups[0]["lr"] in (net.lr, pytest.approx(net.lr / 25))
+    with pytest.raises(ValueError):
+        ib.intrepppid_network(3, optimizer_type="sgd").configure_optimizers()
+
+
+# ---- inference bucketing --------------------------------------------------------------------------------------------------------
+def _ragged_tokens(M, T, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.randint(1, V, (M, T), generator=g)
+    lens = torch.randint(1, T + 1, (M,), generator=g)
+    lens[:4] = torch.tensor([T, T, 1, 5])
+    for m in range(M):
+        tok[m, lens[m]:] = 0
+    tok[6, 2] = 0  # interior <unk>: T1 is a COUNT, so the slice loses the last real token
+    return tok
+
+
+def test_batch1_lengths_match_the_oracle_per_sequence():
+    from intrepppid_b200.infer import batch1_lengths
+
+    M, T, V, E = 24, 40, 30, 32
+    P = R.init_params(vocab=V, E=E, L=1, seed=1)
+    P["emb"][7].zero_()       # an all-zero vocabulary row besides the padding row
+    P["emb"][9, :5].zero_()   # a partially zero row
+    tok = _ragged_tokens(M, T, V, 2)
+    tok[8, :3] = 7
+    t1, te = batch1_lengths(tok, P["emb"])
+    for m in range(M):
+        _, info = R.encoder_forward(tok[m:m + 1], P, num_layers=1, bi_reduce="last", training=False)
+        assert (int(t1[m]), int(te[m])) == (info.T1, info.T_eff), m
+
+
+def test_plan_buckets_is_an_exact_partition_into_homogeneous_groups():
+    from intrepppid_b200.infer import plan_buckets
+
+    g = torch.Generator().manual_seed(5)
+    t1 = torch.randint(1, 12, (300,), generator=g).tolist()
+    keys = [(a, a - (i % 3 == 0 and a > 1)) for i, a in enumerate(t1)]
+    plan = plan_buckets(keys, max_groups=16)
+    seen = []
+    for b, groups in plan:
+        assert b in (8, 4, 2, 1) and 1 <= len(groups) <= 16
+        for grp in groups:
+            assert len(grp) == b and len({keys[m] for m in grp}) == 1  # one (T1, T_eff) per group = batch-of-one semantics
+            seen += grp
+    assert sorted(seen) == list(range(300))
+    # at most 3 groups smaller than 8 per distinct key (binary decomposition of the remainder)
+    small = sum(len(groups) for b, groups in plan if b < 8)
+    assert small <= 3 * len(set(keys))
+    with pytest.raises(ValueError):
+        plan_buckets(keys, group_sizes=(4, 8, 1))
+
+
+def test_infer_pairs_skips_unknown_ids_without_touching_the_gpu():
+    from intrepppid_b200.infer import infer_pairs
+
+    missing = []
+    out = infer_pairs(None, {"A": torch.ones(4, dtype=torch.long)}, [("i0", "A", "B"), ("i1", "C", "A")],
+                      on_missing=lambda *r: missing.append(r))
+    assert out == [] and missing == [("i0", "A", "B"), ("i1", "C", "A")]
