@@ -14,6 +14,7 @@
  *   ib200_pool_fc_fwd / _bwd    encoders/awd_lstm.py:58-71   (bi_reduce on h_n[-2:], fc Linear)
  *   ib200_loss_head_fwd / _bwd  e2e/e2e_triplet.py:113-136   (TripletE2ENet.step: triplet projection, TripletMarginLoss,
  *                               classifier/head/mlp.py:35-68  MLPHead, BCEWithLogitsLoss, beta mix)
+ *   ib200_batch_metrics         e2e/e2e_triplet.py:171-184   (torchmetrics AUROC / AP / MCC / Precision / Recall of the batch)
  *   ib200_adamw_step            e2e/e2e_triplet.py:231-255   (configure_optimizers: torch.optim.AdamW over self.parameters())
  *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
  *
@@ -171,6 +172,16 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
  * proteins, all-gather the [M,H] embeddings, split the pair matrix by rows). */
 int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin, int64_t p_count,
                            const ib200_head_params* params, float* prob_out, void* stream);
+
+/*
+ * Per-step classification metrics of TripletE2ENet.step (e2e/e2e_triplet.py:86-90,171-184): the batch values
+ * of torchmetrics' (0.11.1) binary AUROC, AveragePrecision, MatthewsCorrCoef(threshold), Precision and Recall, in one launch and
+ * without a host sync.  y_hat float [B] logits (squashed with a sigmoid unless every value already lies in [0,1], as torchmetrics
+ * does), y int64 [B] labels, 1 <= B <= 1024.  metrics_out float [5] = {auroc, ap, mcc, precision, recall} (a missing class: auroc 0,
+ * ap NaN without positives; 0/0 -> 0 for mcc / precision / recall); confusion_out int32 [4] = {tp, fp, tn, fn} or NULL.
+ */
+int ib200_batch_metrics(int32_t B, const float* y_hat, const int64_t* y, float threshold, float* metrics_out, int32_t* confusion_out,
+                        void* stream);
 
 /*
  * Multi-tensor AdamW: the optimizer step right after the hot path (e2e/e2e_triplet.py:231-255 -- torch.optim.AdamW(self.parameters(), lr)

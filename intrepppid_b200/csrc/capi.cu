@@ -36,10 +36,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -628,6 +628,15 @@ int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin
   if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score_range: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, nullptr, nullptr, (long long)p_count, (long long)p_begin, *hp, prob_out, st), "pair_score_range");
+  return 0;
+}
+
+int ib200_batch_metrics(int32_t B, const float* y_hat, const int64_t* y, float threshold, float* metrics_out, int32_t* confusion_out,
+                        void* stream) {
+  if (B < 1 || B > 1024) return fail(IB200_E_SHAPE, "ib200_batch_metrics: batch must be in [1, 1024]");
+  if (!y_hat || !y || !metrics_out) return fail(IB200_E_NULL, "ib200_batch_metrics: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_METRICS, 1, launch_batch_metrics(B, y_hat, (const long long*)y, threshold, metrics_out, confusion_out, st), "batch_metrics");
   return 0;
 }
 

@@ -197,6 +197,9 @@ cudaError_t launch_l0_grads(const L0GradArgs& a, int precision, cudaStream_t st)
 
 cudaError_t launch_fill_zero(float* p, size_t n, cudaStream_t st);
 
+// ---- per-step classification metrics (metrics.cu): out[5] = auroc, ap, mcc, precision, recall; conf[4] = tp, fp, tn, fn ---------
+cudaError_t launch_batch_metrics(int B, const float* y_hat, const long long* y, float threshold, float* out, int* conf, cudaStream_t st);
+
 // ---- multi-tensor AdamW (optim.cu) -------------------------------------------------------------------------------------------
 constexpr int kAdamMaxTensors = 32;  // tensors per launch (pointer table travels in the kernel parameters)
 struct AdamScalars {

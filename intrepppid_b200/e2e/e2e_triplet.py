@@ -67,6 +67,7 @@ class TripletE2ENet(_Base):
         self.lr = lr
         self.use_projection = use_projection
         self.last_step = None  # dict of detached tensors from the most recent step()
+        self.compute_metrics = True  # log the reference's five per-step metrics (ib200_batch_metrics)
 
     # -- inference API (e2e_triplet.py:105-111): no projection here (quirk Q11); the caller applies sigmoid ---------------------
     def forward(self, x1, x2):
@@ -119,13 +120,12 @@ class TripletE2ENet(_Base):
         self.log(f"{stage}_classifier_loss_step", classifier_loss, on_epoch=False, on_step=True, prog_bar=False)
         self.log(f"{stage}_triplet_loss_step", triplet_loss, on_epoch=False, on_step=True, prog_bar=False)
         self.log(f"{stage}_loss_step", loss, on_epoch=False, on_step=True, prog_bar=False)
-        if torchmetrics is not None:
-            yh = y_hat.detach()
-            self.log(f"{stage}_auroc", self.auroc(yh, y).detach(), on_epoch=True, on_step=False)
-            self.log(f"{stage}_ap", self.average_precision(yh, y).detach(), on_epoch=True, on_step=False)
-            self.log(f"{stage}_mcc", self.mcc(yh, y).detach(), on_epoch=True, on_step=False)
-            self.log(f"{stage}_precision", self.precision_metric(yh, y).detach(), on_epoch=True, on_step=False)
-            self.log(f"{stage}_rec", self.recall(yh, y).detach(), on_epoch=True, on_step=False)
+        # the five torchmetrics forwards of the reference (batch values, e2e_triplet.py:171-184) in one launch, no host sync
+        if self.compute_metrics and y.shape[0] <= 1024:
+            m, conf = ops.batch_metrics(y_hat.detach(), y)
+            self.last_step["metrics"], self.last_step["confusion"] = m, conf
+            for k, name in enumerate(ops.METRIC_NAMES):
+                self.log(f"{stage}_{name}", m[k], on_epoch=True, on_step=False)
         return loss
 
     def training_step(self, batch, batch_idx):

@@ -88,6 +88,7 @@ _TORCH_LIB.define("loss_head_fwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] 
 _TORCH_LIB.define("loss_head_bwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta, Tensor d_loss, Tensor? d_y_hat) "
                   "-> (Tensor, Tensor)")
 _TORCH_LIB.define("pair_score(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, Tensor? idx_a, Tensor? idx_b) -> Tensor")
+_TORCH_LIB.define("batch_metrics(Tensor y_hat, Tensor y, float threshold) -> (Tensor, Tensor)")
 _TORCH_LIB.define("pair_score_range(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int p_begin, int p_count) -> Tensor")
 
 
@@ -216,7 +217,16 @@ def _pair_score_range_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin, p_count):
     return out
 
 
-for _name, _fn in (("pair_score_range", _pair_score_range_cuda), ("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
+def _batch_metrics_cuda(y_hat, y, threshold):
+    """-> (float32 [5] = auroc, ap, mcc, precision, recall ; int32 [4] = tp, fp, tn, fn).  ib200_batch_metrics."""
+    B = y_hat.numel()
+    out = torch.empty(5, dtype=torch.float32, device=y_hat.device)
+    conf = torch.empty(4, dtype=torch.int32, device=y_hat.device)
+    check(lib().ib200_batch_metrics(B, ptr(y_hat), ptr(y), float(threshold), ptr(out), ptr(conf), _stream()), "ib200_batch_metrics")
+    return out, conf
+
+
+for _name, _fn in (("batch_metrics", _batch_metrics_cuda), ("pair_score_range", _pair_score_range_cuda), ("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
                    ("pool_fc_bwd", _pool_fc_bwd_cuda), ("loss_head_fwd", _loss_head_fwd_cuda), ("loss_head_bwd", _loss_head_bwd_cuda),
                    ("pair_score", _pair_score_cuda)):
     _TORCH_LIB.impl(_name, _fn, "CUDA")
@@ -360,3 +370,14 @@ def pair_score_range(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin: int, p_count: int):
     """Scores of the flat upper-triangle pair indices [p_begin, p_begin + p_count) (row-major, i <= j) of the M embeddings in z."""
     _need_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b)
     return _OPS.pair_score_range(_f32c(z), _f32c(fc1_w), _f32c(fc1_b), _f32c(fc2_w), _f32c(fc2_b), int(p_begin), int(p_count))
+
+
+METRIC_NAMES = ("auroc", "ap", "mcc", "precision", "rec")  # suffixes of the reference's log keys (e2e_triplet.py:171-184)
+
+
+@torch.no_grad()
+def batch_metrics(y_hat, y, threshold: float = 0.5):
+    """Batch AUROC / AP / MCC / precision / recall as torchmetrics' binary metrics return them from `metric(y_hat, y)`
+    (e2e_triplet.py:171-184) -> (float32 [5] in METRIC_NAMES order, int32 [4] = tp, fp, tn, fn), one launch, no host sync."""
+    _need_cuda(y_hat, y)
+    return _OPS.batch_metrics(_f32c(y_hat.reshape(-1)), y.reshape(-1).long().contiguous(), float(threshold))

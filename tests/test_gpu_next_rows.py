@@ -231,3 +231,49 @@ def test_many_groups_keep_their_own_lengths_when_the_workspace_is_recycled():
         for i in (0, 40, 95):
             z1 = net.encoder(short[i, :, :int(glen[i])].contiguous())
             assert rel_l2(z_short[i], z1) < 2e-5, i  # no pad is stepped: same as a call on the truncated rows (other CTA shape)
+
+
+# ---- per-step metrics ---------------------------------------------------------------------------------------------------------
+def test_batch_metrics_kernel_matches_the_restatement():
+    import math
+
+    from intrepppid_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    cases = []
+    for trial in range(40):
+        B = (1, 2, 80, 1023, 1024)[trial] if trial < 5 else int(torch.randint(2, 1025, (1,), generator=g))
+        y = torch.randint(0, 2, (B,), generator=g)
+        x = torch.randn(B, generator=g) * 3
+        if trial % 3 == 0:
+            x = torch.round(x * 2) / 2
+        if trial % 7 == 0:
+            x = torch.rand(B, generator=g)
+        if trial == 10:
+            y.zero_()
+        if trial == 11:
+            y.fill_(1)
+        cases.append((x, y))
+    for k, (x, y) in enumerate(cases):
+        ref = R.batch_metrics(x, y)
+        m, conf = ops.batch_metrics(x.cuda(), y.cuda())
+        m, conf = m.cpu().tolist(), tuple(conf.cpu().tolist())
+        assert conf == ref["confusion"], (k, conf, ref["confusion"])
+        for got, name in zip(m, ("auroc", "ap", "mcc", "precision", "recall")):
+            want = ref[name]
+            assert (math.isnan(got) and math.isnan(want)) or abs(got - want) < 2e-5, (k, name, got, want)
+    with pytest.raises(Exception):
+        ops.batch_metrics(torch.zeros(1025, device="cuda"), torch.zeros(1025, dtype=torch.long, device="cuda"))
+
+
+def test_step_logs_the_five_reference_metrics_without_torchmetrics():
+    B, T, V = 16, 40, 60
+    net = build_product(R.init_params(vocab=V, E=64, L=2, seed=5), L=2, bi="last").train()
+    logged = {}
+    net.log = lambda name, value, **kw: logged.__setitem__(name, value)
+    batch = [t.cuda() for t in R.synthetic_batch(B, T, V, seed=6, padded=True)]
+    net.step(batch, "val")
+    ref = R.batch_metrics(net.last_step["y_hat"].cpu(), batch[5].cpu())
+    for key, name in (("val_auroc", "auroc"), ("val_ap", "ap"), ("val_mcc", "mcc"), ("val_precision", "precision"), ("val_rec", "recall")):
+        assert abs(float(logged[key]) - ref[name]) < 2e-5, key
+    assert {"val_loss", "val_classifier_loss", "val_triplet_loss", "val_loss_step"} <= set(logged)

@@ -128,3 +128,45 @@ def test_infer_pairs_skips_unknown_ids_without_touching_the_gpu():
     out = infer_pairs(None, {"A": torch.ones(4, dtype=torch.long)}, [("i0", "A", "B"), ("i1", "C", "A")],
                       on_missing=lambda *r: missing.append(r))
     assert out == [] and missing == [("i0", "A", "B"), ("i1", "C", "A")]
+
+
+# ---- per-step metrics: the restatement of torchmetrics' binary metrics against scikit-learn -------------------------------------
+def _metric_case(trial, g):
+    B = int(torch.randint(2, 300, (1,), generator=g))
+    y = torch.randint(0, 2, (B,), generator=g)
+    if y.sum() == 0 or y.sum() == B:
+        y[0] = 1 - y[0]
+    x = torch.randn(B, generator=g) * 2
+    if trial % 3 == 0:
+        x = torch.round(x * 2) / 2            # tied scores: one curve point per distinct score
+    if trial % 7 == 0:
+        x = torch.rand(B, generator=g)        # all inside [0,1]: torchmetrics does NOT apply the sigmoid
+    return x, y
+
+
+def test_metrics_restatement_matches_scikit_learn():
+    from sklearn import metrics as M
+
+    g = torch.Generator().manual_seed(0)
+    for trial in range(60):
+        x, y = _metric_case(trial, g)
+        m = R.batch_metrics(x, y)
+        s = x if trial % 7 == 0 else torch.sigmoid(x)
+        hard = (s > 0.5).numpy().astype(int)
+        ref = dict(auroc=M.roc_auc_score(y.numpy(), s.numpy()), ap=M.average_precision_score(y.numpy(), s.numpy()),
+                   mcc=M.matthews_corrcoef(y.numpy(), hard), precision=M.precision_score(y.numpy(), hard, zero_division=0),
+                   recall=M.recall_score(y.numpy(), hard, zero_division=0))
+        for k, v in ref.items():
+            assert abs(m[k] - v) < 2e-6, (trial, k, m[k], v)
+
+
+def test_metrics_restatement_degenerate_batches():
+    import math
+
+    x = torch.tensor([2.0, -1.0, 0.3])
+    no_pos = R.batch_metrics(x, torch.zeros(3, dtype=torch.long))
+    assert no_pos["auroc"] == 0.0 and math.isnan(no_pos["ap"]) and no_pos["mcc"] == 0.0 and no_pos["recall"] == 0.0
+    no_neg = R.batch_metrics(x, torch.ones(3, dtype=torch.long))
+    assert no_neg["auroc"] == 0.0 and abs(no_neg["ap"] - 1.0) < 1e-6 and no_neg["precision"] == 1.0
+    assert R.batch_metrics(torch.tensor([0.2, 0.7]), torch.tensor([0, 1]))["confusion"] == (1, 0, 1, 0)  # no sigmoid inside [0,1]
+    assert R.batch_metrics(torch.tensor([0.2, 1.7]), torch.tensor([0, 1]))["confusion"] == (1, 1, 0, 0)  # sigmoid(0.2) > 0.5
