@@ -91,7 +91,8 @@ struct Plan {
   size_t gates[IB200_MAX_LAYERS][2], cst[IB200_MAX_LAYERS][2];
   size_t bwd_scratch;  // dY [R,2H] then dX0 [R,H]
   size_t partial;
-  size_t bias_partial;  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel
+  size_t bias_partial[2];  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel; one buffer per layer
+                           // parity: layer l's reduce (side stream) reads its sums while layer l-1's BPTT kernel writes the other
   size_t l0_scratch;  // R of gemm_l0.cu
   size_t ph_state, ph_sched;  // two-phase rebalancing (common.cuh): [2][N][H][2] floats; sm_load[256] + resume_list[1 + CTAs] ints
   int ctas_per_group;
@@ -154,7 +155,7 @@ Plan make_plan(const ib200_cfg* c) {
     p.partial = take(sizeof(float) * std::max((size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H),  // up to [dW_ih | dW_hh] fused
                                               l0_grad_partial_floats(p.G, 2)));
     p.l0_scratch = take(sizeof(float) * l0_grad_scratch_floats(p.G, 2));
-    p.bias_partial = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
+    for (int i = 0; i < 2; ++i) p.bias_partial[i] = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
   }
   p.total = off;
   return p;
@@ -283,6 +284,38 @@ bool wants_phases(const Plan& p, int ndir) {
   const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir;
   return full_ctas <= 148 && half_ctas > 148 && half_ctas < 2 * 148 && p.T >= 128;
 }
+// One library-owned non-blocking stream + two events per device, used inside ib200_encoder_bwd to run a weight-gradient GEMM under
+// the next recurrent kernel.  All of its work is forked from and joined back into the caller's stream within the call, so the
+// "everything is ordered on the stream you pass" contract of the ABI holds.  Calls on different streams of one device would share
+// it (serialising only those GEMMs).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  // OFF by default.  Measured on B200 (profiles/r1_overlap_ab.txt): the layer-1 dW GEMM run under the layer-0 BPTT kernel makes the
+  // step SLOWER (3.86 -> 3.98 ms): the 200 recurrent CTAs already occupy every SM, a co-resident GEMM CTA lengthens the dependent
+  // chain of its neighbour (BPTT 0.93 -> 1.18 ms) and disturbs the placement the two-phase rebalancing relies on.
+  static const bool enabled = getenv("IB200_OVERLAP") != nullptr;
+  if (!enabled) return nullptr;
+  static std::mutex mu;
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = per_dev[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      s = SideStream{};
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 PhaseArgs phase_args(void* ws, const Plan& p, bool bwd) {
   PhaseArgs a{};
   a.state = at<float>(ws, p.ph_state);
@@ -435,6 +468,8 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
   float* dX0 = dY + p.R * 2 * H;
   float* partial = at<float>(ws, p.partial);
 
+  SideStream* side = side_stream();  // null unless IB200_OVERLAP=1 (experiment; see side_stream())
+  bool pending_join = false;
   for (int l = p.L - 1; l >= 0; --l) {
     const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
     LstmBwdArgs ba{};
@@ -450,7 +485,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
     { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
     ba.planes = planes ? 1 : 0;
-    ba.bias_partial = planes ? at<float>(ws, p.bias_partial) : nullptr;
+    ba.bias_partial = planes ? at<float>(ws, p.bias_partial[l & 1]) : nullptr;
     if (!cluster && wants_phases(p, ndir)) {
       ba.ph = phase_args(ws, p, true);
       TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(ba.ph.sm_load), 257, st), "phase counters");
@@ -462,6 +497,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates
     // (gemm_l0.cu: the token-indexed sums S = dA^T onehot(tok) replace the gathered dW GEMM, the dX_0 GEMM and the atomic scatter)
     bool l0_done = false;
+    if (l == 0 && pending_join) {  // the side stream's GEMMs share the `partial` scratch with everything below
+      CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
+      pending_join = false;
+    }
     if (l == 0 && l0_fused_ok(p, planes)) {
       L0GradArgs la{};
       la.G = p.G; la.B = p.B; la.Tmax = p.T; la.V = p.V; la.H = H; la.dir0 = dir0; la.ndir = ndir;
@@ -473,7 +512,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       }
       la.Y0 = at<float>(ws, p.Y[0]);
       la.emb = P->emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_l0_mask;
-      la.bias_partial = at<float>(ws, p.bias_partial); la.bias_count = bwd_ctas;
+      la.bias_partial = at<float>(ws, p.bias_partial[0]); la.bias_count = bwd_ctas;
       la.partial = partial; la.R = at<float>(ws, p.l0_scratch); la.d_emb = Gr->emb;
       TimedScope ts(F_GEMM_DW, 4, st);
       const cudaError_t e = launch_l0_grads(la, prec, st);
@@ -482,7 +521,8 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       else (void)cudaGetLastError();
     }
 
-    // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l)
+    // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l); `st` = the stream they are issued on
+    auto weight_grads = [&](cudaStream_t st) -> int {
     for (int d = 0; d < 2; ++d) {
       const int K = l == 0 ? H : 2 * H;
       if (!p.live[l][d]) {  // dead chain: exact zeros
@@ -522,7 +562,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         ta.NB = ta.NB1 + H;
         ra.NB = ta.NB; ra.out2 = Gr->w_hh[l][d]; ra.mask = mask_hh;
         ra.out_b1 = Gr->b_ih[l][d]; ra.out_b2 = Gr->b_hh[l][d];
-        ra.cs_ptr = at<float>(ws, p.bias_partial) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
+        ra.cs_ptr = at<float>(ws, p.bias_partial[l & 1]) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
         ra.cs_count = bwd_ctas;
         TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, true), "dW_ih|dW_hh gemm");
         TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
@@ -539,9 +579,12 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       rb.out_b1 = Gr->b_ih[l][d]; rb.out_b2 = Gr->b_hh[l][d];
       TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, rb, prec, st, planes, wide), "dW_hh gemm + reduce");
     }
+    return 0;
+    };
 
     // input gradient of this layer
-    if (l0_done) continue;
+    auto input_grads = [&](cudaStream_t st) -> int {
+    if (l0_done) return 0;
     GemmNTArgs ga{};
     ga.G = p.G; ga.B = p.B; ga.Tmax = p.T; ga.lens = lens;
     ga.nsrc = 0;
@@ -562,7 +605,25 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
       TIMED(F_EMB_GRAD, 2, launch_emb_grad(ea, st), "embedding grad");
     }
+    return 0;
+    };
+
+    if (l > 0 && planes && side != nullptr) {
+      // Upper layers of the TMA path: the next BPTT launch only needs dY, so dY goes first and this layer's weight-gradient GEMM
+      // + reduce (HBM-bound, needed by nobody until the end) run on the library's side stream UNDERNEATH the next layer's
+      // latency-bound recurrent kernel.  Joined before anything else touches the `partial` scratch (top of the l == 0 iteration).
+      if (int rc = input_grads(st)) return rc;
+      CK(cudaEventRecord(side->fork, st), "fork record");
+      CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+      if (int rc = weight_grads(side->stream)) return rc;
+      CK(cudaEventRecord(side->join, side->stream), "join record");
+      pending_join = true;
+    } else {
+      if (int rc = weight_grads(st)) return rc;
+      if (int rc = input_grads(st)) return rc;
+    }
   }
+  if (pending_join) CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
   return 0;
 }
 
