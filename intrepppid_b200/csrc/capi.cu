@@ -284,20 +284,26 @@ bool wants_phases(const Plan& p, int ndir) {
   const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir;
   return full_ctas <= 148 && half_ctas > 148 && half_ctas < 2 * 148 && p.T >= 128;
 }
-// One library-owned non-blocking stream + two events per device, used inside ib200_encoder_bwd to run a weight-gradient GEMM under
-// the next recurrent kernel.  All of its work is forked from and joined back into the caller's stream within the call, so the
-// "everything is ordered on the stream you pass" contract of the ABI holds.  Calls on different streams of one device would share
-// it (serialising only those GEMMs).
+// One library-owned non-blocking stream + two events per device.  Used inside ib200_encoder_fwd / _bwd to run SMALL independent
+// kernels side by side (layer-0 table + W_ih preparation next to the length kernels; the upper layer's dW reduce next to the dY GEMM).
+// All of its work is forked from and joined back into the caller's stream within the call, so the "everything is ordered on the
+// stream you pass" contract of the ABI holds.  Calls on different streams of one device would share it (serialising only those
+// kernels).  IB200_NO_SIDE=1 puts everything back on the caller's stream.
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
+// Experiment (OFF by default): the whole upper-layer dW GEMM under the next layer's BPTT kernel.  Measured on B200
+// (profiles/r1_overlap_ab.txt): the step gets SLOWER (3.86 -> 3.98 ms) -- the 200 recurrent CTAs already occupy every SM, a co-resident
+// GEMM CTA lengthens the dependent chain of its neighbour (BPTT 0.93 -> 1.18 ms) and disturbs the placement the two-phase
+// rebalancing relies on.  Small kernels do not have that problem.
+bool gemm_overlap_enabled() {
+  static const bool on = getenv("IB200_OVERLAP") != nullptr;
+  return on;
+}
 SideStream* side_stream() {
-  // OFF by default.  Measured on B200 (profiles/r1_overlap_ab.txt): the layer-1 dW GEMM run under the layer-0 BPTT kernel makes the
-  // step SLOWER (3.86 -> 3.98 ms): the 200 recurrent CTAs already occupy every SM, a co-resident GEMM CTA lengthens the dependent
-  // chain of its neighbour (BPTT 0.93 -> 1.18 ms) and disturbs the placement the two-phase rebalancing relies on.
-  static const bool enabled = getenv("IB200_OVERLAP") != nullptr;
-  if (!enabled) return nullptr;
+  static const bool disabled = getenv("IB200_NO_SIDE") != nullptr;
+  if (disabled) return nullptr;
   static std::mutex mu;
   static SideStream per_dev[64];
   int dev = 0;
@@ -380,27 +386,38 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
   const int H = p.H, prec = cfg->precision;
   const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
 
+  // the layer-0 table and the W_ih preparation do not depend on the length kernels: they run next to them on the side stream
+  SideStream* side = side_stream();
+  if (side != nullptr) {
+    CK(cudaEventRecord(side->fork, st), "fork record");
+    CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+  }
+  // without a row scale every group has the same table: build it once (inference launches fuse up to hundreds of groups)
+  const bool table_shared = emb_row_scale == nullptr;
+  {
+    cudaStream_t main_st = st;
+    cudaStream_t st = side != nullptr ? side->stream : main_st;
+    TableArgs ta{table_shared ? 1 : p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
+                 {P->b_hh[0][0], P->b_hh[0][1]}, at<float>(ws, p.table)};
+    TIMED(F_L0_TABLE, 1, launch_l0_table(ta, st), "l0 table");
+    for (int l = 0; l < p.L; ++l)
+      for (int d = 0; d < 2; ++d) {
+        if (!p.live[l][d]) continue;
+        const int K = l == 0 ? H : 2 * H;
+        float* w = l > 0 ? at<float>(ws, p.wih_gi[l][d]) : nullptr;
+        float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
+        float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
+        if (l == 0 && l0_fused_ok(p, planes)) wT = nullptr;  // W_ih^T of layer 0 only feeds the dX_0 GEMM, which the fused path replaces
+        if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
+      }
+    if (side != nullptr) CK(cudaEventRecord(side->join, side->stream), "join record");
+  }
+
   LengthArgs la{p.G, p.B, p.T, p.V, H, tokens, cfg->token_dtype, P->emb, emb_row_scale, at<int>(ws, p.tok32), at<int>(ws, p.lens),
                 at<int>(ws, p.row_kind)};
   TIMED(F_LENGTHS, 4, launch_lengths(la, st), "lengths");
   if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
-
-  // without a row scale every group has the same table: build it once (inference launches fuse up to hundreds of groups)
-  const bool table_shared = emb_row_scale == nullptr;
-  TableArgs ta{table_shared ? 1 : p.G, p.V, H, P->emb, emb_row_scale, {P->w_ih[0][0], P->w_ih[0][1]}, {P->b_ih[0][0], P->b_ih[0][1]},
-               {P->b_hh[0][0], P->b_hh[0][1]}, at<float>(ws, p.table)};
-  TIMED(F_L0_TABLE, 1, launch_l0_table(ta, st), "l0 table");
-
-  for (int l = 0; l < p.L; ++l)
-    for (int d = 0; d < 2; ++d) {
-      if (!p.live[l][d]) continue;
-      const int K = l == 0 ? H : 2 * H;
-      float* w = l > 0 ? at<float>(ws, p.wih_gi[l][d]) : nullptr;
-      float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
-      float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
-      if (l == 0 && l0_fused_ok(p, planes)) wT = nullptr;  // W_ih^T of layer 0 only feeds the dX_0 GEMM, which the fused path replaces
-      if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
-    }
+  if (side != nullptr) CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
 
   if (!p.live[p.L - 1][0]) TIMED(F_FILL, 1, launch_fill_zero(hn_top, (size_t)p.N * H, st), "hn zero");
 
@@ -468,7 +485,8 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
   float* dX0 = dY + p.R * 2 * H;
   float* partial = at<float>(ws, p.partial);
 
-  SideStream* side = side_stream();  // null unless IB200_OVERLAP=1 (experiment; see side_stream())
+  SideStream* side = side_stream();
+  const bool overlap_gemm = side != nullptr && gemm_overlap_enabled();
   bool pending_join = false;
   for (int l = p.L - 1; l >= 0; --l) {
     const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
@@ -514,7 +532,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       la.emb = P->emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_l0_mask;
       la.bias_partial = at<float>(ws, p.bias_partial[0]); la.bias_count = bwd_ctas;
       la.partial = partial; la.R = at<float>(ws, p.l0_scratch); la.d_emb = Gr->emb;
-      TimedScope ts(F_GEMM_DW, 4, st);
+      TimedScope ts(F_GEMM_DW, 3, st);
       const cudaError_t e = launch_l0_grads(la, prec, st);
       if (e == cudaSuccess) l0_done = true;
       else if (e != cudaErrorInvalidConfiguration) return cuda_fail(e, "layer-0 gradient gemm");
@@ -564,8 +582,24 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
         ra.out_b1 = Gr->b_ih[l][d]; ra.out_b2 = Gr->b_hh[l][d];
         ra.cs_ptr = at<float>(ws, p.bias_partial[l & 1]) + (size_t)(d - dir0) * bwd_ctas * 4 * H;
         ra.cs_count = bwd_ctas;
+        if (pending_join && st != side->stream) {  // a reduce of this call may still be reading `partial` on the side stream
+          CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
+          pending_join = false;
+        }
         TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, true), "dW_ih|dW_hh gemm");
-        TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
+        if (l > 0 && side != nullptr && st != side->stream) {
+          // the reduce (a small grid) runs on the side stream next to this layer's dY GEMM; joined before `partial` is written again
+          CK(cudaEventRecord(side->fork, st), "fork record");
+          CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+          {
+            cudaStream_t st = side->stream;
+            TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
+          }
+          CK(cudaEventRecord(side->join, side->stream), "join record");
+          pending_join = true;
+        } else {
+          TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
+        }
         continue;
       }
       TIMED(F_GEMM_DW, tn_launches(ta.KA, ta.NB, wide), tn_and_reduce(ta, ra, prec, st, planes, wide), "dW_ih gemm + reduce");
@@ -608,8 +642,8 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     return 0;
     };
 
-    if (l > 0 && planes && side != nullptr) {
-      // Upper layers of the TMA path: the next BPTT launch only needs dY, so dY goes first and this layer's weight-gradient GEMM
+    if (l > 0 && planes && overlap_gemm) {
+      // (experiment) Upper layers of the TMA path: the next BPTT launch only needs dY, so dY goes first and this layer's weight-gradient GEMM
       // + reduce (HBM-bound, needed by nobody until the end) run on the library's side stream UNDERNEATH the next layer's
       // latency-bound recurrent kernel.  Joined before anything else touches the `partial` scratch (top of the l == 0 iteration).
       if (int rc = input_grads(st)) return rc;

@@ -200,11 +200,11 @@ __global__ void __launch_bounds__(kNOut) l0_reduce_kernel(const float* __restric
 
 // dW_hh (per-group DropConnect mask on the forward direction), dW_ih, both bias gradients; one block per (direction slot, gate row k).
 // 256 threads = 64 output columns x 4 slices of the vocabulary; the slices are added in a fixed order.
-__global__ void __launch_bounds__(256) l0_finish_w_kernel(const L0GradArgs p, const float* __restrict__ R) {
+__device__ __forceinline__ void l0_finish_w(const L0GradArgs& p, const float* __restrict__ R, int ds, int k) {
   constexpr int H = 64;
   __shared__ float sr[kNS];        // S_gd[k][v] * scale_g[v]
   __shared__ float part[4][H];
-  const int ds = blockIdx.y, d = p.dir0 + ds, k = blockIdx.x, h = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int d = p.dir0 + ds, h = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int row = gi_to_torch_row(k, H);
   float whh = 0.f, wih = 0.f;
   for (int g = 0; g < p.G; ++g) {
@@ -238,11 +238,11 @@ __global__ void __launch_bounds__(256) l0_finish_w_kernel(const L0GradArgs p, co
 }
 
 // dEmb[v] = sum_g scale_g[v] * sum_d sum_k S_gd[k][v] W_ih,d[row(k)]; one block per vocabulary row, 64 columns x 4 slices of k
-__global__ void __launch_bounds__(256) l0_finish_emb_kernel(const L0GradArgs p, const float* __restrict__ R) {
+__device__ __forceinline__ void l0_finish_emb(const L0GradArgs& p, const float* __restrict__ R, int v) {
   constexpr int H = 64;
   __shared__ float col[256];
   __shared__ float part[4][H];
-  const int v = blockIdx.x, h = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int h = threadIdx.x & 63, q = threadIdx.x >> 6;
   float tot = 0.f;
   if (v != 0) {  // padding_idx = 0 receives no gradient (nn.Embedding(..., padding_idx=0), e2e_triplet.py:345)
     for (int g = 0; g < p.G; ++g) {
@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(256) l0_finish_emb_kernel(const L0GradArgs p, 
   part[q][h] = tot;
   __syncthreads();
   if (q == 0) p.d_emb[(size_t)v * H + h] = (part[0][h] + part[1][h]) + (part[2][h] + part[3][h]);
+}
+
+// both finishing passes in ONE launch (they read the same R and write disjoint outputs): blocks [0, 256*ndir) finish the weights,
+// the remaining V blocks the embedding rows
+__global__ void __launch_bounds__(256) l0_finish_kernel(const L0GradArgs p, const float* __restrict__ R) {
+  const int nw = 256 * p.ndir;
+  if ((int)blockIdx.x < nw) l0_finish_w(p, R, (int)blockIdx.x / 256, (int)blockIdx.x % 256);
+  else l0_finish_emb(p, R, (int)blockIdx.x - nw);
 }
 
 }  // namespace
@@ -304,8 +312,7 @@ cudaError_t launch_l0_grads(const L0GradArgs& a0, int precision, cudaStream_t st
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   l0_reduce_kernel<<<(unsigned)(a.ndir * a.G * 256), kNOut, 0, st>>>(a.partial, a.R, a.ctas_per_group);
-  l0_finish_w_kernel<<<dim3(256, a.ndir), 256, 0, st>>>(a, a.R);
-  l0_finish_emb_kernel<<<a.V, 256, 0, st>>>(a, a.R);
+  l0_finish_kernel<<<256 * a.ndir + a.V, 256, 0, st>>>(a, a.R);
   return cudaGetLastError();
 }
 

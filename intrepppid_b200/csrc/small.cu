@@ -92,36 +92,58 @@ __global__ void zero_int_kernel(int* p, int n) {
 
 // ---- K1a: P[g][d][v][gi] = (scale[g][v] * emb[v]) . w_ih_d[row(gi)] + b_ih_d[row] + b_hh_d[row] -----------------------------------
 // (utils/embedding_do.py:26-43 folded with the layer-0 x W_ih^T of nn.LSTM: the lookup-table identity)
-constexpr int kTableVpb = 8;  // vocabulary rows per block
+constexpr int kTableVpb = 32;  // vocabulary rows per block
 
+// One block = 32 vocabulary rows of one (group, direction).  W_ih is staged once per block, transposed, in shared memory (coalesced
+// global reads; the +1 pitch keeps the transposing stores conflict-free), every thread owns one gate column gi and keeps 32 running
+// sums; the embedding rows are read as broadcast float4.  The sum over k runs in ascending order with fmaf, one accumulator per
+// output, exactly like a plain dot product loop.
 template <int H>
-__global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p, int v_per_block) {
+__global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p) {
+  constexpr int NG = 4 * H, WP = NG + 1;
+  extern __shared__ __align__(16) float tsm[];
+  float* Wt = tsm;                 // [H][WP]: Wt[k][gi] = w_ih[row(gi)][k]
+  float* xs = tsm + H * WP;        // [kTableVpb][H] (16-byte aligned: H is a multiple of 4)
+  static_assert((H * WP) % 4 == 0, "xs alignment");
   const int gi = threadIdx.x, row = gi_to_torch_row(gi, H);
   const int g = blockIdx.y >> 1, d = blockIdx.y & 1;
-  float w[H];
-  const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
-#pragma unroll
-  for (int k = 0; k < H; ++k) w[k] = wr[k];
-  const float bias = p.b_ih[d][row] + p.b_hh[d][row];
-  __shared__ float x[kTableVpb][H];
   const int VT = p.V + kPadRows;  // rows >= V replicate row 0 (pad replicas, kernels.h)
-  const int v0 = blockIdx.x * v_per_block, nv = min(VT - v0, v_per_block);
-  // stage all rows of this block at once: the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
-  for (int i = gi; i < nv * H; i += 4 * H) {
-    const int vt = v0 + i / H, v = vt < p.V ? vt : 0, k = i % H;
-    const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
-    x[i / H][k] = sc * p.emb[(size_t)v * H + k];
+  const int v0 = blockIdx.x * kTableVpb, nv = min(VT - v0, kTableVpb);
+  const float* __restrict__ W = p.w_ih[d];
+  for (int i = gi; i < NG * H; i += NG) {
+    const int r = i / H, k = i % H;             // PyTorch row r = q*H + u  ->  gate-interleaved column 4u + q
+    Wt[k * WP + 4 * (r % H) + r / H] = W[i];
+  }
+  // the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
+  for (int i = gi; i < kTableVpb * H; i += NG) {
+    const int j = i / H, k = i % H, vt = v0 + j, v = vt < p.V ? vt : 0;
+    float x = 0.f;
+    if (j < nv) x = (p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f) * p.emb[(size_t)v * H + k];
+    xs[i] = x;
   }
   __syncthreads();
-  for (int j = 0; j < nv; ++j) {
-    float s = 0.f;
+  float acc[kTableVpb];
 #pragma unroll
-    for (int k = 0; k < H; ++k) s = fmaf(x[j][k], w[k], s);
-    p.table[(((size_t)(g * 2 + d)) * VT + v0 + j) * 4 * H + gi] = s + bias;
+  for (int j = 0; j < kTableVpb; ++j) acc[j] = 0.f;
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+#pragma unroll 2
+  for (int k4 = 0; k4 < H / 4; ++k4) {
+    const float w0 = Wt[(4 * k4 + 0) * WP + gi], w1 = Wt[(4 * k4 + 1) * WP + gi], w2 = Wt[(4 * k4 + 2) * WP + gi],
+                w3 = Wt[(4 * k4 + 3) * WP + gi];
+#pragma unroll
+    for (int j = 0; j < kTableVpb; ++j) {
+      const float4 x = xs4[j * (H / 4) + k4];
+      acc[j] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[j]))));
+    }
   }
+  const float bias = p.b_ih[d][row] + p.b_hh[d][row];
+#pragma unroll
+  for (int j = 0; j < kTableVpb; ++j)  // (compile-time indices keep acc[] in registers)
+    if (j < nv) p.table[(((size_t)(g * 2 + d)) * VT + v0 + j) * 4 * H + gi] = acc[j] + bias;
 }
 
 // any H (used for H > 64, where the weight row no longer fits the register file): same summation order, weights from L2
+constexpr int kTableVpbGeneric = 8;
 __global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p, int v_per_block) {
   extern __shared__ float xs[];  // [H]
   const int H = p.H, g = blockIdx.y >> 1, d = blockIdx.y & 1;
@@ -231,12 +253,21 @@ cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int H>
+cudaError_t launch_l0_table_h(const TableArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)H * (4 * H + 1) + (size_t)kTableVpb * H);
+  const cudaError_t e = cudaFuncSetAttribute(l0_table_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  l0_table_kernel<H><<<dim3((a.V + kPadRows + kTableVpb - 1) / kTableVpb, a.G * 2), 4 * H, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
-  const int vpb = kTableVpb;
+  if (a.H == 64) return launch_l0_table_h<64>(a, st);
+  if (a.H == 32) return launch_l0_table_h<32>(a, st);
+  const int vpb = kTableVpbGeneric;
   dim3 grid((a.V + kPadRows + vpb - 1) / vpb, a.G * 2);
-  if (a.H == 64) l0_table_kernel<64><<<grid, 256, 0, st>>>(a, vpb);
-  else if (a.H == 32) l0_table_kernel<32><<<grid, 128, 0, st>>>(a, vpb);
-  else l0_table_generic_kernel<<<grid, 256, a.H * sizeof(float), st>>>(a, vpb);
+  l0_table_generic_kernel<<<grid, 256, a.H * sizeof(float), st>>>(a, vpb);
   return cudaGetLastError();
 }
 

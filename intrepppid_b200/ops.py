@@ -321,6 +321,7 @@ class _LossHead(torch.autograd.Function):
         params = [_f32c(t) for t in (fc1_w, fc1_b, fc2_w, fc2_b)] + ([_f32c(proj_w), _f32c(proj_b)] if proj_w is not None else [])
         masks = [_f32c(t) for t in (m_fc1, m_do1, m_do2, m_fc2)]
         losses, y_hat = _OPS.loss_head_fwd(z, y, params, masks, float(beta))
+        ctx.set_materialize_grads(False)  # an unused output (normally y_hat) arrives as None instead of a zero-filled tensor
         ctx.beta, ctx.npar = float(beta), len(params)
         ctx.save_for_backward(z, y, *params, *[t for t in masks if t is not None])
         ctx.mask_present = [m is not None for m in masks]
