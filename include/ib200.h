@@ -174,6 +174,24 @@ int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin
                            const ib200_head_params* params, float* prob_out, void* stream);
 
 /*
+ * Production-mode dropout masks: every Bernoulli(keep)/keep mask of a step in one launch (the reference draws its 14 masks per step
+ * with torch's RNG: utils/embedding_do.py:26-28, utils/weightdrop.py:92-102, classifier/head/mlp.py:38-58).  Masks remain
+ * plain inputs of the compute entry points; this only replaces the twelve torch kernels that used to fill them.
+ *   specs          HOST array: out (device, numel floats), keep_prob in (0,1], row_len > 1 = one draw per row of row_len elements
+ *   seed, offset   Philox4x32-10 key / first counter; *counters_used (host, may be NULL) = counters consumed: pass offset + that
+ *                  as the next call's offset.  Element i of mask s = (u < keep ? 1/keep : 0), u from draw (i % 4) of counter
+ *                  offset + first_counter(s) + i / 4 (oracle/restatement.py::draw_masks is the bit-exact restatement).
+ */
+typedef struct ib200_mask_spec {
+  float* out;
+  int64_t numel;
+  float keep_prob;
+  int32_t row_len;
+} ib200_mask_spec;
+int ib200_draw_masks(int32_t n_specs, const ib200_mask_spec* specs, uint64_t seed, uint64_t offset, uint64_t* counters_used,
+                     void* stream);
+
+/*
  * Per-step classification metrics of TripletE2ENet.step (e2e/e2e_triplet.py:86-90,171-184): the batch values
  * of torchmetrics' (0.11.1) binary AUROC, AveragePrecision, MatthewsCorrCoef(threshold), Precision and Recall, in one launch and
  * without a host sync.  y_hat float [B] logits (squashed with a sigmoid unless every value already lies in [0,1], as torchmetrics

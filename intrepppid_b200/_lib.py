@@ -35,13 +35,17 @@ class AdamWHyper(C.Structure):
                                                                                                             ("maximize", C.c_int32)]
 
 
+class MaskSpec(C.Structure):
+    _fields_ = [("out", vp), ("numel", C.c_int64), ("keep_prob", C.c_float), ("row_len", C.c_int32)]
+
+
 class HeadMasks(C.Structure):
     _fields_ = [(n, vp) for n in ("fc1_w", "do1", "do2", "fc2_w")]
 
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_bwd",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn")
 
 _lib = None
@@ -76,6 +80,7 @@ def lib() -> C.CDLL:
     L.ib200_pair_score_range.argtypes = [C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64, C.POINTER(HeadParams), vp, vp]
     L.ib200_adamw_step.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64),
                                    C.POINTER(AdamWHyper), vp]
+    L.ib200_draw_masks.argtypes = [C.c_int32, C.POINTER(MaskSpec), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), vp]
     L.ib200_batch_metrics.argtypes = [C.c_int32, vp, vp, C.c_float, vp, vp, vp]
     L.ib200_dbg_gemm_nt.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]

@@ -36,10 +36,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -723,6 +723,28 @@ int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin
   if (!z || !hp || !prob_out || !hp->fc1_w || !hp->fc1_b || !hp->fc2_w || !hp->fc2_b) return fail(IB200_E_NULL, "ib200_pair_score_range: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_PAIR_SCORE, 1, launch_pair_score(M, H, z, nullptr, nullptr, (long long)p_count, (long long)p_begin, *hp, prob_out, st), "pair_score_range");
+  return 0;
+}
+
+int ib200_draw_masks(int32_t n_specs, const ib200_mask_spec* specs, uint64_t seed, uint64_t offset, uint64_t* counters_used, void* stream) {
+  if (n_specs < 0) return fail(IB200_E_SHAPE, "ib200_draw_masks: negative mask count");
+  if (counters_used) *counters_used = 0;
+  if (n_specs == 0) return 0;
+  if (!specs) return fail(IB200_E_NULL, "ib200_draw_masks: null pointer");
+  for (int i = 0; i < n_specs; ++i) {
+    if (specs[i].numel < 0 || !(specs[i].keep_prob > 0.f && specs[i].keep_prob <= 1.f)) return fail(IB200_E_SHAPE, "ib200_draw_masks: keep_prob must be in (0, 1]");
+    if (specs[i].numel > 0 && !specs[i].out) return fail(IB200_E_NULL, "ib200_draw_masks: null output");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  unsigned long long used = 0;
+  {
+    TimedScope ts__(F_MASKS, 0, st);
+    const cudaError_t e = launch_draw_masks(n_specs, specs, seed, offset, &used, st, &launches);
+    g_launches.fetch_add((unsigned long long)launches);
+    if (e != cudaSuccess) return cuda_fail(e, "draw_masks");
+  }
+  if (counters_used) *counters_used = used;
   return 0;
 }
 

@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(128) dw_reduce_kernel(const DwReduceArgs p) {
   float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!is_mat && p.cs_ptr != nullptr) {
     // bias partials written by the BPTT kernel: [cs_count][KA]
+#pragma unroll 8
     for (int k = 0; k < p.cs_count; ++k) {
       const float4 v = *reinterpret_cast<const float4*>(p.cs_ptr + (size_t)k * p.KA + gi);
       tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(128) dw_reduce_kernel(const DwReduceArgs p) {
   } else {
     for (int g = 0; g < p.G; ++g) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8  // (8 partial blocks in flight per thread; the additions keep their fixed order)
       for (int k = 0; k < p.ctas_per_group; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(p.partial + ((size_t)g * p.ctas_per_group + k) * blk + idx);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kNOut) l0_reduce_kernel(const float* __restric
   const size_t dg = blk / 256, k = blk % 256;
   const int c = threadIdx.x;
   float s = 0.f;
+#pragma unroll 8
   for (int cta = 0; cta < ctas_per_group; ++cta) s += partial[((dg * ctas_per_group + cta) * 256 + k) * kNOut + c];
   R[blk * kNOut + c] = s;
 }
@@ -219,6 +220,7 @@ __device__ __forceinline__ void l0_finish_w(const L0GradArgs& p, const float* __
       whh = fmaf(m, Rk[h], whh);
     }
     float acc = 0.f;
+#pragma unroll 8
     for (int v = q; v < p.V; v += 4) acc = fmaf(sr[v], p.emb[(size_t)v * H + h], acc);
     wih += acc;
   }
@@ -254,6 +256,7 @@ __device__ __forceinline__ void l0_finish_emb(const L0GradArgs& p, const float* 
         col[threadIdx.x] = R[(((size_t)ds * p.G + g) * 256 + threadIdx.x) * kNOut + 64 + v];
         __syncthreads();
         const float* __restrict__ W = p.w_ih[p.dir0 + ds];
+#pragma unroll 16
         for (int k = 64 * q; k < 64 * q + 64; ++k) acc = fmaf(col[k], W[(size_t)gi_to_torch_row(k, H) * H + h], acc);
       }
       tot = fmaf(sc, acc, tot);

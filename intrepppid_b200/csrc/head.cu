@@ -70,12 +70,15 @@ template <int H>
 __device__ __forceinline__ void load_head_weights(HeadSmem<H>& sm, const ib200_head_params& hp, const ib200_head_masks& hm) {
   constexpr int HH = H / 2;
   if constexpr (!HeadSmem<H>::kStaged) return;
+#pragma unroll 4
   for (int i = threadIdx.x; i < HH * H; i += blockDim.x) {
     const float m = hm.fc1_w != nullptr ? hm.fc1_w[i] : 1.0f;
     sm.w1[i / H][i % H] = hp.fc1_w[i] * m;  // WeightDrop on fc1.weight (mlp.py:38-46, weightdrop.py:100-102)
   }
-  if (hp.proj_w != nullptr)
+  if (hp.proj_w != nullptr) {
+#pragma unroll 8
     for (int i = threadIdx.x; i < H * H; i += blockDim.x) sm.wp[i / H][i % H] = hp.proj_w[i];
+  }
 }
 
 // forward pieces of the head for one sample; returns the logit (valid in all lanes) and keeps intermediates for backward

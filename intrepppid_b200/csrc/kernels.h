@@ -1,5 +1,6 @@
 // Internal launcher interface between capi.cu and the kernel translation units.
 #pragma once
+#include "../../include/ib200.h"
 #include "common.cuh"
 
 namespace ib200 {
@@ -196,6 +197,11 @@ size_t l0_grad_partial_floats(int G, int ndir);
 cudaError_t launch_l0_grads(const L0GradArgs& a, int precision, cudaStream_t st);
 
 cudaError_t launch_fill_zero(float* p, size_t n, cudaStream_t st);
+
+// ---- production-mode mask generation (masks.cu) --------------------------------------------------------------------------------
+constexpr int kMaskMaxSpecs = 8;  // masks per launch (table travels in the kernel parameters)
+cudaError_t launch_draw_masks(int n, const ib200_mask_spec* specs, unsigned long long seed, unsigned long long offset,
+                              unsigned long long* counters_used, cudaStream_t st, int* launches);
 
 // ---- per-step classification metrics (metrics.cu): out[5] = auroc, ap, mcc, precision, recall; conf[4] = tp, fp, tn, fn ---------
 cudaError_t launch_batch_metrics(int B, const float* y_hat, const long long* y, float threshold, float* out, int* conf, cudaStream_t st);

@@ -110,12 +110,15 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p) {
   const int VT = p.V + kPadRows;  // rows >= V replicate row 0 (pad replicas, kernels.h)
   const int v0 = blockIdx.x * kTableVpb, nv = min(VT - v0, kTableVpb);
   const float* __restrict__ W = p.w_ih[d];
-  for (int i = gi; i < NG * H; i += NG) {
-    const int r = i / H, k = i % H;             // PyTorch row r = q*H + u  ->  gate-interleaved column 4u + q
+#pragma unroll 16  // (16 independent loads in flight per thread; a rolled loop would pay one L2 round trip per element)
+  for (int it = 0; it < H; ++it) {
+    const int i = gi + it * NG, r = i / H, k = i % H;  // PyTorch row r = q*H + u  ->  gate-interleaved column 4u + q
     Wt[k * WP + 4 * (r % H) + r / H] = W[i];
   }
   // the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
-  for (int i = gi; i < kTableVpb * H; i += NG) {
+#pragma unroll
+  for (int it = 0; it < kTableVpb / 4; ++it) {
+    const int i = gi + it * NG;
     const int j = i / H, k = i % H, vt = v0 + j, v = vt < p.V ? vt : 0;
     float x = 0.f;
     if (j < nv) x = (p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f) * p.emb[(size_t)v * H + k];
@@ -220,6 +223,7 @@ __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz
   for (int k0 = 0; k0 < H; k0 += 32) {
     const int k = k0 + lane;
     float s = 0.f, sb = 0.f;
+#pragma unroll 8  // (loads of 8 rows in flight; the fmaf chain keeps its order)
     for (int n = warp; n < N; n += nwarp) {
       const float d = dz[(size_t)n * H + e];
       if (k < H) s = fmaf(d, pooled[(size_t)n * H + k], s);

@@ -67,6 +67,8 @@ class TripletE2ENet(_Base):
         self.lr = lr
         self.use_projection = use_projection
         self.last_step = None  # dict of detached tensors from the most recent step()
+        self.fused_masks = True   # draw the step's dropout masks in one launch (ib200_draw_masks) instead of torch RNG kernels
+        self._mask_offset = 0     # Philox counters consumed so far by this module
         self.compute_metrics = True  # log the reference's five per-step metrics (ib200_batch_metrics)
 
     # -- inference API (e2e_triplet.py:105-111): no projection here (quirk Q11); the caller applies sigmoid ---------------------
@@ -98,8 +100,7 @@ class TripletE2ENet(_Base):
         p1_seq, p2_seq, omid_anchor_seq, omid_positive_seq, omid_negative_seq, y = batch
         tokens = torch.stack((omid_anchor_seq, omid_positive_seq, omid_negative_seq, p1_seq, p2_seq), dim=0)
         if masks is None:
-            ers, whm = self.encoder.draw_masks(5)
-            head_masks = None
+            ers, whm, head_masks = self._draw_step_masks(y.shape[0])
         else:
             ers, whm, head_masks = masks.emb_row_scale, masks.whh_mask, masks.head
         # draw order of the reference: 5 x (row mask, W_hh mask), then the 4 head masks
@@ -127,6 +128,39 @@ class TripletE2ENet(_Base):
             for k, name in enumerate(ops.METRIC_NAMES):
                 self.log(f"{stage}_{name}", m[k], on_epoch=True, on_step=False)
         return loss
+
+    def _draw_step_masks(self, batch_size: int):
+        """The 14 dropout masks of a training step -> (emb_row_scale [5,V] | None, whh_mask [5,4H,H] | None, head masks
+        | None).  Production mode draws them in one launch (`ib200_draw_masks`, seeded from torch's CUDA seed plus a per-module
+        counter); anything that kernel does not cover (variational row masks, p >= 1, `fused_masks = False`) goes through the
+        torch-RNG draws of the encoder / head modules, which return None for the head so that step() draws them later."""
+        enc, rnn_dp = self.encoder, self.encoder.encoder.rnn_dp
+        p_emb, p_rnn, p_do = float(enc.embedding_droprate or 0.0), float(rnn_dp.dropout or 0.0), float(self.head.do_rate or 0.0)
+        dev = enc.embedder.weight.device
+        if (not self.training or not self.fused_masks or rnn_dp.variational or dev.type != "cuda"
+                or any(not (0.0 <= p < 1.0) for p in (p_emb, p_rnn, p_do))):
+            ers, whm = enc.draw_masks(5)
+            return ers, whm, None
+        V, H = enc.embedder.weight.shape
+        HH = H // 2
+        want = []
+        if p_emb > 0:
+            want.append(("ers", (5, V), 1.0 - p_emb))
+        if p_rnn > 0:
+            want.append(("whm", (5, 4 * H, H), 1.0 - p_rnn))
+        if p_do > 0:
+            want += [("fc1", (HH, H), 1.0 - p_do), ("do1", (batch_size, HH), 1.0 - p_do), ("do2", (batch_size, HH), 1.0 - p_do),
+                     ("fc2", (1, HH), 1.0 - p_do)]
+        got = {}
+        if self._mask_offset == 0 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._mask_offset = torch.distributed.get_rank() << 44  # data-parallel ranks share the seed: disjoint counter ranges
+        if want:
+            tensors, used = ops.draw_masks([(shape, keep, 0) for _, shape, keep in want], dev, torch.cuda.initial_seed(),
+                                           self._mask_offset)
+            self._mask_offset += used
+            got = {name: t for (name, _, _), t in zip(want, tensors)}
+        head = (got.get("fc1"), got.get("do1"), got.get("do2"), got.get("fc2"))
+        return got.get("ers"), got.get("whm"), head
 
     def training_step(self, batch, batch_idx):
         return self.step(batch, "train")

@@ -373,6 +373,31 @@ def pair_score_range(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin: int, p_count: int):
     return _OPS.pair_score_range(_f32c(z), _f32c(fc1_w), _f32c(fc1_b), _f32c(fc2_w), _f32c(fc2_b), int(p_begin), int(p_count))
 
 
+def draw_masks(specs, device, seed: int, offset: int):
+    """All Bernoulli(keep)/keep masks of a step in ONE launch (`ib200_draw_masks`, Philox4x32-10).
+    specs: [(shape, keep_prob, row_len)] with row_len > 1 for one draw per row (variational row masks) or 0.
+    Returns ([mask tensors, views of one flat buffer], counters consumed -- add them to `offset` for the next call)."""
+    import ctypes as C
+
+    sizes = [int(torch.Size(shape).numel()) for shape, _, _ in specs]
+    starts, total = [], 0
+    for n in sizes:
+        starts.append(total)
+        total += (n + 3) // 4 * 4  # every mask starts 16-byte aligned: float4 stores
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    _need_cuda(flat)
+    arr = (_lib.MaskSpec * len(specs))()
+    out = []
+    for i, ((shape, keep, row_len), n, st0) in enumerate(zip(specs, sizes, starts)):
+        view = flat[st0:st0 + n].view(shape)
+        out.append(view)
+        arr[i] = _lib.MaskSpec(view.data_ptr(), n, float(keep), int(row_len))
+    used = C.c_uint64(0)
+    check(lib().ib200_draw_masks(len(specs), arr, int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, C.byref(used),
+                                 _stream()), "ib200_draw_masks")
+    return out, int(used.value)
+
+
 METRIC_NAMES = ("auroc", "ap", "mcc", "precision", "rec")  # suffixes of the reference's log keys (e2e_triplet.py:171-184)
 
 

@@ -277,3 +277,51 @@ def test_step_logs_the_five_reference_metrics_without_torchmetrics():
     for key, name in (("val_auroc", "auroc"), ("val_ap", "ap"), ("val_mcc", "mcc"), ("val_precision", "precision"), ("val_rec", "recall")):
         assert abs(float(logged[key]) - ref[name]) < 2e-5, key
     assert {"val_loss", "val_classifier_loss", "val_triplet_loss", "val_loss_step"} <= set(logged)
+
+
+# ---- production-mode masks ------------------------------------------------------------------------------------------------------
+def test_draw_masks_kernel_is_bit_exact_with_the_philox_restatement():
+    from intrepppid_b200 import ops
+
+    specs = [((5, 250), 0.7, 0), ((3, 128, 32), 0.7, 0), ((32, 64), 0.5, 0), ((9, 32), 0.9, 0), ((1, 32), 0.7, 0), ((7, 16), 0.5, 16),
+             ((3,), 1.0, 0), ((2, 5), 0.25, 0), ((6, 6), 0.7, 0), ((1,), 0.5, 0)]  # 10 masks: two launches
+    got, used = ops.draw_masks(specs, "cuda", seed=1234567890123, offset=77)
+    numels = [int(torch.Size(s).numel()) for s, _, _ in specs]
+    # the second launch starts where the first one stopped: restate it as two calls of 8 and 2 masks
+    first = R.draw_masks(numels[:8], [k for _, k, _ in specs[:8]], 1234567890123, 77, row_lens=[r for _, _, r in specs[:8]])
+    used_first = sum(((n + max(r, 1) - 1) // max(r, 1) + 3) // 4 for n, (_, _, r) in zip(numels[:8], specs[:8]))
+    second = R.draw_masks(numels[8:], [k for _, k, _ in specs[8:]], 1234567890123, 77 + used_first, row_lens=[r for _, _, r in specs[8:]])
+    for g, w, (shape, _, _) in zip(got, first + second, specs):
+        assert g.shape == torch.Size(shape) and torch.equal(g.cpu().reshape(-1), w), shape
+    assert used == used_first + sum((n + 3) // 4 for n in numels[8:])
+    big, _ = ops.draw_masks([((5, 256, 64), 0.7, 0)], "cuda", seed=5, offset=0)
+    assert abs(float((big[0] != 0).float().mean()) - 0.7) < 0.01
+    with pytest.raises(Exception):
+        ops.draw_masks([((4,), 0.0, 0)], "cuda", seed=1, offset=0)
+
+
+def test_step_draws_its_masks_in_one_launch_and_is_reproducible():
+    from intrepppid_b200 import _lib
+
+    B, T, V = 8, 40, 60
+    batch = [t.cuda() for t in R.synthetic_batch(B, T, V, seed=6, padded=True)]
+
+    def run(fused):
+        torch.manual_seed(123)
+        net = build_product(R.init_params(vocab=V, E=64, L=2, seed=5), L=2, bi="last").train()
+        net.fused_masks = fused
+        net.compute_metrics = False
+        net.step(batch, "train")
+        l0 = _lib.launch_count()
+        losses = [float(net.step(batch, "train").detach()) for _ in range(2)]
+        return losses, (_lib.launch_count() - l0) // 2, net
+
+    a, launches_fused, net = run(True)
+    b, _, _ = run(True)
+    c, launches_torch, _ = run(False)
+    assert a == b and a[0] != a[1]            # same seed -> same masks; successive steps -> fresh masks
+    assert all(0.0 < x < 10.0 for x in a + c)
+    assert launches_fused == launches_torch + 1  # the library launches one more kernel (torch launches twelve fewer)
+    assert net._mask_offset > 0
+    net.eval()
+    assert net._draw_step_masks(B) == (None, None, None)

@@ -170,3 +170,22 @@ def test_metrics_restatement_degenerate_batches():
     assert no_neg["auroc"] == 0.0 and abs(no_neg["ap"] - 1.0) < 1e-6 and no_neg["precision"] == 1.0
     assert R.batch_metrics(torch.tensor([0.2, 0.7]), torch.tensor([0, 1]))["confusion"] == (1, 0, 1, 0)  # no sigmoid inside [0,1]
     assert R.batch_metrics(torch.tensor([0.2, 1.7]), torch.tensor([0, 1]))["confusion"] == (1, 1, 0, 0)  # sigmoid(0.2) > 0.5
+
+
+# ---- production-mode mask generator: Philox4x32-10 restatement against the Random123 known-answer vectors -----------------------
+def test_philox_known_answer_vectors():
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        assert tuple(R.philox4x32_10(ctr, key)) == want
+
+
+def test_mask_restatement_is_a_scaled_bernoulli_and_respects_offsets():
+    a, b = R.draw_masks([4000, 10], [0.7, 0.5], seed=11, offset=0)
+    assert set(a.unique().tolist()) <= {0.0, float(torch.tensor(1.0) / torch.tensor(0.7))} and abs(float((a != 0).float().mean()) - 0.7) < 0.03
+    assert set(b.unique().tolist()) <= {0.0, 2.0}
+    a2, = R.draw_masks([4000], [0.7], seed=11, offset=1)  # one counter later = the same stream shifted by 4 draws
+    assert torch.equal(a[4:], a2[:-4])
+    rows, = R.draw_masks([12], [0.5], seed=3, offset=0, row_lens=[4])
+    assert all(len(set(rows[i:i + 4].tolist())) == 1 for i in (0, 4, 8))
