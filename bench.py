@@ -329,7 +329,7 @@ def run_b200(args):
         out["cpu_baseline"] = cpu_baseline(args.variant)
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -398,7 +398,7 @@ def run_reference(args):
     cb = {"value": value, "unit": "seqs/s", "cores": os.cpu_count(), "kind": "port", "threads": torch.get_num_threads(),
           "sample": f"each step = the first {bs} of the {B} samples of the workload batch (5 sequences each, T={T}), "
                     f"fwd+bwd+AdamW, fp32, all host threads"}
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train seqs/sec (fwd+bwd+triplet) @ trunc_len 1500", "value": value, "unit": "seqs/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -407,10 +407,32 @@ def run_reference(args):
                            "ATen LSTM as nn.LSTM); the reference itself is Python and is not present on the GPU box"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1) are pointed at stderr and
+    the result line is written to a saved duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
