@@ -2,9 +2,12 @@
 
 The path shards by samples: every rank holds a full replica (0.87 MB) and 80 samples; the only exchange is ONE mean-allreduce
 of the live gradients (188,161 fp32 = 753 KB) per step, over NCCL/NVLink.  It is latency-bound, so the gradients are packed
-into two flat buckets ordered by backward completion and each bucket is reduced asynchronously as soon as it is complete:
-  bucket 0: head (+ triplet projection) + encoder fc  -- ready before the recurrent BPTT starts, reduced underneath it
-  bucket 1: LSTM + embedding                          -- ready when ib200_encoder_bwd returns
+into three buckets ordered by backward completion and each bucket is reduced asynchronously as soon as it is complete:
+  bucket 0: head (+ triplet projection)  -- the flat buffer ib200_loss_head_bwd wrote; ready before the recurrent BPTT starts
+  bucket 1: encoder fc                   -- the flat buffer ib200_pool_fc_bwd wrote; reduced underneath the BPTT kernels too
+  bucket 2: LSTM + embedding             -- the flat buffer ib200_encoder_bwd wrote; ready when it returns
+Every bucket is exactly one buffer of the kernels, so it is reduced IN PLACE (no torch.cat before, no copy back after), and over
+NCCL the mean is taken by the collective itself (ReduceOp.AVG): no extra kernel at all on the path.
 The reference has no distributed code at all (devices=1 is hard-wired, e2e_triplet.py:392-400); parameters that never
 receive a gradient (encoder.projection.*, quirk Q10) are left out of the buckets.
 """
@@ -17,14 +20,18 @@ import torch.distributed as dist
 
 
 def default_buckets(module: torch.nn.Module) -> List[List[torch.nn.Parameter]]:
-    early, late, seen = [], [], set()
+    head, fc, late, seen = [], [], [], set()
     for name, p in module.named_parameters():  # named_parameters de-duplicates the rnn / rnn_dp.module aliases
         if not p.requires_grad or id(p) in seen or ".projection." in name or name.startswith("projection."):
             continue
         seen.add(id(p))
-        is_late = (".rnn." in name or ".rnn_dp." in name or "embedder" in name)
-        (late if is_late else early).append(p)
-    return [b for b in (early, late) if b]
+        if ".rnn." in name or ".rnn_dp." in name or "embedder" in name:
+            late.append(p)
+        elif name.startswith("encoder.") and ".fc." in name:
+            fc.append(p)
+        else:
+            head.append(p)
+    return [b for b in (head, fc, late) if b]
 
 
 class GradientAllReducer:
@@ -43,6 +50,8 @@ class GradientAllReducer:
             for p in b:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.bytes_per_step = sum(p.numel() * 4 for b in self.buckets for p in b)
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide
+        self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
     def _on_grad(self, p):
         i = self._bucket_of[id(p)]
@@ -68,7 +77,8 @@ class GradientAllReducer:
         flat = base if base is not None else torch.cat([g.reshape(-1) for g in grads])
         self._flat[i] = flat
         if self.world > 1:
-            self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            self._work[i] = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for the outstanding reductions and write the averaged gradients back.  Call after loss.backward()."""
@@ -80,7 +90,7 @@ class GradientAllReducer:
             if self._work[i] is not None:
                 self._work[i].wait()
             flat = self._flat[i]
-            if self.world > 1:
+            if self.world > 1 and not self._avg_in_collective:
                 flat.div_(self.world)
             if not self._inplace[i]:  # (in-place buckets: the gradients ARE views of `flat`)
                 off = 0

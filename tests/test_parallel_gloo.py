@@ -15,7 +15,7 @@ def _free_port():
 
 
 class Toy(nn.Module):
-    """Same naming shape as the product net: an early bucket (head, fc) and a late one (rnn, embedder), plus a dead branch."""
+    """Same naming shape as the product net: head, encoder fc and (rnn, embedder) buckets, plus a dead branch."""
 
     def __init__(self):
         super().__init__()
@@ -39,9 +39,10 @@ def _worker(rank, world, port, q):
     net = Toy()
     buckets = default_buckets(net)
     names = {id(p): n for n, p in net.named_parameters()}
-    assert len(buckets) == 2
+    assert len(buckets) == 3  # head | encoder fc | rnn + embedder: one flat kernel buffer each in the product
     assert all("projection" not in names[id(p)] for b in buckets for p in b)
-    assert all(("rnn" in names[id(p)] or "embedder" in names[id(p)]) for p in buckets[1])
+    assert all(names[id(p)].startswith("head.") for p in buckets[0]) and all(".fc." in names[id(p)] for p in buckets[1])
+    assert all(("rnn" in names[id(p)] or "embedder" in names[id(p)]) for p in buckets[2])
     red = GradientAllReducer(net)
     g = torch.Generator().manual_seed(100)
     x_all = torch.randint(0, 10, (world * 3, 5), generator=g)
