@@ -546,6 +546,10 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
     const int q = warp & 3;
     float* est = Est + q * 32 * 36;
     const int tr = lane >> 3, tc4 = (lane & 7) * 4;
+    float4 bias4[NC / 32];
+#pragma unroll
+    for (int c = 0; c < NC / 32; ++c)
+      bias4[c] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + tc4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * kBM;
@@ -557,16 +561,21 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
       bool ok = rbase + lane < nrows;
       if (ok) ok = (int)((rbase + lane) % p.Tmax) < p.lens[p.G + (int)((rbase + lane) / p.Tmax) / p.B];
       const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-#pragma unroll 1
+      // TMEM loads are software-pipelined over the 32-column chunks: chunk c+1 is in flight while chunk c goes through the
+      // transpose and out to global memory (the bias of this thread's columns was loaded once, before the tile loop)
+      uint32_t r[2][32];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC;
+      tmem_ld32_nowait(t_row, r[0]);
+#pragma unroll
       for (int c = 0; c < NC / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC + c * 32, r);
+        tmem_wait_ld();
+        if (c + 1 < NC / 32) tmem_ld32_nowait(t_row + (c + 1) * 32, r[(c + 1) & 1]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(est + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          *reinterpret_cast<uint4*>(est + lane * 36 + 4 * j) =
+              make_uint4(r[c & 1][4 * j], r[c & 1][4 * j + 1], r[c & 1][4 * j + 2], r[c & 1][4 * j + 3]);
         __syncwarp();
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + tc4));
+        const float4 b = bias4[c];
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int rr = itr * 4 + tr;
