@@ -26,11 +26,16 @@ struct NTBarriers {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ bool nt_tile_live(const GemmNTArgs& p, long long row0, long long nrows) {
+// teff = the T_eff row of lens ([G] ints; the TMA kernel keeps a shared-memory copy: one L2 round trip per tile and role otherwise)
+__device__ __forceinline__ bool nt_tile_live(const GemmNTArgs& p, const int* teff, long long row0, long long nrows) {
   const long long rl = min(row0 + kBM, nrows) - 1;
   const int na = (int)(row0 / p.Tmax), nb = (int)(rl / p.Tmax);
-  return !(na == nb && (int)(row0 % p.Tmax) >= p.lens[p.G + na / p.B]);
+  return !(na == nb && (int)(row0 % p.Tmax) >= teff[na / p.B]);
 }
+__device__ __forceinline__ bool nt_tile_live(const GemmNTArgs& p, long long row0, long long nrows) {
+  return nt_tile_live(p, p.lens + p.G, row0, nrows);
+}
+constexpr int kNTLensSmem = 1024;  // groups whose T_eff is cached in shared memory by the TMA kernel
 
 // write 4 consecutive k (or m) values as bf16 hi / lo into the two planes of a swizzled tile
 template <bool SPLIT>
@@ -456,6 +461,9 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nrows = (long long)p.G * p.B * p.Tmax;
   const int ntiles = (int)((nrows + kBM - 1) / kBM);
+  __shared__ int teff_s[kNTLensSmem];
+  const int* teff = p.G <= kNTLensSmem ? teff_s : p.lens + p.G;
+  for (int i = tid; i < min(p.G, kNTLensSmem); i += 192) teff_s[i] = p.lens[p.G + i];
 
   if (tid == 0) {
     for (int s = 0; s < kStagesNT; ++s) {
@@ -475,6 +483,7 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
     const int f4_per_row = p.K / 4;
     for (int src = 0; src < p.nsrc; ++src) {
       const float* __restrict__ W = src ? p.W[1] : p.W[0];
+#pragma unroll 8  // (8 loads in flight per thread: a rolled loop pays one L2 round trip per 16 bytes)
       for (int i = tid; i < NC * f4_per_row; i += 192) {
         const int n = i / f4_per_row, k4 = i % f4_per_row, k = k4 * 4;
         const float4 v = *reinterpret_cast<const float4*>(W + (size_t)n * p.K + k);
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * kBM;
-        if (!nt_tile_live(p, row0, nrows)) continue;
+        if (!nt_tile_live(p, teff, row0, nrows)) continue;
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int stage = it % kStagesNT, src = kc / kslices, k0 = (kc % kslices) * kBK;
           mbar_wait(&bars->empty[stage], ((it / kStagesNT) & 1) ^ 1);
@@ -513,7 +522,7 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
       constexpr uint32_t idesc = idesc_bf16(kBM, NC, false, false);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (!nt_tile_live(p, (long long)tile * kBM, nrows)) continue;
+        if (!nt_tile_live(p, teff, (long long)tile * kBM, nrows)) continue;
         const uint32_t acc = tl & 1;
         mbar_wait(&bars->tempty[acc], ((tl >> 1) & 1) ^ 1);
         fence_after_sync();
@@ -553,13 +562,13 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * kBM;
-      if (!nt_tile_live(p, row0, nrows)) continue;
+      if (!nt_tile_live(p, teff, row0, nrows)) continue;
       const uint32_t acc = tl & 1;
       mbar_wait(&bars->tfull[acc], (tl >> 1) & 1);
       fence_after_sync();
       const long long rbase = row0 + q * 32;
       bool ok = rbase + lane < nrows;
-      if (ok) ok = (int)((rbase + lane) % p.Tmax) < p.lens[p.G + (int)((rbase + lane) / p.Tmax) / p.B];
+      if (ok) ok = (int)((rbase + lane) % p.Tmax) < teff[(int)((rbase + lane) / p.Tmax) / p.B];
       const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
       // TMEM loads are software-pipelined over the 32-column chunks: chunk c+1 is in flight while chunk c goes through the
       // transpose and out to global memory (the bias of this thread's columns was loaded once, before the tile loop)
