@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p
       const int row = gi_to_torch_row(gi, H);
       const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
       float s = 0.f;
+#pragma unroll 8
       for (int k = 0; k < H; ++k) s = fmaf(xs[k], wr[k], s);
       p.table[(((size_t)(g * 2 + d)) * VT + vt) * 4 * H + gi] = s + (p.b_ih[d][row] + p.b_hh[d][row]);
     }
