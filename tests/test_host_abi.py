@@ -149,3 +149,31 @@ def test_torch_custom_ops_are_registered_cuda_only():
         assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "CPU")
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.pool_fc_fwd(torch.zeros(2, 3, 32), torch.zeros(32, 32), torch.zeros(32), 0)
+
+
+def test_side_entry_points_validate_arguments_before_any_launch(lib):
+    """ib200_adamw_step / ib200_batch_metrics / ib200_draw_masks reject bad arguments on the host (no GPU needed, nothing launched)."""
+    import ctypes as C
+
+    from intrepppid_b200._lib import AdamWHyper, MaskSpec
+
+    launches = lib.ib200_launch_count()
+    h = AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 1e-2, 1.0, 1, 0)
+    assert lib.ib200_adamw_step(0, None, None, None, None, None, h, None) == 0           # nothing to do
+    assert lib.ib200_adamw_step(-1, None, None, None, None, None, h, None) == -2
+    assert lib.ib200_adamw_step(2, None, None, None, None, None, h, None) == -1 and b"null" in lib.ib200_last_error()
+    ptrs, n = (C.c_void_p * 1)(0), (C.c_int64 * 1)(4)
+    bad_step = AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 1e-2, 1.0, 0, 0)
+    assert lib.ib200_adamw_step(1, ptrs, ptrs, ptrs, ptrs, n, bad_step, None) == -2      # steps count from 1
+    bad_beta = AdamWHyper(1e-3, 1.0, 0.999, 1e-8, 1e-2, 1.0, 1, 0)
+    assert lib.ib200_adamw_step(1, ptrs, ptrs, ptrs, ptrs, n, bad_beta, None) == -2      # torch.optim.AdamW raises on beta1 = 1 too
+    assert lib.ib200_batch_metrics(0, None, None, 0.5, None, None, None) == -2
+    assert lib.ib200_batch_metrics(2000, None, None, 0.5, None, None, None) == -2        # one CTA: B <= 1024
+    assert lib.ib200_batch_metrics(8, None, None, 0.5, None, None, None) == -1
+    used = C.c_uint64(7)
+    assert lib.ib200_draw_masks(0, None, 1, 0, C.byref(used), None) == 0 and used.value == 0
+    spec = (MaskSpec * 1)(MaskSpec(None, 16, 0.0, 0))
+    assert lib.ib200_draw_masks(1, spec, 1, 0, None, None) == -2                          # keep_prob must be in (0, 1]
+    spec[0] = MaskSpec(None, 16, 0.7, 0)
+    assert lib.ib200_draw_masks(1, spec, 1, 0, None, None) == -1                          # null output
+    assert lib.ib200_launch_count() == launches
