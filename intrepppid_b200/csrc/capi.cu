@@ -275,7 +275,7 @@ bool l0_fused_ok(const Plan& p, bool planes) { return planes && p.H == 64 && p.V
 // split point of the two-phase rebalancing = (step time of a CTA alone on its SM) / (step time of two co-resident CTAs): the shared
 // SMs and the exclusive SMs then finish phase 1 together.  Measured on B200; IB200_SPLIT_FWD / IB200_SPLIT_BWD override.
 float split_frac(bool bwd) {
-  static const float f[2] = {[] { const char* e = getenv("IB200_SPLIT_FWD"); return e ? (float)atof(e) : 0.69f; }(),
+  static const float f[2] = {[] { const char* e = getenv("IB200_SPLIT_FWD"); return e ? (float)atof(e) : 0.66f; }(),
                              [] { const char* e = getenv("IB200_SPLIT_BWD"); return e ? (float)atof(e) : 0.65f; }()};
   return f[bwd ? 1 : 0];
 }
