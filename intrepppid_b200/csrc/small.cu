@@ -110,10 +110,24 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p) {
   const int VT = p.V + kPadRows;  // rows >= V replicate row 0 (pad replicas, kernels.h)
   const int v0 = blockIdx.x * kTableVpb, nv = min(VT - v0, kTableVpb);
   const float* __restrict__ W = p.w_ih[d];
-#pragma unroll 16  // (16 independent loads in flight per thread; a rolled loop would pay one L2 round trip per element)
-  for (int it = 0; it < H; ++it) {
-    const int i = gi + it * NG, r = i / H, k = i % H;  // PyTorch row r = q*H + u  ->  gate-interleaved column 4u + q
-    Wt[k * WP + 4 * (r % H) + r / H] = W[i];
+  if ((reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    // the whole 4H x H matrix in flight at once: H/4 independent 16-byte loads per thread, then the transposing stores
+    const float4* __restrict__ W4 = reinterpret_cast<const float4*>(W);
+    float4 w4[H / 4];
+#pragma unroll
+    for (int it = 0; it < H / 4; ++it) w4[it] = W4[gi + it * NG];
+#pragma unroll
+    for (int it = 0; it < H / 4; ++it) {
+      const int i4 = gi + it * NG, r = i4 / (H / 4), k = (i4 % (H / 4)) * 4;  // PyTorch row r = q*H + u -> gate-interleaved column 4u + q
+      float* dst = Wt + k * WP + 4 * (r % H) + r / H;
+      dst[0] = w4[it].x; dst[WP] = w4[it].y; dst[2 * WP] = w4[it].z; dst[3 * WP] = w4[it].w;
+    }
+  } else {
+#pragma unroll 16
+    for (int it = 0; it < H; ++it) {
+      const int i = gi + it * NG, r = i / H, k = i % H;
+      Wt[k * WP + 4 * (r % H) + r / H] = W[i];
+    }
   }
   // the reference multiplies mask/(1-p) into the row first (embedding_do.py:26-29)
 #pragma unroll
