@@ -3,8 +3,10 @@
  *
  * This is the drop-in boundary.  Every entry point takes plain structs, raw DEVICE pointers, sizes
  * and a cudaStream_t (as void*); no C++ or torch types cross it.  The caller (PyTorch caching allocator) owns every
- * buffer, including the workspace that carries saved activations from *_fwd to *_bwd.  Launchers are stateless and
- * re-entrant, enqueue on the given stream only, never allocate, never synchronise.
+ * buffer, including the workspace that carries saved activations from *_fwd to *_bwd.  Launchers are re-entrant, never
+ * allocate device memory, never synchronise, and all their work is ordered on the given stream: ib200_encoder_fwd / _bwd may run
+ * small independent kernels on one library-owned side stream per device, forked from and joined back into the given stream
+ * within the call (IB200_NO_SIDE=1 disables that).
  *
  * Reference interfaces replaced (paths relative to /root/reference/intrepppid/):
  *   ib200_encoder_fwd / _bwd    encoders/awd_lstm.py:147-155 (AWDLSTMEncoder.forward: truncation + embedding dropout)
