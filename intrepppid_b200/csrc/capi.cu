@@ -284,11 +284,10 @@ bool wants_phases(const Plan& p, int ndir) {
   const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir;
   return full_ctas <= 148 && half_ctas > 148 && half_ctas < 2 * 148 && p.T >= 128;
 }
-// One library-owned non-blocking stream + two events per device.  Used inside ib200_encoder_fwd / _bwd to run SMALL independent
+// One library-owned non-blocking stream + two events per host thread and device.  Used inside ib200_encoder_fwd / _bwd to run SMALL independent
 // kernels side by side (layer-0 table + W_ih preparation next to the length kernels; the upper layer's dW reduce next to the dY GEMM).
 // All of its work is forked from and joined back into the caller's stream within the call, so the "everything is ordered on the
-// stream you pass" contract of the ABI holds.  Calls on different streams of one device would share it (serialising only those
-// kernels).  IB200_NO_SIDE=1 puts everything back on the caller's stream.
+// stream you pass" contract of the ABI holds.  One per (host thread, device).  IB200_NO_SIDE=1 puts everything back on the caller's stream.
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -304,11 +303,11 @@ bool gemm_overlap_enabled() {
 SideStream* side_stream() {
   static const bool disabled = getenv("IB200_NO_SIDE") != nullptr;
   if (disabled) return nullptr;
-  static std::mutex mu;
-  static SideStream per_dev[64];
+  // per host thread and device: concurrent callers (e.g. the forward on the main thread and autograd's backward worker) never
+  // share a stream or an event, so the fork / join records of one call cannot be overtaken by another
+  thread_local SideStream per_dev[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(mu);
   SideStream& s = per_dev[dev];
   if (s.stream == nullptr) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
