@@ -75,3 +75,30 @@ def test_reference_parameter_census():
     net = ref_shim.build_reference_net()
     assert sum(p.numel() for p in net.parameters()) == 216498
     assert len(net.state_dict()) == 45
+
+
+def test_infer_from_csv_row_loop_matches_reference_batch_of_one():
+    """cli/infer.py:196-225 calls `net(embed_a.unsqueeze(0), embed_b.unsqueeze(0))` per row: the restatement of that loop (the oracle
+    of intrepppid_b200.infer) against the unmodified TripletE2ENet.forward + sigmoid, including a 1-token protein, an interior
+    <unk> and a row with an unknown id."""
+    torch.manual_seed(4)
+    V, E, L, T = 40, 32, 2, 24
+    net = ref_shim.build_reference_net(vocab=V, E=E, L=L, bi_reduce="last", use_projection=True).eval()
+    g = torch.Generator().manual_seed(5)
+    toks = {}
+    for i, n in enumerate((T, 1, 7, 13, 24, 9)):
+        row = torch.zeros(T, dtype=torch.long)
+        row[:n] = torch.randint(1, V, (n,), generator=g)
+        toks[f"P{i}"] = row
+    toks["P3"][2] = 0
+    rows = [("a", "P0", "P1"), ("b", "P2", "P3"), ("c", "P4", "NOPE"), ("d", "P5", "P5"), ("e", "P1", "P3")]
+    P = R.params_from_state_dict(net.state_dict(), L)
+    got = R.infer_from_csv_rows(toks, rows, P, num_layers=L, bi_reduce="last")
+    assert [i for i, _ in got] == ["a", "b", "d", "e"]
+    with torch.no_grad():
+        for (itx, p), (_, a, b) in zip(got, [r for r in rows if r[2] in toks]):
+            ref = float(torch.sigmoid(net(toks[a].unsqueeze(0), toks[b].unsqueeze(0)))[0, 0])
+            assert abs(p - ref) < 1e-6, itx
+        # and the batch-of-one result differs from a mixed-length batch (no packing): the reason the buckets exist
+        mixed = torch.sigmoid(net(torch.stack([toks["P1"], toks["P0"]]), torch.stack([toks["P3"], toks["P0"]])))[0, 0]
+        assert abs(float(mixed) - dict(got)["e"]) > 1e-6
