@@ -115,9 +115,45 @@ def make_case(name, c):
     print(f"{name}: loss={float(loss):.9f} cls={float(cls):.6f} trip={float(trip):.6f}  -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
+def make_infer_rows():
+    """`infer from_csv` (cli/infer.py:196-225): the reference's own row loop -- net(a.unsqueeze(0), b.unsqueeze(0)) + sigmoid at
+    batch 1 -- over a small ragged protein set (a 1-token protein, equal lengths, an interior <unk>, an unknown id)."""
+    torch.manual_seed(7)
+    V, E, L, T = 60, 64, 2, 48
+    net = ref_shim.build_reference_net(vocab=V, E=E, L=L, bi_reduce="last", use_projection=True).eval()
+    g = torch.Generator().manual_seed(8)
+    lens = [T, T, 1, 17, 17, 17, 5, 33, 40, 9, 29, 12]
+    toks = {}
+    for i, n in enumerate(lens):
+        row = torch.zeros(T, dtype=torch.long)
+        row[:n] = torch.randint(1, V, (n,), generator=g)
+        toks[f"P{i:02d}"] = row
+    toks["P07"][3] = 0
+    names = sorted(toks)
+    rows = [(f"itx{i}", names[int(torch.randint(0, len(names), (1,), generator=g))], names[int(torch.randint(0, len(names), (1,), generator=g))])
+            for i in range(40)]
+    rows[4] = ("itx4", "P01", "NOT_THERE")
+    rows[9] = ("itx9", "P02", "P02")
+    scored = []
+    with torch.no_grad():
+        for itx, a, b in rows:
+            if a not in toks or b not in toks:
+                continue  # the reference prints and continues (:203-213)
+            prob = torch.sigmoid(net(toks[a].unsqueeze(0), toks[b].unsqueeze(0)))
+            scored.append((itx, float(prob.detach().cpu().numpy().tolist()[0][0])))
+        z = {n: net.encoder(toks[n].unsqueeze(0))[0].clone() for n in names}
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    out = dict(config=dict(V=V, E=E, L=L, T=T, bi="last"), params={k: v.clone() for k, v in R.params_from_state_dict(sd, L).items()},
+               tokens=toks, rows=rows, scored=scored, z=z)
+    path = os.path.join(OUT, "infer_rows.pt")
+    torch.save(out, path)
+    print(f"infer_rows: {len(scored)} of {len(rows)} rows scored -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     if not ref_shim.available():
         raise SystemExit("the reference is not mounted; golden vectors can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
     for n, c in CASES.items():
         make_case(n, c)
+    make_infer_rows()

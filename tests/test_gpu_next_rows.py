@@ -325,3 +325,20 @@ def test_step_draws_its_masks_in_one_launch_and_is_reproducible():
     assert net._mask_offset > 0
     net.eval()
     assert net._draw_step_masks(B) == (None, None, None)
+
+
+def test_infer_pairs_vs_reference_golden():
+    """The embedding-cache path against numbers recorded from the reference's own batch-of-one row loop (tests/golden/infer_rows.pt)."""
+    from conftest import load_golden
+    from intrepppid_b200 import infer
+
+    gold = load_golden("infer_rows")
+    c = gold["config"]
+    net = build_product(gold["params"], L=c["L"], bi=c["bi"], use_projection=True).eval()
+    got = infer.infer_pairs(net, gold["tokens"], gold["rows"])
+    assert [i for i, _ in got] == [i for i, _ in gold["scored"]]
+    assert max(abs(a - b) for (_, a), (_, b) in zip(got, gold["scored"])) < 2e-5
+    names = sorted(gold["tokens"])
+    z = infer.embed_batch1(net, torch.stack([gold["tokens"][n] for n in names]).cuda())
+    for k, n in enumerate(names):
+        assert rel_l2(z[k], gold["z"][n]) < 1e-4, n

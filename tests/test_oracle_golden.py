@@ -98,3 +98,15 @@ def test_state_dict_contract_of_reference_recorded():
     assert "encoder.encoder.rnn.weight_hh_l0_raw" in keys and "encoder.encoder.rnn.weight_hh_l0" not in keys
     assert "encoder.encoder.rnn_dp.module.weight_hh_l0_raw" in keys
     assert all(k.startswith("encoder.projection.") for k in gold["dead_parameter_keys"])
+
+
+def test_infer_row_loop_matches_reference_golden():
+    """`infer from_csv` at batch 1 (cli/infer.py:196-225): probabilities and per-protein embeddings recorded from the reference."""
+    gold = load_golden("infer_rows")
+    c = gold["config"]
+    got = R.infer_from_csv_rows(gold["tokens"], gold["rows"], gold["params"], num_layers=c["L"], bi_reduce=c["bi"])
+    assert [i for i, _ in got] == [i for i, _ in gold["scored"]] and len(got) == len(gold["rows"]) - 1
+    assert max(abs(a - b) for (_, a), (_, b) in zip(got, gold["scored"])) < 1e-6
+    for name, z in gold["z"].items():
+        z1, _ = R.encoder_forward(gold["tokens"][name].unsqueeze(0), gold["params"], num_layers=c["L"], bi_reduce=c["bi"], training=False)
+        assert rel_l2(z1[0], z) < 1e-5, name
