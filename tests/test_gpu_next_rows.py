@@ -1,7 +1,10 @@
 """GPU parity for the SURVEY 8f rows around the hot path, through the C ABI:
   * ib200_adamw_step / FusedAdamW against torch.optim.AdamW (the reference's optimizer, e2e_triplet.py:231-255);
   * narrowed token ids (IB200_TOK_I32 / I16 / U8) against the int64 ids the reference ships -- bit-identical results;
-  * batch-of-one inference with the embedding cache (cli/infer.py:196-225) against the oracle's per-row batch-1 loop."""
+  * batch-of-one inference with the embedding cache (cli/infer.py:196-225) against the oracle's per-row batch-1 loop and against
+    rows recorded from the reference itself (tests/golden/infer_rows.pt);
+  * ib200_batch_metrics against the restatement of torchmetrics' binary metrics; ib200_draw_masks bit-exact against the Philox
+    restatement; the regression test for launch sets with more than 32 groups."""
 import copy
 
 import pytest
