@@ -24,6 +24,7 @@
  *   - weights are in PyTorch layout: weight_ih [4H,in], weight_hh [4H,H], gate row-blocks in order (i,f,g,o); two biases.
  *   - E == H (nn.LSTM(embedding_size, embedding_size, ...), awd_lstm.py:35-41).  Supported H: multiples of 32 in [32, 256]
  *     (32 / 64: register-resident recurrent kernels + tcgen05/TMA GEMMs; 96..256: thread-block-cluster recurrent kernels).
+ *     2 <= V <= 28672 (the lengths kernel keeps a per-sequence vocabulary histogram in shared memory).
  *   - "group" = one encoder call of the reference.  A training step fuses G=5 calls (anchor, positive, negative, p1, p2 --
  *     e2e_triplet.py:116-129) into one launch set; every group has its own masks and its own truncation lengths.
  *   - masks are INPUTS (nullptr = no drop).  emb_row_scale[g][v] = keep/(1-p) per vocabulary row; whh_l0_mask[g] = scaled
@@ -119,6 +120,16 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Device-side status of the ib200_encoder_fwd call that last filled `workspace`: status_out int32 [3,G] (device memory) =
+ * row 0 T1, row 1 T_eff, row 2 flags (IB200_STATUS_*), copied device-to-device on `stream`.  This is how a caller keeps the reference's
+ * error behaviour WITHOUT a host sync in the step: F.embedding raises on ids outside [0,V) (utils/embedding_do.py:35-43) and nn.LSTM
+ * raises on an all-pad batch (T_eff == 0, encoders/awd_lstm.py:53-56); here the kernels clamp / skip and record, and the
+ * caller reads the word whenever it next touches the host (intrepppid_b200/ops.py checks it lazily, one step late).
+ */
+#define IB200_STATUS_BAD_TOKEN 1 /* a token id outside [0, V) was clamped */
+int ib200_encoder_status(const ib200_cfg* cfg, const void* workspace, size_t workspace_bytes, int32_t* status_out, void* stream);
+
+/*
  * Encoder backward.  `workspace` is the buffer the matching _fwd call filled (cfg.training must have been 1).
  *   d_hn_top        float [2, G*B, H] gradient w.r.t. hn_top (entries of a dead direction are ignored)
  *   grads           overwritten; w_hh[0][0] receives the gradient of the RAW tensor (mask applied per group).
@@ -126,6 +137,17 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
 int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* params, const float* emb_row_scale,
                       const float* whh_l0_mask, const float* d_hn_top, const ib200_encoder_grads* grads,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same backward cut at a layer boundary: runs layers layer_hi, layer_hi-1, ..., layer_lo only (ib200_encoder_bwd is
+ * (L-1, 0)).  A full backward is any sequence of calls that covers L-1 .. 0 in descending order on the same workspace and stream
+ * (the gradient w.r.t. a layer's input stays in the workspace between calls); only the gradient tensors of the layers run are
+ * written (grads->emb with layer 0).  A data-parallel caller uses the cut to start the all-reduce of the upper layers' gradients
+ * while the layer-0 BPTT is still running (intrepppid_b200/parallel.py).
+ */
+int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* params, const float* emb_row_scale,
+                             const float* whh_l0_mask, const float* d_hn_top, const ib200_encoder_grads* grads,
+                             void* workspace, size_t workspace_bytes, int32_t layer_hi, int32_t layer_lo, void* stream);
 
 /* bi_reduce + fc.  hn_top [2,N,H] -> z [N,H].  pooled_out [N,H] and (max only) argmax_out uint8 [N,H] are saved for bwd. */
 int ib200_pool_fc_fwd(int32_t N, int32_t H, int32_t bi_reduce, const float* hn_top, const float* fc_w, const float* fc_b,

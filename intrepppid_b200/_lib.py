@@ -44,7 +44,7 @@ class HeadMasks(C.Structure):
 
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
-           "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_bwd",
+           "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_status", "ib200_encoder_bwd", "ib200_encoder_bwd_layers",
            "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn")
 
@@ -68,8 +68,11 @@ def lib() -> C.CDLL:
     L.ib200_workspace_bytes.restype = C.c_size_t
     L.ib200_workspace_bytes.argtypes = [C.POINTER(Cfg)]
     L.ib200_encoder_fwd.argtypes = [C.POINTER(Cfg), vp, C.POINTER(EncoderParams), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.ib200_encoder_status.argtypes = [C.POINTER(Cfg), vp, C.c_size_t, vp, vp]
     L.ib200_encoder_bwd.argtypes = [C.POINTER(Cfg), C.POINTER(EncoderParams), vp, vp, vp, C.POINTER(EncoderParams), vp,
                                     C.c_size_t, vp]
+    L.ib200_encoder_bwd_layers.argtypes = [C.POINTER(Cfg), C.POINTER(EncoderParams), vp, vp, vp, C.POINTER(EncoderParams), vp,
+                                           C.c_size_t, C.c_int32, C.c_int32, vp]
     L.ib200_pool_fc_fwd.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
     L.ib200_pool_fc_bwd.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ib200_loss_head_fwd.argtypes = [C.c_int32, C.c_int32, C.c_float, vp, vp, C.POINTER(HeadParams), C.POINTER(HeadMasks), vp,

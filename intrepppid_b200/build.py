@@ -17,6 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libib200.so")
+TORCH_LIB = os.path.join(PKG, "libib200_torch.so")  # TORCH_LIBRARY shim (csrc/torch_ops.cpp) over the C ABI
 OBJDIR = os.path.join(ROOT, "build", "obj")
 SOURCES = ["capi.cu", "small.cu", "head.cu", "lstm_fwd.cu", "lstm_bwd.cu", "lstm_cluster.cu", "gemm.cu", "gemm_tc.cu", "gemm_l0.cu", "optim.cu", "metrics.cu", "masks.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -46,7 +47,7 @@ def _digest() -> str:
 def build(verbose: bool = False, force: bool = False) -> str:
     stamp = os.path.join(OBJDIR, "stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(TORCH_LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
@@ -57,7 +58,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with ThreadPoolExecutor(max_workers=len(SOURCES) + 1) as ex:
+        shim = ex.submit(_build_torch_shim)
         results = list(ex.map(compile_one, SOURCES))
     log = []
     for src, obj, r in results:
@@ -72,9 +74,33 @@ def build(verbose: bool = False, force: bool = False) -> str:
     r = subprocess.run([nvcc, "-shared", "-o", LIB, *[o for _, o, _ in results], "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    shim.result()
     with open(stamp, "w") as fh:
         fh.write(dig)
     return LIB
+
+
+def _build_torch_shim() -> str:
+    """g++ build of the operator library: schemas + CUDA dispatch + Meta kernels, linked against libib200.so (rpath $ORIGIN) and
+    the torch libraries of the running interpreter.  No CUDA code in it: it only calls the C ABI."""
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    if not cxx:
+        raise RuntimeError("g++ not found: libib200_torch.so cannot be built")
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    inc = [f"-I{p}" for p in ce.include_paths("cuda")]
+    # libib200.so is named by path (it may not exist yet when this runs beside the nvcc jobs: resolved at load time through the rpath)
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *inc, os.path.join(CSRC, "torch_ops.cpp"), "-o", TORCH_LIB, f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda",
+           "-lc10_cuda", "-Wl,--allow-shlib-undefined", "-Wl,-rpath,$ORIGIN", "-Wl,--no-as-needed", f"-L{PKG}", "-l:libib200.so"]
+    if not os.path.exists(LIB):  # first build: link without naming the library, load order (ops.py loads libib200.so first) resolves it
+        cmd = cmd[:-2]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("torch shim build failed:\n" + r.stdout + r.stderr)
+    return TORCH_LIB
 
 
 if __name__ == "__main__":

@@ -99,6 +99,26 @@ struct Plan {
   size_t total;
 };
 
+// SMs of the current device (148 on B200); 148 when no device can be queried (ib200_workspace_bytes on a CPU-only host)
+int sm_count() {
+  thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 148; }
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    else { (void)cudaGetLastError(); cached = 148; }
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ablation flags for timing experiments (tools/ablate_*.py); read once per process
+int dbg_flags() {
+  static const int v = [] { const char* e = getenv("IB200_DBG"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 bool cfg_ok(const ib200_cfg* c) {
   if (!(c && c->G >= 1 && c->B >= 1 && c->T >= 1 && c->V >= 2 && (c->H == 32 || c->H == 64 || lstm_cluster_supports(c->H)) && c->L >= 1 &&
         c->L <= IB200_MAX_LAYERS && c->bi_reduce >= 0 && c->bi_reduce <= 2 && (c->precision == 0 || c->precision == 1) &&
@@ -107,7 +127,8 @@ bool cfg_ok(const ib200_cfg* c) {
   // token rows are indexed with 32-bit integers inside the kernels; ids are staged as uint16 by the H <= 64 layer-0 kernel, whose
   // per-CTA token stage ((T + 4) x 16 bytes of shared memory) bounds trunc_len
   if ((long long)c->G * c->B * c->T >= (1LL << 31)) return false;
-  if ((c->H == 32 || c->H == 64) && (c->V + kPadRows > 65536 || c->T > 11000)) return false;
+  if (c->V > kMaxVocab) return false;  // the lengths kernel keeps a [V] histogram + a [V] row list in shared memory (small.cu)
+  if ((c->H == 32 || c->H == 64) && c->T > 11000) return false;
   return true;
 }
 
@@ -124,7 +145,7 @@ Plan make_plan(const ib200_cfg* c) {
   }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
-  p.lens = take(sizeof(int) * 2 * p.G);
+  p.lens = take(sizeof(int) * 3 * p.G);  // T1 | T_eff | status flags
   p.tok32 = take(sizeof(int) * p.R);
   p.row_kind = take(sizeof(int) * (size_t)p.G * p.V);
   p.table = take(sizeof(float) * (size_t)p.G * 2 * (p.V + kPadRows) * 4 * H);
@@ -151,7 +172,7 @@ Plan make_plan(const ib200_cfg* c) {
           p.cst[l][d] = take(sizeof(float) * p.R * H);
         }
     p.bwd_scratch = p.L > 1 ? p.X[0] : take(sizeof(float) * p.R * 3 * H);  // X is dead once the forward is done
-    p.ctas_per_group = std::max(1, 148 / p.G);
+    p.ctas_per_group = std::max(1, sm_count() / p.G);
     p.partial = take(sizeof(float) * std::max((size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H),  // up to [dW_ih | dW_hh] fused
                                               l0_grad_partial_floats(p.G, 2)));
     p.l0_scratch = take(sizeof(float) * l0_grad_scratch_floats(p.G, 2));
@@ -270,7 +291,10 @@ template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
 
 // gemm_l0.cu covers layer 0 of the TMA path when the vocabulary fits its one-hot tile (the decision must be the same in _fwd and _bwd)
-bool l0_fused_ok(const Plan& p, bool planes) { return planes && p.H == 64 && p.V <= 256 && !getenv("IB200_NO_L0_FUSED"); }
+bool l0_fused_ok(const Plan& p, bool planes) {
+  static const bool disabled = getenv("IB200_NO_L0_FUSED") != nullptr;
+  return planes && p.H == 64 && p.V <= 256 && !disabled;
+}
 
 // split point of the two-phase rebalancing = (step time of a CTA alone on its SM) / (step time of two co-resident CTAs): the shared
 // SMs and the exclusive SMs then finish phase 1 together.  Measured on B200; IB200_SPLIT_FWD / IB200_SPLIT_BWD override.
@@ -281,8 +305,8 @@ float split_frac(bool bwd) {
 }
 // the launchers rebalance in two phases exactly when a HALF launch has between one and two CTAs per SM (lstm_fwd.cu / lstm_bwd.cu)
 bool wants_phases(const Plan& p, int ndir) {
-  const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir;
-  return full_ctas <= 148 && half_ctas > 148 && half_ctas < 2 * 148 && p.T >= 128;
+  const int full_ctas = ((p.B + 7) / 8) * p.G * ndir, half_ctas = ((p.B + 3) / 4) * p.G * ndir, sms = sm_count();
+  return full_ctas <= sms && half_ctas > sms && half_ctas < 2 * sms && p.T >= 128;
 }
 // One library-owned non-blocking stream + two events per host thread and device.  Used inside ib200_encoder_fwd / _bwd to run SMALL independent
 // kernels side by side (layer-0 table + W_ih preparation next to the length kernels; the upper layer's dW reduce next to the dY GEMM).
@@ -320,6 +344,21 @@ SideStream* side_stream() {
   }
   return &s;
 }
+
+// Joins the side stream back into the caller's stream on EVERY exit path of a launcher: an early error return between fork and join
+// must not leave side-stream kernels writing into a workspace the caller is about to free.
+struct SideGuard {
+  SideStream* side;
+  cudaStream_t st;
+  bool armed = false;
+  SideGuard(SideStream* s, cudaStream_t main_st) : side(s), st(main_st) {}
+  ~SideGuard() {
+    if (armed && side != nullptr) {
+      (void)cudaEventRecord(side->join, side->stream);
+      (void)cudaStreamWaitEvent(st, side->join, 0);
+    }
+  }
+};
 
 PhaseArgs phase_args(void* ws, const Plan& p, bool bwd) {
   PhaseArgs a{};
@@ -373,7 +412,7 @@ size_t ib200_workspace_bytes(const ib200_cfg* cfg) {
 
 int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_encoder_params* P, const float* emb_row_scale,
                       const float* whh_l0_mask, int32_t* lengths_out, float* hn_top, void* ws, size_t ws_bytes, void* stream) {
-  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max, token_dtype in IB200_TOK_*, G*B*T < 2^31; for H <= 64 also V <= 65472 and T <= 11000)");
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_fwd: unsupported cfg (H multiple of 32 in [32, 256], 1<=L<=4, bi_reduce in last/mean/max, token_dtype in IB200_TOK_*, G*B*T < 2^31, 2 <= V <= 28672; for H <= 64 also T <= 11000)");
   if (!tokens || !P || !hn_top || !ws || !P->emb) return fail(IB200_E_NULL, "ib200_encoder_fwd: null pointer");
   const Plan p = make_plan(cfg);
   if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_fwd: workspace too small");
@@ -387,9 +426,11 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
 
   // the layer-0 table and the W_ih preparation do not depend on the length kernels: they run next to them on the side stream
   SideStream* side = side_stream();
+  SideGuard guard(side, st);
   if (side != nullptr) {
     CK(cudaEventRecord(side->fork, st), "fork record");
     CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+    guard.armed = true;
   }
   // without a row scale every group has the same table: build it once (inference launches fuse up to hundreds of groups)
   const bool table_shared = emb_row_scale == nullptr;
@@ -416,7 +457,10 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
                 at<int>(ws, p.row_kind)};
   TIMED(F_LENGTHS, 4, launch_lengths(la, st), "lengths");
   if (lengths_out) CK(cudaMemcpyAsync(lengths_out, at<int>(ws, p.lens), sizeof(int) * 2 * p.G, cudaMemcpyDeviceToDevice, st), "lengths copy");
-  if (side != nullptr) CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
+  if (side != nullptr) {
+    CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
+    guard.armed = false;
+  }
 
   if (!p.live[p.L - 1][0]) TIMED(F_FILL, 1, launch_fill_zero(hn_top, (size_t)p.N * H, st), "hn zero");
 
@@ -455,7 +499,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
       fa.cstate[d] = (p.train && p.live[l][d]) ? at<float>(ws, p.cst[l][d]) : nullptr;
     }
     fa.hn = l == p.L - 1 ? hn_top : nullptr;
-    { const char* e = getenv("IB200_DBG"); fa.dbg = e ? atoi(e) : 0; }
+    fa.dbg = dbg_flags();
     if (!cluster && wants_phases(p, ndir)) {  // scheduling state of the two-phase rebalancing
       fa.ph = phase_args(ws, p, false);
       TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(fa.ph.sm_load), 257, st), "phase counters");
@@ -466,16 +510,34 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
   return 0;
 }
 
+int ib200_encoder_status(const ib200_cfg* cfg, const void* ws, size_t ws_bytes, int32_t* status_out, void* stream) {
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_status: unsupported cfg");
+  if (!ws || !status_out) return fail(IB200_E_NULL, "ib200_encoder_status: null pointer");
+  const Plan p = make_plan(cfg);
+  if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_status: workspace too small");
+  CK(cudaMemcpyAsync(status_out, reinterpret_cast<const char*>(ws) + p.lens, sizeof(int) * 3 * p.G, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream), "status copy");
+  return 0;
+}
+
 int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const float* emb_row_scale, const float* whh_l0_mask,
                       const float* d_hn_top, const ib200_encoder_grads* Gr, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg_ok(cfg)) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_bwd: cfg must be the training cfg used for _fwd");
+  return ib200_encoder_bwd_layers(cfg, P, emb_row_scale, whh_l0_mask, d_hn_top, Gr, ws, ws_bytes, cfg->L - 1, 0, stream);
+}
+
+int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P, const float* emb_row_scale, const float* whh_l0_mask,
+                             const float* d_hn_top, const ib200_encoder_grads* Gr, void* ws, size_t ws_bytes, int32_t layer_hi,
+                             int32_t layer_lo, void* stream) {
   if (!cfg_ok(cfg) || !cfg->training) return fail(IB200_E_UNSUPPORTED, "ib200_encoder_bwd: cfg must be the training cfg used for _fwd");
   if (!P || !d_hn_top || !Gr || !ws) return fail(IB200_E_NULL, "ib200_encoder_bwd: null pointer");
+  if (layer_lo < 0 || layer_hi >= cfg->L || layer_lo > layer_hi) return fail(IB200_E_SHAPE, "ib200_encoder_bwd_layers: need 0 <= layer_lo <= layer_hi < L");
   const Plan p = make_plan(cfg);
   if (ws_bytes < p.total) return fail(IB200_E_WORKSPACE, "ib200_encoder_bwd: workspace too small");
-  for (int l = 0; l < p.L; ++l)
+  for (int l = layer_lo; l <= layer_hi; ++l)
     for (int d = 0; d < 2; ++d)
       if (!Gr->w_ih[l][d] || !Gr->w_hh[l][d] || !Gr->b_ih[l][d] || !Gr->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_bwd: null gradient tensor");
-  if (!Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
+  if (layer_lo == 0 && !Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
   const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
@@ -485,9 +547,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
   float* partial = at<float>(ws, p.partial);
 
   SideStream* side = side_stream();
+  SideGuard guard(side, st);  // armed from the first fork on: any exit path joins the side stream (a redundant join is harmless)
   const bool overlap_gemm = side != nullptr && gemm_overlap_enabled();
   bool pending_join = false;
-  for (int l = p.L - 1; l >= 0; --l) {
+  for (int l = layer_hi; l >= layer_lo; --l) {
     const int dir0 = p.live[l][0] ? 0 : 1, ndir = p.live[l][0] ? 2 : 1;
     LstmBwdArgs ba{};
     ba.G = p.G; ba.B = p.B; ba.Tmax = p.T; ba.dir0 = dir0; ba.ndir = ndir; ba.lens = lens;
@@ -500,7 +563,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     ba.dy = l == p.L - 1 ? nullptr : dY;
     ba.dy_stride = 2 * H;
     ba.dhn = l == p.L - 1 ? d_hn_top : nullptr;
-    { const char* e = getenv("IB200_DBG"); ba.dbg = e ? atoi(e) : 0; }
+    ba.dbg = dbg_flags();
     ba.planes = planes ? 1 : 0;
     ba.bias_partial = planes ? at<float>(ws, p.bias_partial[l & 1]) : nullptr;
     if (!cluster && wants_phases(p, ndir)) {
@@ -532,10 +595,10 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       la.bias_partial = at<float>(ws, p.bias_partial[0]); la.bias_count = bwd_ctas;
       la.partial = partial; la.R = at<float>(ws, p.l0_scratch); la.d_emb = Gr->emb;
       TimedScope ts(F_GEMM_DW, 3, st);
+      // no fallback: the forward skipped the W_ih^T preparation of layer 0 because this path was chosen (same l0_fused_ok decision)
       const cudaError_t e = launch_l0_grads(la, prec, st);
-      if (e == cudaSuccess) l0_done = true;
-      else if (e != cudaErrorInvalidConfiguration) return cuda_fail(e, "layer-0 gradient gemm");
-      else (void)cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "layer-0 gradient gemm");
+      l0_done = true;
     }
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l); `st` = the stream they are issued on
@@ -590,6 +653,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
           // the reduce (a small grid) runs on the side stream next to this layer's dY GEMM; joined before `partial` is written again
           CK(cudaEventRecord(side->fork, st), "fork record");
           CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+          guard.armed = true;
           {
             cudaStream_t st = side->stream;
             TIMED(F_DW_REDUCE, 1, launch_dw_reduce(ra, st), "dW reduce");
@@ -648,6 +712,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
       if (int rc = input_grads(st)) return rc;
       CK(cudaEventRecord(side->fork, st), "fork record");
       CK(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait");
+      guard.armed = true;
       if (int rc = weight_grads(side->stream)) return rc;
       CK(cudaEventRecord(side->join, side->stream), "join record");
       pending_join = true;
@@ -657,6 +722,7 @@ int ib200_encoder_bwd(const ib200_cfg* cfg, const ib200_encoder_params* P, const
     }
   }
   if (pending_join) CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
+  guard.armed = false;
   return 0;
 }
 

@@ -134,7 +134,7 @@ constexpr int kPhaseCheck = 16;  // step at which a phase-1 CTA looks at its SM'
 __device__ __forceinline__ int sm_id() {
   unsigned id;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
-  return (int)id;
+  return (int)(id & 255u);  // index into PhaseArgs::sm_load[256]
 }
 // which (tile, group, direction slot) this CTA works on; false: nothing to do (phase 2 CTA beyond the list)
 __device__ __forceinline__ bool phase_cta(const PhaseArgs& ph, int G, int& bx, int& g, int& dz) {

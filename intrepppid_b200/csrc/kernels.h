@@ -13,9 +13,12 @@ struct LengthArgs {
   const float* emb;            // [V,H]
   const float* emb_row_scale;  // [G,V] or null
   int* tok32;                  // [G*B, Tin]
-  int* lens;                   // [2,G]: T1 then T_eff (zeroed by the launcher)
+  int* lens;                   // [3,G]: T1, T_eff, status flags (kStatus*), all zeroed by the launcher
   int* row_kind;               // scratch [G,V]
 };
+constexpr int kStatusBadToken = 1;            // a token id outside [0, V) was clamped (F.embedding raises on it in the reference)
+constexpr size_t kLen2MaxSmem = 224 * 1024;   // len2_kernel keeps a [V] histogram + a [V] list in shared memory
+constexpr int kMaxVocab = (int)(kLen2MaxSmem / (2 * sizeof(int)));  // = 28672 vocabulary rows
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st);
 
 // ---- K1a: layer-0 input-projection table P[g][d][v][4H] (GI order) --------------------------------------------------------

@@ -13,16 +13,18 @@ __global__ void len1_kernel(const LengthArgs p) {
   const int n = blockIdx.x, g = n / p.B;
   const TOK* __restrict__ src = (const TOK*)p.tokens + (size_t)n * p.Tin;
   int* __restrict__ dst = p.tok32 + (size_t)n * p.Tin;
-  int cnt = 0;
+  int cnt = 0, bad = 0;
   for (int t = threadIdx.x; t < p.Tin; t += blockDim.x) {
     const long long v64 = (long long)src[t];
-    // ids outside [0, V) make F.embedding raise in the reference (the Python layer checks that when check_lengths is on); here
-    // they are clamped so that no kernel can index outside the [V, .] tables
+    // ids outside [0, V) make F.embedding raise in the reference; here they are clamped so that no kernel can index outside the
+    // [V, .] tables, and the group's sticky status flag (lens row 2, bit 0) records it for the caller's lazy check (no host sync)
     const int v = v64 < 0 ? 0 : (v64 >= p.V ? p.V - 1 : (int)v64);
+    bad |= (v64 < 0 || v64 >= p.V);
     dst[t] = v;
     cnt += (v64 != 0);
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(p.lens + 2 * p.G + g, kStatusBadToken);
   __shared__ int ws[32];
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
   __syncthreads();
@@ -259,7 +261,13 @@ __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz
 }  // namespace
 
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
-  zero_int_kernel<<<(2 * a.G + 63) / 64, 64, 0, st>>>(a.lens, 2 * a.G);
+  const size_t hist_bytes = 2 * (size_t)a.V * sizeof(int);
+  if (hist_bytes > kLen2MaxSmem) return cudaErrorInvalidConfiguration;  // cfg_ok bounds V (kMaxVocab) so that this cannot happen
+  if (hist_bytes > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(len2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  zero_int_kernel<<<(3 * a.G + 63) / 64, 64, 0, st>>>(a.lens, 3 * a.G);
   switch (a.token_dtype) {
     case IB200_TOK_I64: len1_kernel<long long><<<a.G * a.B, 256, 0, st>>>(a); break;
     case IB200_TOK_I32: len1_kernel<int><<<a.G * a.B, 256, 0, st>>>(a); break;
@@ -268,7 +276,7 @@ cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
     default: return cudaErrorInvalidValue;
   }
   nz_rows_kernel<<<dim3((a.V + 7) / 8, a.G), 256, 0, st>>>(a, a.row_kind);
-  len2_kernel<<<a.G * a.B, 128, 2 * a.V * sizeof(int), st>>>(a, a.row_kind);
+  len2_kernel<<<a.G * a.B, 128, hist_bytes, st>>>(a, a.row_kind);
   return cudaGetLastError();
 }
 

@@ -162,6 +162,16 @@ class TripletE2ENet(_Base):
         head = (got.get("fc1"), got.get("do1"), got.get("do2"), got.get("fc2"))
         return got.get("ers"), got.get("whm"), head
 
+    # -- checkpoint hooks (Lightning calls them; the state_dict keys stay exactly the reference's 45) ---------------------------------
+    def on_save_checkpoint(self, checkpoint):
+        checkpoint["ib200_mask_offset"] = int(self._mask_offset)  # Philox counters consumed: a resumed run continues the mask stream
+
+    def on_load_checkpoint(self, checkpoint):
+        self._mask_offset = int(checkpoint.get("ib200_mask_offset", 0))
+
+    def on_train_epoch_end(self):
+        ops.check_pending(sync=True)  # surface any error the kernels recorded (out-of-range ids, all-pad batch) at the latest here
+
     def training_step(self, batch, batch_idx):
         return self.step(batch, "train")
 

@@ -91,12 +91,24 @@ class AWDLSTMEncoder(nn.Module):
     def __init__(self, embedder: nn.Module, embedding_size: int, embedding_droprate: float, rnn_num_layers: int,
                  rnn_dropout_rate: float, variational_dropout: bool, bi_reduce: str):
         super().__init__()
+        # the kernels implement exactly what the reference passes to F.embedding (utils/embedding_do.py:30-43 with the embedder of
+        # e2e_triplet.py:345): padding_idx 0 (row 0 never receives a gradient), no max_norm renormalisation, no frequency scaling
+        if isinstance(embedder, nn.Embedding):
+            pad = embedder.padding_idx
+            if pad is None:
+                pad = -1  # embedding_do.py:31-32 turns None into -1 (= no padding row); the kernels always skip row 0
+            if pad != 0 or embedder.max_norm is not None or embedder.scale_grad_by_freq or embedder.sparse:
+                raise ValueError("AWDLSTMEncoder on the sm_100a kernels needs nn.Embedding(V, E, padding_idx=0) without max_norm, "
+                                 "scale_grad_by_freq or sparse gradients (the reference's embedder, e2e_triplet.py:345)")
         self.embedder = embedder
         self.embedding_droprate = embedding_droprate
         self.encoder = AWDLSTM(embedding_size, rnn_num_layers, rnn_dropout_rate, variational_dropout, bi_reduce)
         self.projection = Projection(self.encoder.embedding_size, self.encoder.embedding_size * 2, 3)
         self.precision = "fp32"       # "fp32" (bf16x2-split tensor-core, 1e-4 class) or "bf16" (2e-2 class)
-        self.check_lengths = True     # raise like nn.LSTM on an all-pad batch (costs one host sync per call)
+        # True: errors of the reference (id outside [0,V) -> IndexError, all-pad batch -> RuntimeError) are detected on the device
+        # and raised at the next call / ops.check_pending(), without a host sync; "sync": raised before returning (one host sync,
+        # the reference pays two per call); False: not checked
+        self.check_lengths = True
         self.last_lengths: Optional[torch.Tensor] = None  # int32 [2,G] (T1, T_eff) of the most recent call, on device
 
     # -- masks ---------------------------------------------------------------------------------------------------------------

@@ -74,6 +74,12 @@ def embed_batch1(net, tokens: torch.Tensor, max_groups: int = 128) -> torch.Tens
         raise RuntimeError("embed_batch1 is an inference API: call net.eval() first (cli/infer.py:171)")
     if not tokens.is_cuda:
         raise ops._lib.IB200Error("embed_batch1 needs CUDA tokens (no CPU fallback)")
+    rnn_dp = enc.encoder.rnn_dp
+    if rnn_dp.variational and float(rnn_dp.dropout or 0.0) > 0.0:
+        # the reference re-draws a W_hh row mask on EVERY call, eval included (utils/weightdrop.py:92-95, quirk Q8), so a cached
+        # embedding is not defined for such a model; encode per protein with net.encoder(x) (which draws the mask) instead
+        raise RuntimeError("embed_batch1 / EmbeddingCache need a deterministic eval encoder: variational_dropout=True draws a fresh "
+                           "weight_hh_l0 row mask per call even in eval mode (reference quirk Q8)")
     M = tokens.shape[0]
     E = enc.embedder.weight.shape[1]
     t1, t_eff = batch1_lengths(tokens, enc.embedder.weight)

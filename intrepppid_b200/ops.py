@@ -1,9 +1,11 @@
 """torch custom ops + autograd wiring over the C ABI (include/ib200.h).  Torch is plumbing here: device memory, streams, the
 dispatcher and the autograd graph.
 
-The raw launchers are registered with the PyTorch dispatcher as `torch.ops.intrepppid_b200.*` (schemas below, CUDA kernels only:
-there is no CPU / Meta implementation, a CPU tensor fails in the dispatcher or earlier with IB200Error):
-  encoder_fwd, encoder_bwd, pool_fc_fwd, pool_fc_bwd, loss_head_fwd, loss_head_bwd, pair_score
+The raw launchers are registered with the PyTorch dispatcher as `torch.ops.intrepppid_b200.*` by the C++ operator library
+libib200_torch.so (csrc/torch_ops.cpp: TORCH_LIBRARY schemas, CUDA implementations that call the C ABI, Meta shape functions;
+there is no CPU kernel -- a CPU tensor fails in the dispatcher or earlier with IB200Error):
+  encoder_fwd, encoder_bwd, encoder_bwd_layers, pool_fc_fwd, pool_fc_bwd, loss_head_fwd, loss_head_bwd, pair_score,
+  pair_score_range, batch_metrics
 On top of them, three differentiable ops:
   encode_hidden   tokens[G,B,T] -> top-layer final hidden states hn[2,G*B,H]   (ib200_encoder_fwd / _bwd)
   pool_fc         hn -> z[G*B,H]                                               (ib200_pool_fc_fwd / _bwd)
@@ -18,7 +20,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import Cfg, EncoderParams, HeadMasks, HeadParams, check, lib, ptr
+from ._lib import Cfg, check, lib
 
 
 def _stream() -> int:
@@ -63,174 +65,99 @@ def lstm_param_order(num_layers: int) -> List[str]:
     return names
 
 
-def _fill_encoder_struct(emb, lstm: Sequence[torch.Tensor], L: int) -> EncoderParams:
-    s = EncoderParams()
-    s.emb = ptr(emb)
-    i = 0
-    for l in range(L):
-        for d in range(2):
-            s.w_ih[l][d], s.w_hh[l][d], s.b_ih[l][d], s.b_hh[l][d] = (ptr(lstm[i + k]) for k in range(4))
-            i += 4
-    return s
+# ------------------------------------------------------------------------------------------------------------------------------
+# operator library: torch.ops.intrepppid_b200.*  (C++ TORCH_LIBRARY shim csrc/torch_ops.cpp: CUDA kernels + Meta shape functions)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _load_operator_library():
+    import os
+
+    path = os.path.join(_lib.PKG, "libib200_torch.so")
+    if not os.path.exists(path):
+        raise _lib.IB200Error(f"{path} is missing: build it with `python -m intrepppid_b200.build` "
+                              "(intrepppid_b200 has no CPU or PyTorch fallback)")
+    lib()  # libib200.so first: the shim resolves the C ABI against it
+    torch.ops.load_library(path)
+    return torch.ops.intrepppid_b200
+
+
+class _Ops:
+    """torch.ops.intrepppid_b200 with the C ABI's status codes surfaced as IB200Error (the shim raises them as RuntimeError
+    tagged "[ib200]"; everything else -- dispatcher errors for CPU tensors, shape errors -- passes through unchanged)."""
+
+    def __init__(self, ns):
+        self._ns = ns
+
+    def __getattr__(self, name):
+        op = getattr(self._ns, name)
+
+        def call(*args):
+            try:
+                return op(*args)
+            except RuntimeError as e:
+                if "[ib200]" in str(e):
+                    raise _lib.IB200Error(str(e).split("\n")[0]) from None
+                raise
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
+
+
+_OPS = _Ops(_load_operator_library())
+
+_TOKEN_DTYPES = (torch.int64, torch.int32, torch.int16, torch.uint8)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
-# dispatcher registration: torch.ops.intrepppid_b200.*  (CUDA only)
+# error behaviour without host syncs.  The reference raises immediately on a token id outside [0,V) (F.embedding,
+# utils/embedding_do.py:35-43) and on an all-pad batch (nn.LSTM: "Expected sequence length to be larger than 0", quirk Q13) -- it
+# pays two host syncs per encoder call for its truncations anyway (awd_lstm.py:53-54,149-150).  Here the kernels record both
+# conditions in a device-side status word (ib200_encoder_status); it travels to pinned host memory asynchronously and is
+# examined the next time the op is entered (or when `check_pending(sync=True)` is called), i.e. at most one call late and
+# without ever blocking the host.  `check_lengths="sync"` restores the immediate (synchronising) check.
 # ------------------------------------------------------------------------------------------------------------------------------
-_TORCH_LIB = torch.library.Library("intrepppid_b200", "DEF")
-_TORCH_LIB.define("encoder_fwd(Tensor tokens, Tensor emb, Tensor[] lstm, Tensor? emb_row_scale, Tensor? whh_mask, int num_layers, "
-                  "int bi_reduce, int precision, bool training) -> (Tensor, Tensor, Tensor)")
-_TORCH_LIB.define("encoder_bwd(Tensor(a!) ws, Tensor d_hn, Tensor emb, Tensor[] lstm, Tensor? emb_row_scale, Tensor? whh_mask, int G, "
-                  "int B, int T, int num_layers, int bi_reduce, int precision) -> Tensor")
-_TORCH_LIB.define("pool_fc_fwd(Tensor hn, Tensor fc_w, Tensor fc_b, int bi_reduce) -> (Tensor, Tensor, Tensor)")
-_TORCH_LIB.define("pool_fc_bwd(Tensor dz, Tensor pooled, Tensor? argmax, Tensor fc_w, int bi_reduce) -> (Tensor, Tensor)")
-_TORCH_LIB.define("loss_head_fwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta) -> (Tensor, Tensor)")
-_TORCH_LIB.define("loss_head_bwd(Tensor z, Tensor y, Tensor[] params, Tensor?[] masks, float beta, Tensor d_loss, Tensor? d_y_hat) "
-                  "-> (Tensor, Tensor)")
-_TORCH_LIB.define("pair_score(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, Tensor? idx_a, Tensor? idx_b) -> Tensor")
-_TORCH_LIB.define("batch_metrics(Tensor y_hat, Tensor y, float threshold) -> (Tensor, Tensor)")
-_TORCH_LIB.define("pair_score_range(Tensor z, Tensor fc1_w, Tensor fc1_b, Tensor fc2_w, Tensor fc2_b, int p_begin, int p_count) -> Tensor")
+class _PendingStatus:
+    __slots__ = ("host", "event", "V")
+
+    def __init__(self, status: torch.Tensor, V: int):
+        self.host = torch.empty(status.shape, dtype=torch.int32, pin_memory=True)
+        self.host.copy_(status, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.V = V
+
+    def examine(self):
+        st = self.host
+        if int(st[2].max()) & 1:
+            raise IndexError(f"token id out of range: ids must lie in [0, {self.V}) (detected by the encoder kernels; the ids were "
+                             "clamped for memory safety)")
+        if int(st[1].min()) <= 0:
+            raise RuntimeError("Expected sequence length to be larger than 0 in RNN")
 
 
-_TOKEN_DTYPES = {torch.int64: _lib.TOKEN_DTYPE["int64"], torch.int32: _lib.TOKEN_DTYPE["int32"],
-                 torch.int16: _lib.TOKEN_DTYPE["int16"], torch.uint8: _lib.TOKEN_DTYPE["uint8"]}
+_PENDING: List[_PendingStatus] = []
 
 
-def _cfg(G, B, T, V, H, L, bi_reduce, precision, training, token_dtype=0) -> Cfg:
-    return Cfg(G, B, T, V, H, L, bi_reduce, precision, 1 if training else 0, token_dtype)
+def check_pending(sync: bool = False) -> None:
+    """Raise the errors recorded by earlier encoder calls (out-of-range token id -> IndexError, all-pad batch -> RuntimeError).
+    sync=False looks only at status words that have already arrived on the host (never blocks); sync=True waits for all."""
+    while _PENDING:
+        head = _PENDING[0]
+        if sync:
+            head.event.synchronize()
+        elif not head.event.query():
+            return
+        _PENDING.pop(0)
+        try:
+            head.examine()
+        except Exception:
+            _PENDING.clear()
+            raise
 
 
-def _encoder_fwd_cuda(tokens, emb, lstm, emb_row_scale, whh_mask, num_layers, bi_reduce, precision, training):
-    """-> (hn_top [2,G*B,H], lengths int32 [2,G], workspace uint8).  ib200_encoder_fwd."""
-    G, B, T = tokens.shape
-    V, H = emb.shape
-    if tokens.dtype not in _TOKEN_DTYPES:
-        raise _lib.IB200Error(f"token ids must be int64 / int32 / int16 / uint8, got {tokens.dtype}")
-    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, training, _TOKEN_DTYPES[tokens.dtype])
-    nbytes = lib().ib200_workspace_bytes(cfg)
-    if nbytes == 0:
-        raise _lib.IB200Error(f"unsupported encoder configuration for the sm_100a kernels: H={H} (multiple of 32 in 32..256), "
-                              f"L={num_layers} (1..4), G*B*T={G * B * T} (< 2^31), T={T} (<= 11000 when H <= 64), V={V}")
-    dev = tokens.device
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    lens = torch.empty(2, G, dtype=torch.int32, device=dev)
-    hn = torch.empty(2, G * B, H, dtype=torch.float32, device=dev)
-    P = _fill_encoder_struct(emb, lstm, num_layers)
-    check(lib().ib200_encoder_fwd(cfg, ptr(tokens), P, ptr(emb_row_scale), ptr(whh_mask), ptr(lens), ptr(hn), ptr(ws), nbytes,
-                                  _stream()), "ib200_encoder_fwd")
-    return hn, lens, ws
-
-
-def _encoder_bwd_cuda(ws, d_hn, emb, lstm, emb_row_scale, whh_mask, G, B, T, num_layers, bi_reduce, precision):
-    """-> one flat fp32 gradient buffer: [d_emb | d_lstm tensors in `lstm` order] (a single allreduce bucket).  ib200_encoder_bwd."""
-    V, H = emb.shape
-    cfg = _cfg(G, B, T, V, H, num_layers, bi_reduce, precision, True)
-    sizes = [emb.numel()] + [p.numel() for p in lstm]
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=emb.device)
-    views, off = [], 0
-    for n, ref in zip(sizes, [emb] + list(lstm)):
-        views.append(flat[off:off + n].view(ref.shape))
-        off += n
-    Gs = _fill_encoder_struct(views[0], views[1:], num_layers)
-    P = _fill_encoder_struct(emb, lstm, num_layers)
-    check(lib().ib200_encoder_bwd(cfg, P, ptr(emb_row_scale), ptr(whh_mask), ptr(d_hn), Gs, ptr(ws), ws.numel(), _stream()),
-          "ib200_encoder_bwd")
-    return flat
-
-
-def _pool_fc_fwd_cuda(hn, fc_w, fc_b, mode):
-    _, N, H = hn.shape
-    z = torch.empty(N, H, dtype=torch.float32, device=hn.device)
-    pooled = torch.empty(N, H, dtype=torch.float32, device=hn.device)
-    argmax = torch.empty((N, H) if mode == 2 else (0,), dtype=torch.uint8, device=hn.device)
-    check(lib().ib200_pool_fc_fwd(N, H, mode, ptr(hn), ptr(fc_w), ptr(fc_b), ptr(z), ptr(pooled), ptr(argmax) if mode == 2 else None,
-                                  _stream()), "ib200_pool_fc_fwd")
-    return z, pooled, argmax
-
-
-def _pool_fc_bwd_cuda(dz, pooled, argmax, fc_w, mode):
-    N, H = dz.shape
-    d_hn = torch.empty(2, N, H, dtype=torch.float32, device=dz.device)
-    flat = torch.empty(H * H + H, dtype=torch.float32, device=dz.device)
-    d_w, d_b = flat[:H * H].view(H, H), flat[H * H:]
-    check(lib().ib200_pool_fc_bwd(N, H, mode, ptr(dz), ptr(pooled), ptr(argmax) if mode == 2 else None, ptr(fc_w), ptr(d_hn), ptr(d_w),
-                                  ptr(d_b), _stream()), "ib200_pool_fc_bwd")
-    return d_hn, flat
-
-
-def _head_structs(params, masks):
-    params = list(params) + [None] * (6 - len(params))
-    hp = HeadParams(*(ptr(t) for t in params))
-    hm = HeadMasks(*(ptr(m) for m in masks))
-    return hp, hm
-
-
-def _loss_head_fwd_cuda(z, y, params, masks, beta):
-    """params = [fc1_w, fc1_b, fc2_w, fc2_b (, proj_w, proj_b)], masks = [fc1_w, do1, do2, fc2_w] (None = no drop)."""
-    _, B, H = z.shape
-    hp, hm = _head_structs(params, masks)
-    losses = torch.empty(3, dtype=torch.float32, device=z.device)
-    y_hat = torch.empty(B, dtype=torch.float32, device=z.device)
-    check(lib().ib200_loss_head_fwd(B, H, float(beta), ptr(z), ptr(y), hp, hm, ptr(losses), ptr(y_hat), _stream()),
-          "ib200_loss_head_fwd")
-    return losses, y_hat
-
-
-def _loss_head_bwd_cuda(z, y, params, masks, beta, d_loss, d_y_hat):
-    """-> (dz [5,B,H], flat gradient buffer [fc1_w | fc1_b | fc2_w | fc2_b (| proj_w | proj_b)])."""
-    _, B, H = z.shape
-    has_proj = len(params) == 6
-    hp, hm = _head_structs(params, masks)
-    dz = torch.empty_like(z)
-    HH = H // 2
-    n_flat = HH * H + HH + HH + 1 + (H * H + H if has_proj else 0)
-    flat = torch.empty(n_flat, dtype=torch.float32, device=z.device)
-    o = 0
-    g_fc1_w = flat[o:o + HH * H]; o += HH * H
-    g_fc1_b = flat[o:o + HH]; o += HH
-    g_fc2_w = flat[o:o + HH]; o += HH
-    g_fc2_b = flat[o:o + 1]; o += 1
-    g_pw = g_pb = None
-    if has_proj:
-        g_pw = flat[o:o + H * H]; o += H * H
-        g_pb = flat[o:o + H]
-    hg = HeadParams(ptr(g_fc1_w), ptr(g_fc1_b), ptr(g_fc2_w), ptr(g_fc2_b), ptr(g_pw), ptr(g_pb))
-    check(lib().ib200_loss_head_bwd(B, H, float(beta), ptr(z), ptr(y), hp, hm, ptr(d_loss), ptr(d_y_hat), ptr(dz), hg, _stream()),
-          "ib200_loss_head_bwd")
-    return dz, flat
-
-
-def _pair_score_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, idx_a, idx_b):
-    M, H = z.shape
-    P = idx_a.numel() if idx_a is not None else M * (M + 1) // 2
-    out = torch.empty(P, dtype=torch.float32, device=z.device)
-    hp = HeadParams(ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), None, None)
-    check(lib().ib200_pair_score(M, H, ptr(z), ptr(idx_a), ptr(idx_b), P, hp, ptr(out), _stream()), "ib200_pair_score")
-    return out
-
-
-def _pair_score_range_cuda(z, fc1_w, fc1_b, fc2_w, fc2_b, p_begin, p_count):
-    M, H = z.shape
-    out = torch.empty(p_count, dtype=torch.float32, device=z.device)
-    hp = HeadParams(ptr(fc1_w), ptr(fc1_b), ptr(fc2_w), ptr(fc2_b), None, None)
-    check(lib().ib200_pair_score_range(M, H, ptr(z), int(p_begin), int(p_count), hp, ptr(out), _stream()), "ib200_pair_score_range")
-    return out
-
-
-def _batch_metrics_cuda(y_hat, y, threshold):
-    """-> (float32 [5] = auroc, ap, mcc, precision, recall ; int32 [4] = tp, fp, tn, fn).  ib200_batch_metrics."""
-    B = y_hat.numel()
-    out = torch.empty(5, dtype=torch.float32, device=y_hat.device)
-    conf = torch.empty(4, dtype=torch.int32, device=y_hat.device)
-    check(lib().ib200_batch_metrics(B, ptr(y_hat), ptr(y), float(threshold), ptr(out), ptr(conf), _stream()), "ib200_batch_metrics")
-    return out, conf
-
-
-for _name, _fn in (("batch_metrics", _batch_metrics_cuda), ("pair_score_range", _pair_score_range_cuda), ("encoder_fwd", _encoder_fwd_cuda), ("encoder_bwd", _encoder_bwd_cuda), ("pool_fc_fwd", _pool_fc_fwd_cuda),
-                   ("pool_fc_bwd", _pool_fc_bwd_cuda), ("loss_head_fwd", _loss_head_fwd_cuda), ("loss_head_bwd", _loss_head_bwd_cuda),
-                   ("pair_score", _pair_score_cuda)):
-    _TORCH_LIB.impl(_name, _fn, "CUDA")
-_OPS = torch.ops.intrepppid_b200
+# Data-parallel hook (parallel.GradientAllReducer): called from inside the encoder backward as soon as the gradients of the layers
+# >= 1 are final, with the flat fp32 slice that holds them -- the all-reduce of that slice then runs under the layer-0 BPTT kernel.
+EARLY_GRAD_HOOKS: list = []
 
 
 class _EncodeHidden(torch.autograd.Function):
@@ -243,6 +170,8 @@ class _EncodeHidden(torch.autograd.Function):
         L = econf.num_layers
         training = any(ctx.needs_input_grad[6:])  # (grad mode is off inside Function.forward; this is the reliable signal)
         _need_cuda(tokens, emb, emb_row_scale, whh_mask, *lstm)
+        if check_lengths:
+            check_pending()  # errors recorded by earlier calls whose status word has reached the host by now (non-blocking)
         if tokens.dtype not in _TOKEN_DTYPES:  # int64 as the reference ships them, or narrowed ids (SURVEY 8f input feeding)
             tokens = tokens.long()
         tokens = tokens.contiguous()
@@ -254,26 +183,42 @@ class _EncodeHidden(torch.autograd.Function):
         if whm is not None and tuple(whm.shape) != (G, 4 * H, H):
             raise ValueError(f"whh_l0_mask must be [G={G}, {4 * H}, {H}], got {tuple(whm.shape)}")
         cfg = econf.cfg(G, B, T, V, H, training)  # validates bi_reduce (concat raises like the reference)
-        hn, lens, ws = _OPS.encoder_fwd(tokens, emb_c, lstm_c, ers, whm, L, cfg.bi_reduce, cfg.precision, training)
+        hn, status, ws = _OPS.encoder_fwd(tokens, emb_c, lstm_c, ers, whm, L, cfg.bi_reduce, cfg.precision, training)
         if lengths_holder is not None:
-            lengths_holder.append(lens)
+            lengths_holder.append(status[:2])
         if check_lengths:
-            lo, hi = int(tokens.min()), int(tokens.max())
-            if lo < 0 or hi >= V:  # F.embedding raises on such ids; the kernels clamp them for memory safety only
-                raise IndexError(f"token id out of range: ids must lie in [0, {V}), got [{lo}, {hi}]")
-            if int(lens[1].min()) <= 0:  # one host sync; the reference does two per encoder call (awd_lstm.py:53-54,149-150)
-                raise RuntimeError("Expected sequence length to be larger than 0 in RNN")
+            _PENDING.append(_PendingStatus(status, V))
+            if check_lengths == "sync":  # the reference's timing: raise before returning (one host sync)
+                check_pending(sync=True)
         if training:
             ctx.dims = (G, B, T, L, cfg.bi_reduce, cfg.precision)
+            ctx.consumed = False
             ctx.save_for_backward(ws, emb_c, ers, whm, *lstm_c)
         return hn
 
     @staticmethod
     def backward(ctx, d_hn):
+        if ctx.consumed:
+            # ib200_encoder_bwd overwrites the saved gates in place with the gate gradients: a second pass would read garbage
+            raise RuntimeError("the encoder's saved activations were consumed by the first backward (the BPTT kernels work in place); "
+                               "retain_graph=True / double backward through encode_hidden is not supported")
+        ctx.consumed = True
         ws, emb, ers, whm, *lstm = ctx.saved_tensors
-        flat = _OPS.encoder_bwd(ws, _f32c(d_hn), emb, lstm, ers, whm, *ctx.dims)
+        G, B, T, L, bi, prec = ctx.dims
+        refs = [emb] + list(lstm)
+        flat = torch.empty(sum(r.numel() for r in refs), dtype=torch.float32, device=emb.device)
+        d_hn = _f32c(d_hn)
+        if L > 1 and EARLY_GRAD_HOOKS:
+            # layers L-1 .. 1 first; their gradients (the tail of `flat`) are final here and can be all-reduced under layer 0's BPTT
+            _OPS.encoder_bwd_layers(ws, d_hn, emb, lstm, ers, whm, G, B, T, L, bi, prec, flat, L - 1, 1)
+            upper = flat[sum(r.numel() for r in refs[:9]):]
+            for hook in list(EARLY_GRAD_HOOKS):
+                hook(upper)
+            _OPS.encoder_bwd_layers(ws, d_hn, emb, lstm, ers, whm, G, B, T, L, bi, prec, flat, 0, 0)
+        else:
+            _OPS.encoder_bwd_layers(ws, d_hn, emb, lstm, ers, whm, G, B, T, L, bi, prec, flat, L - 1, 0)
         views, off = [], 0
-        for ref in [emb] + list(lstm):
+        for ref in refs:
             views.append(flat[off:off + ref.numel()].view(ref.shape))
             off += ref.numel()
         return (None, None, None, None, None, None, *views)
@@ -308,7 +253,9 @@ def pool_fc(bi_reduce: str, hn, fc_w, fc_b):
 
 
 class _LossHead(torch.autograd.Function):
-    """z[5,B,H], y -> losses[3], y_hat[B].  Backward recomputes the (tiny) forward intermediates inside the kernel."""
+    """z[5,B,H], y -> loss, classifier_loss, triplet_loss, y_hat[B].  Only `loss` and `y_hat` are differentiable: the reference
+    logs the two component losses detached (e2e_triplet.py:138-170), and marking them non-differentiable makes a backward through
+    them an autograd error instead of a silently dropped gradient.  Backward recomputes the (tiny) forward intermediates."""
 
     @staticmethod
     def forward(ctx, beta, z, y, m_fc1, m_do1, m_do2, m_fc2, fc1_w, fc1_b, fc2_w, fc2_b, proj_w, proj_b):
@@ -325,21 +272,22 @@ class _LossHead(torch.autograd.Function):
         ctx.beta, ctx.npar = float(beta), len(params)
         ctx.save_for_backward(z, y, *params, *[t for t in masks if t is not None])
         ctx.mask_present = [m is not None for m in masks]
-        return losses, y_hat
+        loss, classifier_loss, triplet_loss = losses[0], losses[1], losses[2]
+        ctx.mark_non_differentiable(classifier_loss, triplet_loss)
+        return loss, classifier_loss, triplet_loss, y_hat
 
     @staticmethod
-    def backward(ctx, d_losses, d_y_hat):
+    def backward(ctx, d_loss, _d_cl, _d_tl, d_y_hat):
         saved = list(ctx.saved_tensors)
         z, y = saved[0], saved[1]
         params = saved[2:2 + ctx.npar]
         rest = saved[2 + ctx.npar:]
         masks = [rest.pop(0) if present else None for present in ctx.mask_present]
         _, B, H = z.shape
-        if d_losses is None:
+        if d_loss is None:
             d_loss = torch.zeros(1, dtype=torch.float32, device=z.device)
         else:
-            # only `loss` (element 0) is an optimisation target; classifier/triplet losses are logged detached by the reference
-            d_loss = _f32c(d_losses)[0:1].contiguous()
+            d_loss = _f32c(d_loss).reshape(1)
         dz, flat = _OPS.loss_head_bwd(z, y, params, masks, ctx.beta, d_loss, _f32c(d_y_hat))
         HH, o = H // 2, 0
         g_fc1_w = flat[o:o + HH * H].view(HH, H); o += HH * H
@@ -354,7 +302,9 @@ class _LossHead(torch.autograd.Function):
 
 
 def loss_head(beta, z, y, fc1_w, fc1_b, fc2_w, fc2_b, proj_w=None, proj_b=None, masks=(None, None, None, None)):
-    return _LossHead.apply(beta, z, y, *masks, fc1_w, fc1_b, fc2_w, fc2_b, proj_w, proj_b)
+    """-> ((loss, classifier_loss, triplet_loss), y_hat); the two component losses carry no gradient (see _LossHead)."""
+    loss, classifier_loss, triplet_loss, y_hat = _LossHead.apply(beta, z, y, *masks, fc1_w, fc1_b, fc2_w, fc2_b, proj_w, proj_b)
+    return (loss, classifier_loss, triplet_loss), y_hat
 
 
 @torch.no_grad()

@@ -2,12 +2,16 @@
 
 The path shards by samples: every rank holds a full replica (0.87 MB) and 80 samples; the only exchange is ONE mean-allreduce
 of the live gradients (188,161 fp32 = 753 KB) per step, over NCCL/NVLink.  It is latency-bound, so the gradients are packed
-into three buckets ordered by backward completion and each bucket is reduced asynchronously as soon as it is complete:
+into four buckets ordered by backward completion and each bucket is reduced asynchronously as soon as it is complete:
   bucket 0: head (+ triplet projection)  -- the flat buffer ib200_loss_head_bwd wrote; ready before the recurrent BPTT starts
   bucket 1: encoder fc                   -- the flat buffer ib200_pool_fc_bwd wrote; reduced underneath the BPTT kernels too
-  bucket 2: LSTM + embedding             -- the flat buffer ib200_encoder_bwd wrote; ready when it returns
-Every bucket is exactly one buffer of the kernels, so it is reduced IN PLACE (no torch.cat before, no copy back after), and over
-NCCL the mean is taken by the collective itself (ReduceOp.AVG): no extra kernel at all on the path.
+  bucket 2: LSTM layers >= 1             -- the tail of the flat buffer of the encoder backward; final once the upper layers' BPTT and
+                                            weight-gradient GEMMs are done.  The encoder backward is cut at the layer boundary
+                                            (ib200_encoder_bwd_layers) and calls ops.EARLY_GRAD_HOOKS in between, so this bucket -- 80 %
+                                            of all gradient bytes at L = 2 -- is all-reduced UNDER the layer-0 BPTT kernel
+  bucket 3: LSTM layer 0 + embedding     -- the head of the same flat buffer; ready when the backward returns (the only exposed part)
+Every bucket is one contiguous range of a kernel-written buffer, so it is reduced IN PLACE (no torch.cat before, no copy back after),
+and over NCCL the mean is taken by the collective itself (ReduceOp.AVG): no extra kernel at all on the path.
 The reference has no distributed code at all (devices=1 is hard-wired, e2e_triplet.py:392-400); parameters that never
 receive a gradient (encoder.projection.*, quirk Q10) are left out of the buckets.
 """
@@ -15,23 +19,32 @@ from __future__ import annotations
 
 from typing import Iterable, List, Optional, Sequence
 
+import re
+
 import torch
 import torch.distributed as dist
 
+from . import ops
+
+
+_UPPER_LAYER = re.compile(r"_l([1-9][0-9]*)(_reverse)?(_raw)?$")
+
 
 def default_buckets(module: torch.nn.Module) -> List[List[torch.nn.Parameter]]:
-    head, fc, late, seen = [], [], [], set()
+    head, fc, upper, late, seen = [], [], [], [], set()
     for name, p in module.named_parameters():  # named_parameters de-duplicates the rnn / rnn_dp.module aliases
         if not p.requires_grad or id(p) in seen or ".projection." in name or name.startswith("projection."):
             continue
         seen.add(id(p))
-        if ".rnn." in name or ".rnn_dp." in name or "embedder" in name:
+        if ".rnn." in name or ".rnn_dp." in name:
+            (upper if _UPPER_LAYER.search(name) else late).append(p)
+        elif "embedder" in name:
             late.append(p)
         elif name.startswith("encoder.") and ".fc." in name:
             fc.append(p)
         else:
             head.append(p)
-    return [b for b in (head, fc, late) if b]
+    return [b for b in (head, fc, upper, late) if b]
 
 
 class GradientAllReducer:
@@ -50,6 +63,16 @@ class GradientAllReducer:
             for p in b:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.bytes_per_step = sum(p.numel() * 4 for b in self.buckets for p in b)
+        # the bucket of the LSTM layers >= 1 can start mid-backward (ops.EARLY_GRAD_HOOKS); found by name, only in the default layout
+        self._early = None
+        if buckets is None:
+            names = {id(p): n for n, p in module.named_parameters()}
+            for i, b in enumerate(self.buckets):
+                if all((".rnn." in names[id(p)] or ".rnn_dp." in names[id(p)]) and _UPPER_LAYER.search(names[id(p)]) for p in b):
+                    self._early = i
+            if self._early is not None:
+                ops.EARLY_GRAD_HOOKS.append(self._on_early)
+        self._early_done = False
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide
         self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
@@ -57,18 +80,48 @@ class GradientAllReducer:
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
         if self._pending[i] == 0:
-            self._launch(i)
+            if i == self._early and self._early_done:
+                self._check_early_views(i)
+            else:
+                self._launch(i)
+
+    def _on_early(self, upper: torch.Tensor):
+        """Called from inside the encoder backward (ops._EncodeHidden.backward) with the flat slice that holds the final gradients of
+        the LSTM layers >= 1, before the layer-0 BPTT is enqueued: the collective runs underneath that kernel."""
+        i = self._early
+        b = self.buckets[i]
+        if self._early_done or self._flat[i] is not None or upper.numel() != sum(p.numel() for p in b):
+            return
+        if any(p.grad is not None for p in b):
+            return  # gradient accumulation into existing .grad tensors: the regular (post-accumulate) path handles it
+        self._early_done = True
+        self._inplace[i] = True
+        self._flat[i] = upper
+        if self.world > 1:
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            self._work[i] = dist.all_reduce(upper, op=op, group=self.group, async_op=True)
+
+    def _check_early_views(self, i):
+        """The early bucket was reduced in place inside `flat`; autograd normally hands those very views to .grad.  If it copied
+        instead (not the case for freshly created gradients), finish() writes the reduced values back."""
+        flat = self._flat[i]
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        self._inplace[i] = all(lo <= p.grad.data_ptr() < hi for p in self.buckets[i])
 
     @staticmethod
     def _shared_flat(grads):
-        """The kernels hand back the gradients of one op as views of ONE flat buffer (ops.py): when a bucket is exactly such a
-        buffer it is reduced in place -- no torch.cat before and no copy back after the collective."""
+        """The kernels hand back the gradients of one op as views of ONE flat buffer (ops.py): when a bucket is a contiguous range
+        of such a buffer (in any order, without gaps) it is reduced in place -- no torch.cat before, no copy back after."""
         st = grads[0].untyped_storage()
         if any(g.untyped_storage().data_ptr() != st.data_ptr() or not g.is_contiguous() or g.dtype != torch.float32 for g in grads):
             return None
-        if sum(g.numel() for g in grads) * 4 != st.nbytes():
-            return None
-        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, 0, (st.nbytes() // 4,))
+        spans = sorted((g.storage_offset(), g.numel()) for g in grads)
+        pos = spans[0][0]
+        for off, n in spans:
+            if off != pos:
+                return None
+            pos += n
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, spans[0][0], (pos - spans[0][0],))
 
     def _launch(self, i):
         grads = [p.grad for p in self.buckets[i]]
@@ -94,17 +147,24 @@ class GradientAllReducer:
                 flat.div_(self.world)
             if not self._inplace[i]:  # (in-place buckets: the gradients ARE views of `flat`)
                 off = 0
-                for p in b:
+                for p in (self._early_order(b) if i == self._early and self._early_done else b):
                     n = p.numel()
                     p.grad.copy_(flat[off:off + n].view_as(p.grad))
                     off += n
             self._flat[i], self._work[i] = None, None
             self._pending[i] = len(b)
+        self._early_done = False
+
+    @staticmethod
+    def _early_order(b):
+        return b  # named_parameters order of the layers >= 1 == the C-ABI order of the flat buffer (ops.lstm_param_order)
 
     def remove(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self._on_early in ops.EARLY_GRAD_HOOKS:
+            ops.EARLY_GRAD_HOOKS.remove(self._on_early)
 
 
 def shard_range(n_items: int, rank: int, world: int):
