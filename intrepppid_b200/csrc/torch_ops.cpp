@@ -14,6 +14,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
+#include <cstdio>
 #include <tuple>
 #include <vector>
 
@@ -24,11 +25,20 @@ namespace {
 using at::Tensor;
 using c10::optional;
 
-#define IB200_CHECK(call, what)                                                                                          \
-  do {                                                                                                                   \
-    const int st__ = (call);                                                                                             \
-    TORCH_CHECK(st__ == 0, "[ib200] ", what, ": ", (st__ < 0 ? "invalid argument " : "CUDA error "), st__, ": ",          \
-                ib200_last_error());                                                                                     \
+// Every message with numbers in it is formatted with snprintf and handed to TORCH_CHECK as ONE string (c10::str's stream formatting of
+// integer arguments crashed in this build; tests/test_host_abi.py walks the error paths).
+#define IB200_REQUIRE(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      char msg__[640];                                \
+      snprintf(msg__, sizeof(msg__), __VA_ARGS__);    \
+      TORCH_CHECK(false, "[ib200] ", msg__);          \
+    }                                                 \
+  } while (0)
+#define IB200_CHECK(call, what)                                                                                                  \
+  do {                                                                                                                           \
+    const int st__ = (call);                                                                                                     \
+    IB200_REQUIRE(st__ == 0, "%s: %s %d: %s", what, (st__ < 0 ? "invalid argument" : "CUDA error"), st__, ib200_last_error());   \
   } while (0)
 
 void* stream_of(const Tensor& t) { return (void*)c10::cuda::getCurrentCUDAStream(t.get_device()).stream(); }
@@ -50,7 +60,7 @@ int token_dtype_of(const Tensor& tokens) {
     case at::kInt: return IB200_TOK_I32;
     case at::kShort: return IB200_TOK_I16;
     case at::kByte: return IB200_TOK_U8;
-    default: TORCH_CHECK(false, "[ib200] token ids must be int64 / int32 / int16 / uint8, got ", tokens.scalar_type());
+    default: TORCH_CHECK(false, "[ib200] token ids must be int64 / int32 / int16 / uint8, got ", c10::toString(tokens.scalar_type()));
   }
 }
 
@@ -64,9 +74,10 @@ ib200_cfg make_cfg(int64_t G, int64_t B, int64_t T, int64_t V, int64_t H, int64_
 
 size_t workspace_bytes_checked(const ib200_cfg& c) {
   const size_t n = ib200_workspace_bytes(&c);
-  TORCH_CHECK(n != 0, "[ib200] unsupported encoder configuration for the sm_100a kernels: H=", c.H, " (multiple of 32 in 32..256), L=",
-              c.L, " (1..4), G*B*T=", (long long)c.G * c.B * c.T, " (< 2^31), T=", c.T, " (<= 11000 when H <= 64), V=", c.V,
-              " (2..28672), bi_reduce=", c.bi_reduce, " (0 last, 1 mean, 2 max; 'concat' is not functional in the reference either)");
+  IB200_REQUIRE(n != 0,
+                "unsupported encoder configuration for the sm_100a kernels: H=%d (multiple of 32 in 32..256), L=%d (1..4), G*B*T=%lld "
+                "(< 2^31), T=%d (<= 11000 when H <= 64), V=%d (2..28672), bi_reduce=%d (0 last, 1 mean, 2 max; 'concat' is not functional "
+                "in the reference either)", c.H, c.L, (long long)c.G * c.B * c.T, c.T, c.V, c.bi_reduce);
   return n;
 }
 
@@ -82,8 +93,8 @@ void fill_lstm(Struct& s, const std::vector<Ptr>& p, int64_t L) {
 }
 
 ib200_encoder_params encoder_params(const Tensor& emb, at::TensorList lstm, int64_t L) {
-  TORCH_CHECK(L >= 1 && L <= IB200_MAX_LAYERS && (int64_t)lstm.size() == 8 * L, "[ib200] expected ", 8 * L, " LSTM tensors for ", L,
-              " layers, got ", lstm.size());
+  IB200_REQUIRE(L >= 1 && L <= IB200_MAX_LAYERS && (int64_t)lstm.size() == 8 * L, "expected %lld LSTM tensors for %lld layers (1..4), got %zu",
+                (long long)(8 * L), (long long)L, lstm.size());
   need_f32(emb, "emb");
   TORCH_CHECK(emb.dim() == 2, "[ib200] emb must be [V,H]");
   const int64_t H = emb.size(1);
@@ -92,7 +103,7 @@ ib200_encoder_params encoder_params(const Tensor& emb, at::TensorList lstm, int6
     need_f32(lstm[i], "LSTM parameter");
     const int64_t l = (int64_t)i / 8, k = (int64_t)i % 4;
     const int64_t want = k == 0 ? 4 * H * (l == 0 ? H : 2 * H) : (k == 1 ? 4 * H * H : 4 * H);
-    TORCH_CHECK(lstm[i].numel() == want, "[ib200] LSTM tensor ", i, " has ", lstm[i].numel(), " elements, expected ", want);
+    IB200_REQUIRE(lstm[i].numel() == want, "LSTM tensor %zu has %lld elements, expected %lld", i, (long long)lstm[i].numel(), (long long)want);
     ptrs.push_back(fptr(lstm[i]));
   }
   ib200_encoder_params P{};
@@ -113,10 +124,10 @@ void check_encoder_inputs(const Tensor& tokens, const Tensor& emb, const optiona
   TORCH_CHECK(emb.dim() == 2, "[ib200] emb must be [V,H]");
   const int64_t G = tokens.size(0), V = emb.size(0), H = emb.size(1);
   if (ers.has_value() && ers->defined())
-    TORCH_CHECK(ers->dim() == 2 && ers->size(0) == G && ers->size(1) == V, "[ib200] emb_row_scale must be [G=", G, ", V=", V, "]");
+    IB200_REQUIRE(ers->dim() == 2 && ers->size(0) == G && ers->size(1) == V, "emb_row_scale must be [G=%lld, V=%lld]", (long long)G, (long long)V);
   if (whm.has_value() && whm->defined())
-    TORCH_CHECK(whm->dim() == 3 && whm->size(0) == G && whm->size(1) == 4 * H && whm->size(2) == H, "[ib200] whh_l0_mask must be [G=", G,
-                ", ", 4 * H, ", ", H, "]");
+    IB200_REQUIRE(whm->dim() == 3 && whm->size(0) == G && whm->size(1) == 4 * H && whm->size(2) == H, "whh_l0_mask must be [G=%lld, %lld, %lld]",
+                  (long long)G, (long long)(4 * H), (long long)H);
 }
 
 // -> (hn_top [2,G*B,H], status int32 [3,G] = T1 | T_eff | flags, workspace uint8)

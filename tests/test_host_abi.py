@@ -49,6 +49,9 @@ def test_version_and_workspace_are_host_only(lib):
     assert 3e9 < wt < 8e9 and 1e9 < wi < 3e9
     assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 48, 2, 0, 0, 1, 0)) == 0      # unsupported H
     assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 64, 9, 0, 0, 1, 0)) == 0      # too many layers
+    assert lib.ib200_workspace_bytes(Cfg(1, 8, 64, 28672, 64, 1, 0, 0, 0, 0)) > 0         # largest vocabulary the lengths kernel holds
+    assert lib.ib200_workspace_bytes(Cfg(1, 8, 64, 28673, 64, 1, 0, 0, 0, 0)) == 0
+    assert lib.ib200_workspace_bytes(Cfg(1, 8, 64, 40000, 256, 1, 0, 0, 0, 0)) == 0       # ... for every hidden size
     assert lib.ib200_workspace_bytes(Cfg(5, 80, 1500, 250, 64, 2, 3, 0, 1, 0)) == 0      # "concat" is not a mode
 
 
@@ -134,6 +137,71 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", ""), f
 
 
+OP_NAMES = ("encoder_fwd", "encoder_bwd", "encoder_bwd_layers", "pool_fc_fwd", "pool_fc_bwd", "loss_head_fwd", "loss_head_bwd",
+            "pair_score", "pair_score_range", "batch_metrics")
+
+
+def test_operator_library_is_the_cpp_shim():
+    """The ops come from the C++ TORCH_LIBRARY shim (csrc/torch_ops.cpp -> libib200_torch.so), not from Python registrations."""
+    import intrepppid_b200  # noqa: F401
+    from intrepppid_b200 import _lib
+
+    assert os.path.exists(os.path.join(_lib.PKG, "libib200_torch.so"))
+    with open("/proc/self/maps") as fh:
+        assert "libib200_torch.so" in fh.read()
+    src = open(os.path.join(ROOT, "intrepppid_b200", "ops.py")).read()
+    assert "torch.library.Library(" not in src and ".impl(" not in src
+
+
+def test_meta_kernels_infer_shapes_without_a_gpu():
+    """Shape functions (Meta dispatch key): what FakeTensor tracing / torch.compile of the surrounding Lightning step needs."""
+    import intrepppid_b200  # noqa: F401
+    from intrepppid_b200 import _lib
+    from intrepppid_b200.ops import lstm_param_order
+
+    ops = torch.ops.intrepppid_b200
+    G, B, T, V, H, L = 5, 6, 40, 250, 64, 2
+    m = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device="meta")  # noqa: E731
+    lstm = []
+    for l in range(L):
+        for _ in range(2):
+            lstm += [m(4 * H, H if l == 0 else 2 * H), m(4 * H, H), m(4 * H), m(4 * H)]
+    assert len(lstm) == len(lstm_param_order(L))
+    hn, status, ws = ops.encoder_fwd(m(G, B, T, dtype=torch.int64), m(V, H), lstm, m(G, V), m(G, 4 * H, H), L, 0, 0, True)
+    assert hn.shape == (2, G * B, H) and status.shape == (3, G) and status.dtype == torch.int32
+    assert ws.dtype == torch.uint8 and ws.numel() == _lib.lib().ib200_workspace_bytes(_lib.Cfg(G, B, T, V, H, L, 0, 0, 1, 0))
+    n_flat = V * H + sum(t.numel() for t in lstm)
+    assert ops.encoder_bwd(ws, m(2, G * B, H), m(V, H), lstm, None, None, G, B, T, L, 0, 0).shape == (n_flat,)
+    flat = m(n_flat)
+    assert ops.encoder_bwd_layers(ws, m(2, G * B, H), m(V, H), lstm, None, None, G, B, T, L, 0, 0, flat, 1, 1) is None
+    # error paths of the shim (every message that carries numbers): unsupported hidden size / bi_reduce, wrong tensor count / shape
+    with pytest.raises(RuntimeError, match="H=48"):
+        ops.encoder_fwd(m(G, B, T, dtype=torch.int64), m(V, 48), lstm, None, None, L, 0, 0, False)
+    with pytest.raises(RuntimeError, match="bi_reduce=3"):
+        ops.encoder_fwd(m(G, B, T, dtype=torch.int64), m(V, H), lstm, None, None, L, 3, 0, False)
+    with pytest.raises(RuntimeError, match="emb_row_scale must be"):
+        ops.encoder_fwd(m(G, B, T, dtype=torch.int64), m(V, H), lstm, m(G, V + 1), None, L, 0, 0, False)
+    with pytest.raises(RuntimeError, match="whh_l0_mask must be"):
+        ops.encoder_fwd(m(G, B, T, dtype=torch.int64), m(V, H), lstm, None, m(G, 4 * H, H + 1), L, 0, 0, False)
+    with pytest.raises(RuntimeError, match="int64 / int32 / int16 / uint8"):
+        ops.encoder_fwd(m(G, B, T, dtype=torch.float32), m(V, H), lstm, None, None, L, 0, 0, False)
+    z, pooled, argmax = ops.pool_fc_fwd(hn, m(H, H), m(H), 2)
+    assert z.shape == (G * B, H) and pooled.shape == (G * B, H) and argmax.shape == (G * B, H) and argmax.dtype == torch.uint8
+    assert ops.pool_fc_fwd(hn, m(H, H), m(H), 0)[2].numel() == 0
+    d_hn, fc_flat = ops.pool_fc_bwd(z, pooled, None, m(H, H), 0)
+    assert d_hn.shape == (2, G * B, H) and fc_flat.shape == (H * H + H,)
+    head = [m(H // 2, H), m(H // 2), m(1, H // 2), m(1)]
+    losses, y_hat = ops.loss_head_fwd(m(5, B, H), m(B, dtype=torch.int64), head, [None] * 4, 2.0)
+    assert losses.shape == (3,) and y_hat.shape == (B,)
+    dz, hflat = ops.loss_head_bwd(m(5, B, H), m(B, dtype=torch.int64), head + [m(H, H), m(H)], [None] * 4, 2.0, m(1), None)
+    assert dz.shape == (5, B, H) and hflat.numel() == (H // 2) * H + H // 2 + H // 2 + 1 + H * H + H
+    assert ops.pair_score(m(7, H), *head, None, None).shape == (28,)
+    assert ops.pair_score(m(7, H), *head, m(11, dtype=torch.int32), m(11, dtype=torch.int32)).shape == (11,)
+    assert ops.pair_score_range(m(7, H), *head, 3, 9).shape == (9,)
+    mt, conf = ops.batch_metrics(m(B), m(B, dtype=torch.int64), 0.5)
+    assert mt.shape == (5,) and conf.shape == (4,) and conf.dtype == torch.int32
+
+
 def test_torch_custom_ops_are_registered_cuda_only():
     """The launchers are torch custom ops (torch.ops.intrepppid_b200.*) with a CUDA kernel only: the dispatcher has nothing to run
     for CPU tensors, so there is no silent fallback."""
@@ -142,10 +210,11 @@ def test_torch_custom_ops_are_registered_cuda_only():
     import intrepppid_b200  # noqa: F401  (registers the ops)
 
     ops = torch.ops.intrepppid_b200
-    for name in ("encoder_fwd", "encoder_bwd", "pool_fc_fwd", "pool_fc_bwd", "loss_head_fwd", "loss_head_bwd", "pair_score"):
+    for name in OP_NAMES:
         schema = str(getattr(ops, name).default._schema)
         assert schema.startswith(f"intrepppid_b200::{name}("), schema
         assert torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "CUDA")
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "Meta")
         assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"intrepppid_b200::{name}", "CPU")
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.pool_fc_fwd(torch.zeros(2, 3, 32), torch.zeros(32, 32), torch.zeros(32), 0)
