@@ -257,6 +257,25 @@ int ib200_dbg_gemm_tn(int32_t G, int32_t B, int32_t T, const int32_t* lens, cons
                       int32_t V, int32_t NB, float* partial, int32_t ctas_per_group, int32_t colsum, int32_t precision,
                       int32_t impl, void* stream);
 
+/* Test hooks for the PRODUCTION kernels of the H = 64 path (tests/test_gpu_gemm.py): the TMA-fed tcgen05 GEMMs on bf16 hi|lo plane
+ * operands -- a row of K values is stored over the bytes of K floats as [K bf16 hi | K bf16 lo], exactly what the recurrent kernels
+ * write.  _nt_planes -> gemm_nt_tma_kernel (xproj / dY), _tn_planes -> gemm_tn_tma_kernel (dW_ih | dW_hh in one pass: first B source
+ * dense planes or gathered scale*emb rows, optional second dense source shifted by +-1 step), _l0_grads -> l0_grad_gemm_kernel +
+ * reduce + finish (layer-0 dW_hh, dW_ih, bias and embedding gradients from one pass over the dgates). */
+int ib200_dbg_gemm_nt_planes(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                             int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc,
+                             int32_t NC, int32_t accumulate, int32_t precision, void* stream);
+int ib200_dbg_gemm_tn_planes(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, const float* Bsrc, int32_t ldb,
+                             int32_t col0, int32_t shift, const int32_t* tok, const float* emb, const float* emb_row_scale, int32_t V,
+                             int32_t NB1, const float* Bsrc2, int32_t ldb2, int32_t col02, int32_t shift2, int32_t NB2, float* partial,
+                             int32_t ctas_per_group, int32_t precision, void* stream);
+size_t ib200_dbg_l0_scratch_floats(int32_t G, int32_t ndir, int32_t which); /* 0: `partial` floats, 1: `scratch` floats */
+int ib200_dbg_l0_grads(int32_t G, int32_t B, int32_t T, int32_t V, const int32_t* lens, const int32_t* tok, const float* const* dA,
+                       const float* Y0, const float* emb, const float* emb_row_scale, const float* whh_mask, const float* const* w_ih,
+                       const float* bias_partial, int32_t bias_count, int32_t dir0, int32_t ndir, float* partial, float* scratch,
+                       float* const* d_wih, float* const* d_whh, float* const* d_bih, float* const* d_bhh, float* d_emb,
+                       int32_t precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         return src, obj, r
 
     with ThreadPoolExecutor(max_workers=len(SOURCES) + 1) as ex:
-        shim = ex.submit(_build_torch_shim)
+        shim = ex.submit(_compile_torch_shim)
         results = list(ex.map(compile_one, SOURCES))
     log = []
     for src, obj, r in results:
@@ -74,32 +74,42 @@ def build(verbose: bool = False, force: bool = False) -> str:
     r = subprocess.run([nvcc, "-shared", "-o", LIB, *[o for _, o, _ in results], "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    shim.result()
+    _link_torch_shim(shim.result())
     with open(stamp, "w") as fh:
         fh.write(dig)
     return LIB
 
 
-def _build_torch_shim() -> str:
-    """g++ build of the operator library: schemas + CUDA dispatch + Meta kernels, linked against libib200.so (rpath $ORIGIN) and
-    the torch libraries of the running interpreter.  No CUDA code in it: it only calls the C ABI."""
+def _compile_torch_shim() -> str:
+    """g++ -c of the operator library (schemas + CUDA dispatch + Meta kernels; no CUDA code in it: it only calls the C ABI).
+    Runs beside the nvcc jobs; linked by _link_torch_shim once libib200.so exists."""
     import torch
     from torch.utils import cpp_extension as ce
 
     cxx = os.environ.get("CXX") or shutil.which("g++")
     if not cxx:
         raise RuntimeError("g++ not found: libib200_torch.so cannot be built")
-    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    obj = os.path.join(OBJDIR, "torch_ops.o")
     inc = [f"-I{p}" for p in ce.include_paths("cuda")]
-    # libib200.so is named by path (it may not exist yet when this runs beside the nvcc jobs: resolved at load time through the rpath)
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
-           *inc, os.path.join(CSRC, "torch_ops.cpp"), "-o", TORCH_LIB, f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda",
-           "-lc10_cuda", "-Wl,--allow-shlib-undefined", "-Wl,-rpath,$ORIGIN", "-Wl,--no-as-needed", f"-L{PKG}", "-l:libib200.so"]
-    if not os.path.exists(LIB):  # first build: link without naming the library, load order (ops.py loads libib200.so first) resolves it
-        cmd = cmd[:-2]
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-c", "-Wno-deprecated-declarations",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", *inc, os.path.join(CSRC, "torch_ops.cpp"), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("torch shim build failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("torch shim compile failed:\n" + r.stdout + r.stderr)
+    return obj
+
+
+def _link_torch_shim(obj: str) -> str:
+    """Link against libib200.so (NEEDED entry, found through the $ORIGIN rpath) and the torch libraries of the running interpreter."""
+    import torch
+
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = [cxx, "-shared", obj, "-o", TORCH_LIB, f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda",
+           "-Wl,-rpath,$ORIGIN", "-Wl,--no-as-needed", f"-L{PKG}", "-l:libib200.so"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("torch shim link failed:\n" + r.stdout + r.stderr)
     return TORCH_LIB
 
 

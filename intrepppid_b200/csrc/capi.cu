@@ -36,10 +36,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_L0_GRADS, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks", "l0_grads"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -594,7 +594,7 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
       la.emb = P->emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_l0_mask;
       la.bias_partial = at<float>(ws, p.bias_partial[0]); la.bias_count = bwd_ctas;
       la.partial = partial; la.R = at<float>(ws, p.l0_scratch); la.d_emb = Gr->emb;
-      TimedScope ts(F_GEMM_DW, 3, st);
+      TimedScope ts(F_L0_GRADS, 3, st);
       // no fallback: the forward skipped the W_ih^T preparation of layer 0 because this path was chosen (same l0_fused_ok decision)
       const cudaError_t e = launch_l0_grads(la, prec, st);
       if (e != cudaSuccess) return cuda_fail(e, "layer-0 gradient gemm");
@@ -878,6 +878,56 @@ int ib200_dbg_gemm_tn(int32_t G, int32_t B, int32_t T, const int32_t* lens, cons
   cudaStream_t st = (cudaStream_t)stream;
   CK(impl == 0 ? launch_gemm_tn(a, precision, st) : (impl == 1 ? launch_gemm_tn_tc(a, precision, st) : gemm_tn_auto(a, precision, st)),
      "dbg gemm tn");
+  return 0;
+}
+
+// ---- test hooks for the PRODUCTION kernels of the H = 64 path (bf16 hi|lo plane operands, TMA-fed tcgen05) -------------------------
+// A row of K values is stored over the bytes of K floats: [K bf16 hi | K bf16 lo] (what the recurrent kernels write in planes mode).
+int ib200_dbg_gemm_nt_planes(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                             int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc,
+                             int32_t NC, int32_t accumulate, int32_t precision, void* stream) {
+  if (!lens || !A0 || !W0 || !C || (nsrc == 2 && (!A1 || !W1))) return fail(IB200_E_NULL, "ib200_dbg_gemm_nt_planes: null pointer");
+  GemmNTArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.nsrc = nsrc; a.A[0] = A0; a.A[1] = A1; a.lda = lda; a.K = K;
+  a.W[0] = W0; a.W[1] = W1; a.bias = bias; a.C = C; a.ldc = ldc; a.NC = NC; a.accumulate = accumulate; a.plane_bytes = K * 2;
+  CK(gemm_nt_auto(a, precision, (cudaStream_t)stream), "dbg gemm nt planes");
+  return 0;
+}
+
+int ib200_dbg_gemm_tn_planes(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, const float* Bsrc, int32_t ldb,
+                             int32_t col0, int32_t shift, const int32_t* tok, const float* emb, const float* emb_row_scale, int32_t V,
+                             int32_t NB1, const float* Bsrc2, int32_t ldb2, int32_t col02, int32_t shift2, int32_t NB2, float* partial,
+                             int32_t ctas_per_group, int32_t precision, void* stream) {
+  if (!lens || !A || !partial || (!tok && !Bsrc) || (NB2 > 0 && !Bsrc2)) return fail(IB200_E_NULL, "ib200_dbg_gemm_tn_planes: null pointer");
+  GemmTNArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.A = A; a.KA = 256; a.Bsrc = Bsrc; a.ldb = ldb; a.col0 = col0; a.shift = shift;
+  a.tok = tok; a.emb = emb; a.emb_row_scale = emb_row_scale; a.V = V; a.NB1 = NB1; a.NB = NB1 + NB2;
+  a.Bsrc2 = Bsrc2; a.ldb2 = ldb2; a.col02 = col02; a.shift2 = shift2; a.partial = partial; a.ctas_per_group = ctas_per_group;
+  CK(launch_gemm_tn_tma(a, precision, (cudaStream_t)stream), "dbg gemm tn planes");
+  return 0;
+}
+
+size_t ib200_dbg_l0_scratch_floats(int32_t G, int32_t ndir, int32_t which) {
+  return which == 0 ? l0_grad_partial_floats(G, ndir) : l0_grad_scratch_floats(G, ndir);
+}
+
+// d_* arrays: [2] pointers indexed by direction (entries of a direction that is not run may be null)
+int ib200_dbg_l0_grads(int32_t G, int32_t B, int32_t T, int32_t V, const int32_t* lens, const int32_t* tok, const float* const* dA,
+                       const float* Y0, const float* emb, const float* emb_row_scale, const float* whh_mask, const float* const* w_ih,
+                       const float* bias_partial, int32_t bias_count, int32_t dir0, int32_t ndir, float* partial, float* scratch,
+                       float* const* d_wih, float* const* d_whh, float* const* d_bih, float* const* d_bhh, float* d_emb,
+                       int32_t precision, void* stream) {
+  if (!lens || !tok || !dA || !Y0 || !emb || !w_ih || !bias_partial || !partial || !scratch || !d_wih || !d_whh || !d_bih || !d_bhh || !d_emb)
+    return fail(IB200_E_NULL, "ib200_dbg_l0_grads: null pointer");
+  L0GradArgs la{};
+  la.G = G; la.B = B; la.Tmax = T; la.V = V; la.H = 64; la.dir0 = dir0; la.ndir = ndir; la.lens = lens; la.tok = tok;
+  for (int d = 0; d < 2; ++d) {
+    la.dA[d] = dA[d]; la.w_ih[d] = w_ih[d];
+    la.d_wih[d] = d_wih[d]; la.d_whh[d] = d_whh[d]; la.d_bih[d] = d_bih[d]; la.d_bhh[d] = d_bhh[d];
+  }
+  la.Y0 = Y0; la.emb = emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_mask;
+  la.bias_partial = bias_partial; la.bias_count = bias_count; la.partial = partial; la.R = scratch; la.d_emb = d_emb;
+  CK(launch_l0_grads(la, precision, (cudaStream_t)stream), "dbg l0 grads");
   return 0;
 }
 

@@ -82,12 +82,32 @@ def _load_operator_library():
 
 class _Ops:
     """torch.ops.intrepppid_b200 with the C ABI's status codes surfaced as IB200Error (the shim raises them as RuntimeError
-    tagged "[ib200]"; everything else -- dispatcher errors for CPU tensors, shape errors -- passes through unchanged)."""
+    tagged "[ib200]"; everything else -- dispatcher errors for CPU tensors, shape errors -- passes through unchanged).
+    The libraries are loaded when the package is imported; if they are missing or stale at that point (a fresh checkout before
+    `python -m intrepppid_b200.build`), the import still succeeds and the FIRST USE raises IB200Error -- there is no fallback."""
 
-    def __init__(self, ns):
-        self._ns = ns
+    def __init__(self):
+        self._ns = None
+        self._error = None
+        self.load()
+
+    def load(self):
+        try:
+            _lib._lib = None
+            self._ns = _load_operator_library()
+            self._error = None
+        except (_lib.IB200Error, OSError, AttributeError) as e:
+            self._ns, self._error = None, e
+        for name in [k for k in self.__dict__ if not k.startswith("_")]:
+            delattr(self, name)
+        return self._ns is not None
 
     def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if self._ns is None and not self.load():
+            raise _lib.IB200Error(f"the CUDA libraries of intrepppid_b200 are not usable ({self._error}); build them with "
+                                  "`python -m intrepppid_b200.build` (there is no CPU or PyTorch fallback)")
         op = getattr(self._ns, name)
 
         def call(*args):
@@ -103,7 +123,7 @@ class _Ops:
         return call
 
 
-_OPS = _Ops(_load_operator_library())
+_OPS = _Ops()
 
 _TOKEN_DTYPES = (torch.int64, torch.int32, torch.int16, torch.uint8)
 

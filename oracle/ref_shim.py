@@ -3,7 +3,9 @@
 This module exists to (a) validate `oracle/restatement.py` against the real reference and
 (b) generate the golden vectors under `tests/golden/` (see `oracle/make_golden.py`).  It only
 works in the build container (where /root/reference is mounted); it is never imported by the
-product package, by `-m gpu` tests, by `smoke()` or by `bench.py` (the GPU box has no reference).
+product package, by `-m gpu` tests or by `smoke()`.  `bench.py`'s CPU legs (`--impl reference`, `cpu_baseline`) use it when
+the reference files are reachable: mounted at /root/reference (build container) or staged byte-for-byte under oracle/_ref by
+oracle/stage_reference.py (the GPU box).
 
 `import intrepppid` fails here (pytorch_lightning / torchmetrics / ranger21 / tables are not
 installed), so the five hot-path files are loaded by path under their real dotted names after
@@ -24,8 +26,24 @@ import types
 import torch
 from torch import nn
 
-REF_ROOT = os.environ.get("IB200_REFERENCE_ROOT", "/root/reference")
+def _find_root() -> str:
+    """The mounted reference (build container), else the byte-for-byte staged copies under oracle/_ref (oracle/stage_reference.py:
+    git-ignored, travels to the GPU box with the snapshot, sha256-verified before use)."""
+    env = os.environ.get("IB200_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/intrepppid/encoders/awd_lstm.py"):
+        return "/root/reference"
+    from . import stage_reference
+
+    if stage_reference.verify():
+        return stage_reference.DEST
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 REF_PKG = os.path.join(REF_ROOT, "intrepppid")
+STAGED = REF_ROOT != "/root/reference" and not os.environ.get("IB200_REFERENCE_ROOT")
 
 
 def available() -> bool:

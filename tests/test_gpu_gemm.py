@@ -118,3 +118,215 @@ def test_tn_fp32_mode(impl, NB, mode):
 def test_tn_bf16_mode_more_ctas_than_items(impl):
     err = _run_tn(impl, 1, G=1, B=2, T=100, lens_eff=[65], NB=64, mode="dense", ctas=7)
     assert err < 1e-2, err
+
+
+# ==================================================================================================================================
+# The kernels the headline bench actually runs (H = 64 "planes" path): gemm_nt_tma_kernel, gemm_tn_tma_kernel, l0_grad_gemm_kernel.
+# Operands are bf16 hi|lo planes: a row of K values lives in the bytes of K floats as [K bf16 hi | K bf16 lo].
+# ==================================================================================================================================
+def _planes(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] -> the plane layout, returned as float32 [rows, K] (a byte container) + the value the planes represent."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous().view(torch.float32), hi, lo
+
+
+def _plane_value(hi, lo, precision):
+    return (hi.double() + lo.double()) if precision == 0 else hi.double()
+
+
+def _valid_rows(G, B, T, lens_eff):
+    valid = torch.zeros(G, B, T, dtype=torch.bool)
+    for gi, te in enumerate(lens_eff):
+        valid[gi, :, :te] = True
+    return valid.reshape(-1).cuda()
+
+
+def _run_nt_planes(precision, G, B, T, lens_eff, nsrc, K, NC, bias=True, accumulate=False, seed=0):
+    from intrepppid_b200._lib import check, lib, ptr
+
+    g = torch.Generator().manual_seed(seed)
+    rows = G * B * T
+    packs = [_planes(torch.randn(rows, K, generator=g).cuda()) for _ in range(nsrc)]
+    W = [(torch.randn(NC, K, generator=g) * 0.1).cuda() for _ in range(nsrc)]
+    b = torch.randn(NC, generator=g).cuda() if bias else None
+    C0 = torch.randn(rows, NC, generator=g).cuda()
+    C = C0.clone()
+    lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().ib200_dbg_gemm_nt_planes(G, B, T, ptr(lens), nsrc, ptr(packs[0][0]), ptr(packs[1][0]) if nsrc > 1 else None, K, K,
+                                         ptr(W[0]), ptr(W[1]) if nsrc > 1 else None, ptr(b), ptr(C), NC, NC, int(accumulate), precision,
+                                         st), "ib200_dbg_gemm_nt_planes")
+    torch.cuda.synchronize()
+    # the kernel splits W into bf16 hi + lo itself (fp32 mode) or rounds it to bf16 (bf16 mode): the products below are what it forms
+    ref = 0
+    for (_, hi, lo), w in zip(packs, W):
+        ref = ref + _plane_value(hi, lo, precision) @ (w.double() if precision == 0 else w.to(torch.bfloat16).double()).T
+    if bias:
+        ref = ref + b.double()
+    if accumulate:
+        ref = ref + C0.double()
+    valid = _valid_rows(G, B, T, lens_eff)
+    err = (C.double() - ref)[valid].norm() / ref[valid].norm()
+    return float(err), torch.equal(C[~valid], C0[~valid])
+
+
+@pytest.mark.parametrize("nsrc,K,NC", [(1, 128, 256), (1, 256, 128), (2, 256, 128), (2, 256, 64)])  # xproj, dY (1 / 2 live directions), dX0
+def test_nt_tma_planes_fp32_mode(nsrc, K, NC):
+    err, untouched = _run_nt_planes(0, G=2, B=3, T=300, lens_eff=[257, 100], nsrc=nsrc, K=K, NC=NC)
+    assert err < 2e-5, err      # hi*hi + hi*lo + lo*hi, fp32 accumulation: the dropped lo*lo term is ~2^-16 relative
+    assert untouched, "rows with t >= T_eff must not be written"
+
+
+def test_nt_tma_planes_bf16_mode_accumulate_and_many_tiles():
+    err, untouched = _run_nt_planes(1, G=1, B=5, T=200, lens_eff=[131], nsrc=1, K=128, NC=256, accumulate=True)
+    assert err < 1e-5 and untouched   # against the bf16-rounded operands the kernel really multiplies: only accumulation order differs
+    # more tiles than SMs (persistent loop, TMEM double buffering, phase wrap-around), ragged groups incl. T_eff = 1 and a dead group tail
+    err, untouched = _run_nt_planes(0, G=4, B=40, T=256, lens_eff=[256, 255, 129, 1], nsrc=1, K=128, NC=256, seed=3)
+    assert err < 2e-5 and untouched
+
+
+def _run_tn_planes(precision, G, B, T, lens_eff, NB1, first, second, ctas=3, seed=0):
+    """first: 'dense' | 'gather' (scale*emb rows by token); second: None | 'prev' (shift -1) | 'next' (shift +1), 64 columns taken
+    at column offset col02 of a 128-wide plane matrix -- exactly the [dW_ih | dW_hh] call of the encoder backward."""
+    from intrepppid_b200._lib import check, lib, ptr
+
+    g = torch.Generator().manual_seed(seed)
+    KA, rows, V = 256, G * B * T, 50
+    NB2 = 64 if second else 0
+    Ap, Ahi, Alo = _planes(torch.randn(rows, KA, generator=g).cuda())
+    lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
+    ldb, col0 = 2 * NB1, 0 if NB1 == 128 else 64   # H = 64: Y_{l-1} is [.,128] -> NB1 = 128 takes all of it; a 64-wide take starts at 64
+    ldb = max(ldb, 128)
+    valid = _valid_rows(G, B, T, lens_eff)
+    B1 = torch.randn(rows, ldb, generator=g).cuda() * valid.unsqueeze(1)     # rows t >= T_eff hold zeros (the forward zeroes the tail row)
+    B1p, B1hi, B1lo = _planes(B1)
+    B2 = torch.randn(rows, 128, generator=g).cuda() * valid.unsqueeze(1)
+    B2p, B2hi, B2lo = _planes(B2)
+    col02 = 64 if second == "next" else 0                                       # reverse direction reads the second half of Y_l
+    shift2 = {None: 0, "prev": -1, "next": 1}[second]
+    tok = torch.randint(0, V, (rows,), generator=g, dtype=torch.int32).cuda()
+    emb = torch.randn(V, NB1, generator=g).cuda()
+    scale = (torch.rand(G, V, generator=g) > 0.3).float().cuda() / 0.7
+    NB = NB1 + NB2
+    partial = torch.full((G, ctas, KA * NB), float("nan")).cuda()
+    gather = first == "gather"
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().ib200_dbg_gemm_tn_planes(G, B, T, ptr(lens), ptr(Ap), None if gather else ptr(B1p), ldb, col0, 0,
+                                         ptr(tok) if gather else None, ptr(emb) if gather else None, ptr(scale) if gather else None, V, NB1,
+                                         ptr(B2p) if second else None, 128, col02, shift2, NB2, ptr(partial), ctas, precision, st),
+          "ib200_dbg_gemm_tn_planes")
+    torch.cuda.synchronize()
+    got = partial.sum(1).double().view(G, KA, NB)
+    A3 = _plane_value(Ahi, Alo, precision).view(G, B, T, KA)
+    b1v = _plane_value(B1hi, B1lo, precision).view(G, B, T, ldb)[..., col0:col0 + NB1]
+    b2v = _plane_value(B2hi, B2lo, precision).view(G, B, T, 128)[..., col02:col02 + 64]
+    tok3 = tok.view(G, B, T).long()
+    worst = 0.0
+    for gi, te in enumerate(lens_eff):
+        a = A3[gi, :, :te]
+        if gather:
+            e = scale[gi][tok3[gi, :, :te]].unsqueeze(-1) * emb[tok3[gi, :, :te]]   # fp32 product, then split by the kernel
+            b = e.double() if precision == 0 else e.to(torch.bfloat16).double()
+        else:
+            b = b1v[gi, :, :te]
+        if second:
+            s = torch.zeros(B, te, 64, dtype=torch.float64, device="cuda")
+            if shift2 == -1:
+                s[:, 1:] = b2v[gi, :, :te - 1]
+            else:
+                s[:, :te - 1] = b2v[gi, :, 1:te]
+            b = torch.cat([b, s], dim=-1)
+        ref = torch.einsum("btk,btn->kn", a, b)
+        worst = max(worst, float((got[gi] - ref).norm() / ref.norm()))
+    return worst
+
+
+@pytest.mark.parametrize("NB1,first,second", [(128, "dense", "prev"), (128, "dense", "next"), (128, "dense", None), (64, "dense", None),
+                                              (64, "gather", None), (64, "gather", "prev"), (64, "gather", "next")])
+def test_tn_tma_planes_fp32_mode(NB1, first, second):
+    err = _run_tn_planes(0, G=2, B=3, T=200, lens_eff=[200, 77], NB1=NB1, first=first, second=second)
+    assert err < 2e-5, err
+
+
+def test_tn_tma_planes_bf16_mode_more_ctas_than_items_and_short_groups():
+    assert _run_tn_planes(1, G=1, B=2, T=100, lens_eff=[65], NB1=128, first="dense", second="prev", ctas=7) < 1e-5
+    assert _run_tn_planes(0, G=3, B=5, T=130, lens_eff=[1, 64, 129], NB1=128, first="dense", second="next", ctas=2, seed=5) < 2e-5
+
+
+def _run_l0_grads(precision, G, B, T, lens_eff, V, dir0, ndir, masked=True, seed=0):
+    """ib200_dbg_l0_grads (l0_grad_gemm_kernel + reduce + finish) against fp64: dW_hh, dW_ih, both bias gradients, dEmb."""
+    import ctypes as C
+
+    from intrepppid_b200._lib import check, lib, ptr
+
+    H, g = 64, torch.Generator().manual_seed(seed)
+    rows = G * B * T
+    valid = _valid_rows(G, B, T, lens_eff)
+    dA = [_planes(torch.randn(rows, 4 * H, generator=g).cuda()) for _ in range(2)]     # gate-interleaved columns k = 4u + q
+    Y0p, Yhi, Ylo = _planes(torch.randn(rows, 2 * H, generator=g).cuda() * valid.unsqueeze(1))
+    tok = torch.randint(0, V, (rows,), generator=g, dtype=torch.int32).cuda()
+    emb = torch.randn(V, H, generator=g).cuda()
+    scale = ((torch.rand(G, V, generator=g) > 0.3).float() / 0.7).cuda() if masked else None
+    whm = ((torch.rand(G, 4 * H, H, generator=g) > 0.3).float() / 0.7).cuda() if masked else None
+    w_ih = [torch.randn(4 * H, H, generator=g).cuda() * 0.1 for _ in range(2)]
+    bias_count = 3
+    lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
+    bias_partial = torch.randn(ndir, bias_count, 4 * H, generator=g).cuda()
+    partial = torch.empty(lib().ib200_dbg_l0_scratch_floats(G, ndir, 0), device="cuda")
+    scratch = torch.empty(lib().ib200_dbg_l0_scratch_floats(G, ndir, 1), device="cuda")
+    out = {n: [torch.full((4 * H, H) if n in ("wih", "whh") else (4 * H,), float("nan"), device="cuda") for _ in range(2)]
+           for n in ("wih", "whh", "bih", "bhh")}
+    d_emb = torch.full((V, H), float("nan"), device="cuda")
+    arr = lambda ts: (C.c_void_p * 2)(*[ptr(t) for t in ts])  # noqa: E731
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().ib200_dbg_l0_grads(G, B, T, V, ptr(lens), ptr(tok), arr([dA[0][0], dA[1][0]]), ptr(Y0p), ptr(emb), ptr(scale), ptr(whm),
+                                   arr(w_ih), ptr(bias_partial), bias_count, dir0, ndir, ptr(partial), ptr(scratch), arr(out["wih"]),
+                                   arr(out["whh"]), arr(out["bih"]), arr(out["bhh"]), ptr(d_emb), precision, st), "ib200_dbg_l0_grads")
+    torch.cuda.synchronize()
+    # torch row r = q*H + u  <->  gate-interleaved column k = 4u + q
+    k_of_row = torch.tensor([4 * (r % H) + r // H for r in range(4 * H)], device="cuda")
+    Yv = _plane_value(Yhi, Ylo, precision).view(G, B, T, 2 * H)
+    tok3 = tok.view(G, B, T).long()
+    worst, demb_ref = 0.0, torch.zeros(V, H, dtype=torch.float64, device="cuda")
+    for ds in range(ndir):
+        d = dir0 + ds
+        Av = _plane_value(dA[d][1], dA[d][2], precision).view(G, B, T, 4 * H)[..., k_of_row]   # torch row order
+        dwhh = torch.zeros(4 * H, H, dtype=torch.float64, device="cuda")
+        dwih = torch.zeros(4 * H, H, dtype=torch.float64, device="cuda")
+        for gi, te in enumerate(lens_eff):
+            a = Av[gi, :, :te]
+            hp = torch.zeros(B, te, H, dtype=torch.float64, device="cuda")   # h of the previous scan position
+            if d == 0:
+                hp[:, 1:] = Yv[gi, :, :te - 1, :H]
+            else:
+                hp[:, :te - 1] = Yv[gi, :, 1:te, H:]
+            m = whm[gi].double() if (whm is not None and d == 0) else 1.0
+            dwhh += m * torch.einsum("btk,bth->kh", a, hp)
+            sc = scale[gi].double() if scale is not None else torch.ones(V, dtype=torch.float64, device="cuda")
+            x = sc[tok3[gi, :, :te]].unsqueeze(-1) * emb.double()[tok3[gi, :, :te]]
+            dwih += torch.einsum("btk,bth->kh", a, x)
+            dx = a @ w_ih[d].double()                                        # [B, te, H]
+            contrib = torch.zeros(V, H, dtype=torch.float64, device="cuda")
+            contrib.index_add_(0, tok3[gi, :, :te].reshape(-1), dx.reshape(-1, H))
+            demb_ref += sc.unsqueeze(1) * contrib
+        bsum = bias_partial[ds].double().sum(0)[k_of_row]
+        for name, ref in (("whh", dwhh), ("wih", dwih), ("bih", bsum), ("bhh", bsum)):
+            worst = max(worst, float((out[name][d].double() - ref).norm() / ref.norm()))
+    demb_ref[0] = 0  # padding_idx
+    assert float(d_emb[0].abs().max()) == 0.0
+    worst = max(worst, float((d_emb.double() - demb_ref).norm() / demb_ref.norm()))
+    for d in range(2):  # a direction that was not run is not written
+        if not (dir0 <= d < dir0 + ndir):
+            assert bool(torch.isnan(out["wih"][d]).all())
+    return worst
+
+
+@pytest.mark.parametrize("dir0,ndir", [(0, 2), (1, 1)])
+def test_l0_grad_kernels_fp32_mode(dir0, ndir):
+    err = _run_l0_grads(0, G=2, B=5, T=150, lens_eff=[150, 67], V=250, dir0=dir0, ndir=ndir)
+    assert err < 2e-5, err
+
+
+def test_l0_grad_kernels_bf16_mode_unmasked_small_vocabulary():
+    assert _run_l0_grads(1, G=3, B=2, T=70, lens_eff=[1, 64, 70], V=21, dir0=0, ndir=2, masked=False, seed=2) < 1e-5

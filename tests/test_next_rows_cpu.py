@@ -189,3 +189,63 @@ def test_mask_restatement_is_a_scaled_bernoulli_and_respects_offsets():
     assert torch.equal(a[4:], a2[:-4])
     rows, = R.draw_masks([12], [0.5], seed=3, offset=0, row_lens=[4])
     assert all(len(set(rows[i:i + 4].tolist())) == 1 for i in (0, 4, 8))
+
+
+# ---- input feeding (intrepppid_b200/feed.py) -----------------------------------------------------------------
+class _ToyPairs(torch.utils.data.Dataset):
+    """Samples shaped like IntrepppidDataset.__getitem__ (data/ppi_oma.py:489-503): five int64 id rows + a label."""
+
+    def __init__(self, n, T, V, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.rows = torch.randint(0, V, (n, 5, T), generator=g)
+        self.y = torch.randint(0, 2, (n,), generator=g)
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    def __getitem__(self, i):
+        r = self.rows[i]
+        return r[0].long(), r[1].long(), r[2].long(), r[3].long(), r[4].long(), self.y[i].long()
+
+
+def test_narrow_collate_matches_the_default_collate():
+    from torch.utils.data import DataLoader
+
+    from intrepppid_b200 import feed
+
+    assert feed.token_dtype_for(250) == torch.uint8 and feed.token_dtype_for(256) == torch.uint8
+    assert feed.token_dtype_for(257) == torch.int16 and feed.token_dtype_for(32768) == torch.int16
+    assert feed.token_dtype_for(32769) == torch.int32
+    for V, dt in ((250, torch.uint8), (5000, torch.int16)):
+        ds = _ToyPairs(23, 40, V, seed=V)
+        ref = list(DataLoader(ds, batch_size=8, shuffle=False))                      # the reference's loader (ppi_oma.py:611-620)
+        got = list(DataLoader(ds, batch_size=8, shuffle=False, collate_fn=feed.narrow_collate(V), num_workers=2))  # through worker IPC
+        assert len(ref) == len(got) == 3
+        for r, g in zip(ref, got):
+            assert isinstance(g, feed.PackedBatch) and len(g) == 6 and g.tokens.dtype == dt
+            assert g.tokens.shape == (5, r[0].shape[0], 40) and g.tokens.is_contiguous()
+            for i in range(5):
+                assert torch.equal(g[i].long(), r[i]) and g[i].data_ptr() == g.tokens[i].data_ptr()
+            assert torch.equal(g[5], r[5]) and g[5].dtype == torch.int64
+
+
+def test_packing_refuses_ids_that_would_wrap():
+    from intrepppid_b200 import feed
+
+    seqs = [torch.randint(0, 250, (3, 9)) for _ in range(5)]
+    y = torch.zeros(3, dtype=torch.long)
+    feed.pack_batch(seqs, y, 250)
+    seqs[3][1, 4] = 250
+    with pytest.raises(IndexError):
+        feed.pack_batch(seqs, y, 250)       # F.embedding would raise on it; a silent uint8 wrap would turn it into id 250 % 256
+    seqs[3][1, 4] = -1
+    with pytest.raises(IndexError):
+        feed.pack_batch(seqs, y, 250)
+    with pytest.raises(IndexError):
+        feed.narrow_collate(250)([tuple([s[1] for s in seqs] + [0])])
+    with pytest.raises(ValueError):
+        feed.pack_batch(seqs[:4], y, 250)
+    with pytest.raises(TypeError):
+        feed.pack_batch([s.float() for s in seqs], y, 250)
+    with pytest.raises(RuntimeError):
+        feed.DeviceFeeder([], "cpu", 250)   # no CPU path

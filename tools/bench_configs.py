@@ -5,7 +5,7 @@
     python tools/bench_configs.py --config 6   # infer from_csv: ragged 20k proteome embedded once at batch-of-one semantics + 1M scored rows
     python tools/bench_configs.py --config 5   # stress encoder: E=256, 3-layer bi-LSTM, mean pooling, T=4000, batch 256 (one GPU's share)
 
-One JSON line per config on stdout.  CUDA-event timing after a warm-up; inputs follow SURVEY.md 8(d) (seeds 4321 / 777)."""
+One JSON line per config on stdout; bench.py imports the same functions for the `other_configs` object of its line.  CUDA-event timing after a warm-up; inputs follow SURVEY.md 8(d) (seeds 4321 / 777)."""
 from __future__ import annotations
 
 import argparse
@@ -45,10 +45,10 @@ def config4(args):
         ms_enc, z = timed(lambda: net.embed(x, bs), warm=1, reps=1)
         P = M * (M + 1) // 2
         ms_pairs, prob = timed(lambda: net.score_pairs(z), warm=1, reps=1)
-    print(json.dumps({"config": 4, "mode": args.mode, "proteins": M, "trunc_len": T, "batch": bs,
+    return ({"config": 4, "mode": args.mode, "proteins": M, "trunc_len": T, "batch": bs,
                       "encode_ms": ms_enc, "encode_seqs_per_s": M / ms_enc * 1e3,
                       "pairs": P, "pairs_ms": ms_pairs, "pairs_per_s": P / ms_pairs * 1e3,
-                      "pairs_out_GBps": P * 4 / ms_pairs / 1e6, "prob_mean": float(prob.mean())}))
+                      "pairs_out_GBps": P * 4 / ms_pairs / 1e6, "prob_mean": float(prob.mean())})
 
 
 def config_csv(args):
@@ -86,14 +86,14 @@ def config_csv(args):
         ms_mixed, _ = timed(lambda: net.embed(x, 512), warm=1, reps=1)
     keys = torch.stack(infer.batch1_lengths(x, net.encoder.embedder.weight), 1).cpu().tolist()
     plan = infer.plan_buckets(keys)
-    print(json.dumps({"config": "from_csv", "mode": args.mode, "proteins": M, "rows": R, "mean_len": float(lens.float().mean()),
+    return ({"config": "from_csv", "mode": args.mode, "proteins": M, "rows": R, "mean_len": float(lens.float().mean()),
                       "distinct_lengths": len({tuple(k) for k in keys}), "launch_sets": len(plan),
                       "groups_by_size": {b: sum(len(gr) for bb, gr in plan if bb == b) for b in (8, 4, 2, 1)},
                       "embed_batch1_ms": ms_enc, "embed_batch1_seqs_per_s": M / ms_enc * 1e3, "kernel_launches": launches,
                       "embed_batch1_kernel_ms": fam, "lengths_ms": (t1 - t0) * 1e3, "plan_ms": (t2 - t1) * 1e3,
                       "score_rows_ms": ms_pairs, "rows_per_s_end_to_end": R / (ms_enc + ms_pairs) * 1e3,
                       "mixed_batch512_embed_ms (different semantics: pads are stepped)": ms_mixed,
-                      "prob_mean": float(prob.mean())}))
+                      "prob_mean": float(prob.mean())})
 
 
 def config5(args):
@@ -127,7 +127,7 @@ def config5(args):
         _lib.timing_enable(False)
         out.update({"train_ms": ms_tr, "train_tokens_per_s": tokens / ms_tr * 1e3, "train_kernel_ms": fam_tr,
                     "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9})
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
@@ -140,4 +140,4 @@ if __name__ == "__main__":
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--rows", type=int, default=1000000)
     a = ap.parse_args()
-    {4: config4, 5: config5, 6: config_csv}[a.config](a)
+    print(json.dumps({4: config4, 5: config5, 6: config_csv}[a.config](a)))
