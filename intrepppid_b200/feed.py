@@ -108,7 +108,8 @@ class DeviceFeeder:
 
     Per pipeline slot: one pinned [5, B, T] staging tensor + label row, one device twin, a `ready` event (H2D done) and a `free`
     event (the consumer's stream is done with the slot).  `__next__` hands out batch k after enqueueing the H2D of batch k+1, so
-    that copy runs under step k; the consumer's stream only ever waits on `ready` events, the host never blocks on the GPU.
+    that copy runs under step k; the consumer's stream waits on `ready`, the copy stream on `free` (both on the GPU), and the host
+    only ever waits for an H2D copy that was issued `depth` batches earlier -- it never waits for compute.
     A batch handed out stays valid until the NEXT batch has been requested (`depth` = 2) -- the Lightning loop's usage pattern.
     Ragged last batches re-use the buffers' leading rows.  Accepts PackedBatches (narrow_collate) or the reference's
     default-collated 6-tuples of int64 tensors (packed here, on the consumer thread)."""
@@ -138,7 +139,7 @@ class DeviceFeeder:
                      host=torch.empty(5, B, T, dtype=self.dtype).pin_memory(), host_y=torch.empty(B, dtype=torch.int64).pin_memory(),
                      dev=torch.empty(5, B, T, dtype=self.dtype, device=self.device),
                      dev_y=torch.empty(B, dtype=torch.int64, device=self.device),
-                     ready=torch.cuda.Event(), free=None)
+                     ready=torch.cuda.Event(), free=None, used=False)
         return s
 
     def _stage(self, k: int, batch) -> PackedBatch:
@@ -152,8 +153,10 @@ class DeviceFeeder:
             tokens = None
         B, T = (tokens.shape[1], tokens.shape[2]) if tokens is not None else tuple(seqs[0].shape)
         s = self._slot(k, B, T)
-        if s["free"] is not None:
-            s["free"].synchronize()  # the step that read this slot `depth` batches ago; long finished in steady state
+        # the HOST only waits for the previous H2D copy out of this pinned buffer (done long ago in steady state); the hazard on the
+        # DEVICE buffer -- the step that still reads it -- is ordered on the GPU: the copy stream waits for the slot's `free` event
+        if s["used"]:
+            s["ready"].synchronize()
         host, host_y = s["host"][:, :B], s["host_y"][:B]
         if tokens is not None:
             host.copy_(tokens)
@@ -163,9 +166,12 @@ class DeviceFeeder:
             host_y.copy_(torch.as_tensor(y).reshape(-1))
         dev, dev_y = s["dev"][:, :B], s["dev_y"][:B]
         with torch.cuda.stream(self._stream):
+            if s["free"] is not None:
+                self._stream.wait_event(s["free"])
             dev.copy_(host, non_blocking=True)
             dev_y.copy_(host_y, non_blocking=True)
             s["ready"].record(self._stream)
+        s["used"] = True
         self.h2d_bytes += host.numel() * host.element_size() + host_y.numel() * 8
         return PackedBatch(dev, dev_y)
 

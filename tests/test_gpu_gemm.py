@@ -194,11 +194,13 @@ def _run_tn_planes(precision, G, B, T, lens_eff, NB1, first, second, ctas=3, see
     g = torch.Generator().manual_seed(seed)
     KA, rows, V = 256, G * B * T, 50
     NB2 = 64 if second else 0
-    Ap, Ahi, Alo = _planes(torch.randn(rows, KA, generator=g).cuda())
     lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
     ldb, col0 = 2 * NB1, 0 if NB1 == 128 else 64   # H = 64: Y_{l-1} is [.,128] -> NB1 = 128 takes all of it; a 64-wide take starts at 64
     ldb = max(ldb, 128)
     valid = _valid_rows(G, B, T, lens_eff)
+    # operand contract of the TMA kernels (whole 64-row boxes are loaded): rows t >= T_eff hold zeros in A and B -- the BPTT kernel
+    # zeroes the dgate rows [T_eff, next multiple of 64] (lstm_bwd.cu), the forward kernel the same rows of Y (lstm_fwd.cu)
+    Ap, Ahi, Alo = _planes(torch.randn(rows, KA, generator=g).cuda() * valid.unsqueeze(1))
     B1 = torch.randn(rows, ldb, generator=g).cuda() * valid.unsqueeze(1)     # rows t >= T_eff hold zeros (the forward zeroes the tail row)
     B1p, B1hi, B1lo = _planes(B1)
     B2 = torch.randn(rows, 128, generator=g).cuda() * valid.unsqueeze(1)
@@ -263,7 +265,7 @@ def _run_l0_grads(precision, G, B, T, lens_eff, V, dir0, ndir, masked=True, seed
     H, g = 64, torch.Generator().manual_seed(seed)
     rows = G * B * T
     valid = _valid_rows(G, B, T, lens_eff)
-    dA = [_planes(torch.randn(rows, 4 * H, generator=g).cuda()) for _ in range(2)]     # gate-interleaved columns k = 4u + q
+    dA = [_planes(torch.randn(rows, 4 * H, generator=g).cuda() * valid.unsqueeze(1)) for _ in range(2)]  # GI columns k = 4u + q; zero tail rows
     Y0p, Yhi, Ylo = _planes(torch.randn(rows, 2 * H, generator=g).cuda() * valid.unsqueeze(1))
     tok = torch.randint(0, V, (rows,), generator=g, dtype=torch.int32).cuda()
     emb = torch.randn(V, H, generator=g).cuda()

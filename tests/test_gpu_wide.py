@@ -121,3 +121,18 @@ def test_config5_full_size_inference_rows_vs_oracle():
             z2 = net.encoder(x.cuda())
         assert torch.equal(z1, z2), "deterministic"
         assert rel_l2(z1[rows].cpu(), zr.float()) < TOL[precision], precision
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config5_full_length_training_vs_fp64_oracle(precision):
+    """BASELINE.json config 5 architecture at its FULL sequence length in TRAINING mode: E=256, 3 layers, mean pooling, T=4000 (all
+    4000 BPTT steps through the DSMEM h all-gather / dh reduce-scatter of the 8-CTA clusters), masks supplied, small batch so that
+    the fp64 CPU oracle finishes in seconds.  Embeddings, T1 / T_eff and every encoder gradient are gated."""
+    z, zr, lens, ref_lens, grads, ref = _encoder_case(256, 3, "mean", 3, 4000, 1, precision, seed=77)
+    tol = TOL[precision]
+    assert torch.equal(lens, ref_lens), "T1 / T_eff must be bit-exact"
+    assert int(ref_lens[1, 0]) > 2500  # the chain really is thousands of steps long after the training-mode truncation
+    assert rel_l2(z, zr) < tol
+    for n, g in ref.items():
+        assert grads[n] is not None, n
+        assert_grad_close(grads[n].cpu(), g, tol, n)
