@@ -276,6 +276,15 @@ int ib200_dbg_l0_grads(int32_t G, int32_t B, int32_t T, int32_t V, const int32_t
                        float* const* d_wih, float* const* d_whh, float* const* d_bih, float* const* d_bhh, float* d_emb,
                        int32_t precision, void* stream);
 
+/* The same for the H = 128 / 192 / 256 path (gemm_wide.cu: both operands streamed by TMA): A_s [rows][K] and W_s [NC][K] plane matrices;
+ * _tn_wide: partial [G][splits][KA][NB1 + NB2] (splits <= 0: library default, returned through *splits_out; partial NULL: query only). */
+int ib200_dbg_gemm_nt_wide(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                           int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc, int32_t NC,
+                           int32_t accumulate, int32_t precision, void* stream);
+int ib200_dbg_gemm_tn_wide(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, int32_t KA, const float* Bsrc, int32_t ldb,
+                           int32_t col0, int32_t shift, int32_t NB1, const float* Bsrc2, int32_t ldb2, int32_t col02, int32_t shift2,
+                           int32_t NB2, float* partial, int32_t splits, int32_t* splits_out, int32_t precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,7 @@ EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_status", "ib200_encoder_bwd", "ib200_encoder_bwd_layers",
            "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn", "ib200_dbg_gemm_nt_planes", "ib200_dbg_gemm_tn_planes", "ib200_dbg_l0_scratch_floats",
-           "ib200_dbg_l0_grads")
+           "ib200_dbg_l0_grads", "ib200_dbg_gemm_nt_wide", "ib200_dbg_gemm_tn_wide")
 
 _lib = None
 
@@ -94,6 +94,9 @@ def lib() -> C.CDLL:
     L.ib200_dbg_gemm_nt_planes.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.ib200_dbg_gemm_tn_planes.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32,
                                            i32, vp]
+    L.ib200_dbg_gemm_nt_wide.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.ib200_dbg_gemm_tn_wide.argtypes = [i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, C.POINTER(i32),
+                                         i32, vp]
     L.ib200_dbg_l0_scratch_floats.restype = C.c_size_t
     L.ib200_dbg_l0_scratch_floats.argtypes = [i32, i32, i32]
     L.ib200_dbg_l0_grads.argtypes = [i32, i32, i32, i32, vp, vp, C.POINTER(vp), vp, vp, vp, vp, C.POINTER(vp), vp, i32, i32, i32, vp, vp,

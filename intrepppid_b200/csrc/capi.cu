@@ -94,6 +94,7 @@ struct Plan {
   size_t bias_partial[2];  // planes mode: [2][G*ceil(B/4)][4H] per-CTA dgate column sums from the BPTT kernel; one buffer per layer
                            // parity: layer l's reduce (side stream) reads its sums while layer l-1's BPTT kernel writes the other
   size_t l0_scratch;  // R of gemm_l0.cu
+  size_t x0p;         // wide tcgen05 path: layer-0 input rows scale*emb[tok] as planes [R,H] (B operand of the layer-0 dW_ih GEMM)
   size_t ph_state, ph_sched;  // two-phase rebalancing (common.cuh): [2][N][H][2] floats; sm_load[256] + resume_list[1 + CTAs] ints
   int ctas_per_group;
   size_t total;
@@ -131,6 +132,8 @@ bool cfg_ok(const ib200_cfg* c) {
   if ((c->H == 32 || c->H == 64) && c->T > 11000) return false;
   return true;
 }
+
+bool wide_tc(int H);  // (defined with the GEMM dispatch below)
 
 Plan make_plan(const ib200_cfg* c) {
   Plan p{};
@@ -176,6 +179,7 @@ Plan make_plan(const ib200_cfg* c) {
     p.partial = take(sizeof(float) * std::max((size_t)p.G * p.ctas_per_group * ((size_t)4 * H * 3 * H + 4 * H),  // up to [dW_ih | dW_hh] fused
                                               l0_grad_partial_floats(p.G, 2)));
     p.l0_scratch = take(sizeof(float) * l0_grad_scratch_floats(p.G, 2));
+    if (wide_tc(H)) p.x0p = take(sizeof(float) * p.R * H);
     for (int i = 0; i < 2; ++i) p.bias_partial[i] = take(sizeof(float) * 2 * (size_t)p.G * ((p.B + 3) / 4) * 4 * H);
   }
   p.total = off;
@@ -200,9 +204,13 @@ bool use_cluster(int H) {
   return force || (H != 32 && H != 64);
 }
 bool use_tc() { return gemm_mode() >= 1; }
-bool use_planes(int H) { return H == 64 && gemm_mode() == 2 && !use_cluster(H); }
+// hidden sizes of the cluster path whose GEMMs run on the TMA-fed tcgen05 kernels of gemm_wide.cu (H = 128, 192, 256); the other
+// cluster sizes (96, 160, 224) and IB200_GEMM=legacy keep the column-blocked mma.sync kernels
+bool wide_tc(int H) { return gemm_wide_supports(H) && gemm_mode() == 2; }
+bool use_planes(int H) { return (H == 64 && gemm_mode() == 2 && !use_cluster(H)) || wide_tc(H); }
 cudaError_t gemm_nt_auto(const GemmNTArgs& a, int prec, cudaStream_t st, bool wide = false) {
-  if (wide) return launch_gemm_nt(a, prec, st);  // H > 64: column-blocked legacy kernel
+  if (wide && a.plane_bytes > 0) return launch_gemm_nt_wide(a, prec, st);  // H = 128 / 192 / 256: streamed-operand tcgen05 kernel
+  if (wide) return launch_gemm_nt(a, prec, st);  // other H > 64: column-blocked legacy kernel
   if (a.plane_bytes > 0) {  // operands are bf16 planes: only the TMA kernels can read them
     cudaError_t e = launch_gemm_nt_tma(a, prec, st);
     if (e != cudaErrorInvalidConfiguration || a.nsrc != 2) return e;
@@ -280,8 +288,8 @@ int tn_launches(int KA, int NB, bool wide) {
     for (int nb0 = 0; nb0 < NB; nb0 += (NB - nb0 >= 128 ? 128 : (NB - nb0 >= 64 ? 64 : 32))) n += 2;
   return n;
 }
-int nt_launches(int NC, bool wide) {
-  if (!wide) return 1;
+int nt_launches(int NC, bool wide, bool planes = false) {
+  if (!wide || planes) return 1;
   int n = 0;
   for (int c0 = 0; c0 < NC; c0 += (NC - c0 >= 256 ? 256 : (NC - c0 >= 128 ? 128 : (NC - c0 >= 64 ? 64 : 32)))) ++n;
   return n;
@@ -448,7 +456,9 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
         float* b = l > 0 ? at<float>(ws, p.b_gi[l][d]) : nullptr;
         float* wT = p.train ? at<float>(ws, p.wihT_gi[l][d]) : nullptr;
         if (l == 0 && l0_fused_ok(p, planes)) wT = nullptr;  // W_ih^T of layer 0 only feeds the dX_0 GEMM, which the fused path replaces
-        if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
+        if ((w || wT) && wide && planes)  // W_ih (and its transpose) as bf16 hi|lo plane matrices: TMA operands of gemm_wide.cu
+          TIMED(F_PREP, 1, launch_prep_wih_planes(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, prec, st), "prep wih planes");
+        else if (w || wT) TIMED(F_PREP, 1, launch_prep_wih(P->w_ih[l][d], P->b_ih[l][d], P->b_hh[l][d], H, K, w, wT, b, st), "prep wih");
       }
     if (side != nullptr) CK(cudaEventRecord(side->join, side->stream), "join record");
   }
@@ -474,7 +484,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
         ga.W[0] = at<float>(ws, p.wih_gi[l][d]); ga.bias = at<float>(ws, p.b_gi[l][d]);
         ga.C = at<float>(ws, p.X[d]); ga.ldc = 4 * H; ga.NC = 4 * H; ga.accumulate = 0;
         ga.plane_bytes = planes ? 2 * H * 2 : 0;
-        TIMED(F_GEMM_XPROJ, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "input projection gemm");
+        TIMED(F_GEMM_XPROJ, nt_launches(ga.NC, wide, planes), gemm_nt_auto(ga, prec, st, wide), "input projection gemm");
       }
     }
     LstmFwdArgs fa{};
@@ -572,7 +582,8 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
     }
     TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st),
           "lstm bwd");
-    const int bwd_ctas = planes ? lstm_bwd_cta_count(ba, prec) : 0;  // CTAs per direction (= number of bias partials)
+    // bias partial rows per direction left by the BPTT kernel
+    const int bwd_ctas = !planes ? 0 : (cluster ? lstm_bwd_cluster_cta_count(ba, H, prec) : lstm_bwd_cta_count(ba, prec));
 
     // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates
     // (gemm_l0.cu: the token-indexed sums S = dA^T onehot(tok) replace the gathered dW GEMM, the dX_0 GEMM and the atomic scatter)
@@ -602,6 +613,7 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
     }
 
     // weight gradients of this layer (read dA = gates buffers, Y_{l-1} / embeddings, Y_l); `st` = the stream they are issued on
+    bool x0_ready = false;
     auto weight_grads = [&](cudaStream_t st) -> int {
     for (int d = 0; d < 2; ++d) {
       const int K = l == 0 ? H : 2 * H;
@@ -648,7 +660,22 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
           CK(cudaStreamWaitEvent(st, side->join, 0), "join wait");
           pending_join = false;
         }
-        TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, true), "dW_ih|dW_hh gemm");
+        if (wide) {
+          if (l == 0) {  // the layer-0 input rows scale*emb[tok] as a dense plane operand (one small gather instead of a gathering GEMM loader)
+            float* x0p = at<float>(ws, p.x0p);
+            if (!x0_ready) {
+              TIMED(F_EMB_GRAD, 1, launch_gather_x0_planes(p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), P->emb, emb_row_scale, x0p, prec, st),
+                    "layer-0 input planes");
+              x0_ready = true;
+            }
+            ta.tok = nullptr; ta.emb = nullptr; ta.emb_row_scale = nullptr;
+            ta.Bsrc = x0p; ta.ldb = H; ta.col0 = 0; ta.shift = 0;
+          }
+          ta.ctas_per_group = ra.ctas_per_group = gemm_tn_wide_splits(ta.KA, ta.NB, H, p.G);
+          TIMED(F_GEMM_DW, 1, launch_gemm_tn_wide(ta, prec, st), "dW_ih|dW_hh gemm (wide)");
+        } else {
+          TIMED(F_GEMM_DW, 1, gemm_tn_auto(ta, prec, st, true), "dW_ih|dW_hh gemm");
+        }
         if (l > 0 && side != nullptr && st != side->stream) {
           // the reduce (a small grid) runs on the side stream next to this layer's dY GEMM; joined before `partial` is written again
           CK(cudaEventRecord(side->fork, st), "fork record");
@@ -695,10 +722,10 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
     ga.plane_bytes = planes ? 4 * H * 2 : 0;
     if (l > 0) {
       ga.C = dY; ga.ldc = 2 * H; ga.NC = 2 * H;
-      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "dY gemm");
+      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide, planes), gemm_nt_auto(ga, prec, st, wide), "dY gemm");
     } else {
       ga.C = dX0; ga.ldc = H; ga.NC = H;
-      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide), gemm_nt_auto(ga, prec, st, wide), "dX0 gemm");
+      TIMED(F_GEMM_DGRAD, nt_launches(ga.NC, wide, planes), gemm_nt_auto(ga, prec, st, wide), "dX0 gemm");
       EmbGradArgs ea{p.G, p.B, p.T, p.V, H, lens, at<int>(ws, p.tok32), dX0, emb_row_scale, Gr->emb};
       TIMED(F_EMB_GRAD, 2, launch_emb_grad(ea, st), "embedding grad");
     }
@@ -928,6 +955,34 @@ int ib200_dbg_l0_grads(int32_t G, int32_t B, int32_t T, int32_t V, const int32_t
   la.Y0 = Y0; la.emb = emb; la.emb_row_scale = emb_row_scale; la.whh_mask = whh_mask;
   la.bias_partial = bias_partial; la.bias_count = bias_count; la.partial = partial; la.R = scratch; la.d_emb = d_emb;
   CK(launch_l0_grads(la, precision, (cudaStream_t)stream), "dbg l0 grads");
+  return 0;
+}
+
+// ---- test hooks for the streamed-operand tcgen05 kernels of the H = 128 / 192 / 256 path (gemm_wide.cu) ----------------------------
+// A_s and W_s are plane matrices ([rows][K] and [NC][K], a row of K values = [K bf16 hi | K bf16 lo] over the bytes of K floats)
+int ib200_dbg_gemm_nt_wide(int32_t G, int32_t B, int32_t T, const int32_t* lens, int32_t nsrc, const float* A0, const float* A1,
+                           int32_t lda, int32_t K, const float* W0, const float* W1, const float* bias, float* C, int32_t ldc, int32_t NC,
+                           int32_t accumulate, int32_t precision, void* stream) {
+  if (!lens || !A0 || !W0 || !C || (nsrc == 2 && (!A1 || !W1))) return fail(IB200_E_NULL, "ib200_dbg_gemm_nt_wide: null pointer");
+  GemmNTArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.nsrc = nsrc; a.A[0] = A0; a.A[1] = A1; a.lda = lda; a.K = K;
+  a.W[0] = W0; a.W[1] = W1; a.bias = bias; a.C = C; a.ldc = ldc; a.NC = NC; a.accumulate = accumulate; a.plane_bytes = K * 2;
+  CK(launch_gemm_nt_wide(a, precision, (cudaStream_t)stream), "dbg gemm nt wide");
+  return 0;
+}
+
+// partial: [G][splits][KA][NB1 + NB2]; splits <= 0 picks gemm_tn_wide_splits; returns the split count through *splits_out
+int ib200_dbg_gemm_tn_wide(int32_t G, int32_t B, int32_t T, const int32_t* lens, const float* A, int32_t KA, const float* Bsrc, int32_t ldb,
+                           int32_t col0, int32_t shift, int32_t NB1, const float* Bsrc2, int32_t ldb2, int32_t col02, int32_t shift2,
+                           int32_t NB2, float* partial, int32_t splits, int32_t* splits_out, int32_t precision, void* stream) {
+  if (!lens || !A || !Bsrc || (NB2 > 0 && !Bsrc2)) return fail(IB200_E_NULL, "ib200_dbg_gemm_tn_wide: null pointer");
+  GemmTNArgs a{};
+  a.G = G; a.B = B; a.Tmax = T; a.lens = lens; a.A = A; a.KA = KA; a.Bsrc = Bsrc; a.ldb = ldb; a.col0 = col0; a.shift = shift;
+  a.NB1 = NB1; a.NB = NB1 + NB2; a.Bsrc2 = Bsrc2; a.ldb2 = ldb2; a.col02 = col02; a.shift2 = shift2; a.partial = partial;
+  a.ctas_per_group = splits > 0 ? splits : gemm_tn_wide_splits(KA, a.NB, KA / 4, G);
+  if (splits_out) *splits_out = a.ctas_per_group;
+  if (!partial) return 0;  // query of the split count only
+  CK(launch_gemm_tn_wide(a, precision, (cudaStream_t)stream), "dbg gemm tn wide");
   return 0;
 }
 

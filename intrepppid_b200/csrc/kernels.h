@@ -85,8 +85,10 @@ cudaError_t launch_lstm_bwd(const LstmBwdArgs& a, int H, int precision, cudaStre
 int lstm_bwd_cta_count(const LstmBwdArgs& a, int precision);  // G * gridDim.x of the launch above (bias partials per direction)
 
 // ---- K2c / K3c: cluster versions for H = 32k, 32 <= H <= 256 (lstm_cluster.cu): W_hh sliced over H/32 CTAs, h exchanged over DSMEM.
-// fp32 y / gates / dgates layouts only (planes must be 0); bias gradients come from the TN GEMM's column sums.
+// planes = 0: fp32 y / dgates, bias gradients from the TN GEMM's column sums; planes = 1: y and dgates as bf16 hi|lo planes (the
+// operands of gemm_wide.cu), bias partials [ndir][lstm_bwd_cluster_cta_count][4H] written by the BPTT kernel.
 bool lstm_cluster_supports(int H);
+int lstm_bwd_cluster_cta_count(const LstmBwdArgs& a, int H, int precision);
 cudaError_t launch_lstm_fwd_cluster(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
 cudaError_t launch_lstm_bwd_cluster(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 
@@ -112,6 +114,16 @@ cudaError_t launch_gemm_nt(const GemmNTArgs& a, int precision, cudaStream_t st);
 cudaError_t launch_gemm_nt_tc(const GemmNTArgs& a, int precision, cudaStream_t st);
 // tcgen05 + TMA version: A_s rows are bf16 hi/lo planes written by the recurrent kernels (plane_bytes > 0)
 cudaError_t launch_gemm_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st);
+
+// tcgen05 + TMA with BOTH operands streamed (gemm_wide.cu; H = 128, 192, 256): A_s rows and W_s ([NC][K], from launch_prep_wih_planes)
+// are bf16 hi|lo plane matrices
+bool gemm_wide_supports(int H);
+cudaError_t launch_gemm_nt_wide(const GemmNTArgs& a, int precision, cudaStream_t st);
+cudaError_t launch_prep_wih_planes(const float* w, const float* b_ih, const float* b_hh, int H, int K, float* out_w, float* out_wT,
+                                   float* out_b, int precision, cudaStream_t st);
+// layer-0 input rows scale[g][tok] * emb[tok] as planes [N*Tmax][H] (zeros in the tail rows of the last 64-row box)
+cudaError_t launch_gather_x0_planes(int G, int B, int Tmax, int V, int H, const int* lens, const int* tok, const float* emb,
+                                    const float* scale, float* out, int precision, cudaStream_t st);
 
 // TN:  P[cta][KA, NB] = sum_{rows of cta} A[row, KA]^T * Bop[row, NB]   (partials; reduced by launch_dw_reduce)
 struct GemmTNArgs {
@@ -142,6 +154,11 @@ cudaError_t launch_gemm_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t s
 // tcgen05 + TMA: A = dgates planes (row = [hi 4H bf16 | lo 4H bf16]); Bsrc = planes rows of ldb floats ([hi ldb bf16 | lo ldb bf16])
 // or gathered embeddings (tok != null); no colsum (the BPTT kernel produces the bias partials)
 cudaError_t launch_gemm_tn_tma(const GemmTNArgs& a, int precision, cudaStream_t st);
+
+// wide version (gemm_wide.cu): KA = 4H, column tiles of H, split-K over a.ctas_per_group = gemm_tn_wide_splits(...) CTAs per tile;
+// partial [G][splits][KA][NB]; dense plane sources only (no gather, no colsum)
+int gemm_tn_wide_splits(int KA, int NB, int BN, int G);
+cudaError_t launch_gemm_tn_wide(const GemmTNArgs& a, int precision, cudaStream_t st);
 
 // out[torch_row(gi)][c] = sum_g mask_g[torch_row][c] * sum_cta partial[g][cta][gi][c];  optional bias outputs
 struct DwReduceArgs {

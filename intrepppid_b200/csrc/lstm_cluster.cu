@@ -16,9 +16,15 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "tc05.cuh"
 
 namespace ib200 {
 namespace {
+
+using tc::mbar_arrive_expect_tx;
+using tc::mbar_init;
+using tc::mbar_init_fence;
+using tc::mbar_wait;
 
 // timing experiments only (IB200_ABLATE=1 builds, env IB200_DBG): 1 no remote h stores, 2 CTA barrier instead of the cluster barrier,
 // 4 no global stores, 8 no MMAs.  Production builds compile the switches out.
@@ -48,11 +54,12 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* local_smem, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(a), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};\n" ::"r"(addr), "f"(a), "f"(b) : "memory");
+// 16-byte asynchronous store into the shared memory of a CTA of the cluster; its completion is counted (complete_tx, 16 bytes) on an
+// mbarrier of THAT CTA, so the receiver waits on a local barrier for "all bytes of this step have landed" -- no cluster-wide barrier
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(addr), "r"(a),
+               "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -117,6 +124,8 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
   __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [NPART][128][ldw]
   __nv_bfloat16* hs = Wsm + (size_t)NPART * kRows * ldw;                      // [2][NPART][H][NSP]
   const int kPartElems = H * NSP, kBufElems = NPART * kPartElems;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hs + (size_t)2 * kBufElems);  // [2]: "all of h for buffer b has landed" (complete_tx bytes)
+  const uint32_t kStepBytes = (uint32_t)(NPART * H * NS * 2);                 // bytes every CTA receives per step: the whole h tile
 
   {
     const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
@@ -124,8 +133,14 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     load_w_slice<SPLIT>(Wsm, W, M, H, rank);
   }
   for (int i = tid; i < 2 * kBufElems / 2; i += kClThreads) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&hbar[0], 1);
+    mbar_init(&hbar[1], 1);
+    mbar_init_fence();
+    if (T > 1) mbar_arrive_expect_tx(&hbar[1], kStepBytes);  // armed for h_0, written at the end of step 0
+  }
   __syncthreads();
-  cluster_arrive();  // every CTA's tiles are initialised before any remote h write lands
+  cluster_arrive();  // every CTA's tiles and barriers are initialised before any remote h write lands
   cluster_wait();
 
   const int ul = 8 * warp + gq, u = kUS * rank + ul;  // the unit of this thread's cells
@@ -158,13 +173,18 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
 
   float4* const G4 = train ? reinterpret_cast<float4*>(dir ? p.gates[1] : p.gates[0]) + u : nullptr;
   float* const Cst = train ? (dir ? p.cstate[1] : p.cstate[0]) + u : nullptr;
-  const bool has_y = p.y != nullptr;
+  const bool has_y = p.y != nullptr, planes = p.planes != 0;
   const int ycol = dir * H + u, ystr = p.y_stride;
 
-  // remote addresses of my h slot (unit u, column 2*tig) in every CTA of the cluster
-  uint32_t hdst[8];
+  // h exchange: the four lanes that share a unit (same gq) hold the 8 columns of an n-tile = one 16-byte piece of the h tile row;
+  // after a 4-lane gather, lane tig sends that piece to CTAs tig and tig + 4 of the cluster with ONE 16-byte st.async each
+  uint32_t hdst[2], rbar[2];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) hdst[r] = r < C ? map_to_rank(hs + (size_t)u * NSP + ncol0 + 2 * tig, (uint32_t)r) : 0u;
+  for (int i = 0; i < 2; ++i) {
+    const int r = tig + 4 * i;
+    hdst[i] = r < C ? map_to_rank(hs + (size_t)u * NSP + ncol0, (uint32_t)r) : 0u;
+    rbar[i] = r < C ? map_to_rank(hbar, (uint32_t)r) : 0u;
+  }
 
   // ldmatrix lane addresses: A (non transposed) row = tile*16 + (lane&7) + (lane&8), k offset (lane&16 ? 8 : 0)
   const __nv_bfloat16* a_lane = Wsm + (size_t)((2 * warp) * 16 + (lane & 7) + (lane & 8)) * ldw + ((lane & 16) ? 8 : 0);
@@ -182,6 +202,8 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     for (int c = 0; c < NCELL; ++c) x[c] = xn[c];
     if (s + 1 < T) load_x(s + 1, xn);  // register prefetch, one step ahead
     const int buf = s & 1;
+    if (s > 0) mbar_wait(&hbar[buf], (uint32_t)(((s - 1) >> 1) & 1));  // all of h_{s-1} has landed in buffer `buf`
+    if (tid == 0 && s + 2 < T) mbar_arrive_expect_tx(&hbar[buf], kStepBytes);  // its next fill is written at the end of step s + 1
 
     // acc[t2][j]: [0]=(row gq, col n0) [1]=(row gq, col n1) [2]=(row gq+8, n0) [3]=(row gq+8, n1); t2=0: rows i,f ; t2=1: rows g,o
     float acc[2][NTW][4];
@@ -235,28 +257,58 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
           G4[row * H] = make_float4(gi, gf, gg, go);
           Cst[row * H] = cst[c];
         }
-        if (has_y) p.y[row * ystr + ycol] = hv[c];
+        if (has_y) {
+          if (planes) {
+            // bf16 hi | lo planes over the bytes of the fp32 row (what the TMA-fed tcgen05 GEMMs read, gemm_wide.cu)
+            __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.y + row * ystr);
+            const __nv_bfloat16 hb16 = __float2bfloat16_rn(hv[c]);
+            yrow[ycol] = hb16;
+            if constexpr (SPLIT) yrow[ystr + ycol] = __float2bfloat16_rn(hv[c] - __bfloat162float(hb16));
+          } else {
+            p.y[row * ystr + ycol] = hv[c];
+          }
+        }
       }
     }
-    // publish my slice of h_t to every CTA of the cluster (buffer buf^1)
-    const uint32_t boff = (uint32_t)((buf ^ 1) * kBufElems) * 2u;
+    // publish my slice of h_t to every CTA of the cluster (buffer buf^1); the receivers count the bytes on their hbar[buf^1].
+    // No barrier: a CTA can only be one step ahead of the slowest one (it needs everybody's h), and with two buffers a buffer is
+    // rewritten only after every reader has sent the h it computed from it.
+    if (s + 1 < T) {
+      const uint32_t boff = (uint32_t)((buf ^ 1) * kBufElems) * 2u, bar_off = (uint32_t)(buf ^ 1) * 8u;
+      const int lbase = lane & ~3;
 #pragma unroll
-    for (int j = 0; j < NTW; ++j) {
-      uint32_t hi, lo = 0u;
-      if constexpr (SPLIT) split_bf16(hv[2 * j], hv[2 * j + 1], hi, lo);
-      else hi = pack_bf16(hv[2 * j], hv[2 * j + 1]);
+      for (int j = 0; j < NTW; ++j) {
+        uint32_t hi, lo = 0u;
+        if constexpr (SPLIT) split_bf16(hv[2 * j], hv[2 * j + 1], hi, lo);
+        else hi = pack_bf16(hv[2 * j], hv[2 * j + 1]);
+        uint32_t wh[4], wl[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < C && !((dbg & 1) && r != rank)) {
-          st_cluster_u32(hdst[r] + boff + j * 16, hi);
-          if constexpr (SPLIT) st_cluster_u32(hdst[r] + boff + (uint32_t)kPartElems * 2u + j * 16, lo);
+        for (int t4 = 0; t4 < 4; ++t4) {
+          wh[t4] = __shfl_sync(0xffffffffu, hi, lbase | t4);
+          if constexpr (SPLIT) wl[t4] = __shfl_sync(0xffffffffu, lo, lbase | t4);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (tig + 4 * i < C) {
+            st_async_v4(hdst[i] + boff + j * 16, wh[0], wh[1], wh[2], wh[3], rbar[i] + bar_off);
+            if constexpr (SPLIT)
+              st_async_v4(hdst[i] + boff + (uint32_t)kPartElems * 2u + j * 16, wl[0], wl[1], wl[2], wl[3], rbar[i] + bar_off);
+          }
+      }
     }
-    if (dbg & 2) {
-      __syncthreads();
-    } else {
-      cluster_arrive();
-      cluster_wait();
+  }
+  cluster_arrive();  // nobody exits while a peer could still be sending to it
+  cluster_wait();
+
+  // planes mode: the weight-gradient GEMM reads whole 64-row TMA boxes (and the row after the last one for the shifted operand): rows
+  // [T, tail_end) of this cluster's sequences must be zeros in this CTA's 32 columns of this direction (both planes)
+  if (has_y && planes) {
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;
+    constexpr int kChunks = kUS * 2 / 16;  // 16-byte chunks of 32 bf16
+    for (int i = tid; i < nvalid * ntail * kChunks * 2; i += kClThreads) {
+      const int cc = i % kChunks, pl = (i / kChunks) & 1, r = (i / (2 * kChunks)) % ntail, q = i / (2 * kChunks * ntail);
+      unsigned char* row = reinterpret_cast<unsigned char*>(p.y + ((size_t)(nbase + q) * Tmax + T + r) * ystr);
+      *reinterpret_cast<uint4*>(row + pl * ystr * 2 + (dir * H + kUS * rank) * 2 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 
@@ -289,18 +341,27 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
   if (T <= 0) return;
   const int b0 = tile * NS, nvalid = min(NS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
   const size_t N = (size_t)p.G * p.B;
-  const bool has_dy = p.dy != nullptr;
+  const bool has_dy = p.dy != nullptr, planes = p.planes != 0;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [NPART][128][ldw]
   __nv_bfloat16* das = Wsm + (size_t)NPART * kRows * ldw;                // [NPART][128][NSP]: da of my units, k = local gate row
   float* xbuf = reinterpret_cast<float*>(das + (size_t)NPART * kRows * NSP);  // [2][C][32][NS] partial dh for my units, per source CTA
   const int kXBuf = C * kUS * NS;
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(xbuf + (size_t)2 * kXBuf);  // [2]: "all C partials of exchange buffer b have landed"
+  const uint32_t kXBytes = (uint32_t)kXBuf * 4u;
 
   {
     const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
     const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
     load_w_slice<SPLIT>(Wsm, W, M, H, rank);
+  }
+  if (tid == 0) {
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    mbar_init_fence();
+    if (T > 1) mbar_arrive_expect_tx(&xbar[1], kXBytes);  // step s fills buffer (s + 1) & 1: step 0 -> buffer 1, step 1 -> buffer 0
+    if (T > 2) mbar_arrive_expect_tx(&xbar[0], kXBytes);
   }
   __syncthreads();
   cluster_arrive();
@@ -339,6 +400,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
   In nxt;
   load_in(0, nxt);
   float ccur[NCELL], dc[NCELL], dhrec[NCELL];
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of my cells' dgates over all steps (bias gradient partials)
 #pragma unroll
   for (int c = 0; c < NCELL; ++c) {
     const int q = ncol0 + 8 * (c >> 1) + 2 * tig + (c & 1);
@@ -373,7 +435,25 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
       const float da_ii = d_i * gi * (1.0f - gi), da_f = d_f * gf * (1.0f - gf);
       const float da_g = d_g * fmaf(-gg, gg, 1.0f), da_o = d_o * go * (1.0f - go);
       in.g[c] = make_float4(da_ii, da_f, da_g, da_o);
-      if (valid[c]) G4[(size_t)(rb[c] + t) * H] = in.g[c];  // dgates overwrite the saved gates in place
+      if (valid[c]) {  // dgates overwrite the saved gates in place
+        if (planes) {
+          // bf16 hi | lo planes over the 4H-float gate row: [4H bf16 hi | 4H bf16 lo], gate-interleaved column 4u + q
+          unsigned char* grow = reinterpret_cast<unsigned char*>(G4 + (size_t)(rb[c] + t) * H) - (size_t)u * 16;  // start of the row
+          uint32_t h0, h1, l0 = 0u, l1 = 0u;
+          if constexpr (SPLIT) {
+            split_bf16(da_ii, da_f, h0, l0);
+            split_bf16(da_g, da_o, h1, l1);
+          } else {
+            h0 = pack_bf16(da_ii, da_f);
+            h1 = pack_bf16(da_g, da_o);
+          }
+          *reinterpret_cast<uint2*>(grow + (size_t)u * 8) = make_uint2(h0, h1);
+          if constexpr (SPLIT) *reinterpret_cast<uint2*>(grow + (size_t)H * 8 + (size_t)u * 8) = make_uint2(l0, l1);
+          bsum.x += da_ii; bsum.y += da_f; bsum.z += da_g; bsum.w += da_o;
+        } else {
+          G4[(size_t)(rb[c] + t) * H] = in.g[c];
+        }
+      }
     }
     if (s + 1 == T) break;
     // da -> smem B tile (bf16 hi / lo), packed pairs of columns (n0, n1)
@@ -422,18 +502,27 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
           }
         }
       }
-      // rows: unit mt*16+gq ([0],[1]) and mt*16+gq+8 ([2],[3]); columns 8j+2tig, +1
-      const uint32_t xdst = map_to_rank(xslot, (uint32_t)(mt >> 1));  // owner CTA: 32 units per CTA = 2 unit tiles
-      const int ul0 = (mt & 1) * 16 + gq;
+      // rows: unit mt*16+gq ([0],[1]) and mt*16+gq+8 ([2],[3]); columns 8j+2tig, +1.  Lane pairs (tig, tig^1) swap halves so that the
+      // even lane owns 4 consecutive columns of row gq and the odd lane 4 consecutive columns of row gq+8: ONE 16-byte st.async each,
+      // counted on the owner CTA's xbar (owner: 32 units per CTA = 2 unit tiles)
+      const uint32_t owner = (uint32_t)(mt >> 1);
+      const uint32_t xdst = map_to_rank(xslot, owner), xbr = map_to_rank(xbar, owner) + (uint32_t)((s + 1) & 1) * 8u;
+      const bool odd = (tig & 1) != 0;
+      const int xrow = (mt & 1) * 16 + gq + (odd ? 8 : 0);
 #pragma unroll
       for (int j = 0; j < NTILE; ++j) {
-        const uint32_t col = (uint32_t)(8 * j + 2 * tig);
-        st_cluster_f32x2(xdst + xoff + ((uint32_t)ul0 * NS + col) * 4u, acc[j][0], acc[j][1]);
-        st_cluster_f32x2(xdst + xoff + ((uint32_t)(ul0 + 8) * NS + col) * 4u, acc[j][2], acc[j][3]);
+        const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[j][0] : acc[j][2], 1);
+        const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[j][1] : acc[j][3], 1);
+        const uint32_t col = (uint32_t)(8 * j + 2 * (tig & ~1));
+        const uint32_t a0 = __float_as_uint(odd ? r0 : acc[j][0]), a1 = __float_as_uint(odd ? r1 : acc[j][1]);
+        const uint32_t a2 = __float_as_uint(odd ? acc[j][2] : r0), a3 = __float_as_uint(odd ? acc[j][3] : r1);
+        st_async_v4(xdst + xoff + ((uint32_t)xrow * NS + col) * 4u, a0, a1, a2, a3, xbr);
       }
     }
-    cluster_arrive();
-    cluster_wait();
+    // all C partials of this step have landed in my buffer (every CTA of the cluster, myself included, sent 32 x NS floats).  No
+    // cluster barrier: passing this wait also means every local warp has finished reading `das` (its sends come after its MMAs)
+    mbar_wait(&xbar[(s + 1) & 1], (uint32_t)((s >> 1) & 1));
+    if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[(s + 1) & 1], kXBytes);  // refilled at step s + 2
     // recurrent gradient of my cells for the next step: sum of the C partials
     const float* xb = xbuf + (size_t)((s + 1) & 1) * kXBuf + (size_t)ul * NS;
 #pragma unroll
@@ -444,15 +533,51 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
       dhrec[c] = sum;
     }
   }
+  cluster_arrive();  // nobody exits while a peer could still be sending to it
+  cluster_wait();
+
+  if (planes) {
+    // (1) bias-gradient partials: one [4H] row (GI order) per (direction slot, group, tile); CTA `rank` owns columns [128 rank, +128)
+    if (p.bias_partial != nullptr) {
+      bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 1); bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 1);
+      bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 1); bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 1);
+      bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 2); bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 2);
+      bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 2); bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 2);
+      float4* red = reinterpret_cast<float4*>(xbuf);  // [NWG][32 units] (the exchange buffers are idle now)
+      __syncthreads();
+      if (tig == 0) red[nh * kUS + ul] = bsum;
+      __syncthreads();
+      if (nh == 0 && tig == 0) {
+        float4 b = red[ul];
+#pragma unroll
+        for (int w2 = 1; w2 < NWG; ++w2) {
+          const float4 o = red[w2 * kUS + ul];
+          b.x += o.x; b.y += o.y; b.z += o.z; b.w += o.w;
+        }
+        const int ntiles = (int)gridDim.x / C;
+        float* dst = p.bias_partial + (((size_t)blockIdx.z * p.G + g) * ntiles + tile) * 4 * H + 4 * u;
+        *reinterpret_cast<float4*>(dst) = b;
+      }
+    }
+    // (2) zero tail rows [T, tail_end) of my sequences in my 128 gate columns (both planes): the TN GEMM reads whole 64-row boxes
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;
+    constexpr int kChunks = kRows * 2 / 16;  // 16-byte chunks of 128 bf16
+    float* const Gbase = dir ? p.gates[1] : p.gates[0];
+    for (int i = tid; i < nvalid * ntail * kChunks * 2; i += 32 * kWarps) {
+      const int cc = i % kChunks, pl = (i / kChunks) & 1, r = (i / (2 * kChunks)) % ntail, q = i / (2 * kChunks * ntail);
+      unsigned char* row = reinterpret_cast<unsigned char*>(Gbase + ((size_t)(nbase + q) * Tmax + T + r) * 4 * H);
+      *reinterpret_cast<uint4*>(row + (size_t)pl * 4 * H * 2 + (size_t)kRows * rank * 2 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
 }
 
 size_t fwd_smem(int H, int ntile, bool split) {
   const int npart = split ? 2 : 1, nsp = 8 * ntile + kNPad;
-  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)2 * npart * H * nsp * 2;
+  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)2 * npart * H * nsp * 2 + 16;  // + hbar[2]
 }
 size_t bwd_smem(int H, int ntile, bool split) {
   const int npart = split ? 2 : 1, ns = 8 * ntile, nsp = ns + kNPad;
-  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)npart * kRows * nsp * 2 + (size_t)2 * (H / kUS) * kUS * ns * 4;
+  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)npart * kRows * nsp * 2 + (size_t)2 * (H / kUS) * kUS * ns * 4 + 16;  // + xbar[2]
 }
 
 // sequences per cluster: as many n-tiles as the batch fills and shared memory allows (4 n-tiles run with two warp groups)
@@ -485,6 +610,12 @@ cudaError_t launch_cluster(Kern kern, const Args& a, int H, int ntile, int nwg, 
 }  // namespace
 
 bool lstm_cluster_supports(int H) { return H % kUS == 0 && H >= kUS && H <= 8 * kUS; }
+
+// bias partial rows written per direction by launch_lstm_bwd_cluster in planes mode: one per (group, sequence tile)
+int lstm_bwd_cluster_cta_count(const LstmBwdArgs& a, int H, int precision) {
+  const int nt = pick_ntile(a.B, H, precision == 0, true);
+  return a.G * ((a.B + 8 * nt - 1) / (8 * nt));
+}
 
 cudaError_t launch_lstm_fwd_cluster(const LstmFwdArgs& a, int H, int precision, cudaStream_t st) {
   if (!lstm_cluster_supports(H)) return cudaErrorInvalidValue;

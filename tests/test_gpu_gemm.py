@@ -332,3 +332,103 @@ def test_l0_grad_kernels_fp32_mode(dir0, ndir):
 
 def test_l0_grad_kernels_bf16_mode_unmasked_small_vocabulary():
     assert _run_l0_grads(1, G=3, B=2, T=70, lens_eff=[1, 64, 70], V=21, dir0=0, ndir=2, masked=False, seed=2) < 1e-5
+
+
+# ==================================================================================================================================
+# gemm_wide.cu: the streamed-operand tcgen05 + TMA kernels behind the cluster recurrent kernels (H = 128, 192, 256; config 5 = 256)
+# ==================================================================================================================================
+def _run_nt_wide(precision, G, B, T, lens_eff, nsrc, K, NC, bias=True, accumulate=False, seed=0):
+    from intrepppid_b200._lib import check, lib, ptr
+
+    g = torch.Generator().manual_seed(seed)
+    rows = G * B * T
+    packs = [_planes(torch.randn(rows, K, generator=g).cuda()) for _ in range(nsrc)]
+    wpacks = [_planes((torch.randn(NC, K, generator=g) * 0.1).cuda()) for _ in range(nsrc)]
+    b = torch.randn(NC, generator=g).cuda() if bias else None
+    C0 = torch.randn(rows, NC, generator=g).cuda()
+    C = C0.clone()
+    lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().ib200_dbg_gemm_nt_wide(G, B, T, ptr(lens), nsrc, ptr(packs[0][0]), ptr(packs[1][0]) if nsrc > 1 else None, K, K,
+                                       ptr(wpacks[0][0]), ptr(wpacks[1][0]) if nsrc > 1 else None, ptr(b), ptr(C), NC, NC, int(accumulate),
+                                       precision, st), "ib200_dbg_gemm_nt_wide")
+    torch.cuda.synchronize()
+    ref = 0
+    for (_, hi, lo), (_, whi, wlo) in zip(packs, wpacks):
+        ref = ref + _plane_value(hi, lo, precision) @ _plane_value(whi, wlo, precision).T
+    if bias:
+        ref = ref + b.double()
+    if accumulate:
+        ref = ref + C0.double()
+    valid = _valid_rows(G, B, T, lens_eff)
+    err = (C.double() - ref)[valid].norm() / ref[valid].norm()
+    return float(err), torch.equal(C[~valid], C0[~valid])
+
+
+@pytest.mark.parametrize("H", [128, 192, 256])
+def test_nt_wide_fp32_mode_all_three_gemm_shapes(H):
+    for nsrc, K, NC in ((1, 2 * H, 4 * H), (2, 4 * H, 2 * H), (2, 4 * H, H)):   # xproj, dY (both directions live), dX0
+        err, untouched = _run_nt_wide(0, G=2, B=3, T=150, lens_eff=[131, 64], nsrc=nsrc, K=K, NC=NC, seed=H + NC)
+        assert err < 2e-5, (H, nsrc, K, NC, err)
+        assert untouched, "rows with t >= T_eff must not be written"
+
+
+def test_nt_wide_bf16_mode_accumulate_and_persistent_loop():
+    err, untouched = _run_nt_wide(1, G=1, B=5, T=200, lens_eff=[131], nsrc=1, K=512, NC=1024, accumulate=True)
+    assert err < 1e-5 and untouched
+    # more (row tile, column tile) items than SMs: persistent loop, TMEM double buffering, stage phase wrap-around, dead tiles skipped
+    err, untouched = _run_nt_wide(0, G=4, B=20, T=256, lens_eff=[256, 255, 129, 1], nsrc=1, K=256, NC=512, seed=3)
+    assert err < 2e-5 and untouched
+
+
+def _run_tn_wide(precision, H, G, B, T, lens_eff, l0, second, splits=0, seed=0):
+    """[dW_ih | dW_hh] of one (layer, direction): A = dgates planes [rows, 4H]; B1 = Y_{l-1} planes [rows, 2H] (all columns) or, for
+    layer 0, the gathered input planes [rows, H]; B2 = H columns of Y_l planes at column offset 0 / H, shifted by -1 / +1."""
+    import ctypes as C
+
+    from intrepppid_b200._lib import check, lib, ptr
+
+    g = torch.Generator().manual_seed(seed)
+    KA, rows = 4 * H, G * B * T
+    NB1, NB2 = (H if l0 else 2 * H), H
+    lens = torch.tensor([[T] * G, lens_eff], dtype=torch.int32).cuda()
+    valid = _valid_rows(G, B, T, lens_eff)
+    Ap, Ahi, Alo = _planes(torch.randn(rows, KA, generator=g).cuda() * valid.unsqueeze(1))
+    B1p, B1hi, B1lo = _planes(torch.randn(rows, NB1, generator=g).cuda() * valid.unsqueeze(1))
+    B2p, B2hi, B2lo = _planes(torch.randn(rows, 2 * H, generator=g).cuda() * valid.unsqueeze(1))
+    col02, shift2 = (H, 1) if second == "next" else (0, -1)
+    n = C.c_int32(0)
+    st = torch.cuda.current_stream().cuda_stream
+    args = (G, B, T, ptr(lens), ptr(Ap), KA, ptr(B1p), NB1, 0, 0, NB1, ptr(B2p), 2 * H, col02, shift2, NB2)
+    check(lib().ib200_dbg_gemm_tn_wide(*args, None, splits, C.byref(n), precision, st), "ib200_dbg_gemm_tn_wide (query)")
+    NB = NB1 + NB2
+    partial = torch.full((G, n.value, KA * NB), float("nan")).cuda()
+    check(lib().ib200_dbg_gemm_tn_wide(*args, ptr(partial), splits, C.byref(n), precision, st), "ib200_dbg_gemm_tn_wide")
+    torch.cuda.synchronize()
+    got = partial.sum(1).double().view(G, KA, NB)
+    A3 = _plane_value(Ahi, Alo, precision).view(G, B, T, KA)
+    b1v = _plane_value(B1hi, B1lo, precision).view(G, B, T, NB1)
+    b2v = _plane_value(B2hi, B2lo, precision).view(G, B, T, 2 * H)[..., col02:col02 + H]
+    worst = 0.0
+    for gi, te in enumerate(lens_eff):
+        a = A3[gi, :, :te]
+        s = torch.zeros(B, te, H, dtype=torch.float64, device="cuda")
+        if shift2 == -1:
+            s[:, 1:] = b2v[gi, :, :te - 1]
+        else:
+            s[:, :te - 1] = b2v[gi, :, 1:te]
+        ref = torch.einsum("btk,btn->kn", a, torch.cat([b1v[gi, :, :te], s], dim=-1))
+        worst = max(worst, float((got[gi] - ref).norm() / ref.norm()))
+    return worst
+
+
+@pytest.mark.parametrize("H", [128, 192, 256])
+@pytest.mark.parametrize("l0,second", [(False, "prev"), (False, "next"), (True, "prev")])
+def test_tn_wide_fp32_mode(H, l0, second):
+    err = _run_tn_wide(0, H, G=2, B=3, T=200, lens_eff=[200, 77], l0=l0, second=second, seed=H)
+    assert err < 2e-5, err
+
+
+def test_tn_wide_bf16_mode_many_splits_and_short_groups():
+    assert _run_tn_wide(1, 256, G=1, B=2, T=100, lens_eff=[65], l0=False, second="prev", splits=5) < 1e-5   # more splits than items
+    assert _run_tn_wide(0, 128, G=3, B=5, T=130, lens_eff=[1, 64, 129], l0=True, second="next", splits=2, seed=5) < 2e-5
