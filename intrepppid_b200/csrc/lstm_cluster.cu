@@ -6,12 +6,17 @@
 //   * CTA r owns hidden units [32r, 32r+32): its 128 gate rows of W_hh stay resident in shared memory as bf16 hi (+ lo) for the
 //     whole kernel, in the row order (warp w: tile (i_u,f_u) then tile (g_u,o_u) for its 8 units) that leaves i,f,g,o of one
 //     cell in one thread after the MMAs -- exactly the fragment mapping of the H=64 kernels;
-//   * forward: every CTA needs the full h_{t-1} (H x NS) as its B operand: each CTA writes its 32-unit slice of h_t into the
-//     h tile of ALL C CTAs through distributed shared memory (st.shared::cluster), double buffered, ONE cluster barrier per step;
+//   * forward: every CTA needs the full h_{t-1} (H x NS) as its B operand: each CTA sends its 32-unit slice of h_t into the h tile
+//     of ALL C CTAs through distributed shared memory with 16-byte st.async stores whose bytes are counted (complete_tx) on an
+//     mbarrier of the RECEIVING CTA, double buffered; a CTA waits on its own barrier for "all of h_t has landed" -- there is no
+//     cluster barrier in the step loop.  The sequence groups of a cluster (warps with the same nh) have their own barriers and run
+//     as independent chains;
 //   * backward: dh = W_hh^T da needs all 4H rows of da as K.  Each CTA multiplies its own 128-row K slice (A = the same
 //     resident W slice read transposed with ldmatrix.trans) into partial sums for ALL H units and REDUCE-SCATTERS them: the
-//     partials of units [32q, 32q+32) go to CTA q's exchange buffer over DSMEM; after the cluster barrier the owner adds the C
-//     partials.  One cluster barrier + one CTA barrier per step.
+//     partials of units [32q, 32q+32) go to CTA q's exchange buffer with the same st.async + mbarrier scheme; the owner adds the C
+//     partials once its barrier reports them complete.
+// Measured on B200 at the config-5 shape (profiles/r2_cluster_*): the kernels are latency bound per warp (ncu: tensor pipe 36 %,
+// issue slots 22 %, 8 warps per SM, ~950 warp-instructions per warp and step), not bound by the exchange or by shared memory.
 // NS = 8*NTILE sequences per cluster (NTILE n-tiles of the m16n8k16 MMA) so large batches amortise the A-fragment traffic.
 #include <algorithm>
 
@@ -124,8 +129,11 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
   __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [NPART][128][ldw]
   __nv_bfloat16* hs = Wsm + (size_t)NPART * kRows * ldw;                      // [2][NPART][H][NSP]
   const int kPartElems = H * NSP, kBufElems = NPART * kPartElems;
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(hs + (size_t)2 * kBufElems);  // [2]: "all of h for buffer b has landed" (complete_tx bytes)
-  const uint32_t kStepBytes = (uint32_t)(NPART * H * NS * 2);                 // bytes every CTA receives per step: the whole h tile
+  // hbar[buffer][sequence group]: "h of this group's columns has landed in buffer b" (complete_tx bytes).  The NWG sequence groups
+  // (warps with the same nh) never read each other's columns, so each group runs its own chain of steps and only waits for its own
+  // columns: the groups drift apart and one group's MMAs fill the exchange / activation latency of the other
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hs + (size_t)2 * kBufElems);
+  const uint32_t kStepBytes = (uint32_t)(NPART * H * (NS / NWG) * 2);  // bytes a group receives per step: its columns of the h tile
 
   {
     const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
@@ -134,10 +142,10 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
   }
   for (int i = tid; i < 2 * kBufElems / 2; i += kClThreads) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
   if (tid == 0) {
-    mbar_init(&hbar[0], 1);
-    mbar_init(&hbar[1], 1);
+    for (int i = 0; i < 2 * NWG; ++i) mbar_init(&hbar[i], 1);
     mbar_init_fence();
-    if (T > 1) mbar_arrive_expect_tx(&hbar[1], kStepBytes);  // armed for h_0, written at the end of step 0
+    if (T > 1)
+      for (int i = 0; i < NWG; ++i) mbar_arrive_expect_tx(&hbar[NWG + i], kStepBytes);  // armed for h_0, written at the end of step 0
   }
   __syncthreads();
   cluster_arrive();  // every CTA's tiles and barriers are initialised before any remote h write lands
@@ -183,8 +191,9 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
   for (int i = 0; i < 2; ++i) {
     const int r = tig + 4 * i;
     hdst[i] = r < C ? map_to_rank(hs + (size_t)u * NSP + ncol0, (uint32_t)r) : 0u;
-    rbar[i] = r < C ? map_to_rank(hbar, (uint32_t)r) : 0u;
+    rbar[i] = r < C ? map_to_rank(hbar + nh, (uint32_t)r) : 0u;
   }
+  const bool group_leader = (tid & (32 * kUnitWarps - 1)) == 0;
 
   // ldmatrix lane addresses: A (non transposed) row = tile*16 + (lane&7) + (lane&8), k offset (lane&16 ? 8 : 0)
   const __nv_bfloat16* a_lane = Wsm + (size_t)((2 * warp) * 16 + (lane & 7) + (lane & 8)) * ldw + ((lane & 16) ? 8 : 0);
@@ -202,8 +211,8 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     for (int c = 0; c < NCELL; ++c) x[c] = xn[c];
     if (s + 1 < T) load_x(s + 1, xn);  // register prefetch, one step ahead
     const int buf = s & 1;
-    if (s > 0) mbar_wait(&hbar[buf], (uint32_t)(((s - 1) >> 1) & 1));  // all of h_{s-1} has landed in buffer `buf`
-    if (tid == 0 && s + 2 < T) mbar_arrive_expect_tx(&hbar[buf], kStepBytes);  // its next fill is written at the end of step s + 1
+    if (s > 0) mbar_wait(&hbar[buf * NWG + nh], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of my group's columns has landed in `buf`
+    if (group_leader && s + 2 < T) mbar_arrive_expect_tx(&hbar[buf * NWG + nh], kStepBytes);  // next fill: end of step s + 1
 
     // acc[t2][j]: [0]=(row gq, col n0) [1]=(row gq, col n1) [2]=(row gq+8, n0) [3]=(row gq+8, n1); t2=0: rows i,f ; t2=1: rows g,o
     float acc[2][NTW][4];
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_fwd_cl_kernel(c
     // No barrier: a CTA can only be one step ahead of the slowest one (it needs everybody's h), and with two buffers a buffer is
     // rewritten only after every reader has sent the h it computed from it.
     if (s + 1 < T) {
-      const uint32_t boff = (uint32_t)((buf ^ 1) * kBufElems) * 2u, bar_off = (uint32_t)(buf ^ 1) * 8u;
+      const uint32_t boff = (uint32_t)((buf ^ 1) * kBufElems) * 2u, bar_off = (uint32_t)((buf ^ 1) * NWG) * 8u;
       const int lbase = lane & ~3;
 #pragma unroll
       for (int j = 0; j < NTW; ++j) {
@@ -348,8 +357,10 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
   __nv_bfloat16* das = Wsm + (size_t)NPART * kRows * ldw;                // [NPART][128][NSP]: da of my units, k = local gate row
   float* xbuf = reinterpret_cast<float*>(das + (size_t)NPART * kRows * NSP);  // [2][C][32][NS] partial dh for my units, per source CTA
   const int kXBuf = C * kUS * NS;
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(xbuf + (size_t)2 * kXBuf);  // [2]: "all C partials of exchange buffer b have landed"
-  const uint32_t kXBytes = (uint32_t)kXBuf * 4u;
+  // xbar[buffer][sequence group]: "all C partials of this group's columns have landed in exchange buffer b".  As in the forward
+  // kernel the NWG sequence groups are independent chains: own columns of `das`, own named barrier, own exchange barrier
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(xbuf + (size_t)2 * kXBuf);
+  const uint32_t kXBytes = (uint32_t)(kXBuf / NWG) * 4u;
 
   {
     const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
@@ -357,11 +368,12 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
     load_w_slice<SPLIT>(Wsm, W, M, H, rank);
   }
   if (tid == 0) {
-    mbar_init(&xbar[0], 1);
-    mbar_init(&xbar[1], 1);
+    for (int i = 0; i < 2 * NWG; ++i) mbar_init(&xbar[i], 1);
     mbar_init_fence();
-    if (T > 1) mbar_arrive_expect_tx(&xbar[1], kXBytes);  // step s fills buffer (s + 1) & 1: step 0 -> buffer 1, step 1 -> buffer 0
-    if (T > 2) mbar_arrive_expect_tx(&xbar[0], kXBytes);
+    for (int i = 0; i < NWG; ++i) {
+      if (T > 1) mbar_arrive_expect_tx(&xbar[NWG + i], kXBytes);  // step s fills buffer (s + 1) & 1: step 0 -> buffer 1, step 1 -> buffer 0
+      if (T > 2) mbar_arrive_expect_tx(&xbar[i], kXBytes);
+    }
   }
   __syncthreads();
   cluster_arrive();
@@ -414,7 +426,8 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
   const int kDaPart = kRows * NSP;
   // A = W slice read transposed: m = unit j (columns of the slice), k = local gate row.  matrix l/8: k + (l&16 ? 8:0), m + (l&8 ? 8:0)
   const __nv_bfloat16* a_lane = Wsm + (size_t)((lane & 7) + ((lane & 16) ? 8 : 0)) * ldw + ((lane & 8) ? 8 : 0);
-  const __nv_bfloat16* b_lane = das + (size_t)(lane & 15) * NSP + ((NTILE > 1 && (lane & 16)) ? 8 : 0);
+  const __nv_bfloat16* b_lane = das + (size_t)(lane & 15) * NSP + ncol0 + ((NTW > 1 && (lane & 16)) ? 8 : 0);
+  const bool group_leader = (tid & (32 * kUnitWarps - 1)) == 0;
   // remote exchange slots: partials of units [32q,32q+32) go to CTA q, slot [src = my rank][unit % 32][column]
   const float* xslot = xbuf + (size_t)rank * kUS * NS;
 
@@ -471,28 +484,29 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
         if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(dst + kDaPart) = lo;
       }
     }
-    __syncthreads();
+    // my group's columns of `das` are complete (the four warps of the group own the 128 gate rows between them)
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + nh), "r"(32 * kUnitWarps) : "memory");
 
-    // partial dh^T[H, NS] = Wslice^T[H, 128] * da[128, NS]; warp w takes the unit tiles mt = w, w+4, ...
+    // partial dh^T[H, my columns] = Wslice^T[H, 128] * da[128, my columns]; warp (ug, nh) takes the unit tiles mt = ug, ug+4, ...
     const uint32_t xoff = (uint32_t)(((s + 1) & 1) * kXBuf) * 4u;
-    for (int mt = wid; mt < MT; mt += kWarps) {
-      float acc[NTILE][4];
+    for (int mt = warp; mt < MT; mt += kUnitWarps) {
+      float acc[NTW][4];
 #pragma unroll
-      for (int j = 0; j < NTILE; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
       for (int kt = 0; kt < kRows / 16; ++kt) {
         uint32_t ah[4], al[4];
         ldmatrix_x4_trans(ah, a_lane + (size_t)kt * 16 * ldw + mt * 16);
         if constexpr (SPLIT) ldmatrix_x4_trans(al, a_lane + (size_t)(kRows + kt * 16) * ldw + mt * 16);
 #pragma unroll
-        for (int jp = 0; jp < (NTILE + 1) / 2; ++jp) {
+        for (int jp = 0; jp < (NTW + 1) / 2; ++jp) {
           uint32_t bh[4], bl[4];
           ldmatrix_x4_trans(bh, b_lane + (size_t)kt * 16 * NSP + jp * 16);
           if constexpr (SPLIT) ldmatrix_x4_trans(bl, b_lane + kDaPart + (size_t)kt * 16 * NSP + jp * 16);
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const int j = 2 * jp + jj;
-            if (j < NTILE) {
+            if (j < NTW) {
               mma_bf16(acc[j], ah, bh[2 * jj], bh[2 * jj + 1]);
               if constexpr (SPLIT) {
                 mma_bf16(acc[j], ah, bl[2 * jj], bl[2 * jj + 1]);
@@ -506,23 +520,23 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
       // even lane owns 4 consecutive columns of row gq and the odd lane 4 consecutive columns of row gq+8: ONE 16-byte st.async each,
       // counted on the owner CTA's xbar (owner: 32 units per CTA = 2 unit tiles)
       const uint32_t owner = (uint32_t)(mt >> 1);
-      const uint32_t xdst = map_to_rank(xslot, owner), xbr = map_to_rank(xbar, owner) + (uint32_t)((s + 1) & 1) * 8u;
+      const uint32_t xdst = map_to_rank(xslot, owner), xbr = map_to_rank(xbar + nh, owner) + (uint32_t)(((s + 1) & 1) * NWG) * 8u;
       const bool odd = (tig & 1) != 0;
       const int xrow = (mt & 1) * 16 + gq + (odd ? 8 : 0);
 #pragma unroll
-      for (int j = 0; j < NTILE; ++j) {
+      for (int j = 0; j < NTW; ++j) {
         const float r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[j][0] : acc[j][2], 1);
         const float r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[j][1] : acc[j][3], 1);
-        const uint32_t col = (uint32_t)(8 * j + 2 * (tig & ~1));
+        const uint32_t col = (uint32_t)(ncol0 + 8 * j + 2 * (tig & ~1));
         const uint32_t a0 = __float_as_uint(odd ? r0 : acc[j][0]), a1 = __float_as_uint(odd ? r1 : acc[j][1]);
         const uint32_t a2 = __float_as_uint(odd ? acc[j][2] : r0), a3 = __float_as_uint(odd ? acc[j][3] : r1);
         st_async_v4(xdst + xoff + ((uint32_t)xrow * NS + col) * 4u, a0, a1, a2, a3, xbr);
       }
     }
-    // all C partials of this step have landed in my buffer (every CTA of the cluster, myself included, sent 32 x NS floats).  No
-    // cluster barrier: passing this wait also means every local warp has finished reading `das` (its sends come after its MMAs)
-    mbar_wait(&xbar[(s + 1) & 1], (uint32_t)((s >> 1) & 1));
-    if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[(s + 1) & 1], kXBytes);  // refilled at step s + 2
+    // all C partials of my group's columns have landed (every CTA of the cluster, myself included, sent 32 units x my columns).
+    // No cluster barrier: passing this wait also means every warp of my group has finished reading `das` (sends follow the MMAs)
+    mbar_wait(&xbar[((s + 1) & 1) * NWG + nh], (uint32_t)((s >> 1) & 1));
+    if (group_leader && s + 3 < T) mbar_arrive_expect_tx(&xbar[((s + 1) & 1) * NWG + nh], kXBytes);  // refilled at step s + 2
     // recurrent gradient of my cells for the next step: sum of the C partials
     const float* xb = xbuf + (size_t)((s + 1) & 1) * kXBuf + (size_t)ul * NS;
 #pragma unroll
@@ -573,11 +587,11 @@ __global__ void __launch_bounds__(32 * kUnitWarps * NWG, 1) lstm_bwd_cl_kernel(c
 
 size_t fwd_smem(int H, int ntile, bool split) {
   const int npart = split ? 2 : 1, nsp = 8 * ntile + kNPad;
-  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)2 * npart * H * nsp * 2 + 16;  // + hbar[2]
+  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)2 * npart * H * nsp * 2 + 64;  // + hbar[2][NWG]
 }
 size_t bwd_smem(int H, int ntile, bool split) {
   const int npart = split ? 2 : 1, ns = 8 * ntile, nsp = ns + kNPad;
-  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)npart * kRows * nsp * 2 + (size_t)2 * (H / kUS) * kUS * ns * 4 + 16;  // + xbar[2]
+  return (size_t)npart * kRows * (H + kWPad) * 2 + (size_t)npart * kRows * nsp * 2 + (size_t)2 * (H / kUS) * kUS * ns * 4 + 64;  // + xbar[2][NWG]
 }
 
 // sequences per cluster: as many n-tiles as the batch fills and shared memory allows (4 n-tiles run with two warp groups)
