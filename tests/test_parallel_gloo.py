@@ -103,3 +103,96 @@ def test_pair_block_partitions_the_triangle_and_balances_pairs():
                 assert a[1] == b[0] and a[2] + a[3] == b[2]
             if M >= 513:  # no rank is more than one row of pairs away from the ideal share
                 assert max(b[3] for b in blocks) - total // w <= M
+
+
+# ---- the early bucket: upper LSTM layers all-reduced from INSIDE the encoder backward (ops.EARLY_GRAD_HOOKS) ---------------------------
+class _FlatGradLinear(torch.autograd.Function):
+    """Stand-in for ops._EncodeHidden: its backward writes the gradients of (l0 weight, l1 weight) into ONE flat buffer [l0 | l1],
+    calls the early hooks with the final l1 slice before "running layer 0", and returns views of the buffer -- exactly the
+    protocol of the CUDA op (intrepppid_b200/ops.py)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, w1):
+        ctx.save_for_backward(x, w0, w1)
+        return torch.tanh(x @ w0.t()) @ w1.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from intrepppid_b200 import ops
+
+        x, w0, w1 = ctx.saved_tensors
+        h = torch.tanh(x @ w0.t())
+        flat = torch.empty(w0.numel() + w1.numel())
+        flat[w0.numel():] = (dy.t() @ h).reshape(-1)          # "layers >= 1" are final first
+        for hook in list(ops.EARLY_GRAD_HOOKS):
+            hook(flat[w0.numel():])
+        dh = (dy @ w1) * (1 - h * h)
+        flat[:w0.numel()] = (dh.t() @ x).reshape(-1)          # then "layer 0"
+        return None, flat[:w0.numel()].view_as(w0), flat[w0.numel():].view_as(w1)
+
+
+class ToyLayers(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.encoder = nn.Module()
+        self.encoder.encoder = nn.Module()
+        self.encoder.encoder.rnn = nn.Module()
+        self.encoder.encoder.rnn.weight_ih_l0 = nn.Parameter(torch.randn(6, 4) * 0.3)
+        self.encoder.encoder.rnn.weight_ih_l1 = nn.Parameter(torch.randn(3, 6) * 0.3)
+        self.head = nn.Linear(3, 1)
+
+    def forward(self, x):
+        r = self.encoder.encoder.rnn
+        return self.head(_FlatGradLinear.apply(x, r.weight_ih_l0, r.weight_ih_l1)).mean()
+
+
+def _worker_early(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from intrepppid_b200 import ops
+    from intrepppid_b200.parallel import GradientAllReducer, default_buckets
+
+    torch.manual_seed(0)
+    net = ToyLayers()
+    names = {id(p): n for n, p in net.named_parameters()}
+    buckets = default_buckets(net)
+    assert [sorted(names[id(p)].split(".")[-1] for p in b) for b in buckets] == [["bias", "weight"], ["weight_ih_l1"], ["weight_ih_l0"]]
+    red = GradientAllReducer(net)
+    assert red._early == 1 and ops.EARLY_GRAD_HOOKS == [red._on_early]
+    x_all = torch.randn(world * 3, 4, generator=torch.Generator().manual_seed(5))
+    seen = []
+    for step in range(3):  # the early path must re-arm itself; step 2 accumulates into existing .grad (regular path takes over)
+        if step < 2:
+            net.zero_grad(set_to_none=True)
+        else:
+            keep = {n: p.grad.clone() for n, p in net.named_parameters()}
+        net(x_all[rank * 3:(rank + 1) * 3]).backward()
+        seen.append(red._early_done)
+        red.finish()
+    mine = {n: p.grad.clone() for n, p in net.named_parameters()}
+    torch.manual_seed(0)
+    ref = ToyLayers()
+    (sum(ref(x_all[r * 3:(r + 1) * 3]) for r in range(world)) / world).backward()
+    want = {n: p.grad for n, p in ref.named_parameters()}
+    ok = seen == [True, True, False]
+    # steps 0 / 1 gave the averaged gradient g; step 2 accumulated a LOCAL gradient onto it and averaged the sum: mean_r(g + g_r) = 2 g
+    ok = ok and all(torch.allclose(keep[n], want[n], atol=1e-6) for n in want)
+    ok = ok and all(torch.allclose(mine[n], 2 * want[n], atol=1e-6) for n in want)
+    red.remove()
+    ok = ok and ops.EARLY_GRAD_HOOKS == []
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_early_bucket_is_reduced_from_inside_the_backward():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_early, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
