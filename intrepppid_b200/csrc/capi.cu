@@ -204,6 +204,14 @@ bool use_cluster(int H) {
   return force || (H != 32 && H != 64);
 }
 bool use_tc() { return gemm_mode() >= 1; }
+// cluster path on the tcgen05 recurrent kernels (lstm_cluster_tc.cu): H = 128 / 256 with plane operands; IB200_CLUSTER_TC=0 keeps the
+// mma.sync cluster kernels (the tests cross-check the two)
+// (2 / 3: only the forward / only the backward kernel -- the HBM layouts are identical, so the two families mix freely)
+bool use_cluster_tc(int H, bool planes, bool bwd) {
+  static const int mode = [] { const char* e = getenv("IB200_CLUSTER_TC"); return e ? atoi(e) : 1; }();
+  const bool on = mode == 1 || (mode == 2 && !bwd) || (mode == 3 && bwd);
+  return on && planes && use_cluster(H) && lstm_cluster_tc_supports(H);
+}
 // hidden sizes of the cluster path whose GEMMs run on the TMA-fed tcgen05 kernels of gemm_wide.cu (H = 128, 192, 256); the other
 // cluster sizes (96, 160, 224) and IB200_GEMM=legacy keep the column-blocked mma.sync kernels
 bool wide_tc(int H) { return gemm_wide_supports(H) && gemm_mode() == 2; }
@@ -430,7 +438,7 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
       if (!P->w_ih[l][d] || !P->w_hh[l][d] || !P->b_ih[l][d] || !P->b_hh[l][d]) return fail(IB200_E_NULL, "ib200_encoder_fwd: null LSTM parameter");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
-  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
+  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64, cluster_tc = use_cluster_tc(H, planes, false);
 
   // the layer-0 table and the W_ih preparation do not depend on the length kernels: they run next to them on the side stream
   SideStream* side = side_stream();
@@ -514,7 +522,9 @@ int ib200_encoder_fwd(const ib200_cfg* cfg, const void* tokens, const ib200_enco
       fa.ph = phase_args(ws, p, false);
       TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(fa.ph.sm_load), 257, st), "phase counters");
     }
-    TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1, cluster ? launch_lstm_fwd_cluster(fa, H, prec, st) : launch_lstm_fwd(fa, H, prec, st),
+    TIMED(l == 0 ? F_LSTM_FWD_L0 : F_LSTM_FWD_UP, 1,
+          cluster_tc ? launch_lstm_fwd_cluster_tc(fa, H, prec, st)
+                     : (cluster ? launch_lstm_fwd_cluster(fa, H, prec, st) : launch_lstm_fwd(fa, H, prec, st)),
           "lstm fwd");
   }
   return 0;
@@ -550,7 +560,7 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
   if (layer_lo == 0 && !Gr->emb) return fail(IB200_E_NULL, "ib200_encoder_bwd: null embedding gradient");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = p.H, prec = cfg->precision;
-  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64;
+  const bool planes = use_planes(H), cluster = use_cluster(H), wide = H != 32 && H != 64, cluster_tc = use_cluster_tc(H, planes, true);
   const int* lens = at<int>(ws, p.lens);
   float* dY = at<float>(ws, p.bwd_scratch);
   float* dX0 = dY + p.R * 2 * H;
@@ -580,10 +590,13 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
       ba.ph = phase_args(ws, p, true);
       TIMED(F_FILL, 1, launch_fill_zero(reinterpret_cast<float*>(ba.ph.sm_load), 257, st), "phase counters");
     }
-    TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1, cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st),
+    TIMED(l == 0 ? F_LSTM_BWD_L0 : F_LSTM_BWD_UP, 1,
+          cluster_tc ? launch_lstm_bwd_cluster_tc(ba, H, prec, st)
+                     : (cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st)),
           "lstm bwd");
     // bias partial rows per direction left by the BPTT kernel
-    const int bwd_ctas = !planes ? 0 : (cluster ? lstm_bwd_cluster_cta_count(ba, H, prec) : lstm_bwd_cta_count(ba, prec));
+    const int bwd_ctas = !planes ? 0 : (cluster_tc ? lstm_bwd_cluster_tc_cta_count(ba)
+                                                   : (cluster ? lstm_bwd_cluster_cta_count(ba, H, prec) : lstm_bwd_cta_count(ba, prec)));
 
     // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates
     // (gemm_l0.cu: the token-indexed sums S = dA^T onehot(tok) replace the gathered dW GEMM, the dX_0 GEMM and the atomic scatter)

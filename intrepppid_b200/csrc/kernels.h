@@ -92,6 +92,14 @@ int lstm_bwd_cluster_cta_count(const LstmBwdArgs& a, int H, int precision);
 cudaError_t launch_lstm_fwd_cluster(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
 cudaError_t launch_lstm_bwd_cluster(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 
+// ---- K2t / K3t: tcgen05 cluster versions for H = 128 / 256 (lstm_cluster_tc.cu): W_hh slice resident as a UMMA operand, gates^T /
+// dh^T accumulated in TMEM, h all-gather by bulk DSMEM copies, dh reduce-scatter by st.async.  Same arguments / layouts as above;
+// 32 sequences per cluster.
+bool lstm_cluster_tc_supports(int H);
+int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a);
+cudaError_t launch_lstm_fwd_cluster_tc(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
+cudaError_t launch_lstm_bwd_cluster_tc(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
+
 // ---- tensor-core GEMMs over token rows -------------------------------------------------------------------------------------
 // NT:  C[row, NC] (=|+=) sum_s A_s[row, K] * W_s[NC, K]^T (+ bias)   for rows (n,t), t < T_eff[group(n)]
 struct GemmNTArgs {

@@ -1,0 +1,687 @@
+// K2t / K3t: recurrent forward and BPTT kernels for H = 128 / 256 on the 5th-generation tensor cores (tcgen05 + TMEM), e.g. the stress
+// configuration E = H = 256, 3 layers (BASELINE config 5).  Same math and the same HBM layouts as lstm_cluster.cu / lstm_fwd.cu
+// (reference: nn.LSTM inside encoders/awd_lstm.py:35-41,56); the mma.sync cluster kernels stay for the other hidden sizes.
+//
+// A thread-block CLUSTER of C = H/32 CTAs shares one tile of 32 sequences.  CTA r owns hidden units [32r, 32r+32): its 128 gate rows
+// of W_hh stay resident in shared memory for the whole kernel as bf16 hi (+ lo) in the 128-byte-swizzled K-major operand layout, row
+// order L = 4*unit + gate.  Per step and CTA the product is ONE accumulator tile in TMEM:
+//   forward : gates^T[128 rows, 32 seq] = Wslice[128, H] h_{t-1}[H, 32]          (A = W slice K-major, B = h tile, K = H)
+//   backward: dh^T[H units, 32 seq]     = Wslice^T[H, 128] da_t[128, 32]         (A = the SAME bytes read MN-major, B = da tile, K = 128)
+// issued by one thread as tcgen05.mma M=128, N=32 (3 MMAs per product in fp32 mode: hi*hi + hi*lo + lo*hi).  Measured on B200
+// (tools/microbench_cl.cu, profiles/r2_microbench_cl.txt): such an MMA costs ~55 cycles whatever N <= 64 is, i.e. 0.54 us (bf16
+// mode) / 1.35 us (fp32 mode) of tensor time per step, against ~3.3 us of HMMA + ldmatrix time in the mma.sync kernels.
+//   * forward: eight warps read the accumulator (tcgen05.ld: lane = gate row, column = sequence), add the input projection, apply
+//     the gate nonlinearity on all 128 lanes at once (tanh as 2*sigmoid(2x) - 1, so the code is uniform), transpose 4x4 over the four
+//     lanes of a unit so that every lane owns whole cells, update c / h and write their slice of h_t (bf16 hi | lo) in the B-operand
+//     layout of the next step.  The slice goes to the other CTAs with ONE cp.async.bulk shared::cta -> shared::cluster per
+//     destination, counted (complete_tx) on the destination's mbarrier: no cluster barrier in the loop, and the receiving tensor
+//     core reads what the async proxy wrote.
+//   * backward: the cell warps form da_t, store the dgates and write the bf16 da tile; the MMA result -- partial sums for ALL H
+//     units -- is reduce-scattered: every warp sends its TMEM rows to the CTA that owns those units with 16-byte st.async stores
+//     counted on the owner's mbarrier; the owner adds the C partials.
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace ib200 {
+namespace {
+
+using namespace tc;
+
+constexpr int kUS = 32;                 // hidden units per CTA
+constexpr int kRows = 4 * kUS;          // gate rows per CTA = UMMA M
+constexpr int kNS = 32;                 // sequences per cluster = UMMA N
+constexpr int kCellWarps = 8;           // warps 0..7: TMEM read-out + cell math; warp 8: MMA issuer and TMEM owner
+constexpr int kCellThreads = 32 * kCellWarps;
+constexpr int kThreads = kCellThreads + 32;
+constexpr int kWBlk = kRows * 128;      // one [128 gate rows x 64 units] bf16 block of the resident W slice (128-byte swizzle)
+constexpr int kHSlice = 4 * kNS * 16;   // forward: h slice of one source CTA and one part: [4 unit chunks][32 sequences][16 B]
+constexpr int kDaLbo = kNS * 16 + 16;   // backward: byte pitch of one 8-row k chunk of the da tile (+16: bank spread of the writers)
+constexpr int kXSlice = kUS * kNS * 4;  // backward: partial dh of one source CTA for my 32 units: [32 units][32 sequences] fp32
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+// bulk copy shared::cta -> shared memory of a CTA of the cluster (async proxy); completes `bytes` on an mbarrier of THAT CTA
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(addr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(remote_bar)
+               : "memory");
+}
+// shared-memory matrix descriptor without swizzle (K-major "interleaved" canonical layout): core matrices of 8 rows x 16 bytes
+// (128 contiguous bytes); sbo = bytes between 8-row groups along M/N, lbo = bytes between the two 16-byte chunks along K
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100); layout type 0 = no swizzle
+  return d;
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i of the warp reads lane base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void cell_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCellThreads) : "memory"); }
+
+// 16 lanes x 256 bits, two repetitions (16 columns): thread t of the warp gets, for each 8-column block b, rows t/4 and t/4 + 8 of
+// the 16-lane window at columns 8b + 2(t%4), +1 -- the mma.sync accumulator fragment: r[4b + 2*(row half) + column parity]
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// resident W slice as the A operand: Wsm[part][k block of 64 units][128 rows x 128 B], 128-byte swizzle.  Row L holds
+// W_hh[gate*H + 32*rank + local unit][.] (masked per group for layer 0, forward direction) with
+//   GATE_MAJOR (forward) : L = 32*(unit/8) + 8*gate + unit%8 -- rows q, q+8, q+16, q+24 of a 32-lane TMEM quarter are i,f,g,o of one unit
+//   otherwise (backward) : L = 4*unit + gate                 -- the four dgates of a cell are consecutive k of the da tile
+template <bool SPLIT, bool GATE_MAJOR>
+__device__ __forceinline__ void load_w_slice_tc(unsigned char* Wsm, const float* __restrict__ W, const float* __restrict__ M, int H, int rank) {
+  const int KB = H / 64;
+  for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += blockDim.x) {
+    const int L = idx / (H / 2), k = (idx % (H / 2)) * 2;
+    const int gate = GATE_MAJOR ? (L >> 3) & 3 : L & 3, ul = GATE_MAJOR ? 8 * (L >> 5) + (L & 7) : L >> 2;
+    const size_t src = ((size_t)gate * H + kUS * rank + ul) * H + k;
+    float w0 = W[src], w1 = W[src + 1];
+    if (M != nullptr) {
+      w0 *= M[src];
+      w1 *= M[src + 1];
+    }
+    uint32_t hi, lo = 0u;
+    if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
+    else hi = pack_bf16(w0, w1);
+    const uint32_t off = (uint32_t)(k >> 6) * kWBlk + sw128_offset((uint32_t)L, (uint32_t)(k & 63) >> 3) + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
+    if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + (size_t)KB * kWBlk + off) = lo;
+  }
+}
+
+// =================================================================================================================================
+// forward
+// =================================================================================================================================
+template <bool SPLIT, bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFwdArgs p, const int H) {
+  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr bool FAST = !SPLIT;
+  const int C = H / kUS, KB = H / 64;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank(), tile = (int)blockIdx.x / C;
+  const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
+  const int T = p.lens[p.G + g];
+  if (T <= 0) return;  // uniform over the cluster
+  const int b0 = tile * kNS, nvalid = min(kNS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
+  const bool layer0 = p.tok != nullptr;
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Wsm = smem;                                   // [NPART][KB][kWBlk]
+  unsigned char* hB = Wsm + (size_t)NPART * KB * kWBlk;        // [2 buffers][C source CTAs][NPART][kHSlice]: B operand of the step
+  const uint32_t sliceBytes = NPART * kHSlice, bufBytes = (uint32_t)C * sliceBytes;
+  // hbar[buffer][source CTA]: "the slice of h that CTA `source` owns has landed in buffer b" -- the MMAs of a step start on the
+  // slices that are there (my own first) while the others are still in flight
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hB + 2 * (size_t)bufBytes);
+  uint64_t* mma_bar = hbar + 2 * C;                            // "the step's MMAs have completed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  {
+    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
+    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
+    load_w_slice_tc<SPLIT, true>(Wsm, W, M, H, rank);
+  }
+  for (int i = tid; i < (int)(2 * bufBytes / 4); i += kThreads) reinterpret_cast<uint32_t*>(hB)[i] = 0u;  // h_{-1} = 0
+  if (tid == 0) {
+    for (int i = 0; i < 2 * C; ++i) mbar_init(&hbar[i], 1);
+    mbar_init(mma_bar, 1);
+    mbar_init_fence();
+    for (int r = 0; r < C; ++r) {
+      if (r == rank) continue;  // (my own slice: a plain arrive of the publishing thread)
+      if (T > 1) mbar_arrive_expect_tx(&hbar[C + r], sliceBytes);  // h_0 -> buffer 1
+      if (T > 2) mbar_arrive_expect_tx(&hbar[r], sliceBytes);      // h_1 -> buffer 0
+    }
+  }
+  if (wid == kCellWarps) tmem_alloc(tmem_slot, 32);
+  fence_async_smem();  // the generic-proxy writes above (W slice, zero h tile) are operands of the tensor core (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  cluster_sync_all();  // every CTA's tiles and barriers exist before any remote copy lands
+  const uint32_t tb = *tmem_slot;
+
+  if (wid == kCellWarps) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kRows, kNS, false, false);
+      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, 0);
+      const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kNS * 16);
+      const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
+      for (int s = 0; s < T; ++s) {
+        const int buf = s & 1;
+        const uint32_t par = (uint32_t)(((s - 1) >> 1) & 1);
+        const uint64_t bb = b_base + (uint64_t)(((uint32_t)buf * bufBytes) >> 4);
+        for (int i = 0; i < C; ++i) {
+          const int r = rank + i < C ? rank + i : rank + i - C;  // source CTA: mine first, then in ring order
+          if (s > 0) {
+            mbar_wait(&hbar[buf * C + r], par);
+            if (r != rank && s + 2 < T) mbar_arrive_expect_tx(&hbar[buf * C + r], sliceBytes);  // next fill: h_{s+1}
+          }
+          fence_after_sync();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            // units [32 r + 16 j, +16): A = 32 bytes of every row of block (2r + j) / 4; B = unit chunks 2j, 2j + 1 of source r
+            const int k16 = 2 * r + j;
+            const uint64_t ah = a_base + (uint64_t)(((uint32_t)(k16 >> 2) * kWBlk + (uint32_t)(k16 & 3) * 32u) >> 4);
+            const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes + (uint32_t)j * 2u * (kNS * 16)) >> 4);
+            mma_bf16_ss(tb, ah, bh, idesc, (i | j) != 0);
+            if constexpr (SPLIT) {
+              mma_bf16_ss(tb, ah, bh + b_lo, idesc, true);
+              mma_bf16_ss(tb, ah + a_lo, bh, idesc, true);
+            }
+          }
+        }
+        mma_commit(mma_bar);
+      }
+    }
+  } else {
+    // ===================== cell warps =====================
+    // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) x columns [16 half, +16) with the 16x256b shape:
+    // rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit 8 quarter + gq, for the
+    // sequences 16 half + 8 b + 2 tig + (0, 1): four whole cells per thread, no exchange between lanes
+    const int quarter = wid & 3, half = wid >> 2, gq = lane >> 2, tig = lane & 3;
+    const int u = kUS * rank + 8 * quarter + gq;
+    const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
+    const int pad_row = p.V + (int)((tile + gridDim.x / C * (blockIdx.y + gridDim.y * blockIdx.z)) % kPadRows);
+    int ncell[4], rowb[4];   // sequence of cell e inside the tile; its first token row (columns beyond the batch: clamped, never stored)
+    uint32_t xoff[4];
+    bool valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ncell[e] = 16 * half + 8 * (e >> 1) + 2 * tig + (e & 1);
+      valid[e] = ncell[e] < nvalid;
+      const int ncl = min(ncell[e], nvalid - 1);
+      rowb[e] = (nbase + ncl) * Tmax;
+      xoff[e] = (uint32_t)ncl * (uint32_t)Tmax * (uint32_t)H;  // float4 units, relative to the tile's first sequence
+    }
+    // layer >= 1: dense input projection rows [N, Tmax, 4H] (GI: one float4 per cell); layer 0: table rows by token
+    const float4* const xdense = layer0 ? nullptr : reinterpret_cast<const float4*>(dir ? p.xproj[1] : p.xproj[0]) + (size_t)nbase * Tmax * H + u;
+    const float4* const xtab = layer0 ? reinterpret_cast<const float4*>(p.table) + (size_t)((p.table_shared ? 0 : g) * 2 + dir) * (p.V + kPadRows) * H + u : nullptr;
+    auto load_tok = [&](int s, int (&tk)[4]) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tk[e] = __ldg(p.tok + (size_t)rowb[e] + t_first + s * dt);
+    };
+    auto load_x = [&](int s, const int (&tk)[4], float4 (&x)[4]) {
+      if (layer0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = __ldg(xtab + (size_t)(tk[e] == 0 ? pad_row : tk[e]) * H);  // pads: this cluster's copy of row 0
+      } else {
+        const float4* xt = xdense + (ptrdiff_t)(t_first + s * dt) * H;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = __ldg(xt + xoff[e]);
+      }
+    };
+
+    float4* const G4 = TRAIN ? reinterpret_cast<float4*>(dir ? p.gates[1] : p.gates[0]) + u : nullptr;
+    float* const Cst = TRAIN ? (dir ? p.cstate[1] : p.cstate[0]) + u : nullptr;
+    const bool has_y = p.y != nullptr;
+    const int ycol = dir * H + u, ystr = p.y_stride;
+    float cst[4] = {0.f, 0.f, 0.f, 0.f}, hv[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t my_slot = smem_u32(hB) + (uint32_t)rank * sliceBytes;  // + buffer offset: my slice of the h tile
+    unsigned char* const my_slot_ptr = hB + (size_t)rank * sliceBytes;
+    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * half);
+
+    // one step; xc = this step's input projection, xn / tk_*: register prefetch of the next step's (tokens two steps ahead).  The
+    // step loop is unrolled by two over ping-pong register sets so that no loaded value has to be moved (a move waits for its load)
+    auto step = [&](const int s, float4 (&xc)[4], float4 (&xn)[4], int (&tk_use)[4], int (&tk_fill)[4]) {
+      if (s + 1 < T) {
+        load_x(s + 1, tk_use, xn);
+        if (layer0 && s + 2 < T) load_tok(s + 2, tk_fill);
+      }
+      const int buf = s & 1;
+      mbar_wait(mma_bar, (uint32_t)(s & 1));
+      fence_after_sync();
+      uint32_t ra[8], rb[8];
+      tmem_ld_16x256b_x2(taddr, ra);
+      tmem_ld_16x256b_x2(taddr + (16u << 16), rb);
+      tmem_wait_ld();
+      fence_before_sync();
+
+      const int t = t_first + s * dt;
+      float gi[4], gf[4], gg[4], go[4];
+      __nv_bfloat16 hb16[4], lb16[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ia = 4 * (e >> 1) + (e & 1);
+        gi[e] = sigmoid_f<FAST>(__uint_as_float(ra[ia]) + xc[e].x);
+        gf[e] = sigmoid_f<FAST>(__uint_as_float(ra[ia + 2]) + xc[e].y);
+        gg[e] = tanh_f<FAST>(__uint_as_float(rb[ia]) + xc[e].z);
+        go[e] = sigmoid_f<FAST>(__uint_as_float(rb[ia + 2]) + xc[e].w);
+        cst[e] = fmaf(gf[e], cst[e], gi[e] * gg[e]);
+        hv[e] = go[e] * tanh_f<FAST>(cst[e]);
+        hb16[e] = __float2bfloat16_rn(hv[e]);
+        lb16[e] = __float2bfloat16_rn(hv[e] - __bfloat162float(hb16[e]));
+      }
+      if (s + 1 < T) {  // my elements of the next step's B operand: [part][unit chunk = quarter][sequence][8 units x bf16]
+        unsigned char* dst = my_slot_ptr + (size_t)(buf ^ 1) * bufBytes + quarter * (kNS * 16) + gq * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
+          if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
+        }
+        fence_async_smem();  // my slice (generic-proxy stores) is read by the bulk copies and by my own tensor core (async proxy)
+        cell_bar_sync();
+        if (tid < C) {
+          const uint32_t boff = (uint32_t)(buf ^ 1) * bufBytes;
+          uint64_t* bar = &hbar[(buf ^ 1) * C + rank];  // slot `rank` of the receiver's barriers
+          if (tid == rank) mbar_arrive(bar);
+          else bulk_s2c(map_to_rank(my_slot + boff, (uint32_t)tid), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), (uint32_t)tid));
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (valid[e]) {
+          const size_t row = (size_t)(rowb[e] + t);
+          if constexpr (TRAIN) {
+            G4[row * H] = make_float4(gi[e], gf[e], gg[e], go[e]);
+            Cst[row * H] = cst[e];
+          }
+          if (has_y) {  // bf16 hi | lo planes over the bytes of the fp32 row (operands of the TMA-fed GEMMs, gemm_wide.cu)
+            __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.y + row * ystr);
+            yrow[ycol] = hb16[e];
+            if constexpr (SPLIT) yrow[ystr + ycol] = lb16[e];
+          }
+        }
+      }
+    };
+
+    float4 xE[4], xO[4];
+    int tkE[4] = {0, 0, 0, 0}, tkO[4] = {0, 0, 0, 0};
+    if (layer0) {
+      load_tok(0, tkE);
+      if (T > 1) load_tok(1, tkO);
+    }
+    load_x(0, tkE, xE);
+    for (int s = 0; s < T; s += 2) {
+      step(s, xE, xO, tkO, tkE);
+      if (s + 1 < T) step(s + 1, xO, xE, tkE, tkO);
+    }
+
+    if (p.hn != nullptr) {
+      const size_t N = (size_t)p.G * p.B;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (valid[e]) p.hn[((size_t)dir * N + nbase + ncell[e]) * H + u] = hv[e];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits while a peer's copy could still read from or write to it
+  if (wid == kCellWarps) tmem_dealloc(tb, 32);
+
+  // planes mode: the weight-gradient GEMM reads whole 64-row TMA boxes (and the row after the last one for the shifted operand): rows
+  // [T, tail_end) of this cluster's sequences must be zeros in this CTA's 32 columns of this direction (both planes)
+  if (p.y != nullptr) {
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;
+    constexpr int kChunks = kUS * 2 / 16;  // 16-byte chunks of 32 bf16
+    for (int i = tid; i < nvalid * ntail * kChunks * 2; i += kThreads) {
+      const int cc = i % kChunks, pl = (i / kChunks) & 1, rr = (i / (2 * kChunks)) % ntail, qq = i / (2 * kChunks * ntail);
+      unsigned char* row = reinterpret_cast<unsigned char*>(p.y + ((size_t)(nbase + qq) * Tmax + T + rr) * p.y_stride);
+      *reinterpret_cast<uint4*>(row + pl * p.y_stride * 2 + (dir * H + kUS * rank) * 2 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// =================================================================================================================================
+// backward
+// =================================================================================================================================
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBwdArgs p, const int H) {
+  constexpr int NPART = SPLIT ? 2 : 1;
+  constexpr bool FAST = !SPLIT;
+  const int C = H / kUS, KB = H / 64, NACC = H / 128;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank(), tile = (int)blockIdx.x / C;
+  const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
+  const int T = p.lens[p.G + g];
+  if (T <= 0) return;
+  const int b0 = tile * kNS, nvalid = min(kNS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
+  const size_t N = (size_t)p.G * p.B;
+  const bool has_dy = p.dy != nullptr, planes = p.planes != 0;
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Wsm = smem;                                   // [NPART][KB][kWBlk]
+  unsigned char* daB = Wsm + (size_t)NPART * KB * kWBlk;       // [NPART][16 k chunks][kDaLbo]: B operand (da of my 128 gate rows)
+  constexpr uint32_t kDaPart = 16 * kDaLbo;
+  float* xbuf = reinterpret_cast<float*>(daB + NPART * kDaPart);  // [2][C sources][32 units][32 seq] partial dh for my units (16-byte swizzle)
+  const uint32_t xBufBytes = (uint32_t)C * kXSlice;
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xbuf) + 2 * (size_t)xBufBytes);  // [2]
+  uint64_t* da_bar = xbar + 2;   // "the da tile of this step is complete" (all cell threads arrive)
+  uint64_t* mma_bar = xbar + 3;  // [2]: "the step's MMAs into accumulator a have completed" (accumulator 0 is sent while 1 is computed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 5);
+
+  {
+    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
+    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
+    load_w_slice_tc<SPLIT, false>(Wsm, W, M, H, rank);
+  }
+  for (int i = tid; i < (int)(NPART * kDaPart / 4); i += kThreads) reinterpret_cast<uint32_t*>(daB)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    mbar_init(da_bar, kCellThreads);
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_init_fence();
+    if (T > 1) mbar_arrive_expect_tx(&xbar[1], xBufBytes);  // step s fills buffer (s + 1) & 1: step 0 -> buffer 1, step 1 -> buffer 0
+    if (T > 2) mbar_arrive_expect_tx(&xbar[0], xBufBytes);
+  }
+  if (wid == kCellWarps) tmem_alloc(tmem_slot, 64);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  cluster_sync_all();
+  const uint32_t tb = *tmem_slot;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of my cells' dgates over all steps (bias gradient partials)
+
+  if (wid == kCellWarps) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, kNS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
+      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
+      const uint64_t b_base = smem_desc_nosw(smem_u32(daB), 128, kDaLbo);
+      const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kDaPart >> 4);
+      for (int s = 0; s + 1 < T; ++s) {
+        mbar_wait(da_bar, (uint32_t)(s & 1));
+        fence_after_sync();
+        for (int a = 0; a < NACC; ++a) {
+#pragma unroll
+          for (int k16 = 0; k16 < kRows / 16; ++k16) {
+            // k = gate rows [16 k16, +16): A = 16 k-rows of 128 bytes inside the two 64-unit blocks 2a, 2a+1; B = k chunks 2 k16, +1
+            const uint64_t ah = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk + (uint32_t)k16 * 16u * 128u) >> 4);
+            const uint64_t bh = b_base + (uint64_t)(((uint32_t)(2 * k16) * kDaLbo) >> 4);
+            mma_bf16_ss(tb + (uint32_t)a * kNS, ah, bh, idesc, k16 != 0);
+            if constexpr (SPLIT) {
+              mma_bf16_ss(tb + (uint32_t)a * kNS, ah, bh + b_lo, idesc, true);
+              mma_bf16_ss(tb + (uint32_t)a * kNS, ah + a_lo, bh, idesc, true);
+            }
+          }
+          mma_commit(&mma_bar[a]);
+        }
+      }
+    }
+  } else {
+    // ===================== cell warps: lane = local unit, warp wi owns sequences 4 wi .. 4 wi + 3 =====================
+    const int wi = wid, u = kUS * rank + lane, s0 = 4 * wi;
+    const int t_first = dir ? 0 : T - 1, dt = dir ? 1 : -1;  // backward scan: t = T-1..0 (forward chain) or 0..T-1 (reverse chain)
+    float4* const G4 = reinterpret_cast<float4*>(dir ? p.gates[1] : p.gates[0]) + u;
+    const float* const Cst = (dir ? p.cstate[1] : p.cstate[0]) + u;
+    const float* const DY = has_dy ? p.dy + dir * H + u : nullptr;
+    const int dy_stride = p.dy_stride;
+    bool valid[4];
+    int rowb[4];  // first token row of my cell's sequence (columns beyond the batch: clamped for loads, zeroed, never stored)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      valid[e] = s0 + e < nvalid;
+      rowb[e] = (nbase + min(s0 + e, nvalid - 1)) * Tmax;
+    }
+    struct In {
+      float4 g[4];
+      float cprev[4], dy[4];
+    };
+    auto load_in = [&](int s, In& in) {
+      const int t = t_first + s * dt;
+      const bool has_prev = s + 1 < T;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const size_t row = (size_t)(rowb[e] + t);
+        in.g[e] = G4[row * H];
+        in.cprev[e] = has_prev ? Cst[(row + dt) * H] : 0.f;  // c of the scan predecessor; 0 at the chain start
+        in.dy[e] = has_dy ? DY[row * dy_stride] : 0.f;
+      }
+    };
+    // everything of a cell step that does not depend on the recurrent gradient is formed ahead of it (while the previous step's MMAs
+    // and exchange are in flight):  dh = dhrec + dy;  dct = dh * A + dc;  da = (dct Fi, dct Ff, dct Fg, dh Fo);  dc' = dct * gf
+    float fA[4], fI[4], fF[4], fG[4], fO[4], fDy[4], fGf[4];
+    auto prep = [&](const In& in, const float (&ccur)[4]) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = valid[e];
+        const float gi = ok ? in.g[e].x : 0.f, gf = ok ? in.g[e].y : 0.f, gg = ok ? in.g[e].z : 0.f, go = ok ? in.g[e].w : 0.f;
+        const float tc = tanh_f<FAST>(ccur[e]);
+        fA[e] = go * fmaf(-tc, tc, 1.0f);
+        fI[e] = gg * gi * (1.0f - gi);
+        fF[e] = in.cprev[e] * gf * (1.0f - gf);
+        fG[e] = gi * fmaf(-gg, gg, 1.0f);
+        fO[e] = tc * go * (1.0f - go);
+        fDy[e] = ok ? in.dy[e] : 0.f;
+        fGf[e] = gf;
+      }
+    };
+    float dc[4] = {0.f, 0.f, 0.f, 0.f}, dhrec[4];
+    // my da values in the B tile: k = 4 lane + gate -> chunk lane/2, bytes (lane & 1) * 8 of the 16-byte row of sequence n
+    unsigned char* const da_put = daB + (size_t)(lane >> 1) * kDaLbo + (size_t)(lane & 1) * 8 + (size_t)s0 * 16;
+    // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) x columns [16 half, +16) of every accumulator; lane = unit
+    // 128 a + 32 quarter + lane, which CTA 4a + quarter owns as its local unit `lane`
+    const int quarter = wid & 3, half = wid >> 2;
+    const uint32_t xb_local = smem_u32(xbuf), xbar_local = smem_u32(xbar);
+
+    auto step = [&](const int s, In& cur, In& nxt) {
+      if (s + 1 < T) load_in(s + 1, nxt);  // register prefetch, one step ahead (ping-pong sets: no loaded value is ever moved)
+      const int t = t_first + s * dt;
+      const bool more = s + 1 < T;
+      uint32_t h0[4], h1[4], l0[4], l1[4];
+      float da[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float dh = dhrec[e] + fDy[e];
+        const float dct = fmaf(dh, fA[e], dc[e]);
+        dc[e] = dct * fGf[e];
+        da[e][0] = dct * fI[e];
+        da[e][1] = dct * fF[e];
+        da[e][2] = dct * fG[e];
+        da[e][3] = dh * fO[e];
+        l0[e] = l1[e] = 0u;
+        if constexpr (SPLIT) {
+          split_bf16(da[e][0], da[e][1], h0[e], l0[e]);
+          split_bf16(da[e][2], da[e][3], h1[e], l1[e]);
+        } else {
+          h0[e] = pack_bf16(da[e][0], da[e][1]);
+          h1[e] = pack_bf16(da[e][2], da[e][3]);
+        }
+        if (more) {
+          *reinterpret_cast<uint2*>(da_put + e * 16) = make_uint2(h0[e], h1[e]);
+          if constexpr (SPLIT) *reinterpret_cast<uint2*>(da_put + kDaPart + e * 16) = make_uint2(l0[e], l1[e]);
+        }
+      }
+      if (more) {
+        fence_async_smem();  // the da tile (generic-proxy stores) is the tensor core's B operand (async proxy)
+        mbar_arrive(da_bar);
+      }
+      // off the chain: dgates overwrite the saved gates in place; bias-gradient column sums
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (valid[e]) {
+          float4* gp = G4 + (size_t)(rowb[e] + t) * H;
+          if (planes) {
+            // bf16 hi | lo planes over the 4H-float gate row: [4H bf16 hi | 4H bf16 lo], gate-interleaved column 4u + q
+            unsigned char* grow = reinterpret_cast<unsigned char*>(gp) - (size_t)u * 16;  // start of the row
+            *reinterpret_cast<uint2*>(grow + (size_t)u * 8) = make_uint2(h0[e], h1[e]);
+            if constexpr (SPLIT) *reinterpret_cast<uint2*>(grow + (size_t)H * 8 + (size_t)u * 8) = make_uint2(l0[e], l1[e]);
+            bsum.x += da[e][0]; bsum.y += da[e][1]; bsum.z += da[e][2]; bsum.w += da[e][3];
+          } else {
+            *gp = make_float4(da[e][0], da[e][1], da[e][2], da[e][3]);
+          }
+        }
+      }
+      if (!more) return;
+      {  // the next step's factors: its c is this step's c_prev
+        float cn[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cn[e] = cur.cprev[e];
+        prep(nxt, cn);
+      }
+
+      // partial dh^T[H, 32] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter my TMEM rows to the owners of those units
+      const int xb = (s + 1) & 1;
+      for (int a = 0; a < NACC; ++a) {
+        mbar_wait(&mma_bar[a], (uint32_t)(s & 1));
+        fence_after_sync();
+        uint32_t r[16];
+        tmem_ld16(tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)a * kNS + (uint32_t)(16 * half), r);
+        const uint32_t owner = (uint32_t)(4 * a + quarter);
+        const uint32_t dst = map_to_rank(xb_local, owner) + (uint32_t)xb * xBufBytes + (uint32_t)rank * kXSlice + (uint32_t)lane * (kNS * 4);
+        const uint32_t bar = map_to_rank(xbar_local, owner) + (uint32_t)xb * 8u;
+#pragma unroll
+        for (int sg = 0; sg < 4; ++sg)  // 16-byte piece = sequences [4 (4 half + sg), +4); stored at piece index ^ (unit & 7)
+          st_async_v4(dst + (uint32_t)(((4 * half + sg) ^ (lane & 7)) * 16), __uint_as_float(r[4 * sg]), __uint_as_float(r[4 * sg + 1]),
+                      __uint_as_float(r[4 * sg + 2]), __uint_as_float(r[4 * sg + 3]), bar);
+      }
+      fence_before_sync();
+      // all C partials of my units have landed (every CTA of the cluster, myself included, sent 32 units x 32 sequences)
+      mbar_wait(&xbar[xb], (uint32_t)((s >> 1) & 1));
+      if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[xb], xBufBytes);  // refilled at step s + 2
+      // recurrent gradient of my cells for the next step: sum of the C partials (sequences 4 wi .. 4 wi + 3 = piece wi of my unit row)
+      const float* xr = xbuf + (size_t)xb * (xBufBytes / 4) + (size_t)lane * kNS + (size_t)((wi ^ (lane & 7)) * 4);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r2 = 0; r2 < C; ++r2) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + (size_t)r2 * (kXSlice / 4));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      dhrec[0] = acc.x; dhrec[1] = acc.y; dhrec[2] = acc.z; dhrec[3] = acc.w;
+    };
+
+    In inE, inO;
+    load_in(0, inE);
+    {
+      float c0v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        c0v[e] = Cst[(size_t)(rowb[e] + t_first) * H];
+        dhrec[e] = (valid[e] && p.dhn != nullptr) ? p.dhn[((size_t)dir * N + nbase + s0 + e) * H + u] : 0.f;
+      }
+      prep(inE, c0v);
+    }
+    for (int s = 0; s < T; s += 2) {
+      step(s, inE, inO);
+      if (s + 1 < T) step(s + 1, inO, inE);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits while a peer could still be sending to it
+  if (wid == kCellWarps) tmem_dealloc(tb, 64);
+
+  if (planes) {
+    // (1) bias-gradient partials: one [4H] row (GI order) per (direction slot, group, tile); CTA `rank` owns columns [128 rank, +128)
+    if (p.bias_partial != nullptr) {
+      float4* red = reinterpret_cast<float4*>(xbuf);  // [8 warps][32 units] (the exchange buffers are idle now)
+      if (wid < kCellWarps) red[wid * kUS + lane] = bsum;
+      __syncthreads();
+      if (wid == 0) {
+        float4 b = red[lane];
+#pragma unroll
+        for (int w2 = 1; w2 < kCellWarps; ++w2) {
+          const float4 o = red[w2 * kUS + lane];
+          b.x += o.x; b.y += o.y; b.z += o.z; b.w += o.w;
+        }
+        const int ntiles = (int)gridDim.x / C;
+        float* dst = p.bias_partial + (((size_t)blockIdx.z * p.G + g) * ntiles + tile) * 4 * H + 4 * (kUS * rank + lane);
+        *reinterpret_cast<float4*>(dst) = b;
+      }
+    }
+    // (2) zero tail rows [T, tail_end) of my sequences in my 128 gate columns (both planes): the TN GEMM reads whole 64-row boxes
+    const int tail_end = min(Tmax, ((T + 63) / 64) * 64 + 1), ntail = tail_end - T;
+    constexpr int kChunks = kRows * 2 / 16;  // 16-byte chunks of 128 bf16
+    float* const Gbase = dir ? p.gates[1] : p.gates[0];
+    for (int i = tid; i < nvalid * ntail * kChunks * 2; i += kThreads) {
+      const int cc = i % kChunks, pl = (i / kChunks) & 1, rr = (i / (2 * kChunks)) % ntail, qq = i / (2 * kChunks * ntail);
+      unsigned char* row = reinterpret_cast<unsigned char*>(Gbase + ((size_t)(nbase + qq) * Tmax + T + rr) * 4 * H);
+      *reinterpret_cast<uint4*>(row + (size_t)pl * 4 * H * 2 + (size_t)kRows * rank * 2 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+size_t fwd_smem_tc(int H, bool split) {
+  const int npart = split ? 2 : 1;
+  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)2 * (H / kUS) * npart * kHSlice + (size_t)(2 * (H / kUS) + 1) * 8 + 64;
+}
+size_t bwd_smem_tc(int H, bool split) {
+  const int npart = split ? 2 : 1;
+  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)npart * 16 * kDaLbo + (size_t)2 * (H / kUS) * kXSlice + 64;
+}
+
+template <typename Kern, typename Args>
+cudaError_t launch_cluster_tc(Kern kern, const Args& a, int H, size_t smem, int ndir, cudaStream_t st) {
+  const int C = H / kUS;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(C * ((a.B + kNS - 1) / kNS)), (unsigned)a.G, (unsigned)ndir);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a, H);
+}
+
+}  // namespace
+
+bool lstm_cluster_tc_supports(int H) { return H == 128 || H == 256; }
+
+// bias partial rows written per direction by launch_lstm_bwd_cluster_tc in planes mode: one per (group, sequence tile)
+int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a) { return a.G * ((a.B + kNS - 1) / kNS); }
+
+cudaError_t launch_lstm_fwd_cluster_tc(const LstmFwdArgs& a, int H, int precision, cudaStream_t st) {
+  if (!lstm_cluster_tc_supports(H)) return cudaErrorInvalidValue;
+  const bool split = precision == 0;
+  const size_t smem = fwd_smem_tc(H, split);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  if (a.y != nullptr && !a.planes) return cudaErrorInvalidValue;  // this path writes y as bf16 planes only
+  const bool train = a.gates[a.dir0] != nullptr;
+  if (split) return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<true, true>, a, H, smem, a.ndir, st)
+                          : launch_cluster_tc(lstm_fwd_cltc_kernel<true, false>, a, H, smem, a.ndir, st);
+  return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<false, true>, a, H, smem, a.ndir, st)
+               : launch_cluster_tc(lstm_fwd_cltc_kernel<false, false>, a, H, smem, a.ndir, st);
+}
+
+cudaError_t launch_lstm_bwd_cluster_tc(const LstmBwdArgs& a, int H, int precision, cudaStream_t st) {
+  if (!lstm_cluster_tc_supports(H)) return cudaErrorInvalidValue;
+  const bool split = precision == 0;
+  const size_t smem = bwd_smem_tc(H, split);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  return split ? launch_cluster_tc(lstm_bwd_cltc_kernel<true>, a, H, smem, a.ndir, st)
+               : launch_cluster_tc(lstm_bwd_cltc_kernel<false>, a, H, smem, a.ndir, st);
+}
+
+}  // namespace ib200

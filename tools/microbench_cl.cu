@@ -24,7 +24,7 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 
 // ---- (1) -------------------------------------------------------------------------------------------------------------------------
 // smem: A_hi | A_lo: [4 k-blocks][128 rows x 128 B]; B_hi | B_lo: [4 k-blocks][N rows x 128 B]
-template <int N, int NPARTS, bool TS>
+template <int N, int NPARTS, bool TS, int NACC = 1>
 __global__ void __launch_bounds__(160, 1) k_mma(long long* cyc, int steps, int do_ld) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(160, 1) k_mma(long long* cyc, int steps, int d
   // loop-invariant base descriptors: every MMA's descriptor is base + a compile-time constant (start address field, 16-byte units)
   const uint64_t ah0 = smem_desc_sw128(smem_u32(A), 1024, 0), al0 = smem_desc_sw128(smem_u32(A) + 4 * kABlk, 1024, 0);
   const uint64_t bh0 = smem_desc_sw128(smem_u32(B), 1024, 0), bl0 = smem_desc_sw128(smem_u32(B) + 4 * kBBlk, 1024, 0);
-  const uint32_t dcol = 256;
   long long t0 = clock64();
   for (int s = 0; s < steps; ++s) {
     if (tid == 128) {
@@ -59,7 +58,8 @@ __global__ void __launch_bounds__(160, 1) k_mma(long long* cyc, int steps, int d
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
           const uint64_t bo = (uint64_t)((kb * kBBlk + k16 * 32) >> 4), ao = (uint64_t)((kb * kABlk + k16 * 32) >> 4);
-          const bool first = kb == 0 && k16 == 0;
+          const bool first = (kb * 4 + k16) < NACC;
+          const uint32_t dcol = 256 + ((kb * 4 + k16) % NACC) * N;  // NACC accumulators used round-robin
           if constexpr (TS) {
             const uint32_t ah = tb + (kb * 4 + k16) * 8, al = tb + 128 + (kb * 4 + k16) * 8;
             mma_bf16_ts(tb + dcol, ah, bh0 + bo, idesc, !first);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(160, 1) k_mma(long long* cyc, int steps, int d
       fence_after_sync();
       if (do_ld) {
         uint32_t r[32];
-        tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + dcol, r);
+        tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + 256, r);
         if (r[0] == 0x12345678u && r[31] == 0x9abcdef0u) cyc[1] = 1;
       }
       fence_before_sync();
@@ -96,19 +96,19 @@ __global__ void __launch_bounds__(160, 1) k_mma(long long* cyc, int steps, int d
   if (warp == 4) tmem_dealloc(tb, 512);
 }
 
-template <int N, int NPARTS, bool TS>
+template <int N, int NPARTS, bool TS, int NACC = 1>
 void run_mma(long long* dCyc, int steps) {
   const size_t smem = 1024 + 2 * 4 * 128 * 128 + 2 * 4 * N * 128 + 64;
-  cudaFuncSetAttribute(k_mma<N, NPARTS, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_mma<N, NPARTS, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int do_ld = 0; do_ld < 2; ++do_ld) {
     cudaMemset(dCyc, 0, 16);
-    k_mma<N, NPARTS, TS><<<1, 160, smem>>>(dCyc, steps, do_ld);
+    k_mma<N, NPARTS, TS, NACC><<<1, 160, smem>>>(dCyc, steps, do_ld);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("k_mma: %s\n", cudaGetErrorString(e)); exit(1); }
     long long c;
     cudaMemcpy(&c, dCyc, 8, cudaMemcpyDeviceToHost);
     const int nm = 16 * NPARTS;
-    printf("mma M=128 N=%3d %s  %2d MMAs (K=256, %d part%s) %s : %8.1f cycles/step  (%.1f per MMA)\n", N, TS ? "TS" : "SS", nm, NPARTS,
+    printf("mma M=128 N=%3d %s %d acc  %2d MMAs (K=256, %d part%s) %s : %8.1f cycles/step  (%.1f per MMA)\n", N, TS ? "TS" : "SS", NACC, nm, NPARTS,
            NPARTS > 1 ? "s" : " ", do_ld ? "+ld" : "   ", (double)c / steps, (double)c / steps / nm);
   }
 }
@@ -186,12 +186,11 @@ int main() {
   long long* dCyc;
   cudaMalloc(&dCyc, 1024 * 8);
   const int steps = 2000;
-  run_mma<16, 1, false>(dCyc, steps); run_mma<16, 3, false>(dCyc, steps);
-  run_mma<32, 1, false>(dCyc, steps); run_mma<32, 3, false>(dCyc, steps);
-  run_mma<64, 1, false>(dCyc, steps); run_mma<64, 3, false>(dCyc, steps);
-  run_mma<128, 1, false>(dCyc, steps); run_mma<128, 3, false>(dCyc, steps);
-  run_mma<32, 1, true>(dCyc, steps); run_mma<32, 3, true>(dCyc, steps);
-  run_mma<64, 1, true>(dCyc, steps); run_mma<64, 3, true>(dCyc, steps);
+  run_mma<32, 1, false, 1>(dCyc, steps); run_mma<32, 3, false, 1>(dCyc, steps);
+  run_mma<32, 1, false, 2>(dCyc, steps); run_mma<32, 3, false, 2>(dCyc, steps);
+  run_mma<32, 1, false, 4>(dCyc, steps); run_mma<32, 3, false, 4>(dCyc, steps);
+  run_mma<32, 3, true, 2>(dCyc, steps);
+  if (getenv("MB_XCHG") == nullptr) return 0;
   for (int nclusters : {1, 16})
   for (int C : {4, 8})
     for (int bytes : {1024, 2048, 4096})
