@@ -22,6 +22,8 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 SOURCES = ["capi.cu", "small.cu", "head.cu", "lstm_fwd.cu", "lstm_bwd.cu", "lstm_cluster.cu", "lstm_cluster_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_l0.cu", "gemm_wide.cu", "optim.cu", "metrics.cu", "masks.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+if os.environ.get("IB200_PROF"):  # timing experiments only: per-phase cycle counters printed by the tcgen05 cluster kernels
+    NVCC_FLAGS.append("-DIB200_PROF")
 if os.environ.get("IB200_ABLATE"):  # timing experiments only (tools/ablate_fwd.py): in-kernel ablation switches of IB200_DBG
     NVCC_FLAGS.append("-DIB200_ABLATE")
 

@@ -20,6 +20,7 @@
 //     units -- is reduce-scattered: every warp sends its TMEM rows to the CTA that owns those units with 16-byte st.async stores
 //     counted on the owner's mbarrier; the owner adds the C partials.
 #include <algorithm>
+#include <cstdio>
 
 #include "kernels.h"
 #include "tc05.cuh"
@@ -28,6 +29,17 @@ namespace ib200 {
 namespace {
 
 using namespace tc;
+
+// IB200_PROF builds (timing experiments only): per-phase cycle counters of cluster 0, printed at the end of the kernel
+#ifdef IB200_PROF
+#define PROF_DECL long long pf_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt_ = clock64()
+#define PROF_MARK(i) do { const long long now_ = clock64(); pf_[i] += now_ - pt_; pt_ = now_; } while (0)
+#define PROF_PRINT(tag, cond, T) do { if (cond) printf("%s T=%d cycles/step: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", tag, T, pf_[0] / T, pf_[1] / T, pf_[2] / T, pf_[3] / T, pf_[4] / T, pf_[5] / T, pf_[6] / T, pf_[7] / T, pf_[8] / T, pf_[9] / T); } while (0)
+#else
+#define PROF_DECL do { } while (0)
+#define PROF_MARK(i) do { } while (0)
+#define PROF_PRINT(tag, cond, T) do { } while (0)
+#endif
 
 constexpr int kUS = 32;                 // hidden units per CTA
 constexpr int kRows = 4 * kUS;          // gate rows per CTA = UMMA M
@@ -85,6 +97,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+// tcgen05.mma / commit issued from WARP-UNIFORM code: all 32 lanes execute the instruction stream, one elected lane issues.  With
+// `if (lane == 0)` around a plain tcgen05.mma, ptxas cannot prove the descriptors uniform and wraps every MMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~100 cycles of issue per MMA, measured: the issue, not the tensor pipe, set the
+// step time).
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+      " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2c_elect(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}\n" ::"r"(dst_cluster),
+      "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n @e mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cell_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCellThreads) : "memory"); }
 
 // 16 lanes x 256 bits, two repetitions (16 columns): thread t of the warp gets, for each 8-column block b, rows t/4 and t/4 + 8 of
@@ -173,38 +219,43 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   const uint32_t tb = *tmem_slot;
 
   if (wid == kCellWarps) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = idesc_bf16(kRows, kNS, false, false);
       const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, 0);
       const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kNS * 16);
       const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
+      PROF_DECL;
       for (int s = 0; s < T; ++s) {
         const int buf = s & 1;
         const uint32_t par = (uint32_t)(((s - 1) >> 1) & 1);
         const uint64_t bb = b_base + (uint64_t)(((uint32_t)buf * bufBytes) >> 4);
         for (int i = 0; i < C; ++i) {
           const int r = rank + i < C ? rank + i : rank + i - C;  // source CTA: mine first, then in ring order
+          PROF_MARK(1);
           if (s > 0) {
             mbar_wait(&hbar[buf * C + r], par);
-            if (r != rank && s + 2 < T) mbar_arrive_expect_tx(&hbar[buf * C + r], sliceBytes);  // next fill: h_{s+1}
+            if (r != rank && s + 2 < T) mbar_arrive_expect_tx_elect(&hbar[buf * C + r], sliceBytes);  // next fill: h_{s+1}
           }
-          fence_after_sync();
+          PROF_MARK(i == 0 ? 0 : (i == 1 ? 2 : 3));  // wait for: my own slice | the first remote slice | the others
+          if (i == 0) fence_after_sync();  // (the cell warps' tcgen05.ld of the previous step precede these MMAs)
+          // units [32 r, +32) = two k16 steps: A = 64 bytes of every row of block r / 2; B = the four unit chunks of source r
+          const uint64_t ah = a_base + (uint64_t)(((uint32_t)(r >> 1) * kWBlk + (uint32_t)(r & 1) * 64u) >> 4);
+          const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes) >> 4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            // units [32 r + 16 j, +16): A = 32 bytes of every row of block (2r + j) / 4; B = unit chunks 2j, 2j + 1 of source r
-            const int k16 = 2 * r + j;
-            const uint64_t ah = a_base + (uint64_t)(((uint32_t)(k16 >> 2) * kWBlk + (uint32_t)(k16 & 3) * 32u) >> 4);
-            const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes + (uint32_t)j * 2u * (kNS * 16)) >> 4);
-            mma_bf16_ss(tb, ah, bh, idesc, (i | j) != 0);
+            const uint64_t ahj = ah + (uint64_t)(j * 2), bhj = bh + (uint64_t)(j * ((2 * kNS * 16) >> 4));
+            mma_bf16_ss_elect(tb, ahj, bhj, idesc, (i | j) != 0);
             if constexpr (SPLIT) {
-              mma_bf16_ss(tb, ah, bh + b_lo, idesc, true);
-              mma_bf16_ss(tb, ah + a_lo, bh, idesc, true);
+              mma_bf16_ss_elect(tb, ahj, bhj + b_lo, idesc, true);
+              mma_bf16_ss_elect(tb, ahj + a_lo, bhj, idesc, true);
             }
           }
         }
-        mma_commit(mma_bar);
+        mma_commit_elect(mma_bar);
+        PROF_MARK(1);
       }
+      PROF_PRINT("fwd mma  [own-wait issue first-remote-wait other-remote-waits]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
     }
   } else {
     // ===================== cell warps =====================
@@ -255,19 +306,23 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 
     // one step; xc = this step's input projection, xn / tk_*: register prefetch of the next step's (tokens two steps ahead).  The
     // step loop is unrolled by two over ping-pong register sets so that no loaded value has to be moved (a move waits for its load)
+    PROF_DECL;
     auto step = [&](const int s, float4 (&xc)[4], float4 (&xn)[4], int (&tk_use)[4], int (&tk_fill)[4]) {
       if (s + 1 < T) {
         load_x(s + 1, tk_use, xn);
         if (layer0 && s + 2 < T) load_tok(s + 2, tk_fill);
       }
       const int buf = s & 1;
+      PROF_MARK(0);
       mbar_wait(mma_bar, (uint32_t)(s & 1));
+      PROF_MARK(1);
       fence_after_sync();
       uint32_t ra[8], rb[8];
       tmem_ld_16x256b_x2(taddr, ra);
       tmem_ld_16x256b_x2(taddr + (16u << 16), rb);
       tmem_wait_ld();
       fence_before_sync();
+      PROF_MARK(2);
 
       const int t = t_first + s * dt;
       float gi[4], gf[4], gg[4], go[4];
@@ -291,14 +346,18 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
           *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
           if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
         }
+        PROF_MARK(3);
         fence_async_smem();  // my slice (generic-proxy stores) is read by the bulk copies and by my own tensor core (async proxy)
+        PROF_MARK(4);
         cell_bar_sync();
-        if (tid < C) {
+        PROF_MARK(5);
+        if (wid < C) {  // warp w sends my slice to CTA w (one elected lane): the eight copies are issued side by side
           const uint32_t boff = (uint32_t)(buf ^ 1) * bufBytes;
           uint64_t* bar = &hbar[(buf ^ 1) * C + rank];  // slot `rank` of the receiver's barriers
-          if (tid == rank) mbar_arrive(bar);
-          else bulk_s2c(map_to_rank(my_slot + boff, (uint32_t)tid), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), (uint32_t)tid));
+          if (wid == rank) mbar_arrive_elect(bar);
+          else bulk_s2c_elect(map_to_rank(my_slot + boff, (uint32_t)wid), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), (uint32_t)wid));
         }
+        PROF_MARK(6);
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -315,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
           }
         }
       }
+      PROF_MARK(7);
     };
 
     float4 xE[4], xO[4];
@@ -328,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       step(s, xE, xO, tkO, tkE);
       if (s + 1 < T) step(s + 1, xO, xE, tkE, tkO);
     }
+    PROF_PRINT("fwd cell [prefetch-issue wait-mma tmem-ld math+sts fence bar bulk-issue stores]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
 
     if (p.hn != nullptr) {
       const size_t N = (size_t)p.G * p.B;
@@ -409,30 +470,35 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of my cells' dgates over all steps (bias gradient partials)
 
   if (wid == kCellWarps) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = idesc_bf16(128, kNS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
       const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
       const uint64_t b_base = smem_desc_nosw(smem_u32(daB), 128, kDaLbo);
       const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kDaPart >> 4);
+      PROF_DECL;
       for (int s = 0; s + 1 < T; ++s) {
         mbar_wait(da_bar, (uint32_t)(s & 1));
+        PROF_MARK(0);
         fence_after_sync();
         for (int a = 0; a < NACC; ++a) {
+          const uint64_t aa = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk) >> 4);
 #pragma unroll
           for (int k16 = 0; k16 < kRows / 16; ++k16) {
             // k = gate rows [16 k16, +16): A = 16 k-rows of 128 bytes inside the two 64-unit blocks 2a, 2a+1; B = k chunks 2 k16, +1
-            const uint64_t ah = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk + (uint32_t)k16 * 16u * 128u) >> 4);
-            const uint64_t bh = b_base + (uint64_t)(((uint32_t)(2 * k16) * kDaLbo) >> 4);
-            mma_bf16_ss(tb + (uint32_t)a * kNS, ah, bh, idesc, k16 != 0);
+            const uint64_t ah = aa + (uint64_t)((k16 * 16 * 128) >> 4);
+            const uint64_t bh = b_base + (uint64_t)((2 * k16 * kDaLbo) >> 4);
+            mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah, bh, idesc, k16 != 0);
             if constexpr (SPLIT) {
-              mma_bf16_ss(tb + (uint32_t)a * kNS, ah, bh + b_lo, idesc, true);
-              mma_bf16_ss(tb + (uint32_t)a * kNS, ah + a_lo, bh, idesc, true);
+              mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah, bh + b_lo, idesc, true);
+              mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah + a_lo, bh, idesc, true);
             }
           }
-          mma_commit(&mma_bar[a]);
+          mma_commit_elect(&mma_bar[a]);
         }
+        PROF_MARK(1);
       }
+      PROF_PRINT("bwd mma  [wait-da issue]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
     }
   } else {
     // ===================== cell warps: lane = local unit, warp wi owns sequences 4 wi .. 4 wi + 3 =====================
@@ -490,8 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     const int quarter = wid & 3, half = wid >> 2;
     const uint32_t xb_local = smem_u32(xbuf), xbar_local = smem_u32(xbar);
 
+    PROF_DECL;
     auto step = [&](const int s, In& cur, In& nxt) {
       if (s + 1 < T) load_in(s + 1, nxt);  // register prefetch, one step ahead (ping-pong sets: no loaded value is ever moved)
+      PROF_MARK(0);
       const int t = t_first + s * dt;
       const bool more = s + 1 < T;
       uint32_t h0[4], h1[4], l0[4], l1[4];
@@ -518,10 +586,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
           if constexpr (SPLIT) *reinterpret_cast<uint2*>(da_put + kDaPart + e * 16) = make_uint2(l0[e], l1[e]);
         }
       }
+      PROF_MARK(1);
       if (more) {
         fence_async_smem();  // the da tile (generic-proxy stores) is the tensor core's B operand (async proxy)
         mbar_arrive(da_bar);
       }
+      PROF_MARK(2);
       // off the chain: dgates overwrite the saved gates in place; bias-gradient column sums
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -538,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
           }
         }
       }
+      PROF_MARK(3);
       if (!more) return;
       {  // the next step's factors: its c is this step's c_prev
         float cn[4];
@@ -545,25 +616,38 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         for (int e = 0; e < 4; ++e) cn[e] = cur.cprev[e];
         prep(nxt, cn);
       }
+      PROF_MARK(4);
 
-      // partial dh^T[H, 32] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter my TMEM rows to the owners of those units
+      // partial dh^T[H, 32] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter: my TMEM rows of accumulator a are units of CTA
+      // 4a + quarter.  They are staged in the IDLE receive buffer (xbuf[s & 1] took step s-1's partials, summed long ago), slot = the
+      // destination, and go out as ONE bulk copy per destination (the copy engine moves them: 16-byte remote stores from the cell
+      // warps kept the load/store pipe busy for ~2500 cycles per step).  Slot d of the idle buffer is next written by CTA d's own
+      // step-(s+1) copy, which CTA d can only issue after it has received this one.
       const int xb = (s + 1) & 1;
       for (int a = 0; a < NACC; ++a) {
         mbar_wait(&mma_bar[a], (uint32_t)(s & 1));
+        PROF_MARK(5);
         fence_after_sync();
         uint32_t r[16];
         tmem_ld16(tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)a * kNS + (uint32_t)(16 * half), r);
         const uint32_t owner = (uint32_t)(4 * a + quarter);
-        const uint32_t dst = map_to_rank(xb_local, owner) + (uint32_t)xb * xBufBytes + (uint32_t)rank * kXSlice + (uint32_t)lane * (kNS * 4);
-        const uint32_t bar = map_to_rank(xbar_local, owner) + (uint32_t)xb * 8u;
+        float* stg = xbuf + (size_t)(s & 1) * (xBufBytes / 4) + (size_t)owner * (kXSlice / 4) + (size_t)lane * kNS;
 #pragma unroll
         for (int sg = 0; sg < 4; ++sg)  // 16-byte piece = sequences [4 (4 half + sg), +4); stored at piece index ^ (unit & 7)
-          st_async_v4(dst + (uint32_t)(((4 * half + sg) ^ (lane & 7)) * 16), __uint_as_float(r[4 * sg]), __uint_as_float(r[4 * sg + 1]),
-                      __uint_as_float(r[4 * sg + 2]), __uint_as_float(r[4 * sg + 3]), bar);
+          *reinterpret_cast<uint4*>(stg + ((4 * half + sg) ^ (lane & 7)) * 4) = make_uint4(r[4 * sg], r[4 * sg + 1], r[4 * sg + 2], r[4 * sg + 3]);
+        fence_async_smem();
+        pair_bar_sync(2 + quarter);  // the two warps (quarter, half 0 | 1) hold the 32 sequences of this slice between them
+        if (half == 0) {
+          const uint32_t src = xb_local + (uint32_t)(s & 1) * xBufBytes + owner * kXSlice;
+          bulk_s2c_elect(map_to_rank(xb_local, owner) + (uint32_t)xb * xBufBytes + (uint32_t)rank * kXSlice, src, kXSlice,
+                         map_to_rank(xbar_local, owner) + (uint32_t)xb * 8u);
+        }
+        PROF_MARK(6);
       }
       fence_before_sync();
       // all C partials of my units have landed (every CTA of the cluster, myself included, sent 32 units x 32 sequences)
       mbar_wait(&xbar[xb], (uint32_t)((s >> 1) & 1));
+      PROF_MARK(7);
       if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[xb], xBufBytes);  // refilled at step s + 2
       // recurrent gradient of my cells for the next step: sum of the C partials (sequences 4 wi .. 4 wi + 3 = piece wi of my unit row)
       const float* xr = xbuf + (size_t)xb * (xBufBytes / 4) + (size_t)lane * kNS + (size_t)((wi ^ (lane & 7)) * 4);
@@ -573,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       dhrec[0] = acc.x; dhrec[1] = acc.y; dhrec[2] = acc.z; dhrec[3] = acc.w;
+      PROF_MARK(8);
     };
 
     In inE, inO;
@@ -590,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
       step(s, inE, inO);
       if (s + 1 < T) step(s + 1, inO, inE);
     }
+    PROF_PRINT("bwd cell [prefetch-issue chain-math+sts fence+arrive dgate-stores prep wait-mma ld+send wait-xchg sum]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
   }
   fence_before_sync();
   __syncthreads();
