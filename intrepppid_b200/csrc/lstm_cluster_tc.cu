@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 #pragma unroll
       for (int e = 0; e < 4; ++e) tk[e] = __ldg(p.tok + (size_t)rowb[e] + t_first + s * dt);
     };
-    auto load_x = [&](int s, const int (&tk)[4], float4 (&x)[4]) {
+    auto load_x = [&](int s, const int (&tk)[4], float4 (&x)[4]) {  // (layer 0: tk = the tokens of step s)
       if (layer0) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) x[e] = __ldg(xtab + (size_t)(tk[e] == 0 ? pad_row : tk[e]) * H);  // pads: this cluster's copy of row 0
@@ -304,14 +304,15 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     unsigned char* const my_slot_ptr = hB + (size_t)rank * sliceBytes;
     const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * half);
 
-    // one step; xc = this step's input projection, xn / tk_*: register prefetch of the next step's (tokens two steps ahead).  The
-    // step loop is unrolled by two over ping-pong register sets so that no loaded value has to be moved (a move waits for its load)
+    // input projection of the current step (register prefetch: the next step's loads are issued right after this step's values have
+    // been consumed and the h slice is on its way; tokens two steps ahead)
+    float4 xc[4];
+    int tk[4] = {0, 0, 0, 0};
+    if (layer0) load_tok(0, tk);
+    load_x(0, tk, xc);
+    if (layer0 && T > 1) load_tok(1, tk);
     PROF_DECL;
-    auto step = [&](const int s, float4 (&xc)[4], float4 (&xn)[4], int (&tk_use)[4], int (&tk_fill)[4]) {
-      if (s + 1 < T) {
-        load_x(s + 1, tk_use, xn);
-        if (layer0 && s + 2 < T) load_tok(s + 2, tk_fill);
-      }
+    for (int s = 0; s < T; ++s) {
       const int buf = s & 1;
       PROF_MARK(0);
       mbar_wait(mma_bar, (uint32_t)(s & 1));
@@ -358,6 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
           else bulk_s2c_elect(map_to_rank(my_slot + boff, (uint32_t)wid), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), (uint32_t)wid));
         }
         PROF_MARK(6);
+        load_x(s + 1, tk, xc);
+        if (layer0 && s + 2 < T) load_tok(s + 2, tk);
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -375,20 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         }
       }
       PROF_MARK(7);
-    };
-
-    float4 xE[4], xO[4];
-    int tkE[4] = {0, 0, 0, 0}, tkO[4] = {0, 0, 0, 0};
-    if (layer0) {
-      load_tok(0, tkE);
-      if (T > 1) load_tok(1, tkO);
     }
-    load_x(0, tkE, xE);
-    for (int s = 0; s < T; s += 2) {
-      step(s, xE, xO, tkO, tkE);
-      if (s + 1 < T) step(s + 1, xO, xE, tkE, tkO);
-    }
-    PROF_PRINT("fwd cell [prefetch-issue wait-mma tmem-ld math+sts fence bar bulk-issue stores]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
+    PROF_PRINT("fwd cell [loop wait-mma tmem-ld math+sts fence bar bulk-issue stores]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
 
     if (p.hn != nullptr) {
       const size_t N = (size_t)p.G * p.B;
@@ -548,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         fGf[e] = gf;
       }
     };
-    float dc[4] = {0.f, 0.f, 0.f, 0.f}, dhrec[4];
+    float dc[4] = {0.f, 0.f, 0.f, 0.f}, dhrec[4] = {0.f, 0.f, 0.f, 0.f};
     // my da values in the B tile: k = 4 lane + gate -> chunk lane/2, bytes (lane & 1) * 8 of the 16-byte row of sequence n
     unsigned char* const da_put = daB + (size_t)(lane >> 1) * kDaLbo + (size_t)(lane & 1) * 8 + (size_t)s0 * 16;
     // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) x columns [16 half, +16) of every accumulator; lane = unit
@@ -556,9 +547,22 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     const int quarter = wid & 3, half = wid >> 2;
     const uint32_t xb_local = smem_u32(xbuf), xbar_local = smem_u32(xbar);
 
+    // `in` holds the saved gates / c / dy of the NEXT step (register prefetch: loaded one step ahead, consumed by prep() in the shadow
+    // of this step's MMAs, reloaded right after); ccur = the cell state of the step whose factors prep() forms next
+    In in;
+    float ccur[4];
+    load_in(0, in);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ccur[e] = Cst[(size_t)(rowb[e] + t_first) * H];
+      dhrec[e] = (valid[e] && p.dhn != nullptr) ? p.dhn[((size_t)dir * N + nbase + s0 + e) * H + u] : 0.f;
+    }
+    prep(in, ccur);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ccur[e] = in.cprev[e];
+    if (T > 1) load_in(1, in);
     PROF_DECL;
-    auto step = [&](const int s, In& cur, In& nxt) {
-      if (s + 1 < T) load_in(s + 1, nxt);  // register prefetch, one step ahead (ping-pong sets: no loaded value is ever moved)
+    for (int s = 0; s < T; ++s) {
       PROF_MARK(0);
       const int t = t_first + s * dt;
       const bool more = s + 1 < T;
@@ -609,13 +613,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         }
       }
       PROF_MARK(3);
-      if (!more) return;
-      {  // the next step's factors: its c is this step's c_prev
-        float cn[4];
+      if (!more) break;
+      prep(in, ccur);  // the next step's factors
 #pragma unroll
-        for (int e = 0; e < 4; ++e) cn[e] = cur.cprev[e];
-        prep(nxt, cn);
-      }
+      for (int e = 0; e < 4; ++e) ccur[e] = in.cprev[e];
+      if (s + 2 < T) load_in(s + 2, in);
       PROF_MARK(4);
 
       // partial dh^T[H, 32] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter: my TMEM rows of accumulator a are units of CTA
@@ -658,24 +660,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
       }
       dhrec[0] = acc.x; dhrec[1] = acc.y; dhrec[2] = acc.z; dhrec[3] = acc.w;
       PROF_MARK(8);
-    };
-
-    In inE, inO;
-    load_in(0, inE);
-    {
-      float c0v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        c0v[e] = Cst[(size_t)(rowb[e] + t_first) * H];
-        dhrec[e] = (valid[e] && p.dhn != nullptr) ? p.dhn[((size_t)dir * N + nbase + s0 + e) * H + u] : 0.f;
-      }
-      prep(inE, c0v);
     }
-    for (int s = 0; s < T; s += 2) {
-      step(s, inE, inO);
-      if (s + 1 < T) step(s + 1, inO, inE);
-    }
-    PROF_PRINT("bwd cell [prefetch-issue chain-math+sts fence+arrive dgate-stores prep wait-mma ld+send wait-xchg sum]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
+    PROF_PRINT("bwd cell [loop chain-math+sts fence+arrive dgate-stores prep+prefetch wait-mma ld+send wait-xchg sum]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
   }
   fence_before_sync();
   __syncthreads();
