@@ -48,8 +48,9 @@ constexpr int kCellWarps = 8;           // warps 0..7: TMEM read-out + cell math
 constexpr int kCellThreads = 32 * kCellWarps;
 constexpr int kThreads = kCellThreads + 32;
 constexpr int kWBlk = kRows * 128;      // one [128 gate rows x 64 units] bf16 block of the resident W slice (128-byte swizzle)
-constexpr int kHSlice = 4 * kNS * 16;   // forward: h slice of one source CTA and one part: [4 unit chunks][32 sequences][16 B]
-constexpr int kDaLbo = kNS * 16 + 16;   // backward: byte pitch of one 8-row k chunk of the da tile (+16: bank spread of the writers)
+constexpr int kChunk = kNS * 16 + 16;   // byte pitch of one 8-row k chunk [32 sequences][16 B] of a B operand tile (+16: bank spread)
+constexpr int kHSlice = 4 * kChunk;     // forward: h slice of one source CTA and one part: [4 unit chunks][32 sequences][16 B]
+constexpr int kDaLbo = kChunk;          // backward: k-chunk pitch of the da tile
 constexpr int kXSlice = kUS * kNS * 4;  // backward: partial dh of one source CTA for my 32 units: [32 units][32 sequences] fp32
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -142,28 +143,50 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                : "memory");
 }
 
-// resident W slice as the A operand: Wsm[part][k block of 64 units][128 rows x 128 B], 128-byte swizzle.  Row L holds
-// W_hh[gate*H + 32*rank + local unit][.] (masked per group for layer 0, forward direction) with
-//   GATE_MAJOR (forward) : L = 32*(unit/8) + 8*gate + unit%8 -- rows q, q+8, q+16, q+24 of a 32-lane TMEM quarter are i,f,g,o of one unit
-//   otherwise (backward) : L = 4*unit + gate                 -- the four dgates of a cell are consecutive k of the da tile
-template <bool SPLIT, bool GATE_MAJOR>
+// resident W slice as the A operand, 128-byte swizzle, MN-major for the forward product and K-major for the backward one -- in both
+// kernels a k16 step of the MMA then reads 2 KB of CONTIGUOUS shared memory per 64-wide block (measured: 46 cycles per M=128 MMA
+// against 55-75 when the same step gathers 32 bytes from each of 128 rows):
+//   forward : Wsm[part][m block of 64 gate rows][H k-rows (units) x 128 B]; gate row L = 32*(unit/8) + 8*gate + unit%8, so that rows
+//             q, q+8, q+16, q+24 of a 32-lane TMEM quarter are i,f,g,o of one unit
+//   backward: Wsm[part][block of 64 units][128 gate rows x 128 B]; gate row L = 4*unit + gate (k of the backward product: the four
+//             dgates of a cell are consecutive k of the da tile); read MN-major: M = units
+// Row L holds W_hh[gate*H + 32*rank + local unit][.] (masked per group for layer 0, forward direction).
+template <bool SPLIT, bool FWD>
 __device__ __forceinline__ void load_w_slice_tc(unsigned char* Wsm, const float* __restrict__ W, const float* __restrict__ M, int H, int rank) {
-  const int KB = H / 64;
-  for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += blockDim.x) {
-    const int L = idx / (H / 2), k = (idx % (H / 2)) * 2;
-    const int gate = GATE_MAJOR ? (L >> 3) & 3 : L & 3, ul = GATE_MAJOR ? 8 * (L >> 5) + (L & 7) : L >> 2;
-    const size_t src = ((size_t)gate * H + kUS * rank + ul) * H + k;
-    float w0 = W[src], w1 = W[src + 1];
-    if (M != nullptr) {
-      w0 *= M[src];
-      w1 *= M[src + 1];
+  const size_t part = (size_t)(H / 64) * kWBlk;  // == 2 * H * 128: both layouts take H * 256 bytes per part
+  if constexpr (FWD) {
+    for (int idx = threadIdx.x; idx < (kRows / 2) * H; idx += blockDim.x) {
+      const int L = (idx / H) * 2, k = idx % H;  // rows L, L + 1 (two consecutive units of one gate), column k
+      const int gate = (L >> 3) & 3, ul = 8 * (L >> 5) + (L & 7);
+      const size_t src = ((size_t)gate * H + kUS * rank + ul) * H + k;
+      float w0 = W[src], w1 = W[src + H];
+      if (M != nullptr) {
+        w0 *= M[src];
+        w1 *= M[src + H];
+      }
+      uint32_t hi, lo = 0u;
+      if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
+      else hi = pack_bf16(w0, w1);
+      const uint32_t off = (uint32_t)(L >> 6) * (uint32_t)(H * 128) + sw128_offset((uint32_t)k, (uint32_t)(L & 63) >> 3) + (uint32_t)(L & 7) * 2u;
+      *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
+      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + part + off) = lo;
     }
-    uint32_t hi, lo = 0u;
-    if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
-    else hi = pack_bf16(w0, w1);
-    const uint32_t off = (uint32_t)(k >> 6) * kWBlk + sw128_offset((uint32_t)L, (uint32_t)(k & 63) >> 3) + (uint32_t)(k & 7) * 2u;
-    *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
-    if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + (size_t)KB * kWBlk + off) = lo;
+  } else {
+    for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += blockDim.x) {
+      const int L = idx / (H / 2), k = (idx % (H / 2)) * 2;
+      const size_t src = ((size_t)(L & 3) * H + kUS * rank + (L >> 2)) * H + k;
+      float w0 = W[src], w1 = W[src + 1];
+      if (M != nullptr) {
+        w0 *= M[src];
+        w1 *= M[src + 1];
+      }
+      uint32_t hi, lo = 0u;
+      if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
+      else hi = pack_bf16(w0, w1);
+      const uint32_t off = (uint32_t)(k >> 6) * kWBlk + sw128_offset((uint32_t)L, (uint32_t)(k & 63) >> 3) + (uint32_t)(k & 7) * 2u;
+      *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
+      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + part + off) = lo;
+    }
   }
 }
 
@@ -221,9 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
     {
-      constexpr uint32_t idesc = idesc_bf16(kRows, kNS, false, false);
-      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, 0);
-      const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kNS * 16);
+      constexpr uint32_t idesc = idesc_bf16(kRows, kNS, true, false);  // A = W slice MN-major (M = gate rows), B = h tile K-major
+      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, (uint32_t)H * 128u);
+      const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kChunk);
       const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
       PROF_DECL;
       for (int s = 0; s < T; ++s) {
@@ -239,12 +262,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
           }
           PROF_MARK(i == 0 ? 0 : (i == 1 ? 2 : 3));  // wait for: my own slice | the first remote slice | the others
           if (i == 0) fence_after_sync();  // (the cell warps' tcgen05.ld of the previous step precede these MMAs)
-          // units [32 r, +32) = two k16 steps: A = 64 bytes of every row of block r / 2; B = the four unit chunks of source r
-          const uint64_t ah = a_base + (uint64_t)(((uint32_t)(r >> 1) * kWBlk + (uint32_t)(r & 1) * 64u) >> 4);
+          // units [32 r, +32) = two k16 steps: A = k-rows [32 r, +32) of both 64-row blocks; B = the four unit chunks of source r
+          const uint64_t ah = a_base + (uint64_t)(((uint32_t)r * 32u * 128u) >> 4);
           const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes) >> 4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint64_t ahj = ah + (uint64_t)(j * 2), bhj = bh + (uint64_t)(j * ((2 * kNS * 16) >> 4));
+            const uint64_t ahj = ah + (uint64_t)(j * ((16 * 128) >> 4)), bhj = bh + (uint64_t)(j * ((2 * kChunk) >> 4));
             mma_bf16_ss_elect(tb, ahj, bhj, idesc, (i | j) != 0);
             if constexpr (SPLIT) {
               mma_bf16_ss_elect(tb, ahj, bhj + b_lo, idesc, true);
@@ -341,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         lb16[e] = __float2bfloat16_rn(hv[e] - __bfloat162float(hb16[e]));
       }
       if (s + 1 < T) {  // my elements of the next step's B operand: [part][unit chunk = quarter][sequence][8 units x bf16]
-        unsigned char* dst = my_slot_ptr + (size_t)(buf ^ 1) * bufBytes + quarter * (kNS * 16) + gq * 2;
+        unsigned char* dst = my_slot_ptr + (size_t)(buf ^ 1) * bufBytes + quarter * kChunk + gq * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
