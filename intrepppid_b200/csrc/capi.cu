@@ -595,7 +595,7 @@ int ib200_encoder_bwd_layers(const ib200_cfg* cfg, const ib200_encoder_params* P
                      : (cluster ? launch_lstm_bwd_cluster(ba, H, prec, st) : launch_lstm_bwd(ba, H, prec, st)),
           "lstm bwd");
     // bias partial rows per direction left by the BPTT kernel
-    const int bwd_ctas = !planes ? 0 : (cluster_tc ? lstm_bwd_cluster_tc_cta_count(ba)
+    const int bwd_ctas = !planes ? 0 : (cluster_tc ? lstm_bwd_cluster_tc_cta_count(ba, H, prec)
                                                    : (cluster ? lstm_bwd_cluster_cta_count(ba, H, prec) : lstm_bwd_cta_count(ba, prec)));
 
     // layer 0 of the TMA path: dW_hh, dW_ih, the bias gradients and the embedding gradient from ONE pass over the dgates

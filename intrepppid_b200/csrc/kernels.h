@@ -96,7 +96,7 @@ cudaError_t launch_lstm_bwd_cluster(const LstmBwdArgs& a, int H, int precision, 
 // dh^T accumulated in TMEM, h all-gather by bulk DSMEM copies, dh reduce-scatter by st.async.  Same arguments / layouts as above;
 // 32 sequences per cluster.
 bool lstm_cluster_tc_supports(int H);
-int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a);
+int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a, int H, int precision);
 cudaError_t launch_lstm_fwd_cluster_tc(const LstmFwdArgs& a, int H, int precision, cudaStream_t st);
 cudaError_t launch_lstm_bwd_cluster_tc(const LstmBwdArgs& a, int H, int precision, cudaStream_t st);
 

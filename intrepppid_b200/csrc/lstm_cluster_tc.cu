@@ -21,6 +21,10 @@
 //     counted on the owner's mbarrier; the owner adds the C partials.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "kernels.h"
 #include "tc05.cuh"
@@ -43,15 +47,21 @@ using namespace tc;
 
 constexpr int kUS = 32;                 // hidden units per CTA
 constexpr int kRows = 4 * kUS;          // gate rows per CTA = UMMA M
-constexpr int kNS = 32;                 // sequences per cluster = UMMA N
+// sequences per cluster = UMMA N = 8 * NB (NB = 4 or 5 blocks of eight): 15 clusters of 8 CTAs are co-resident on a B200
+// (tools/probe_clusters.cu), so 256 sequences x 2 directions in tiles of 32 (16 clusters) would run in TWO waves; tiles of 40
+// (14 clusters) run in one
 constexpr int kCellWarps = 8;           // warps 0..7: TMEM read-out + cell math; warp 8: MMA issuer and TMEM owner
 constexpr int kCellThreads = 32 * kCellWarps;
 constexpr int kThreads = kCellThreads + 32;
 constexpr int kWBlk = kRows * 128;      // one [128 gate rows x 64 units] bf16 block of the resident W slice (128-byte swizzle)
-constexpr int kChunk = kNS * 16 + 16;   // byte pitch of one 8-row k chunk [32 sequences][16 B] of a B operand tile (+16: bank spread)
-constexpr int kHSlice = 4 * kChunk;     // forward: h slice of one source CTA and one part: [4 unit chunks][32 sequences][16 B]
-constexpr int kDaLbo = kChunk;          // backward: k-chunk pitch of the da tile
-constexpr int kXSlice = kUS * kNS * 4;  // backward: partial dh of one source CTA for my 32 units: [32 units][32 sequences] fp32
+template <int NB>
+struct TileT {
+  static constexpr int NS = 8 * NB;
+  static constexpr int kChunk = NS * 16 + 16;   // byte pitch of one 8-row k chunk [NS sequences][16 B] of a B operand tile (+16: bank spread)
+  static constexpr int kHSlice = 4 * kChunk;    // forward: h slice of one source CTA and one part: [4 unit chunks][NS sequences][16 B]
+  static constexpr int kXSlice = NS * kUS * 4;  // backward: partial dh of one source CTA for my 32 units: [NS sequences][32 units] fp32
+  static constexpr int JB = (NB + 1) / 2;       // 8-sequence blocks per cell warp (warp `half` takes the blocks b with b % 2 == half)
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -88,15 +98,20 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t sbo_
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100); layout type 0 = no swizzle
   return d;
 }
-// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread i of the warp reads lane base+i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+// 32 lanes x 8 consecutive 32-bit columns -> 8 registers per thread (thread i of the warp reads lane base+i); no wait
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// 16 lanes x 256 bits (8 columns): thread t of the warp gets rows t/4 and t/4 + 8 of the 16-lane window at columns 2(t%4), +1 -- the
+// mma.sync accumulator fragment: r[2*(row half) + column parity]; no wait
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
 }
 // tcgen05.mma / commit issued from WARP-UNIFORM code: all 32 lanes execute the instruction stream, one elected lane issues.  With
 // `if (lane == 0)` around a plain tcgen05.mma, ptxas cannot prove the descriptors uniform and wraps every MMA in an
@@ -133,15 +148,6 @@ __device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
 }
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cell_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCellThreads) : "memory"); }
-
-// 16 lanes x 256 bits, two repetitions (16 columns): thread t of the warp gets, for each 8-column block b, rows t/4 and t/4 + 8 of
-// the 16-lane window at columns 8b + 2(t%4), +1 -- the mma.sync accumulator fragment: r[4b + 2*(row half) + column parity]
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
 
 // resident W slice as the A operand, 128-byte swizzle, MN-major for the forward product and K-major for the backward one -- in both
 // kernels a k16 step of the MMA then reads 2 KB of CONTIGUOUS shared memory per 64-wide block (measured: 46 cycles per M=128 MMA
@@ -193,9 +199,12 @@ __device__ __forceinline__ void load_w_slice_tc(unsigned char* Wsm, const float*
 // =================================================================================================================================
 // forward
 // =================================================================================================================================
-template <bool SPLIT, bool TRAIN>
+template <int NB, bool SPLIT, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFwdArgs p, const int H) {
-  constexpr int NPART = SPLIT ? 2 : 1;
+  using TT = TileT<NB>;
+  constexpr int NS = TT::NS, JB = TT::JB, NCELL = 2 * JB, NPART = SPLIT ? 2 : 1;
+  constexpr int kChunk = TT::kChunk, kHSlice = TT::kHSlice;
+  constexpr uint32_t kTmemCols = NS <= 32 ? 32 : 64;
   constexpr bool FAST = !SPLIT;
   const int C = H / kUS, KB = H / 64;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -203,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];
   if (T <= 0) return;  // uniform over the cluster
-  const int b0 = tile * kNS, nvalid = min(kNS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
+  const int b0 = tile * NS, nvalid = min(NS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
   const bool layer0 = p.tok != nullptr;
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* Wsm = smem;                                   // [NPART][KB][kWBlk]
+  unsigned char* Wsm = smem;                                   // [NPART][2 m blocks][H k-rows x 128 B]
   unsigned char* hB = Wsm + (size_t)NPART * KB * kWBlk;        // [2 buffers][C source CTAs][NPART][kHSlice]: B operand of the step
   const uint32_t sliceBytes = NPART * kHSlice, bufBytes = (uint32_t)C * sliceBytes;
   // hbar[buffer][source CTA]: "the slice of h that CTA `source` owns has landed in buffer b" -- the MMAs of a step start on the
@@ -228,12 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     mbar_init(mma_bar, 1);
     mbar_init_fence();
     for (int r = 0; r < C; ++r) {
-      if (r == rank) continue;  // (my own slice: a plain arrive of the publishing thread)
+      if (r == rank) continue;  // (my own slice: a plain arrive of the publishing warp)
       if (T > 1) mbar_arrive_expect_tx(&hbar[C + r], sliceBytes);  // h_0 -> buffer 1
       if (T > 2) mbar_arrive_expect_tx(&hbar[r], sliceBytes);      // h_1 -> buffer 0
     }
   }
-  if (wid == kCellWarps) tmem_alloc(tmem_slot, 32);
+  if (wid == kCellWarps) tmem_alloc(tmem_slot, kTmemCols);
   fence_async_smem();  // the generic-proxy writes above (W slice, zero h tile) are operands of the tensor core (async proxy)
   fence_before_sync();
   __syncthreads();
@@ -243,78 +252,78 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 
   if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = idesc_bf16(kRows, kNS, true, false);  // A = W slice MN-major (M = gate rows), B = h tile K-major
-      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, (uint32_t)H * 128u);
-      const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kChunk);
-      const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
-      PROF_DECL;
-      for (int s = 0; s < T; ++s) {
-        const int buf = s & 1;
-        const uint32_t par = (uint32_t)(((s - 1) >> 1) & 1);
-        const uint64_t bb = b_base + (uint64_t)(((uint32_t)buf * bufBytes) >> 4);
-        for (int i = 0; i < C; ++i) {
-          const int r = rank + i < C ? rank + i : rank + i - C;  // source CTA: mine first, then in ring order
-          PROF_MARK(1);
-          if (s > 0) {
-            mbar_wait(&hbar[buf * C + r], par);
-            if (r != rank && s + 2 < T) mbar_arrive_expect_tx_elect(&hbar[buf * C + r], sliceBytes);  // next fill: h_{s+1}
-          }
-          PROF_MARK(i == 0 ? 0 : (i == 1 ? 2 : 3));  // wait for: my own slice | the first remote slice | the others
-          if (i == 0) fence_after_sync();  // (the cell warps' tcgen05.ld of the previous step precede these MMAs)
-          // units [32 r, +32) = two k16 steps: A = k-rows [32 r, +32) of both 64-row blocks; B = the four unit chunks of source r
-          const uint64_t ah = a_base + (uint64_t)(((uint32_t)r * 32u * 128u) >> 4);
-          const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes) >> 4);
+    constexpr uint32_t idesc = idesc_bf16(kRows, NS, true, false);  // A = W slice MN-major (M = gate rows), B = h tile K-major
+    const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, (uint32_t)H * 128u);
+    const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kChunk);
+    const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
+    PROF_DECL;
+    for (int s = 0; s < T; ++s) {
+      const int buf = s & 1;
+      const uint32_t par = (uint32_t)(((s - 1) >> 1) & 1);
+      const uint64_t bb = b_base + (uint64_t)(((uint32_t)buf * bufBytes) >> 4);
+      for (int i = 0; i < C; ++i) {
+        const int r = rank + i < C ? rank + i : rank + i - C;  // source CTA: mine first, then in ring order
+        PROF_MARK(1);
+        if (s > 0) {
+          mbar_wait(&hbar[buf * C + r], par);
+          if (r != rank && s + 2 < T) mbar_arrive_expect_tx_elect(&hbar[buf * C + r], sliceBytes);  // next fill: h_{s+1}
+        }
+        PROF_MARK(i == 0 ? 0 : (i == 1 ? 2 : 3));  // wait for: my own slice | the first remote slice | the others
+        if (i == 0) fence_after_sync();  // (the cell warps' tcgen05.ld of the previous step precede these MMAs)
+        // units [32 r, +32) = two k16 steps: A = k-rows [32 r, +32) of both 64-row blocks; B = the four unit chunks of source r
+        const uint64_t ah = a_base + (uint64_t)(((uint32_t)r * 32u * 128u) >> 4);
+        const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes) >> 4);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t ahj = ah + (uint64_t)(j * ((16 * 128) >> 4)), bhj = bh + (uint64_t)(j * ((2 * kChunk) >> 4));
-            mma_bf16_ss_elect(tb, ahj, bhj, idesc, (i | j) != 0);
-            if constexpr (SPLIT) {
-              mma_bf16_ss_elect(tb, ahj, bhj + b_lo, idesc, true);
-              mma_bf16_ss_elect(tb, ahj + a_lo, bhj, idesc, true);
-            }
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t ahj = ah + (uint64_t)(j * ((16 * 128) >> 4)), bhj = bh + (uint64_t)(j * ((2 * kChunk) >> 4));
+          mma_bf16_ss_elect(tb, ahj, bhj, idesc, (i | j) != 0);
+          if constexpr (SPLIT) {
+            mma_bf16_ss_elect(tb, ahj, bhj + b_lo, idesc, true);
+            mma_bf16_ss_elect(tb, ahj + a_lo, bhj, idesc, true);
           }
         }
-        mma_commit_elect(mma_bar);
-        PROF_MARK(1);
       }
-      PROF_PRINT("fwd mma  [own-wait issue first-remote-wait other-remote-waits]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
+      mma_commit_elect(mma_bar);
+      PROF_MARK(1);
     }
+    PROF_PRINT("fwd mma  [own-wait issue first-remote-wait other-remote-waits]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
   } else {
     // ===================== cell warps =====================
-    // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) x columns [16 half, +16) with the 16x256b shape:
-    // rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit 8 quarter + gq, for the
-    // sequences 16 half + 8 b + 2 tig + (0, 1): four whole cells per thread, no exchange between lanes
+    // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) with the 16x256b shape, 8-column blocks
+    // b = 2 jb + half: rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit
+    // 8 quarter + gq, for the sequences 8 b + 2 tig + (0, 1): whole cells per thread, no exchange between lanes
     const int quarter = wid & 3, half = wid >> 2, gq = lane >> 2, tig = lane & 3;
     const int u = kUS * rank + 8 * quarter + gq;
     const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
     const int pad_row = p.V + (int)((tile + gridDim.x / C * (blockIdx.y + gridDim.y * blockIdx.z)) % kPadRows);
-    int ncell[4], rowb[4];   // sequence of cell e inside the tile; its first token row (columns beyond the batch: clamped, never stored)
-    uint32_t xoff[4];
-    bool valid[4];
+    int ncell[NCELL], rowb[NCELL];  // sequence of cell e inside the tile; its first token row (beyond the batch: clamped, never stored)
+    uint32_t xoff[NCELL];
+    bool valid[NCELL];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ncell[e] = 16 * half + 8 * (e >> 1) + 2 * tig + (e & 1);
-      valid[e] = ncell[e] < nvalid;
+    for (int e = 0; e < NCELL; ++e) {
+      const int b = 2 * (e >> 1) + half;  // (a block b >= NB exists only for odd NB, half 1: its cells are computed and dropped)
+      ncell[e] = 8 * b + 2 * tig + (e & 1);
+      valid[e] = b < NB && ncell[e] < nvalid;
       const int ncl = min(ncell[e], nvalid - 1);
       rowb[e] = (nbase + ncl) * Tmax;
       xoff[e] = (uint32_t)ncl * (uint32_t)Tmax * (uint32_t)H;  // float4 units, relative to the tile's first sequence
     }
+    const int nblk = (NB - half + 1) / 2;  // blocks of this warp
     // layer >= 1: dense input projection rows [N, Tmax, 4H] (GI: one float4 per cell); layer 0: table rows by token
     const float4* const xdense = layer0 ? nullptr : reinterpret_cast<const float4*>(dir ? p.xproj[1] : p.xproj[0]) + (size_t)nbase * Tmax * H + u;
     const float4* const xtab = layer0 ? reinterpret_cast<const float4*>(p.table) + (size_t)((p.table_shared ? 0 : g) * 2 + dir) * (p.V + kPadRows) * H + u : nullptr;
-    auto load_tok = [&](int s, int (&tk)[4]) {
+    auto load_tok = [&](int s, int (&tk)[NCELL]) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) tk[e] = __ldg(p.tok + (size_t)rowb[e] + t_first + s * dt);
+      for (int e = 0; e < NCELL; ++e) tk[e] = __ldg(p.tok + (size_t)rowb[e] + t_first + s * dt);
     };
-    auto load_x = [&](int s, const int (&tk)[4], float4 (&x)[4]) {  // (layer 0: tk = the tokens of step s)
+    auto load_x = [&](int s, const int (&tk)[NCELL], float4 (&x)[NCELL]) {  // (layer 0: tk = the tokens of step s)
       if (layer0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) x[e] = __ldg(xtab + (size_t)(tk[e] == 0 ? pad_row : tk[e]) * H);  // pads: this cluster's copy of row 0
+        for (int e = 0; e < NCELL; ++e) x[e] = __ldg(xtab + (size_t)(tk[e] == 0 ? pad_row : tk[e]) * H);  // pads: this cluster's copy of row 0
       } else {
         const float4* xt = xdense + (ptrdiff_t)(t_first + s * dt) * H;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) x[e] = __ldg(xt + xoff[e]);
+        for (int e = 0; e < NCELL; ++e) x[e] = __ldg(xt + xoff[e]);
       }
     };
 
@@ -322,15 +331,19 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     float* const Cst = TRAIN ? (dir ? p.cstate[1] : p.cstate[0]) + u : nullptr;
     const bool has_y = p.y != nullptr;
     const int ycol = dir * H + u, ystr = p.y_stride;
-    float cst[4] = {0.f, 0.f, 0.f, 0.f}, hv[4] = {0.f, 0.f, 0.f, 0.f};
+    float cst[NCELL], hv[NCELL];
+#pragma unroll
+    for (int e = 0; e < NCELL; ++e) cst[e] = hv[e] = 0.f;
     const uint32_t my_slot = smem_u32(hB) + (uint32_t)rank * sliceBytes;  // + buffer offset: my slice of the h tile
     unsigned char* const my_slot_ptr = hB + (size_t)rank * sliceBytes;
-    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(16 * half);
+    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(8 * half);
 
     // input projection of the current step (register prefetch: the next step's loads are issued right after this step's values have
     // been consumed and the h slice is on its way; tokens two steps ahead)
-    float4 xc[4];
-    int tk[4] = {0, 0, 0, 0};
+    float4 xc[NCELL];
+    int tk[NCELL];
+#pragma unroll
+    for (int e = 0; e < NCELL; ++e) tk[e] = 0;
     if (layer0) load_tok(0, tk);
     load_x(0, tk, xc);
     if (layer0 && T > 1) load_tok(1, tk);
@@ -341,23 +354,30 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       mbar_wait(mma_bar, (uint32_t)(s & 1));
       PROF_MARK(1);
       fence_after_sync();
-      uint32_t ra[8], rb[8];
-      tmem_ld_16x256b_x2(taddr, ra);
-      tmem_ld_16x256b_x2(taddr + (16u << 16), rb);
+      uint32_t ra[JB][4], rb[JB][4];
+#pragma unroll
+      for (int jb = 0; jb < JB; ++jb) {
+        if (jb < nblk) {
+          tmem_ld_16x256b_x1(taddr + (uint32_t)(16 * jb), ra[jb]);
+          tmem_ld_16x256b_x1(taddr + (uint32_t)(16 * jb) + (16u << 16), rb[jb]);
+        } else {
+          ra[jb][0] = ra[jb][1] = ra[jb][2] = ra[jb][3] = rb[jb][0] = rb[jb][1] = rb[jb][2] = rb[jb][3] = 0u;
+        }
+      }
       tmem_wait_ld();
       fence_before_sync();
       PROF_MARK(2);
 
       const int t = t_first + s * dt;
-      float gi[4], gf[4], gg[4], go[4];
-      __nv_bfloat16 hb16[4], lb16[4];
+      float gi[NCELL], gf[NCELL], gg[NCELL], go[NCELL];
+      __nv_bfloat16 hb16[NCELL], lb16[NCELL];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ia = 4 * (e >> 1) + (e & 1);
-        gi[e] = sigmoid_f<FAST>(__uint_as_float(ra[ia]) + xc[e].x);
-        gf[e] = sigmoid_f<FAST>(__uint_as_float(ra[ia + 2]) + xc[e].y);
-        gg[e] = tanh_f<FAST>(__uint_as_float(rb[ia]) + xc[e].z);
-        go[e] = sigmoid_f<FAST>(__uint_as_float(rb[ia + 2]) + xc[e].w);
+      for (int e = 0; e < NCELL; ++e) {
+        const int jb = e >> 1, pc = e & 1;
+        gi[e] = sigmoid_f<FAST>(__uint_as_float(ra[jb][pc]) + xc[e].x);
+        gf[e] = sigmoid_f<FAST>(__uint_as_float(ra[jb][2 + pc]) + xc[e].y);
+        gg[e] = tanh_f<FAST>(__uint_as_float(rb[jb][pc]) + xc[e].z);
+        go[e] = sigmoid_f<FAST>(__uint_as_float(rb[jb][2 + pc]) + xc[e].w);
         cst[e] = fmaf(gf[e], cst[e], gi[e] * gg[e]);
         hv[e] = go[e] * tanh_f<FAST>(cst[e]);
         hb16[e] = __float2bfloat16_rn(hv[e]);
@@ -366,9 +386,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       if (s + 1 < T) {  // my elements of the next step's B operand: [part][unit chunk = quarter][sequence][8 units x bf16]
         unsigned char* dst = my_slot_ptr + (size_t)(buf ^ 1) * bufBytes + quarter * kChunk + gq * 2;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
-          if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
+        for (int e = 0; e < NCELL; ++e) {
+          if ((e >> 1) < nblk) {
+            *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
+            if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
+          }
         }
         PROF_MARK(3);
         fence_async_smem();  // my slice (generic-proxy stores) is read by the bulk copies and by my own tensor core (async proxy)
@@ -386,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         if (layer0 && s + 2 < T) load_tok(s + 2, tk);
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NCELL; ++e) {
         if (valid[e]) {
           const size_t row = (size_t)(rowb[e] + t);
           if constexpr (TRAIN) {
@@ -407,14 +429,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     if (p.hn != nullptr) {
       const size_t N = (size_t)p.G * p.B;
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
+      for (int e = 0; e < NCELL; ++e)
         if (valid[e]) p.hn[((size_t)dir * N + nbase + ncell[e]) * H + u] = hv[e];
     }
   }
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // nobody exits while a peer's copy could still read from or write to it
-  if (wid == kCellWarps) tmem_dealloc(tb, 32);
+  if (wid == kCellWarps) tmem_dealloc(tb, kTmemCols);
 
   // planes mode: the weight-gradient GEMM reads whole 64-row TMA boxes (and the row after the last one for the shifted operand): rows
   // [T, tail_end) of this cluster's sequences must be zeros in this CTA's 32 columns of this direction (both planes)
@@ -432,28 +454,35 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 // =================================================================================================================================
 // backward
 // =================================================================================================================================
-template <bool SPLIT>
+template <int NB, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBwdArgs p, const int H) {
-  constexpr int NPART = SPLIT ? 2 : 1;
+  using TT = TileT<NB>;
+  constexpr int NS = TT::NS, JB = TT::JB, NPART = SPLIT ? 2 : 1;
+  constexpr int kChunk = TT::kChunk, kXSlice = TT::kXSlice;
   constexpr bool FAST = !SPLIT;
   const int C = H / kUS, KB = H / 64, NACC = H / 128;
+  const uint32_t kTmemCols = NACC * NS <= 32 ? 32 : (NACC * NS <= 64 ? 64 : 128);
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank(), tile = (int)blockIdx.x / C;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
   const int T = p.lens[p.G + g];
   if (T <= 0) return;
-  const int b0 = tile * kNS, nvalid = min(kNS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
+  const int b0 = tile * NS, nvalid = min(NS, p.B - b0), nbase = g * p.B + b0, Tmax = p.Tmax;
   const size_t N = (size_t)p.G * p.B;
   const bool has_dy = p.dy != nullptr, planes = p.planes != 0;
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* Wsm = smem;                                   // [NPART][KB][kWBlk]
-  unsigned char* daB = Wsm + (size_t)NPART * KB * kWBlk;       // [NPART][16 k chunks][kDaLbo]: B operand (da of my 128 gate rows)
-  constexpr uint32_t kDaPart = 16 * kDaLbo;
-  float* xbuf = reinterpret_cast<float*>(daB + NPART * kDaPart);  // [2][C sources][32 units][32 seq] partial dh for my units (16-byte swizzle)
-  const uint32_t xBufBytes = (uint32_t)C * kXSlice;
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xbuf) + 2 * (size_t)xBufBytes);  // [2]
+  unsigned char* daB = Wsm + (size_t)NPART * KB * kWBlk;       // [NPART][16 k chunks][kChunk]: B operand (da of my 128 gate rows)
+  constexpr uint32_t kDaPart = 16 * kChunk;
+  // partial dh for my 32 units: xbuf[2 buffers][C - 1 remote CTAs][NS sequences][32 units] fp32 (slot of CTA r: (r - rank - 1) mod C)
+  // + xown[NS][32]: my own partial.  The idle receive buffer doubles as the staging area of the outgoing slices (see below).
+  float* xbuf = reinterpret_cast<float*>(daB + NPART * kDaPart);
+  const uint32_t xBufBytes = (uint32_t)(C - 1) * kXSlice;
+  float* xown = xbuf + 2 * (size_t)(xBufBytes / 4);
+  // xbar[buffer]: "all partials of this step are in place": C - 1 bulk copies (complete_tx) + the two warps that wrote xown
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(xown + kXSlice / 4);
   uint64_t* da_bar = xbar + 2;   // "the da tile of this step is complete" (all cell threads arrive)
   uint64_t* mma_bar = xbar + 3;  // [2]: "the step's MMAs into accumulator a have completed" (accumulator 0 is sent while 1 is computed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 5);
@@ -465,8 +494,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   }
   for (int i = tid; i < (int)(NPART * kDaPart / 4); i += kThreads) reinterpret_cast<uint32_t*>(daB)[i] = 0u;
   if (tid == 0) {
-    mbar_init(&xbar[0], 1);
-    mbar_init(&xbar[1], 1);
+    mbar_init(&xbar[0], 3);
+    mbar_init(&xbar[1], 3);
     mbar_init(da_bar, kCellThreads);
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
@@ -474,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     if (T > 1) mbar_arrive_expect_tx(&xbar[1], xBufBytes);  // step s fills buffer (s + 1) & 1: step 0 -> buffer 1, step 1 -> buffer 0
     if (T > 2) mbar_arrive_expect_tx(&xbar[0], xBufBytes);
   }
-  if (wid == kCellWarps) tmem_alloc(tmem_slot, 64);
+  if (wid == kCellWarps) tmem_alloc(tmem_slot, kTmemCols);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -485,59 +514,57 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
 
   if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = idesc_bf16(128, kNS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
-      const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
-      const uint64_t b_base = smem_desc_nosw(smem_u32(daB), 128, kDaLbo);
-      const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kDaPart >> 4);
-      PROF_DECL;
-      for (int s = 0; s + 1 < T; ++s) {
-        mbar_wait(da_bar, (uint32_t)(s & 1));
-        PROF_MARK(0);
-        fence_after_sync();
-        for (int a = 0; a < NACC; ++a) {
-          const uint64_t aa = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk) >> 4);
+    constexpr uint32_t idesc = idesc_bf16(128, NS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
+    const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
+    const uint64_t b_base = smem_desc_nosw(smem_u32(daB), 128, kChunk);
+    const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kDaPart >> 4);
+    PROF_DECL;
+    for (int s = 0; s + 1 < T; ++s) {
+      mbar_wait(da_bar, (uint32_t)(s & 1));
+      PROF_MARK(0);
+      fence_after_sync();
+      for (int a = 0; a < NACC; ++a) {
+        const uint64_t aa = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk) >> 4);
 #pragma unroll
-          for (int k16 = 0; k16 < kRows / 16; ++k16) {
-            // k = gate rows [16 k16, +16): A = 16 k-rows of 128 bytes inside the two 64-unit blocks 2a, 2a+1; B = k chunks 2 k16, +1
-            const uint64_t ah = aa + (uint64_t)((k16 * 16 * 128) >> 4);
-            const uint64_t bh = b_base + (uint64_t)((2 * k16 * kDaLbo) >> 4);
-            mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah, bh, idesc, k16 != 0);
-            if constexpr (SPLIT) {
-              mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah, bh + b_lo, idesc, true);
-              mma_bf16_ss_elect(tb + (uint32_t)a * kNS, ah + a_lo, bh, idesc, true);
-            }
+        for (int k16 = 0; k16 < kRows / 16; ++k16) {
+          // k = gate rows [16 k16, +16): A = 16 k-rows of 128 bytes inside the two 64-unit blocks 2a, 2a+1; B = k chunks 2 k16, +1
+          const uint64_t ah = aa + (uint64_t)((k16 * 16 * 128) >> 4);
+          const uint64_t bh = b_base + (uint64_t)((2 * k16 * kChunk) >> 4);
+          mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah, bh, idesc, k16 != 0);
+          if constexpr (SPLIT) {
+            mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah, bh + b_lo, idesc, true);
+            mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah + a_lo, bh, idesc, true);
           }
-          mma_commit_elect(&mma_bar[a]);
         }
-        PROF_MARK(1);
+        mma_commit_elect(&mma_bar[a]);
       }
-      PROF_PRINT("bwd mma  [wait-da issue]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
+      PROF_MARK(1);
     }
+    PROF_PRINT("bwd mma  [wait-da issue]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
   } else {
-    // ===================== cell warps: lane = local unit, warp wi owns sequences 4 wi .. 4 wi + 3 =====================
-    const int wi = wid, u = kUS * rank + lane, s0 = 4 * wi;
+    // ===================== cell warps: lane = local unit, warp wi owns sequences NB wi .. NB wi + NB - 1 =====================
+    const int wi = wid, u = kUS * rank + lane, s0 = NB * wi;
     const int t_first = dir ? 0 : T - 1, dt = dir ? 1 : -1;  // backward scan: t = T-1..0 (forward chain) or 0..T-1 (reverse chain)
     float4* const G4 = reinterpret_cast<float4*>(dir ? p.gates[1] : p.gates[0]) + u;
     const float* const Cst = (dir ? p.cstate[1] : p.cstate[0]) + u;
     const float* const DY = has_dy ? p.dy + dir * H + u : nullptr;
     const int dy_stride = p.dy_stride;
-    bool valid[4];
-    int rowb[4];  // first token row of my cell's sequence (columns beyond the batch: clamped for loads, zeroed, never stored)
+    bool valid[NB];
+    int rowb[NB];  // first token row of my cell's sequence (columns beyond the batch: clamped for loads, zeroed, never stored)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NB; ++e) {
       valid[e] = s0 + e < nvalid;
       rowb[e] = (nbase + min(s0 + e, nvalid - 1)) * Tmax;
     }
     struct In {
-      float4 g[4];
-      float cprev[4], dy[4];
+      float4 g[NB];
+      float cprev[NB], dy[NB];
     };
     auto load_in = [&](int s, In& in) {
       const int t = t_first + s * dt;
       const bool has_prev = s + 1 < T;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NB; ++e) {
         const size_t row = (size_t)(rowb[e] + t);
         in.g[e] = G4[row * H];
         in.cprev[e] = has_prev ? Cst[(row + dt) * H] : 0.f;  // c of the scan predecessor; 0 at the chain start
@@ -546,10 +573,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     };
     // everything of a cell step that does not depend on the recurrent gradient is formed ahead of it (while the previous step's MMAs
     // and exchange are in flight):  dh = dhrec + dy;  dct = dh * A + dc;  da = (dct Fi, dct Ff, dct Fg, dh Fo);  dc' = dct * gf
-    float fA[4], fI[4], fF[4], fG[4], fO[4], fDy[4], fGf[4];
-    auto prep = [&](const In& in, const float (&ccur)[4]) {
+    float fA[NB], fI[NB], fF[NB], fG[NB], fO[NB], fDy[NB], fGf[NB];
+    auto prep = [&](const In& in, const float (&ccur)[NB]) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NB; ++e) {
         const bool ok = valid[e];
         const float gi = ok ? in.g[e].x : 0.f, gf = ok ? in.g[e].y : 0.f, gg = ok ? in.g[e].z : 0.f, go = ok ? in.g[e].w : 0.f;
         const float tc = tanh_f<FAST>(ccur[e]);
@@ -562,37 +589,39 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         fGf[e] = gf;
       }
     };
-    float dc[4] = {0.f, 0.f, 0.f, 0.f}, dhrec[4] = {0.f, 0.f, 0.f, 0.f};
+    float dc[NB], dhrec[NB];
     // my da values in the B tile: k = 4 lane + gate -> chunk lane/2, bytes (lane & 1) * 8 of the 16-byte row of sequence n
-    unsigned char* const da_put = daB + (size_t)(lane >> 1) * kDaLbo + (size_t)(lane & 1) * 8 + (size_t)s0 * 16;
-    // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) x columns [16 half, +16) of every accumulator; lane = unit
+    unsigned char* const da_put = daB + (size_t)(lane >> 1) * kChunk + (size_t)(lane & 1) * 8 + (size_t)s0 * 16;
+    // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) of every accumulator, 8-column groups 2 j + half; lane = unit
     // 128 a + 32 quarter + lane, which CTA 4a + quarter owns as its local unit `lane`
     const int quarter = wid & 3, half = wid >> 2;
+    const int ngrp = (NB - half + 1) / 2;
     const uint32_t xb_local = smem_u32(xbuf), xbar_local = smem_u32(xbar);
 
     // `in` holds the saved gates / c / dy of the NEXT step (register prefetch: loaded one step ahead, consumed by prep() in the shadow
     // of this step's MMAs, reloaded right after); ccur = the cell state of the step whose factors prep() forms next
     In in;
-    float ccur[4];
+    float ccur[NB];
     load_in(0, in);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NB; ++e) {
       ccur[e] = Cst[(size_t)(rowb[e] + t_first) * H];
+      dc[e] = 0.f;
       dhrec[e] = (valid[e] && p.dhn != nullptr) ? p.dhn[((size_t)dir * N + nbase + s0 + e) * H + u] : 0.f;
     }
     prep(in, ccur);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ccur[e] = in.cprev[e];
+    for (int e = 0; e < NB; ++e) ccur[e] = in.cprev[e];
     if (T > 1) load_in(1, in);
     PROF_DECL;
     for (int s = 0; s < T; ++s) {
       PROF_MARK(0);
       const int t = t_first + s * dt;
       const bool more = s + 1 < T;
-      uint32_t h0[4], h1[4], l0[4], l1[4];
-      float da[4][4];
+      uint32_t h0[NB], h1[NB], l0[NB], l1[NB];
+      float da[NB][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NB; ++e) {
         const float dh = dhrec[e] + fDy[e];
         const float dct = fmaf(dh, fA[e], dc[e]);
         dc[e] = dct * fGf[e];
@@ -621,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
       PROF_MARK(2);
       // off the chain: dgates overwrite the saved gates in place; bias-gradient column sums
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NB; ++e) {
         if (valid[e]) {
           float4* gp = G4 + (size_t)(rowb[e] + t) * H;
           if (planes) {
@@ -639,49 +668,62 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
       if (!more) break;
       prep(in, ccur);  // the next step's factors
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ccur[e] = in.cprev[e];
+      for (int e = 0; e < NB; ++e) ccur[e] = in.cprev[e];
       if (s + 2 < T) load_in(s + 2, in);
       PROF_MARK(4);
 
-      // partial dh^T[H, 32] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter: my TMEM rows of accumulator a are units of CTA
-      // 4a + quarter.  They are staged in the IDLE receive buffer (xbuf[s & 1] took step s-1's partials, summed long ago), slot = the
-      // destination, and go out as ONE bulk copy per destination (the copy engine moves them: 16-byte remote stores from the cell
-      // warps kept the load/store pipe busy for ~2500 cycles per step).  Slot d of the idle buffer is next written by CTA d's own
-      // step-(s+1) copy, which CTA d can only issue after it has received this one.
+      // partial dh^T[H, NS] = Wslice^T da is in TMEM once mma_bar flips; reduce-scatter: my TMEM rows of accumulator a are units of CTA
+      // 4a + quarter.  They are staged in the IDLE receive buffer (xbuf[s & 1] took step s-1's partials, summed long ago), in the slot
+      // of the destination, and go out as ONE bulk copy per destination (the copy engine moves them: 16-byte remote stores from the
+      // cell warps kept the load/store pipe busy for ~2500 cycles per step).  The slot of CTA d in my idle buffer is next written by
+      // CTA d's own step-(s+1) copy, which CTA d can only issue after it has received this one.  My own partial goes to xown.
       const int xb = (s + 1) & 1;
       for (int a = 0; a < NACC; ++a) {
         mbar_wait(&mma_bar[a], (uint32_t)(s & 1));
         PROF_MARK(5);
         fence_after_sync();
-        uint32_t r[16];
-        tmem_ld16(tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)a * kNS + (uint32_t)(16 * half), r);
-        const uint32_t owner = (uint32_t)(4 * a + quarter);
-        float* stg = xbuf + (size_t)(s & 1) * (xBufBytes / 4) + (size_t)owner * (kXSlice / 4) + (size_t)lane * kNS;
+        uint32_t r[JB][8];
 #pragma unroll
-        for (int sg = 0; sg < 4; ++sg)  // 16-byte piece = sequences [4 (4 half + sg), +4); stored at piece index ^ (unit & 7)
-          *reinterpret_cast<uint4*>(stg + ((4 * half + sg) ^ (lane & 7)) * 4) = make_uint4(r[4 * sg], r[4 * sg + 1], r[4 * sg + 2], r[4 * sg + 3]);
-        fence_async_smem();
-        pair_bar_sync(2 + quarter);  // the two warps (quarter, half 0 | 1) hold the 32 sequences of this slice between them
-        if (half == 0) {
-          const uint32_t src = xb_local + (uint32_t)(s & 1) * xBufBytes + owner * kXSlice;
-          bulk_s2c_elect(map_to_rank(xb_local, owner) + (uint32_t)xb * xBufBytes + (uint32_t)rank * kXSlice, src, kXSlice,
-                         map_to_rank(xbar_local, owner) + (uint32_t)xb * 8u);
+        for (int j = 0; j < JB; ++j)
+          if (j < ngrp) tmem_ld8_nowait(tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * NS + 8 * (2 * j + half)), r[j]);
+        tmem_wait_ld();
+        const int owner = 4 * a + quarter;
+        const int slot = owner - rank - 1 + (owner > rank ? 0 : C);  // (owner - rank - 1) mod C; == C - 1 for my own units
+        float* stg = owner == rank ? xown : xbuf + (size_t)(s & 1) * (xBufBytes / 4) + (size_t)slot * (kXSlice / 4);
+#pragma unroll
+        for (int j = 0; j < JB; ++j)
+          if (j < ngrp) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stg[(8 * (2 * j + half) + i) * kUS + lane] = __uint_as_float(r[j][i]);
+          }
+        if (owner == rank) {
+          __syncwarp();
+          mbar_arrive_elect(&xbar[xb]);  // (release: the cell threads that wait on xbar see my rows of xown)
+        } else {
+          fence_async_smem();
+          pair_bar_sync(2 + quarter);  // the two warps (quarter, half 0 | 1) hold the NS sequences of this slice between them
+          if (half == 0) {
+            const int back = rank - owner - 1 + (rank > owner ? 0 : C);  // my slot in the owner's buffers
+            bulk_s2c_elect(map_to_rank(xb_local, (uint32_t)owner) + (uint32_t)xb * xBufBytes + (uint32_t)back * kXSlice,
+                           xb_local + (uint32_t)(s & 1) * xBufBytes + (uint32_t)slot * kXSlice, kXSlice,
+                           map_to_rank(xbar_local, (uint32_t)owner) + (uint32_t)xb * 8u);
+          }
         }
         PROF_MARK(6);
       }
       fence_before_sync();
-      // all C partials of my units have landed (every CTA of the cluster, myself included, sent 32 units x 32 sequences)
+      // all C partials of my units are in place
       mbar_wait(&xbar[xb], (uint32_t)((s >> 1) & 1));
       PROF_MARK(7);
       if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[xb], xBufBytes);  // refilled at step s + 2
-      // recurrent gradient of my cells for the next step: sum of the C partials (sequences 4 wi .. 4 wi + 3 = piece wi of my unit row)
-      const float* xr = xbuf + (size_t)xb * (xBufBytes / 4) + (size_t)lane * kNS + (size_t)((wi ^ (lane & 7)) * 4);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r2 = 0; r2 < C; ++r2) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + (size_t)r2 * (kXSlice / 4));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      // recurrent gradient of my cells for the next step: sum of the C partials
+      const float* xr = xbuf + (size_t)xb * (xBufBytes / 4) + (size_t)s0 * kUS + lane;
+#pragma unroll
+      for (int e = 0; e < NB; ++e) dhrec[e] = xown[(s0 + e) * kUS + lane];
+      for (int r2 = 0; r2 < C - 1; ++r2) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) dhrec[e] += xr[(size_t)r2 * (kXSlice / 4) + e * kUS];
       }
-      dhrec[0] = acc.x; dhrec[1] = acc.y; dhrec[2] = acc.z; dhrec[3] = acc.w;
       PROF_MARK(8);
     }
     PROF_PRINT("bwd cell [loop chain-math+sts fence+arrive dgate-stores prep+prefetch wait-mma ld+send wait-xchg sum]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 255), T);
@@ -689,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // nobody exits while a peer could still be sending to it
-  if (wid == kCellWarps) tmem_dealloc(tb, 64);
+  if (wid == kCellWarps) tmem_dealloc(tb, kTmemCols);
 
   if (planes) {
     // (1) bias-gradient partials: one [4H] row (GI order) per (direction slot, group, tile); CTA `rank` owns columns [128 rank, +128)
@@ -721,22 +763,60 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   }
 }
 
+template <int NB>
 size_t fwd_smem_tc(int H, bool split) {
-  const int npart = split ? 2 : 1;
-  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)2 * (H / kUS) * npart * kHSlice + (size_t)(2 * (H / kUS) + 1) * 8 + 64;
+  const int npart = split ? 2 : 1, C = H / kUS;
+  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)2 * C * npart * TileT<NB>::kHSlice + (size_t)(2 * C + 1) * 8 + 64;
 }
+template <int NB>
 size_t bwd_smem_tc(int H, bool split) {
-  const int npart = split ? 2 : 1;
-  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)npart * 16 * kDaLbo + (size_t)2 * (H / kUS) * kXSlice + 64;
+  const int npart = split ? 2 : 1, C = H / kUS;
+  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)npart * 16 * TileT<NB>::kChunk + (size_t)(2 * (C - 1) + 1) * TileT<NB>::kXSlice + 64;
+}
+
+// clusters of C CTAs of this kernel that are co-resident on the device (cached per kernel and shared-memory size)
+template <typename Kern>
+int max_active_clusters(Kern kern, int C, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, size_t>, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(reinterpret_cast<const void*>(kern), smem * 64 + (size_t)C);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(C * 64));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  if (n <= 0) n = C == 8 ? 15 : 148 / C;  // (measured on B200; only used when the query is not available)
+  cache[key] = n;
+  return n;
+}
+
+// tile width: 32 sequences per cluster unless tiles of 40 save a whole wave of clusters (a tile of 40 costs ~15 % more per step)
+int pick_nb(int clusters32, int clusters40, int max_active) {
+  const int w32 = (clusters32 + max_active - 1) / max_active, w40 = (clusters40 + max_active - 1) / max_active;
+  return 1.15 * w40 < (double)w32 ? 5 : 4;
 }
 
 template <typename Kern, typename Args>
-cudaError_t launch_cluster_tc(Kern kern, const Args& a, int H, size_t smem, int ndir, cudaStream_t st) {
+cudaError_t launch_cluster_tc(Kern kern, const Args& a, int H, int NS, size_t smem, int ndir, cudaStream_t st) {
   const int C = H / kUS;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(C * ((a.B + kNS - 1) / kNS)), (unsigned)a.G, (unsigned)ndir);
+  cfg.gridDim = dim3((unsigned)(C * ((a.B + NS - 1) / NS)), (unsigned)a.G, (unsigned)ndir);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -750,33 +830,69 @@ cudaError_t launch_cluster_tc(Kern kern, const Args& a, int H, size_t smem, int 
   return cudaLaunchKernelEx(&cfg, kern, a, H);
 }
 
+int forced_nb() {  // IB200_CLUSTER_NB = 4 | 5 pins the tile width (tests)
+  static const int v = [] { const char* e = getenv("IB200_CLUSTER_NB"); return e ? atoi(e) : 0; }();
+  return v == 4 || v == 5 ? v : 0;
+}
+
+int bwd_nb(const LstmBwdArgs& a, int H, bool split) {
+  if (forced_nb()) return forced_nb();
+  const int C = H / kUS, per = a.G * a.ndir;
+  const int ma = split ? max_active_clusters(lstm_bwd_cltc_kernel<4, true>, C, bwd_smem_tc<4>(H, true))
+                       : max_active_clusters(lstm_bwd_cltc_kernel<4, false>, C, bwd_smem_tc<4>(H, false));
+  if (bwd_smem_tc<5>(H, split) > 227 * 1024) return 4;
+  return pick_nb(per * ((a.B + 31) / 32), per * ((a.B + 39) / 40), ma);
+}
+
 }  // namespace
 
 bool lstm_cluster_tc_supports(int H) { return H == 128 || H == 256; }
 
 // bias partial rows written per direction by launch_lstm_bwd_cluster_tc in planes mode: one per (group, sequence tile)
-int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a) { return a.G * ((a.B + kNS - 1) / kNS); }
+int lstm_bwd_cluster_tc_cta_count(const LstmBwdArgs& a, int H, int precision) {
+  const int ns = 8 * bwd_nb(a, H, precision == 0);
+  return a.G * ((a.B + ns - 1) / ns);
+}
 
 cudaError_t launch_lstm_fwd_cluster_tc(const LstmFwdArgs& a, int H, int precision, cudaStream_t st) {
   if (!lstm_cluster_tc_supports(H)) return cudaErrorInvalidValue;
-  const bool split = precision == 0;
-  const size_t smem = fwd_smem_tc(H, split);
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   if (a.y != nullptr && !a.planes) return cudaErrorInvalidValue;  // this path writes y as bf16 planes only
-  const bool train = a.gates[a.dir0] != nullptr;
-  if (split) return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<true, true>, a, H, smem, a.ndir, st)
-                          : launch_cluster_tc(lstm_fwd_cltc_kernel<true, false>, a, H, smem, a.ndir, st);
-  return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<false, true>, a, H, smem, a.ndir, st)
-               : launch_cluster_tc(lstm_fwd_cltc_kernel<false, false>, a, H, smem, a.ndir, st);
+  const bool split = precision == 0, train = a.gates[a.dir0] != nullptr;
+  const int C = H / kUS, per = a.G * a.ndir;
+  int nb = forced_nb();
+  if (!nb) {
+    const size_t s4 = fwd_smem_tc<4>(H, split);
+    const int ma = split ? max_active_clusters(lstm_fwd_cltc_kernel<4, true, true>, C, s4) : max_active_clusters(lstm_fwd_cltc_kernel<4, false, true>, C, s4);
+    nb = fwd_smem_tc<5>(H, split) > 227 * 1024 ? 4 : pick_nb(per * ((a.B + 31) / 32), per * ((a.B + 39) / 40), ma);
+  }
+#define IB200_FWD_TC(NB_)                                                                                                          \
+  {                                                                                                                                \
+    const size_t smem = fwd_smem_tc<NB_>(H, split);                                                                                \
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;                                                                   \
+    if (split) return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<NB_, true, true>, a, H, 8 * NB_, smem, a.ndir, st)            \
+                            : launch_cluster_tc(lstm_fwd_cltc_kernel<NB_, true, false>, a, H, 8 * NB_, smem, a.ndir, st);          \
+    return train ? launch_cluster_tc(lstm_fwd_cltc_kernel<NB_, false, true>, a, H, 8 * NB_, smem, a.ndir, st)                      \
+                 : launch_cluster_tc(lstm_fwd_cltc_kernel<NB_, false, false>, a, H, 8 * NB_, smem, a.ndir, st);                    \
+  }
+  if (nb == 5) IB200_FWD_TC(5)
+  IB200_FWD_TC(4)
+#undef IB200_FWD_TC
 }
 
 cudaError_t launch_lstm_bwd_cluster_tc(const LstmBwdArgs& a, int H, int precision, cudaStream_t st) {
   if (!lstm_cluster_tc_supports(H)) return cudaErrorInvalidValue;
   const bool split = precision == 0;
-  const size_t smem = bwd_smem_tc(H, split);
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  return split ? launch_cluster_tc(lstm_bwd_cltc_kernel<true>, a, H, smem, a.ndir, st)
-               : launch_cluster_tc(lstm_bwd_cltc_kernel<false>, a, H, smem, a.ndir, st);
+  const int nb = bwd_nb(a, H, split);
+#define IB200_BWD_TC(NB_)                                                                                       \
+  {                                                                                                             \
+    const size_t smem = bwd_smem_tc<NB_>(H, split);                                                             \
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;                                                \
+    return split ? launch_cluster_tc(lstm_bwd_cltc_kernel<NB_, true>, a, H, 8 * NB_, smem, a.ndir, st)          \
+                 : launch_cluster_tc(lstm_bwd_cltc_kernel<NB_, false>, a, H, 8 * NB_, smem, a.ndir, st);        \
+  }
+  if (nb == 5) IB200_BWD_TC(5)
+  IB200_BWD_TC(4)
+#undef IB200_BWD_TC
 }
 
 }  // namespace ib200
