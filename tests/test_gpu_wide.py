@@ -49,10 +49,11 @@ def _encoder_case(E, L, bi, B, T, G, precision, seed=31):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("E,L,bi,B,T,G", [(128, 3, "mean", 9, 70, 2),     # 4-CTA clusters, 8 sequences per cluster
-                                          (256, 3, "mean", 13, 48, 1),    # config-5 architecture, 8-CTA clusters, 16 per cluster
-                                          (256, 2, "last", 27, 40, 1),    # 32 sequences per cluster, ragged last tile, dead chain
-                                          (96, 2, "max", 5, 33, 1)])      # 3-CTA clusters, column blocks 256+128 / 128+64
+@pytest.mark.parametrize("E,L,bi,B,T,G", [(128, 3, "mean", 9, 70, 2),     # 4-CTA clusters (tcgen05 kernels), one ragged tile per group
+                                          (256, 3, "mean", 13, 48, 1),    # config-5 architecture, 8-CTA clusters
+                                          (256, 2, "last", 27, 40, 1),    # ragged tile, dead chain
+                                          (256, 1, "mean", 75, 21, 1),    # several tiles per direction (3 of 32 / 2 of 40), ragged last one
+                                          (96, 2, "max", 5, 33, 1)])      # 3-CTA clusters (mma.sync kernels), column blocks 256+128 / 128+64
 def test_wide_encoder_vs_fp64_oracle(E, L, bi, B, T, G, precision):
     if bi == "max" and precision == "bf16":
         pytest.skip("max pooling routes the gradient through an argmax: bf16-level noise flips near-ties, no meaningful L2 gate")
@@ -71,6 +72,17 @@ def test_cluster_kernels_match_register_kernels_at_64():
     env = dict(os.environ, IB200_FORCE_CLUSTER="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                         "-k", "golden or fp64_oracle or seeded"], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env", [{"IB200_CLUSTER_TC": "0"}, {"IB200_CLUSTER_NB": "5"}, {"IB200_CLUSTER_NB": "4"}],
+                         ids=["mma_sync_cluster_kernels", "tcgen05_tiles_of_40", "tcgen05_tiles_of_32"])
+def test_wide_kernel_variants_agree_with_the_oracle(env):
+    """H = 128 / 256 run on the tcgen05 cluster kernels (lstm_cluster_tc.cu) with 32 or 40 sequences per cluster (chosen per launch
+    from the number of co-resident clusters); IB200_CLUSTER_TC=0 keeps the mma.sync cluster kernels.  Every variant must pass the
+    fp64-oracle parity cases of this file, so all three implementations of the wide recurrence stay pinned."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "wide_encoder_vs_fp64 or wide_training_step"], env=dict(os.environ, **env), capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
