@@ -52,7 +52,12 @@ constexpr int kRows = 4 * kUS;          // gate rows per CTA = UMMA M
 // (14 clusters) run in one
 constexpr int kCellWarps = 8;           // warps 0..7: TMEM read-out + cell math; warp 8: MMA issuer and TMEM owner
 constexpr int kCellThreads = 32 * kCellWarps;
-constexpr int kThreads = kCellThreads + 32;
+// 12 warps = three warpgroups: two of cell warps, one with the MMA issuer (+ three idle warps that only complete the warpgroup).  A CTA
+// of 9..12 warps gets 168 registers per thread at launch (three warps per scheduler partition); the third warpgroup hands its
+// registers back (setmaxnreg.dec) and the cell warps grow to 208 (setmaxnreg.inc): the cell code keeps its prefetched inputs and the
+// step's state in registers without spilling (a spilled prefetch register turns the prefetch into a blocking load).
+constexpr int kThreads = kCellThreads + 128;
+constexpr int kCellRegs = 208, kAuxRegs = 64;
 constexpr int kWBlk = kRows * 128;      // one [128 gate rows x 64 units] bf16 block of the resident W slice (128-byte swizzle)
 template <int NB>
 struct TileT {
@@ -147,6 +152,10 @@ __device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
   asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n @e mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+template <int REGS>
+__device__ __forceinline__ void reg_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 __device__ __forceinline__ void cell_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCellThreads) : "memory"); }
 
 // resident W slice as the A operand, 128-byte swizzle, MN-major for the forward product and K-major for the backward one -- in both
@@ -250,7 +259,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   cluster_sync_all();  // every CTA's tiles and barriers exist before any remote copy lands
   const uint32_t tb = *tmem_slot;
 
-  if (wid == kCellWarps) {
+  if (wid >= kCellWarps) {
+    reg_shrink<kAuxRegs>();
+  }
+  if (wid > kCellWarps) {
+    // (idle warps of the third warpgroup)
+  } else if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
     constexpr uint32_t idesc = idesc_bf16(kRows, NS, true, false);  // A = W slice MN-major (M = gate rows), B = h tile K-major
     const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, (uint32_t)H * 128u);
@@ -292,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) with the 16x256b shape, 8-column blocks
     // b = 2 jb + half: rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit
     // 8 quarter + gq, for the sequences 8 b + 2 tig + (0, 1): whole cells per thread, no exchange between lanes
+    reg_grow<kCellRegs>();
     const int quarter = wid & 3, half = wid >> 2, gq = lane >> 2, tig = lane & 3;
     const int u = kUS * rank + 8 * quarter + gq;
     const int t_first = dir ? T - 1 : 0, dt = dir ? -1 : 1;
@@ -512,7 +527,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   const uint32_t tb = *tmem_slot;
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of my cells' dgates over all steps (bias gradient partials)
 
-  if (wid == kCellWarps) {
+  if (wid >= kCellWarps) {
+    reg_shrink<kAuxRegs>();
+  }
+  if (wid > kCellWarps) {
+    // (idle warps of the third warpgroup)
+  } else if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
     constexpr uint32_t idesc = idesc_bf16(128, NS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
     const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
@@ -543,6 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     PROF_PRINT("bwd mma  [wait-da issue]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
   } else {
     // ===================== cell warps: lane = local unit, warp wi owns sequences NB wi .. NB wi + NB - 1 =====================
+    reg_grow<kCellRegs>();
     const int wi = wid, u = kUS * rank + lane, s0 = NB * wi;
     const int t_first = dir ? 0 : T - 1, dt = dir ? 1 : -1;  // backward scan: t = T-1..0 (forward chain) or 0..T-1 (reverse chain)
     float4* const G4 = reinterpret_cast<float4*>(dir ? p.gates[1] : p.gates[0]) + u;
