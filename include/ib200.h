@@ -46,7 +46,9 @@ extern "C" {
 
 enum { IB200_REDUCE_LAST = 0, IB200_REDUCE_MEAN = 1, IB200_REDUCE_MAX = 2 };
 /* IB200_PREC_FP32: bf16 hi/lo split operands (3 tensor-core MMAs per product, ~2^-16 operand error), fp32 state, exact-ish
- * exp/rcp activations, fp32 activation storage.  IB200_PREC_BF16: single bf16 MMA, tanh.approx, bf16 activation storage. */
+ * exp/rcp activations.  IB200_PREC_BF16: single bf16 MMA per product, tanh.approx activations.  In BOTH modes the saved
+ * activations (gates, c) are fp32 and the workspace size is the same; on the plane paths (H = 64 / 128 / 192 / 256) the layer
+ * outputs and dgates that feed the GEMMs are stored as bf16 planes (hi | lo in fp32 mode, hi only in bf16 mode). */
 enum { IB200_PREC_FP32 = 0, IB200_PREC_BF16 = 1 };
 /* Token id storage.  The reference ships int64 ids (data/ppi_oma.py:388-390, 8 B/token over PCIe); ids < V <= 256 fit a byte.
  * Narrow types are read as they are by the lengths kernel (which also makes the int32 working copy), so a caller that feeds
