@@ -444,10 +444,16 @@ cudaError_t launch_tn_tc(const GemmTNArgs& a, int precision, cudaStream_t st) {
 // ==============================================================================================================================
 struct NTTmaMaps {
   CUtensorMap a[2][2];  // [source][plane]: 2D {K, rows}, box {64, 128}
+  CUtensorMap c;        // TSTORE: the fp32 result, 2D {NC, rows}, box {32, 32}, 128-byte swizzle
 };
+constexpr int kNTStoreTile = 32 * 128;  // TSTORE: one staging tile [32 rows x 32 floats]; 4 epilogue warps x (1 or 2) tiles
 
-template <int NC, bool SPLIT>
-__global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_constant__ NTTmaMaps maps, const GemmNTArgs p) {
+// TSTORE (C = ..., not +=): the epilogue writes 32x32 blocks into swizzled staging tiles and hands them to the TMA store unit
+// (cp.async.bulk.tensor, double buffered per warp) instead of transposing through shared memory and storing row by row from the
+// threads.  Whole 32-row boxes are written: rows t >= T_eff of a live tile receive values nobody reads (the consumers of the input
+// projection and of dY only touch rows t < T_eff).
+template <int NC, bool SPLIT, bool TSTORE>
+__global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_constant__ NTTmaMaps maps, const GemmNTArgs p, const int nbuf) {
   constexpr int NPART = SPLIT ? 2 : 1;
   constexpr uint32_t kWTile = NC * 128;
   constexpr uint32_t kTmemCols = 2 * NC < 32 ? 32 : 2 * NC;
@@ -457,11 +463,16 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
   unsigned char* Wres = smem;
   unsigned char* Ast = Wres + (size_t)KC * NPART * kWTile;
   float* Est = reinterpret_cast<float*>(Ast + (size_t)kStagesNT * NPART * kTileBytes);
-  NTBarriers* bars = reinterpret_cast<NTBarriers*>(Est + 4 * 32 * 36);
+  NTBarriers* bars = reinterpret_cast<NTBarriers*>(reinterpret_cast<unsigned char*>(Est) + (TSTORE ? 4 * nbuf * kNTStoreTile : 4 * 32 * 36 * (int)sizeof(float)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nrows = (long long)p.G * p.B * p.Tmax;
   const int ntiles = (int)((nrows + kBM - 1) / kBM);
   __shared__ int teff_s[kNTLensSmem];
+  __shared__ __align__(16) float bias_s[TSTORE ? NC : 4];
+  if constexpr (TSTORE) {
+    for (int i = tid; i < NC; i += 192) bias_s[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+    if (tid == 0) tma_prefetch_desc(&maps.c);
+  }
   const int* teff = p.G <= kNTLensSmem ? teff_s : p.lens + p.G;
   for (int i = tid; i < min(p.G, kNTLensSmem); i += 192) teff_s[i] = p.lens[p.G + i];
 
@@ -551,8 +562,60 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (TMEM -> smem transpose -> coalesced stores) =====================
+    // ===================== epilogue =====================
     const int q = warp & 3;
+    if constexpr (TSTORE) {
+      // TMEM -> registers (+ bias) -> swizzled 32x32 staging tile -> TMA store; two staging tiles per warp
+      unsigned char* stage = reinterpret_cast<unsigned char*>(Est) + q * (nbuf * kNTStoreTile);
+      uint32_t tl = 0, nst = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * kBM;
+        if (!nt_tile_live(p, teff, row0, nrows)) continue;
+        const uint32_t acc = tl & 1;
+        mbar_wait(&bars->tfull[acc], (tl >> 1) & 1);
+        fence_after_sync();
+        const int rbase = (int)(row0 + q * 32);
+        bool ok = row0 + q * 32 + lane < nrows;
+        if (ok) ok = (int)((row0 + q * 32 + lane) % p.Tmax) < teff[(int)((row0 + q * 32 + lane) / p.Tmax) / p.B];
+        const bool live_box = __ballot_sync(0xffffffffu, ok) != 0u;  // a 32-row box without a valid row is not stored
+        uint32_t r[2][32];
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NC;
+        if (live_box) tmem_ld32_nowait(t_row, r[0]);
+#pragma unroll
+        for (int c = 0; c < NC / 32; ++c) {
+          if (!live_box) break;
+          tmem_wait_ld();
+          if (c + 1 < NC / 32) tmem_ld32_nowait(t_row + (c + 1) * 32, r[(c + 1) & 1]);
+          unsigned char* buf = stage + (nbuf == 2 ? (nst & 1) : 0) * kNTStoreTile;
+          if (lane == 0) {  // the store issued from this buffer (two blocks ago with two buffers) has read it
+            if (nbuf == 2) bulk_wait_group_read<1>();
+            else bulk_wait_group_read<0>();
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
+            float4 o;
+            o.x = __uint_as_float(r[c & 1][4 * j]) + b.x;
+            o.y = __uint_as_float(r[c & 1][4 * j + 1]) + b.y;
+            o.z = __uint_as_float(r[c & 1][4 * j + 2]) + b.z;
+            o.w = __uint_as_float(r[c & 1][4 * j + 3]) + b.w;
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&maps.c, buf, c * 32, rbase);
+            bulk_commit_group();
+          }
+          ++nst;
+        }
+        fence_before_sync();
+        mbar_arrive(&bars->tempty[acc]);
+        ++tl;
+      }
+      if (lane == 0) bulk_wait_group_read<0>();
+    } else {
     float* est = Est + q * 32 * 36;
     const int tr = lane >> 3, tc4 = (lane & 7) * 4;
     float4 bias4[NC / 32];
@@ -606,6 +669,7 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_tma_kernel(const __grid_consta
       ++tl;
     }
   }
+    }
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
@@ -792,11 +856,22 @@ template <int NC>
 cudaError_t launch_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st) {
   const int npart = precision == 0 ? 2 : 1;
   const int KC = a.nsrc * (a.K / kBK);
-  const size_t smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + 4 * 32 * 36 * sizeof(float) +
-                      sizeof(NTBarriers) + 64;
+  static const bool no_tstore = getenv("IB200_NO_TMA_STORE") != nullptr;
+  const size_t base_smem = 1024 + (size_t)KC * npart * NC * 128 + (size_t)kStagesNT * npart * kTileBytes + sizeof(NTBarriers) + 64;
+  const size_t static_smem = kNTLensSmem * sizeof(int) + NC * sizeof(float) + 64, limit = 227 * 1024 - static_smem;
+  const int nbuf = base_smem + 8 * kNTStoreTile <= limit ? 2 : 1;  // two staging tiles per epilogue warp when they fit
+  // (with a single staging tile per warp the store and the next block's fill serialise: measured slower than the thread stores)
+  bool tstore = !no_tstore && !a.accumulate && a.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && nbuf == 2;
+  const size_t smem = base_smem + (tstore ? (size_t)(4 * nbuf * kNTStoreTile) : 4 * 32 * 36 * sizeof(float));
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   NTTmaMaps maps;
   if (!nt_maps(a, npart, 0, &maps)) return cudaErrorInvalidConfiguration;
+  if (tstore) {
+    const uint64_t dc[2] = {(uint64_t)NC, (uint64_t)((long long)a.G * a.B * a.Tmax)}, sc[1] = {(uint64_t)a.ldc * 4};
+    const uint32_t bc[2] = {32, 32};
+    if (!make_tmap_f32_sw128(&maps.c, a.C, 2, dc, sc, bc)) tstore = false;
+  }
+  if (!tstore && smem != base_smem + 4 * 32 * 36 * sizeof(float)) return cudaErrorInvalidConfiguration;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -804,15 +879,18 @@ cudaError_t launch_nt_tma(const GemmNTArgs& a, int precision, cudaStream_t st) {
   const int ntiles = (int)((nrows + kBM - 1) / kBM);
   const unsigned grid = (unsigned)std::min(ntiles, sms);
   cudaError_t e;
-  if (precision == 0) {
-    e = cudaFuncSetAttribute(gemm_nt_tma_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm_nt_tma_kernel<NC, true><<<grid, 192, smem, st>>>(maps, a);
-  } else {
-    e = cudaFuncSetAttribute(gemm_nt_tma_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm_nt_tma_kernel<NC, false><<<grid, 192, smem, st>>>(maps, a);
+#define IB200_NT_LAUNCH(SP_, TS_)                                                                                          \
+  {                                                                                                                       \
+    e = cudaFuncSetAttribute(gemm_nt_tma_kernel<NC, SP_, TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return e;                                                                                       \
+    gemm_nt_tma_kernel<NC, SP_, TS_><<<grid, 192, smem, st>>>(maps, a, nbuf);                                             \
   }
+  if (precision == 0) {
+    if (tstore) IB200_NT_LAUNCH(true, true) else IB200_NT_LAUNCH(true, false)
+  } else {
+    if (tstore) IB200_NT_LAUNCH(false, true) else IB200_NT_LAUNCH(false, false)
+  }
+#undef IB200_NT_LAUNCH
   return cudaGetLastError();
 }
 

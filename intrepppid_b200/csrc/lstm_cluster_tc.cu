@@ -129,6 +129,21 @@ __device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t ades
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// the same with the A operand in TMEM (lane = M row, 8 columns of packed bf16 pairs per k16 step)
+__device__ __forceinline__ void mma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+      " @e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns <- 8 registers per thread (thread i of the warp writes lane base+i)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
@@ -158,51 +173,69 @@ template <int REGS>
 __device__ __forceinline__ void reg_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 __device__ __forceinline__ void cell_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kCellThreads) : "memory"); }
 
-// resident W slice as the A operand, 128-byte swizzle, MN-major for the forward product and K-major for the backward one -- in both
-// kernels a k16 step of the MMA then reads 2 KB of CONTIGUOUS shared memory per 64-wide block (measured: 46 cycles per M=128 MMA
-// against 55-75 when the same step gathers 32 bytes from each of 128 rows):
-//   forward : Wsm[part][m block of 64 gate rows][H k-rows (units) x 128 B]; gate row L = 32*(unit/8) + 8*gate + unit%8, so that rows
-//             q, q+8, q+16, q+24 of a 32-lane TMEM quarter are i,f,g,o of one unit
-//   backward: Wsm[part][block of 64 units][128 gate rows x 128 B]; gate row L = 4*unit + gate (k of the backward product: the four
-//             dgates of a cell are consecutive k of the da tile); read MN-major: M = units
-// Row L holds W_hh[gate*H + 32*rank + local unit][.] (masked per group for layer 0, forward direction).
-template <bool SPLIT, bool FWD>
-__device__ __forceinline__ void load_w_slice_tc(unsigned char* Wsm, const float* __restrict__ W, const float* __restrict__ M, int H, int rank) {
-  const size_t part = (size_t)(H / 64) * kWBlk;  // == 2 * H * 128: both layouts take H * 256 bytes per part
-  if constexpr (FWD) {
-    for (int idx = threadIdx.x; idx < (kRows / 2) * H; idx += blockDim.x) {
-      const int L = (idx / H) * 2, k = idx % H;  // rows L, L + 1 (two consecutive units of one gate), column k
-      const int gate = (L >> 3) & 3, ul = 8 * (L >> 5) + (L & 7);
-      const size_t src = ((size_t)gate * H + kUS * rank + ul) * H + k;
-      float w0 = W[src], w1 = W[src + H];
-      if (M != nullptr) {
-        w0 *= M[src];
-        w1 *= M[src + H];
-      }
-      uint32_t hi, lo = 0u;
-      if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
-      else hi = pack_bf16(w0, w1);
-      const uint32_t off = (uint32_t)(L >> 6) * (uint32_t)(H * 128) + sw128_offset((uint32_t)k, (uint32_t)(L & 63) >> 3) + (uint32_t)(L & 7) * 2u;
-      *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
-      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + part + off) = lo;
-    }
-  } else {
-    for (int idx = threadIdx.x; idx < kRows * (H / 2); idx += blockDim.x) {
-      const int L = idx / (H / 2), k = (idx % (H / 2)) * 2;
-      const size_t src = ((size_t)(L & 3) * H + kUS * rank + (L >> 2)) * H + k;
+// The resident W slice is the A operand of every MMA and lives in TENSOR MEMORY (lane = M row, one 32-bit column = two consecutive
+// k as packed bf16; hi part, then lo part): the 48 MMAs of a step then read only their small B tiles from shared memory.  With the
+// slice in shared memory (128 KB, 4 KB per MMA) the operand reads shared the memory pipe with the DSMEM exchange and the cell warps
+// and an MMA took 68-85 cycles in the kernel against 50 in isolation.
+//   forward : M = gate row L = 32*(unit/8) + 8*gate + unit%8 (rows q, q+8, q+16, q+24 of a 32-lane TMEM quarter are i,f,g,o of one
+//             unit), K = all H units: H/2 columns per part
+//   backward: M = unit (accumulator a holds units [128a, 128a+128)), K = my 128 gate rows L = 4*local unit + gate (the four dgates of
+//             a cell are consecutive k of the da tile): 64 columns per part and accumulator
+// Row L of the slice is W_hh[gate*H + 32*rank + local unit][.] (masked per group for layer 0, forward direction).  Called by the eight
+// cell warps: warp (quarter, half) fills its TMEM lane quarter, `half` selects the column half.
+template <bool SPLIT>
+__device__ __forceinline__ void load_w_tmem_fwd(uint32_t tb, const float* __restrict__ W, const float* __restrict__ M, int H, int rank) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = wid & 3, half = wid >> 2;
+  const int L = 32 * quarter + lane, gate = (L >> 3) & 3, ul = 8 * (L >> 5) + (L & 7);
+  const size_t row = ((size_t)gate * H + kUS * rank + ul) * H;
+  const int KC = H / 2, c_begin = half * (KC / 2), c_end = c_begin + KC / 2;  // packed columns of this warp
+  const uint32_t lane_addr = tb + ((uint32_t)(32 * quarter) << 16);
+  for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t src = row + 2 * (c0 + j);
       float w0 = W[src], w1 = W[src + 1];
       if (M != nullptr) {
         w0 *= M[src];
         w1 *= M[src + 1];
       }
-      uint32_t hi, lo = 0u;
-      if constexpr (SPLIT) split_bf16(w0, w1, hi, lo);
-      else hi = pack_bf16(w0, w1);
-      const uint32_t off = (uint32_t)(k >> 6) * kWBlk + sw128_offset((uint32_t)L, (uint32_t)(k & 63) >> 3) + (uint32_t)(k & 7) * 2u;
-      *reinterpret_cast<uint32_t*>(Wsm + off) = hi;
-      if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(Wsm + part + off) = lo;
+      lo[j] = 0u;
+      if constexpr (SPLIT) split_bf16(w0, w1, hi[j], lo[j]);
+      else hi[j] = pack_bf16(w0, w1);
+    }
+    tmem_st8(lane_addr + (uint32_t)c0, hi);
+    if constexpr (SPLIT) tmem_st8(lane_addr + (uint32_t)(KC + c0), lo);
+  }
+  tmem_wait_st();
+}
+template <bool SPLIT>
+__device__ __forceinline__ void load_w_tmem_bwd(uint32_t tb, const float* __restrict__ W, const float* __restrict__ M, int H, int rank) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = wid & 3, half = wid >> 2;
+  const int NACC = H / 128;
+  const uint32_t lane_addr = tb + ((uint32_t)(32 * quarter) << 16);
+  for (int a = 0; a < NACC; ++a) {
+    const int unit = 128 * a + 32 * quarter + lane;  // M row of this thread = a column of W_hh
+    for (int c0 = 32 * half; c0 < 32 * half + 32; c0 += 8) {  // packed columns: k = gate rows 2c, 2c+1
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int L0 = 2 * (c0 + j);  // L0 even: gates (0,1) or (2,3) of local unit L0 / 4
+        const size_t s0 = ((size_t)(L0 & 3) * H + kUS * rank + (L0 >> 2)) * H + unit, s1 = s0 + (size_t)H * H;  // gate + 1: H rows further
+        float w0 = W[s0], w1 = W[s1];
+        if (M != nullptr) {
+          w0 *= M[s0];
+          w1 *= M[s1];
+        }
+        lo[j] = 0u;
+        if constexpr (SPLIT) split_bf16(w0, w1, hi[j], lo[j]);
+        else hi[j] = pack_bf16(w0, w1);
+      }
+      tmem_st8(lane_addr + (uint32_t)(a * 64 + c0), hi);
+      if constexpr (SPLIT) tmem_st8(lane_addr + (uint32_t)(NACC * 64 + a * 64 + c0), lo);
     }
   }
+  tmem_wait_st();
 }
 
 // =================================================================================================================================
@@ -213,9 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   using TT = TileT<NB>;
   constexpr int NS = TT::NS, JB = TT::JB, NCELL = 2 * JB, NPART = SPLIT ? 2 : 1;
   constexpr int kChunk = TT::kChunk, kHSlice = TT::kHSlice;
-  constexpr uint32_t kTmemCols = NS <= 32 ? 32 : 64;
+  constexpr uint32_t kTmemCols = 512;  // W slice: H/2 columns per part (<= 256), accumulator at column 256
+  constexpr uint32_t kDCol = 256;
   constexpr bool FAST = !SPLIT;
-  const int C = H / kUS, KB = H / 64;
+  const int C = H / kUS;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank(), tile = (int)blockIdx.x / C;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
@@ -226,8 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* Wsm = smem;                                   // [NPART][2 m blocks][H k-rows x 128 B]
-  unsigned char* hB = Wsm + (size_t)NPART * KB * kWBlk;        // [2 buffers][C source CTAs][NPART][kHSlice]: B operand of the step
+  unsigned char* hB = smem;                                    // [2 buffers][C source CTAs][NPART][kHSlice]: B operand of the step
   const uint32_t sliceBytes = NPART * kHSlice, bufBytes = (uint32_t)C * sliceBytes;
   // hbar[buffer][source CTA]: "the slice of h that CTA `source` owns has landed in buffer b" -- the MMAs of a step start on the
   // slices that are there (my own first) while the others are still in flight
@@ -235,11 +268,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
   uint64_t* mma_bar = hbar + 2 * C;                            // "the step's MMAs have completed"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
-  {
-    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
-    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
-    load_w_slice_tc<SPLIT, true>(Wsm, W, M, H, rank);
-  }
   for (int i = tid; i < (int)(2 * bufBytes / 4); i += kThreads) reinterpret_cast<uint32_t*>(hB)[i] = 0u;  // h_{-1} = 0
   if (tid == 0) {
     for (int i = 0; i < 2 * C; ++i) mbar_init(&hbar[i], 1);
@@ -252,12 +280,20 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     }
   }
   if (wid == kCellWarps) tmem_alloc(tmem_slot, kTmemCols);
-  fence_async_smem();  // the generic-proxy writes above (W slice, zero h tile) are operands of the tensor core (async proxy)
+  fence_async_smem();  // the generic-proxy writes above (zero h tile) are operands of the tensor core (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = *tmem_slot;
+  if (wid < kCellWarps) {
+    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
+    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
+    load_w_tmem_fwd<SPLIT>(tb, W, M, H, rank);
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   cluster_sync_all();  // every CTA's tiles and barriers exist before any remote copy lands
-  const uint32_t tb = *tmem_slot;
 
   if (wid >= kCellWarps) {
     reg_shrink<kAuxRegs>();
@@ -266,10 +302,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     // (idle warps of the third warpgroup)
   } else if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
-    constexpr uint32_t idesc = idesc_bf16(kRows, NS, true, false);  // A = W slice MN-major (M = gate rows), B = h tile K-major
-    const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, (uint32_t)H * 128u);
+    constexpr uint32_t idesc = idesc_bf16(kRows, NS, false, false);  // A = W slice in TMEM (M = gate rows), B = h tile K-major
     const uint64_t b_base = smem_desc_nosw(smem_u32(hB), 128, kChunk);
-    const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kHSlice >> 4);
+    const uint64_t b_lo = (uint64_t)(kHSlice >> 4);
+    const uint32_t a_lo = (uint32_t)(H / 2);
     PROF_DECL;
     for (int s = 0; s < T; ++s) {
       const int buf = s & 1;
@@ -284,16 +320,17 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         }
         PROF_MARK(i == 0 ? 0 : (i == 1 ? 2 : 3));  // wait for: my own slice | the first remote slice | the others
         if (i == 0) fence_after_sync();  // (the cell warps' tcgen05.ld of the previous step precede these MMAs)
-        // units [32 r, +32) = two k16 steps: A = k-rows [32 r, +32) of both 64-row blocks; B = the four unit chunks of source r
-        const uint64_t ah = a_base + (uint64_t)(((uint32_t)r * 32u * 128u) >> 4);
+        // units [32 r, +32) = two k16 steps: A = 8 TMEM columns each; B = the four unit chunks of source r
+        const uint32_t ah = tb + (uint32_t)(16 * r);
         const uint64_t bh = bb + (uint64_t)(((uint32_t)r * sliceBytes) >> 4);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint64_t ahj = ah + (uint64_t)(j * ((16 * 128) >> 4)), bhj = bh + (uint64_t)(j * ((2 * kChunk) >> 4));
-          mma_bf16_ss_elect(tb, ahj, bhj, idesc, (i | j) != 0);
+          const uint32_t ahj = ah + (uint32_t)(8 * j);
+          const uint64_t bhj = bh + (uint64_t)(j * ((2 * kChunk) >> 4));
+          mma_bf16_ts_elect(tb + kDCol, ahj, bhj, idesc, (i | j) != 0);
           if constexpr (SPLIT) {
-            mma_bf16_ss_elect(tb, ahj, bhj + b_lo, idesc, true);
-            mma_bf16_ss_elect(tb, ahj + a_lo, bhj, idesc, true);
+            mma_bf16_ts_elect(tb + kDCol, ahj, bhj + b_lo, idesc, true);
+            mma_bf16_ts_elect(tb + kDCol, ahj + a_lo, bhj, idesc, true);
           }
         }
       }
@@ -351,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     for (int e = 0; e < NCELL; ++e) cst[e] = hv[e] = 0.f;
     const uint32_t my_slot = smem_u32(hB) + (uint32_t)rank * sliceBytes;  // + buffer offset: my slice of the h tile
     unsigned char* const my_slot_ptr = hB + (size_t)rank * sliceBytes;
-    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(8 * half);
+    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + kDCol + (uint32_t)(8 * half);
 
     // input projection of the current step (register prefetch: the next step's loads are issued right after this step's values have
     // been consumed and the h slice is on its way; tokens two steps ahead)
@@ -475,8 +512,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   constexpr int NS = TT::NS, JB = TT::JB, NPART = SPLIT ? 2 : 1;
   constexpr int kChunk = TT::kChunk, kXSlice = TT::kXSlice;
   constexpr bool FAST = !SPLIT;
-  const int C = H / kUS, KB = H / 64, NACC = H / 128;
-  const uint32_t kTmemCols = NACC * NS <= 32 ? 32 : (NACC * NS <= 64 ? 64 : 128);
+  const int C = H / kUS, NACC = H / 128;
+  constexpr uint32_t kTmemCols = 512;  // W slice: 64 columns per part and accumulator (<= 256), accumulators from column 256
+  constexpr uint32_t kDCol = 256;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank(), tile = (int)blockIdx.x / C;
   const int g = blockIdx.y, dir = p.dir0 + (int)blockIdx.z;
@@ -488,8 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* Wsm = smem;                                   // [NPART][KB][kWBlk]
-  unsigned char* daB = Wsm + (size_t)NPART * KB * kWBlk;       // [NPART][16 k chunks][kChunk]: B operand (da of my 128 gate rows)
+  unsigned char* daB = smem;                                   // [NPART][16 k chunks][kChunk]: B operand (da of my 128 gate rows)
   constexpr uint32_t kDaPart = 16 * kChunk;
   // partial dh for my 32 units: xbuf[2 buffers][C - 1 remote CTAs][NS sequences][32 units] fp32 (slot of CTA r: (r - rank - 1) mod C)
   // + xown[NS][32]: my own partial.  The idle receive buffer doubles as the staging area of the outgoing slices (see below).
@@ -502,11 +539,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   uint64_t* mma_bar = xbar + 3;  // [2]: "the step's MMAs into accumulator a have completed" (accumulator 0 is sent while 1 is computed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 5);
 
-  {
-    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
-    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
-    load_w_slice_tc<SPLIT, false>(Wsm, W, M, H, rank);
-  }
   for (int i = tid; i < (int)(NPART * kDaPart / 4); i += kThreads) reinterpret_cast<uint32_t*>(daB)[i] = 0u;
   if (tid == 0) {
     mbar_init(&xbar[0], 3);
@@ -523,8 +555,16 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  cluster_sync_all();
   const uint32_t tb = *tmem_slot;
+  if (wid < kCellWarps) {
+    const float* __restrict__ W = dir ? p.whh[1] : p.whh[0];
+    const float* __restrict__ M = (dir == 0 && p.whh_mask != nullptr) ? p.whh_mask + (size_t)g * 4 * H * H : nullptr;
+    load_w_tmem_bwd<SPLIT>(tb, W, M, H, rank);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  cluster_sync_all();
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of my cells' dgates over all steps (bias gradient partials)
 
   if (wid >= kCellWarps) {
@@ -534,26 +574,26 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     // (idle warps of the third warpgroup)
   } else if (wid == kCellWarps) {
     // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
-    constexpr uint32_t idesc = idesc_bf16(128, NS, true, false);  // A = W slice read MN-major (transposed), B = da tile K-major
-    const uint64_t a_base = smem_desc_sw128(smem_u32(Wsm), 1024, kWBlk);
+    constexpr uint32_t idesc = idesc_bf16(128, NS, false, false);  // A = W slice^T in TMEM (M = units), B = da tile K-major
     const uint64_t b_base = smem_desc_nosw(smem_u32(daB), 128, kChunk);
-    const uint64_t a_lo = (uint64_t)(((uint32_t)KB * kWBlk) >> 4), b_lo = (uint64_t)(kDaPart >> 4);
+    const uint64_t b_lo = (uint64_t)(kDaPart >> 4);
+    const uint32_t a_lo = (uint32_t)(NACC * 64);
     PROF_DECL;
     for (int s = 0; s + 1 < T; ++s) {
       mbar_wait(da_bar, (uint32_t)(s & 1));
       PROF_MARK(0);
       fence_after_sync();
       for (int a = 0; a < NACC; ++a) {
-        const uint64_t aa = a_base + (uint64_t)(((uint32_t)(2 * a) * kWBlk) >> 4);
+        const uint32_t aa = tb + (uint32_t)(64 * a), dd = tb + kDCol + (uint32_t)a * NS;
 #pragma unroll
         for (int k16 = 0; k16 < kRows / 16; ++k16) {
-          // k = gate rows [16 k16, +16): A = 16 k-rows of 128 bytes inside the two 64-unit blocks 2a, 2a+1; B = k chunks 2 k16, +1
-          const uint64_t ah = aa + (uint64_t)((k16 * 16 * 128) >> 4);
+          // k = gate rows [16 k16, +16): A = 8 TMEM columns of accumulator a's slice; B = k chunks 2 k16, +1
+          const uint32_t ah = aa + (uint32_t)(8 * k16);
           const uint64_t bh = b_base + (uint64_t)((2 * k16 * kChunk) >> 4);
-          mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah, bh, idesc, k16 != 0);
+          mma_bf16_ts_elect(dd, ah, bh, idesc, k16 != 0);
           if constexpr (SPLIT) {
-            mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah, bh + b_lo, idesc, true);
-            mma_bf16_ss_elect(tb + (uint32_t)a * NS, ah + a_lo, bh, idesc, true);
+            mma_bf16_ts_elect(dd, ah, bh + b_lo, idesc, true);
+            mma_bf16_ts_elect(dd, ah + a_lo, bh, idesc, true);
           }
         }
         mma_commit_elect(&mma_bar[a]);
@@ -706,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         uint32_t r[JB][8];
 #pragma unroll
         for (int j = 0; j < JB; ++j)
-          if (j < ngrp) tmem_ld8_nowait(tb + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * NS + 8 * (2 * j + half)), r[j]);
+          if (j < ngrp) tmem_ld8_nowait(tb + ((uint32_t)(32 * quarter) << 16) + kDCol + (uint32_t)(a * NS + 8 * (2 * j + half)), r[j]);
         tmem_wait_ld();
         const int owner = 4 * a + quarter;
         const int slot = owner - rank - 1 + (owner > rank ? 0 : C);  // (owner - rank - 1) mod C; == C - 1 for my own units
@@ -787,12 +827,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
 template <int NB>
 size_t fwd_smem_tc(int H, bool split) {
   const int npart = split ? 2 : 1, C = H / kUS;
-  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)2 * C * npart * TileT<NB>::kHSlice + (size_t)(2 * C + 1) * 8 + 64;
+  return 1024 + (size_t)2 * C * npart * TileT<NB>::kHSlice + (size_t)(2 * C + 1) * 8 + 64;
 }
 template <int NB>
 size_t bwd_smem_tc(int H, bool split) {
   const int npart = split ? 2 : 1, C = H / kUS;
-  return 1024 + (size_t)npart * (H / 64) * kWBlk + (size_t)npart * 16 * TileT<NB>::kChunk + (size_t)(2 * (C - 1) + 1) * TileT<NB>::kXSlice + 64;
+  return 1024 + (size_t)npart * 16 * TileT<NB>::kChunk + (size_t)(2 * (C - 1) + 1) * TileT<NB>::kXSlice + 64;
 }
 
 // clusters of C CTAs of this kernel that are co-resident on the device (cached per kernel and shared-memory size)

@@ -161,29 +161,38 @@ __global__ void __launch_bounds__(4 * H) l0_table_kernel(const TableArgs p) {
     if (j < nv) p.table[(((size_t)(g * 2 + d)) * VT + v0 + j) * 4 * H + gi] = acc[j] + bias;
 }
 
-// any H (used for H > 64, where the weight row no longer fits the register file): same summation order, weights from L2
+// any H (used for H > 64, where the weight row no longer fits the register file): same summation order, weights from L2.  A block
+// covers kTableVpbGeneric vocabulary rows at once, so every weight is read once per block instead of once per vocabulary row (the
+// per-row version took 1.1 ms per call at H = 256: a thread walks its own weight row, 32 sectors per warp request)
 constexpr int kTableVpbGeneric = 8;
-__global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p, int v_per_block) {
-  extern __shared__ float xs[];  // [H]
+__global__ void __launch_bounds__(256) l0_table_generic_kernel(const TableArgs p) {
+  extern __shared__ float xs[];  // [kTableVpbGeneric][H]
   const int H = p.H, g = blockIdx.y >> 1, d = blockIdx.y & 1;
   const int VT = p.V + kPadRows;
-  const int vend = min(VT, (int)(blockIdx.x + 1) * v_per_block);
-  for (int vt = blockIdx.x * v_per_block; vt < vend; ++vt) {
-    const int v = vt < p.V ? vt : 0;
-    __syncthreads();
-    for (int e = threadIdx.x; e < H; e += blockDim.x) {
-      const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
-      xs[e] = sc * p.emb[(size_t)v * H + e];
+  const int v0 = blockIdx.x * kTableVpbGeneric;
+  for (int i = threadIdx.x; i < kTableVpbGeneric * H; i += blockDim.x) {
+    const int j = i / H, e = i % H, vt = v0 + j;
+    const int v = vt < p.V ? vt : 0;  // rows >= V: replicas of row 0 (pad rows, kernels.h); beyond V + kPadRows: unused
+    const float sc = p.emb_row_scale != nullptr ? p.emb_row_scale[(size_t)g * p.V + v] : 1.0f;
+    xs[i] = vt < VT ? sc * p.emb[(size_t)v * H + e] : 0.f;
+  }
+  __syncthreads();
+  for (int gi = threadIdx.x; gi < 4 * H; gi += blockDim.x) {
+    const int row = gi_to_torch_row(gi, H);
+    const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
+    float s[kTableVpbGeneric];
+#pragma unroll
+    for (int j = 0; j < kTableVpbGeneric; ++j) s[j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+      const float w = wr[k];
+#pragma unroll
+      for (int j = 0; j < kTableVpbGeneric; ++j) s[j] = fmaf(xs[j * H + k], w, s[j]);
     }
-    __syncthreads();
-    for (int gi = threadIdx.x; gi < 4 * H; gi += blockDim.x) {
-      const int row = gi_to_torch_row(gi, H);
-      const float* __restrict__ wr = p.w_ih[d] + (size_t)row * H;
-      float s = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < H; ++k) s = fmaf(xs[k], wr[k], s);
-      p.table[(((size_t)(g * 2 + d)) * VT + vt) * 4 * H + gi] = s + (p.b_ih[d][row] + p.b_hh[d][row]);
-    }
+    const float bias = p.b_ih[d][row] + p.b_hh[d][row];
+#pragma unroll
+    for (int j = 0; j < kTableVpbGeneric; ++j)
+      if (v0 + j < VT) p.table[(((size_t)(g * 2 + d)) * VT + v0 + j) * 4 * H + gi] = s[j] + bias;
   }
 }
 
@@ -294,7 +303,7 @@ cudaError_t launch_l0_table(const TableArgs& a, cudaStream_t st) {
   if (a.H == 32) return launch_l0_table_h<32>(a, st);
   const int vpb = kTableVpbGeneric;
   dim3 grid((a.V + kPadRows + vpb - 1) / vpb, a.G * 2);
-  l0_table_generic_kernel<<<grid, 256, a.H * sizeof(float), st>>>(a, vpb);
+  l0_table_generic_kernel<<<grid, 256, (size_t)vpb * a.H * sizeof(float), st>>>(a);
   return cudaGetLastError();
 }
 

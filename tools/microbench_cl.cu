@@ -190,6 +190,9 @@ int main() {
   run_mma<32, 1, false, 2>(dCyc, steps); run_mma<32, 3, false, 2>(dCyc, steps);
   run_mma<32, 1, false, 4>(dCyc, steps); run_mma<32, 3, false, 4>(dCyc, steps);
   run_mma<32, 3, true, 2>(dCyc, steps);
+  run_mma<40, 1, false, 1>(dCyc, steps); run_mma<40, 3, false, 1>(dCyc, steps);
+  run_mma<48, 1, false, 1>(dCyc, steps); run_mma<48, 3, false, 1>(dCyc, steps);
+  run_mma<64, 3, false, 1>(dCyc, steps);
   if (getenv("MB_XCHG") == nullptr) return 0;
   for (int nclusters : {1, 16})
   for (int C : {4, 8})
