@@ -19,6 +19,7 @@
  *   ib200_batch_metrics         e2e/e2e_triplet.py:171-184   (torchmetrics AUROC / AP / MCC / Precision / Recall of the batch)
  *   ib200_adamw_step            e2e/e2e_triplet.py:231-255   (configure_optimizers: torch.optim.AdamW over self.parameters())
  *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
+ *   ib200_p2p_allreduce_mean    (no reference counterpart: the reference trains on one device, e2e/e2e_triplet.py:392-400)
  *
  * Conventions
  *   - weights are in PyTorch layout: weight_ih [4H,in], weight_hh [4H,H], gate row-blocks in order (i,f,g,o); two biases.
@@ -244,6 +245,25 @@ typedef struct ib200_adamw_hyper {
 } ib200_adamw_hyper;
 int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                      float* const* exp_avg_sq, const int64_t* numel, const ib200_adamw_hyper* hyper, void* stream);
+
+/* Data-parallel gradient exchange (the reference itself is single-GPU, e2e/e2e_triplet.py:392-400): one-shot MEAN all-reduce
+ * of a small bucket over NVLink peer memory, in place.  Every rank owns a staging region of 2 * stage_floats floats (two parity halves)
+ * and a flag array of `world` 32-bit words per bucket, both zero-initialised and mapped by every peer (CUDA IPC; the caller exchanges
+ * the handles, e.g. intrepppid_b200.parallel.P2PAllReduce).  The call copies `data` into my half (epoch & 1), publishes the epoch to
+ * every rank's flags, waits for all ranks, sums the `world` staged copies straight from the peers' memory and writes the mean to `data`.
+ *   stage_ptrs / flag_ptrs   HOST arrays [world] of DEVICE pointers: the base of each rank's staging region / flag array of THIS bucket
+ *   epoch                    1, 2, 3, ... : the call count of this bucket, identical on every rank
+ * Every rank must issue the same sequence of calls per bucket; world <= 8. */
+int ib200_p2p_allreduce_mean(int32_t world, int32_t rank, void* const* stage_ptrs, void* const* flag_ptrs, size_t stage_floats,
+                             float* data, size_t n, uint32_t epoch, void* stream);
+/* Peer-mappable device memory for the exchange above.  ib200_p2p_alloc: `bytes` of zeroed device memory on the current device + its
+ * 64-byte CUDA IPC handle (send it to the other ranks of the node by any host channel).  ib200_p2p_open: map a peer's region into
+ * this process for kernels of the CURRENT device (enables peer access to the owning GPU).  _close / _free release them. */
+#define IB200_P2P_HANDLE_BYTES 64
+int ib200_p2p_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+int ib200_p2p_open(const unsigned char* handle, void** ptr_out);
+int ib200_p2p_close(void* ptr);
+int ib200_p2p_free(void* ptr);
 
 /* Test hook (tests/test_gpu_gemm.py): the token-row NT GEMM in isolation.  impl: 0 legacy mma.sync, 1 tcgen05, 2 auto.
  * C[row,NC] (=|+=) sum_s A_s[row,K] W_s[NC,K]^T (+bias) for rows (n,t) with t < lens[G + n/B] of the [G*B, T] row space. */

@@ -45,7 +45,7 @@ class HeadMasks(C.Structure):
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_status", "ib200_encoder_bwd", "ib200_encoder_bwd_layers",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks", "ib200_p2p_allreduce_mean", "ib200_p2p_alloc", "ib200_p2p_open", "ib200_p2p_close", "ib200_p2p_free",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn", "ib200_dbg_gemm_nt_planes", "ib200_dbg_gemm_tn_planes", "ib200_dbg_l0_scratch_floats",
            "ib200_dbg_l0_grads", "ib200_dbg_gemm_nt_wide", "ib200_dbg_gemm_tn_wide")
 
@@ -84,6 +84,11 @@ def lib() -> C.CDLL:
     L.ib200_pair_score_range.argtypes = [C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64, C.POINTER(HeadParams), vp, vp]
     L.ib200_adamw_step.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64),
                                    C.POINTER(AdamWHyper), vp]
+    L.ib200_p2p_allreduce_mean.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_size_t, vp, C.c_size_t, C.c_uint32, vp]
+    L.ib200_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.ib200_p2p_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.ib200_p2p_close.argtypes = [vp]
+    L.ib200_p2p_free.argtypes = [vp]
     L.ib200_draw_masks.argtypes = [C.c_int32, C.POINTER(MaskSpec), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), vp]
     L.ib200_batch_metrics.argtypes = [C.c_int32, vp, vp, C.c_float, vp, vp, vp]
     L.ib200_dbg_gemm_nt.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp,

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -36,10 +37,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_L0_GRADS, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_L0_GRADS, F_ALLREDUCE, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks", "l0_grads"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks", "l0_grads", "p2p_allreduce"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -859,6 +860,60 @@ int ib200_batch_metrics(int32_t B, const float* y_hat, const int64_t* y, float t
   if (!y_hat || !y || !metrics_out) return fail(IB200_E_NULL, "ib200_batch_metrics: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   TIMED(F_METRICS, 1, launch_batch_metrics(B, y_hat, (const long long*)y, threshold, metrics_out, confusion_out, st), "batch_metrics");
+  return 0;
+}
+
+int ib200_p2p_allreduce_mean(int32_t world, int32_t rank, void* const* stage_ptrs, void* const* flag_ptrs, size_t stage_floats,
+                             float* data, size_t n, uint32_t epoch, void* stream) {
+  if (world < 1 || world > kP2PMaxWorld || rank < 0 || rank >= world) return fail(IB200_E_SHAPE, "ib200_p2p_allreduce_mean: need 1 <= world <= 8, 0 <= rank < world");
+  if (!stage_ptrs || !flag_ptrs || (!data && n > 0)) return fail(IB200_E_NULL, "ib200_p2p_allreduce_mean: null pointer");
+  if (n > stage_floats) return fail(IB200_E_SHAPE, "ib200_p2p_allreduce_mean: bucket larger than a staging half");
+  if (epoch == 0) return fail(IB200_E_SHAPE, "ib200_p2p_allreduce_mean: epochs count from 1 (the flags start at 0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  P2PArgs a{};
+  a.world = world; a.rank = rank; a.data = data; a.n = n; a.epoch = epoch;
+  const size_t half = (size_t)(epoch & 1u) * stage_floats;
+  for (int r = 0; r < world; ++r) {
+    if (!stage_ptrs[r] || !flag_ptrs[r]) return fail(IB200_E_NULL, "ib200_p2p_allreduce_mean: null peer pointer");
+    if ((reinterpret_cast<uintptr_t>(stage_ptrs[r]) & 15) != 0 || (stage_floats & 3) != 0)
+      return fail(IB200_E_ALIGN, "ib200_p2p_allreduce_mean: staging regions must be 16-byte aligned, stage_floats a multiple of 4");
+    a.stage[r] = reinterpret_cast<const float*>(stage_ptrs[r]) + half;
+    a.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+  }
+  TIMED(F_ALLREDUCE, 3, launch_p2p_allreduce_mean(a, reinterpret_cast<float*>(stage_ptrs[rank]) + half, st), "p2p allreduce");
+  return 0;
+}
+
+int ib200_p2p_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out) {
+  if (!ptr_out || !handle_out || bytes == 0) return fail(IB200_E_NULL, "ib200_p2p_alloc: null pointer / zero size");
+  static_assert(sizeof(cudaIpcMemHandle_t) == IB200_P2P_HANDLE_BYTES, "CUDA IPC handle size");
+  void* p = nullptr;
+  CK(cudaMalloc(&p, bytes), "p2p alloc");
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    (void)cudaFree(p);
+    return cuda_fail(e, "p2p alloc (memset / ipc handle)");
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return 0;
+}
+int ib200_p2p_open(const unsigned char* handle, void** ptr_out) {
+  if (!handle || !ptr_out) return fail(IB200_E_NULL, "ib200_p2p_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CK(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess), "p2p open");
+  return 0;
+}
+int ib200_p2p_close(void* ptr) {
+  if (ptr) CK(cudaIpcCloseMemHandle(ptr), "p2p close");
+  return 0;
+}
+int ib200_p2p_free(void* ptr) {
+  if (ptr) CK(cudaFree(ptr), "p2p free");
   return 0;
 }
 

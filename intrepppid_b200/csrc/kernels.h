@@ -234,6 +234,18 @@ cudaError_t launch_draw_masks(int n, const ib200_mask_spec* specs, unsigned long
 // ---- per-step classification metrics (metrics.cu): out[5] = auroc, ap, mcc, precision, recall; conf[4] = tp, fp, tn, fn ---------
 cudaError_t launch_batch_metrics(int B, const float* y_hat, const long long* y, float threshold, float* out, int* conf, cudaStream_t st);
 
+// ---- one-shot mean all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------------------------
+constexpr int kP2PMaxWorld = 8;
+struct P2PArgs {
+  int world, rank;
+  const float* stage[kP2PMaxWorld];   // every rank's staged copy of this bucket (peer-mapped device pointers; [rank] is my own)
+  uint32_t* flags[kP2PMaxWorld];      // every rank's flag array of this bucket ([world] words each)
+  float* data;                        // my bucket: n floats, reduced in place
+  size_t n;
+  uint32_t epoch;                     // 1, 2, 3, ... per bucket
+};
+cudaError_t launch_p2p_allreduce_mean(const P2PArgs& a, float* my_stage, cudaStream_t st);
+
 // ---- multi-tensor AdamW (optim.cu) -------------------------------------------------------------------------------------------
 constexpr int kAdamMaxTensors = 32;  // tensors per launch (pointer table travels in the kernel parameters)
 struct AdamScalars {

@@ -47,6 +47,110 @@ def default_buckets(module: torch.nn.Module) -> List[List[torch.nn.Parameter]]:
     return [b for b in (head, fc, upper, late) if b]
 
 
+class _EventWork:
+    """`.wait()` of a reduction that ran on the reducer's own stream: the caller's stream waits for its event (no host sync)."""
+
+    def __init__(self, event: "torch.cuda.Event"):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class P2PAllReduce:
+    """One-shot mean all-reduce of small buckets over NVLink peer memory (`ib200_p2p_allreduce_mean`, csrc/p2p.cu).
+
+    Every rank allocates, per bucket, a staging tensor of two parity halves and a flag row; the CUDA IPC handles are exchanged once
+    through the process group (`all_gather_object`) and every rank maps the regions of all its peers.  A reduction is then two
+    launches on this rank -- stage, then publish / wait / sum the peers' copies straight out of their memory -- instead of a ring or
+    tree of sends: the exchange of the training step is latency bound (753 KB in four buckets).  All ranks must sit on one node with
+    peer access (NVLink / NVSwitch) and issue the same sequence of reductions per bucket."""
+
+    MAX_WORLD = 8
+
+    def __init__(self, bucket_numels: Sequence[int], device, process_group=None):
+        from . import _lib
+
+        self._lib = _lib
+        self.group = process_group
+        self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if self.world > self.MAX_WORLD:
+            raise ValueError(f"P2PAllReduce supports up to {self.MAX_WORLD} ranks")
+        self.device = torch.device(device)
+        self.stage_floats = [(int(n) + 3) // 4 * 4 for n in bucket_numels]
+        # ONE peer-mappable allocation per rank: [bucket 0: 2 parity halves][bucket 1: ...] ... [flags: buckets x 8 words], zeroed
+        import ctypes as C
+
+        offs, off = [], 0
+        for n in self.stage_floats:
+            offs.append(off)
+            off += (2 * n * 4 + 255) // 256 * 256
+        flag_off, total = off, off + len(bucket_numels) * self.MAX_WORLD * 4
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            base, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(L.ib200_p2p_alloc(total, C.byref(base), handle), "ib200_p2p_alloc")
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handle.raw, group=process_group)
+            self._base, self._opened, bases = base, [], []
+            for r, h in enumerate(everyone):
+                if r == self.rank:
+                    bases.append(base.value)
+                    continue
+                p = C.c_void_p()
+                _lib.check(L.ib200_p2p_open(h, C.byref(p)), "ib200_p2p_open")
+                self._opened.append(p)
+                bases.append(p.value)
+        arr = C.c_void_p * self.world
+        self._stage_arr = [arr(*[b + o for b in bases]) for o in offs]
+        self._flag_arr = [arr(*[b + flag_off + 4 * self.MAX_WORLD * i for b in bases]) for i in range(len(bucket_numels))]
+        self._epoch = [0] * len(bucket_numels)
+        self.stream = torch.cuda.Stream(self.device)
+        dist.barrier(group=process_group)  # nobody publishes before everybody has mapped everything
+
+    def close(self):
+        """Unmap the peers' regions and free mine (after a barrier: nobody may still be reading)."""
+        if getattr(self, "_base", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        L = self._lib.lib()
+        for p in self._opened:
+            L.ib200_p2p_close(p)
+        L.ib200_p2p_free(self._base)
+        self._base, self._opened = None, []
+
+    def all_reduce_mean_(self, bucket: int, flat: torch.Tensor) -> _EventWork:
+        """Average `flat` (fp32, contiguous, at most the bucket's size) over all ranks, in place, ordered after the work already on
+        the current stream; returns a handle whose .wait() orders the current stream after the reduction."""
+        if flat.dtype != torch.float32 or not flat.is_contiguous() or flat.numel() > self.stage_floats[bucket]:
+            raise ValueError("P2PAllReduce: fp32 contiguous tensor of at most the bucket's size expected")
+        self._epoch[bucket] += 1
+        ready = torch.cuda.Event()
+        ready.record()
+        self.stream.wait_event(ready)
+        self._lib.check(self._lib.lib().ib200_p2p_allreduce_mean(self.world, self.rank, self._stage_arr[bucket], self._flag_arr[bucket],
+                                                                 self.stage_floats[bucket], flat.data_ptr(), flat.numel(),
+                                                                 self._epoch[bucket] & 0xFFFFFFFF or 1, self.stream.cuda_stream),
+                        "ib200_p2p_allreduce_mean")
+        flat.record_stream(self.stream)
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        return _EventWork(done)
+
+
+def _p2p_wanted(total_bytes: int, process_group) -> bool:
+    """IB200_ALLREDUCE = nccl (default) | p2p: the peer-memory reduction is opt-in.  Measured on 8 B200 (profiles/r2_p2p_ab.txt) the
+    NCCL collectives launched from the gradient hooks leave 0.14 ms of the exchange exposed per step; see there for the p2p figure."""
+    import os
+
+    mode = os.environ.get("IB200_ALLREDUCE", "nccl").lower()
+    if mode != "p2p" or not dist.is_initialized() or dist.get_backend(process_group) != "nccl":
+        return False
+    world = dist.get_world_size(process_group)
+    return 2 <= world <= P2PAllReduce.MAX_WORLD
+
+
 class GradientAllReducer:
     def __init__(self, module: torch.nn.Module, buckets: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None,
                  process_group=None):
@@ -75,6 +179,12 @@ class GradientAllReducer:
         self._early_done = False
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide
         self._avg_in_collective = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        # small exchanges between the GPUs of one node: one-shot reduction over NVLink peer memory instead of the NCCL collective
+        self._p2p = None
+        if self.world > 1 and _p2p_wanted(self.bytes_per_step, process_group):
+            dev = next(p.device for b in self.buckets for p in b)
+            self._p2p = P2PAllReduce([sum(p.numel() for p in b) for b in self.buckets], dev, process_group)
+            self._avg_in_collective = True  # (the kernel writes the mean)
 
     def _on_grad(self, p):
         i = self._bucket_of[id(p)]
@@ -98,8 +208,7 @@ class GradientAllReducer:
         self._inplace[i] = True
         self._flat[i] = upper
         if self.world > 1:
-            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
-            self._work[i] = dist.all_reduce(upper, op=op, group=self.group, async_op=True)
+            self._work[i] = self._reduce(i, upper)
 
     def _check_early_views(self, i):
         """The early bucket was reduced in place inside `flat`; autograd normally hands those very views to .grad.  If it copied
@@ -130,8 +239,13 @@ class GradientAllReducer:
         flat = base if base is not None else torch.cat([g.reshape(-1) for g in grads])
         self._flat[i] = flat
         if self.world > 1:
-            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
-            self._work[i] = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
+            self._work[i] = self._reduce(i, flat)
+
+    def _reduce(self, i, flat):
+        if self._p2p is not None:
+            return self._p2p.all_reduce_mean_(i, flat)
+        op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+        return dist.all_reduce(flat, op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for the outstanding reductions and write the averaged gradients back.  Call after loss.backward()."""
@@ -165,6 +279,9 @@ class GradientAllReducer:
         self._hooks = []
         if self._on_early in ops.EARLY_GRAD_HOOKS:
             ops.EARLY_GRAD_HOOKS.remove(self._on_early)
+        if self._p2p is not None:
+            self._p2p.close()
+            self._p2p = None
 
 
 def shard_range(n_items: int, rank: int, world: int):
