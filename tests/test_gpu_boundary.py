@@ -140,3 +140,36 @@ def test_large_vocabulary_lengths_and_embeddings(V):
     from intrepppid_b200 import ops
 
     ops.check_pending(sync=True)
+
+
+def test_p2p_allreduce_world_of_one_is_the_identity():
+    """ib200_p2p_alloc / ib200_p2p_allreduce_mean / ib200_p2p_free on one GPU: with world = 1 the staged copy, the flag handshake with
+    myself and the mean over one rank must give the bucket back unchanged, for both parity halves, unaligned views and odd sizes
+    (the multi-GPU equivalence with NCCL is tests/p2p_check.py under torchrun)."""
+    import ctypes as C
+
+    from intrepppid_b200 import _lib
+
+    L = _lib.lib()
+    stage_floats, world = 4096, 1
+    total = 2 * stage_floats * 4 + 256
+    base, handle = C.c_void_p(), C.create_string_buffer(64)
+    _lib.check(L.ib200_p2p_alloc(total, C.byref(base), handle), "ib200_p2p_alloc")
+    try:
+        assert any(handle.raw), "an IPC handle was written"
+        arr = C.c_void_p * 1
+        stage, flags = arr(base.value), arr(base.value + 2 * stage_floats * 4)
+        st = torch.cuda.current_stream().cuda_stream
+        for epoch, n, off in ((1, 4096, 0), (2, 1001, 1), (3, 7, 3), (4, 1, 0)):
+            x = torch.randn(n + 4, device="cuda")[off:off + n]
+            ref = x.clone()
+            _lib.check(L.ib200_p2p_allreduce_mean(world, 0, stage, flags, stage_floats, x.data_ptr(), n, epoch, st), "p2p")
+            torch.cuda.synchronize()
+            assert torch.equal(x, ref), (epoch, n)
+        # argument validation
+        assert L.ib200_p2p_allreduce_mean(world, 0, stage, flags, stage_floats, 0, 8, 5, st) < 0          # null data
+        assert L.ib200_p2p_allreduce_mean(world, 0, stage, flags, 16, base.value, 17, 5, st) < 0          # bucket > staging half
+        assert L.ib200_p2p_allreduce_mean(world, 0, stage, flags, stage_floats, base.value, 8, 0, st) < 0  # epochs count from 1
+        assert L.ib200_p2p_allreduce_mean(9, 0, stage, flags, stage_floats, base.value, 8, 5, st) < 0      # world > 8
+    finally:
+        _lib.check(L.ib200_p2p_free(base), "ib200_p2p_free")

@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from conftest import rel_l2
 from helpers import run_oracle_step, run_product_step
+from intrepppid_b200 import ops
 from oracle import restatement as R
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
@@ -15,10 +16,10 @@ rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
 t0 = time.time()
 for case in range(n_cases):
-    E = rng.choice([32, 64, 64, 64, 96, 128])
+    E = rng.choice([32, 64, 64, 96, 128, 128, 192, 256, 256])
     L = rng.choice([1, 2, 2, 3])
     bi = rng.choice(["last", "last", "mean", "max"])
-    B = rng.choice([1, 2, 3, 5, 8, 9, 13, 17, 24, 31])
+    B = rng.choice([1, 2, 3, 5, 8, 9, 13, 17, 24, 31, 33, 41, 70])
     T = rng.choice([1, 2, 7, 33, 64, 65, 100, 130, 257])
     V = rng.choice([11, 60, 250, 256, 257, 400])
     proj = rng.random() < 0.3
@@ -37,12 +38,14 @@ for case in range(n_cases):
         except RuntimeError as e:  # all-pad batch: the product must raise too
             try:
                 run_product_step(P, batch, masks, p_rnn=p, p_do=p, precision=prec, **kw)
+                ops.check_pending(sync=True)  # the length checks are a device-side status word: raised lazily, at the latest here
                 print(f"[{case}] FAIL (oracle raised {e!r}, product did not): {desc}")
                 bad += 1
             except RuntimeError:
                 print(f"[{case}] ok (both raise): {desc}")
             continue
         got = run_product_step(P, batch, masks, p_rnn=p, p_do=p, precision=prec, **kw)
+        ops.check_pending(sync=True)
         tol = 1e-4 if prec == "fp32" else 2e-2
         worst, where = 0.0, ""
         assert torch.equal(got["lengths"].cpu(), ref["lengths"]), "lengths"
