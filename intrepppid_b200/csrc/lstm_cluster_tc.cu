@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       const uint32_t par = (uint32_t)(((s - 1) >> 1) & 1);
       const uint64_t bb = b_base + (uint64_t)(((uint32_t)buf * bufBytes) >> 4);
       for (int i = 0; i < C; ++i) {
-        const int r = rank + i < C ? rank + i : rank + i - C;  // source CTA: mine first, then in ring order
+        const int r = rank - i >= 0 ? rank - i : rank - i + C;  // source CTA: mine first, then rank-1, rank-2, ... (arrival order)
         PROF_MARK(1);
         if (s > 0) {
           mbar_wait(&hbar[buf * C + r], par);
@@ -449,11 +449,17 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         PROF_MARK(4);
         cell_bar_sync();
         PROF_MARK(5);
-        if (wid < C) {  // warp w sends my slice to CTA w (one elected lane): the eight copies are issued side by side
+        if (wid == 0) {
+          // one warp issues the copies in RING order (to rank+1 first, rank+2 next, ...): the copy engine works through them roughly
+          // in order, so at every receiver the slices arrive staggered (from rank-1 first) and its MMAs start on the early ones while
+          // the late ones are still in flight; eight warps issuing side by side made all slices land together at the end
           const uint32_t boff = (uint32_t)(buf ^ 1) * bufBytes;
           uint64_t* bar = &hbar[(buf ^ 1) * C + rank];  // slot `rank` of the receiver's barriers
-          if (wid == rank) mbar_arrive_elect(bar);
-          else bulk_s2c_elect(map_to_rank(my_slot + boff, (uint32_t)wid), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), (uint32_t)wid));
+          mbar_arrive_elect(bar);
+          for (int i = 1; i < C; ++i) {
+            const uint32_t d = (uint32_t)(rank + i < C ? rank + i : rank + i - C);
+            bulk_s2c_elect(map_to_rank(my_slot + boff, d), my_slot + boff, sliceBytes, map_to_rank(smem_u32(bar), d));
+          }
         }
         PROF_MARK(6);
         load_x(s + 1, tk, xc);
