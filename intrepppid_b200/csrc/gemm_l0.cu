@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues: tc05.cuh) =====================
+    {
       constexpr uint32_t idesc_hh = idesc_bf16(128, 64, true, true), idesc_s = idesc_bf16(128, kNS, true, true);
       const uint32_t d_hh = tmem_base, d_s = tmem_base + 64;
       for (int it = 0; it < my_items; ++it) {
@@ -116,18 +116,18 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
           const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, kBlk), yh = smem_desc_sw128(y_hi + ko, 1024, kBlk);
           const uint64_t ohd = smem_desc_sw128(oh + ko, 1024, kBlk);
           const bool acc = (it | k16) != 0;
-          mma_bf16_ss(d_hh, ah, yh, idesc_hh, acc);
-          mma_bf16_ss(d_s, ah, ohd, idesc_s, acc);
+          mma_bf16_ss_elect(d_hh, ah, yh, idesc_hh, acc);
+          mma_bf16_ss_elect(d_s, ah, ohd, idesc_s, acc);
           if constexpr (SPLIT) {
             const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, kBlk), yl = smem_desc_sw128(y_lo + ko, 1024, kBlk);
-            mma_bf16_ss(d_hh, ah, yl, idesc_hh, true);
-            mma_bf16_ss(d_hh, al, yh, idesc_hh, true);
-            mma_bf16_ss(d_s, al, ohd, idesc_s, true);
+            mma_bf16_ss_elect(d_hh, ah, yl, idesc_hh, true);
+            mma_bf16_ss_elect(d_hh, al, yh, idesc_hh, true);
+            mma_bf16_ss_elect(d_s, al, ohd, idesc_s, true);
           }
         }
-        mma_commit(&bars->empty[stage]);
+        mma_commit_elect(&bars->empty[stage]);
       }
-      mma_commit(&bars->done);
+      mma_commit_elect(&bars->done);
     }
   } else {
     // ===================== one-hot writers (4 warps): thread r < 64 owns k-row r of the tile =====================

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(416, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // (whole warp, uniform control flow; one elected lane issues: tc05.cuh)
       constexpr uint32_t idesc = idesc_bf16(kBM, NC, false, false);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -161,16 +161,16 @@ __global__ void __launch_bounds__(416, 1) gemm_nt_tc_kernel(const GemmNTArgs p) 
           for (int k16 = 0; k16 < kBK / 16; ++k16) {
             const uint32_t ko = k16 * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
             const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, 0), bh = smem_desc_sw128(b_hi + ko, 1024, 0);
-            mma_bf16_ss(d_tmem, ah, bh, idesc, (kc | k16) != 0);
+            mma_bf16_ss_elect(d_tmem, ah, bh, idesc, (kc | k16) != 0);
             if constexpr (SPLIT) {
               const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, 0), bl = smem_desc_sw128(b_lo + ko, 1024, 0);
-              mma_bf16_ss(d_tmem, ah, bl, idesc, true);
-              mma_bf16_ss(d_tmem, al, bh, idesc, true);
+              mma_bf16_ss_elect(d_tmem, ah, bl, idesc, true);
+              mma_bf16_ss_elect(d_tmem, al, bh, idesc, true);
             }
           }
-          mma_commit(&bars->empty[stage]);  // stage free once these MMAs have read it
+          mma_commit_elect(&bars->empty[stage]);  // stage free once these MMAs have read it
         }
-        mma_commit(&bars->tfull[acc]);
+        mma_commit_elect(&bars->tfull[acc]);
         ++tl;
       }
     }
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // (whole warp, uniform control flow; one elected lane issues: tc05.cuh)
       constexpr uint32_t idesc = idesc_bf16(128, NB, true, true);
       for (int it = 0; it < my_items; ++it) {
         const int stage = it % kStagesTN;
@@ -764,17 +764,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_tma_kernel(const __grid_consta
             const uint32_t mo = mt * 2 * kBlkBytes;
             const uint64_t ah = smem_desc_sw128(a_hi + mo + ko, 1024, kBlkBytes);
             const uint32_t d = tmem_base + mt * NB;
-            mma_bf16_ss(d, ah, bh, idesc, (it | k16) != 0);
+            mma_bf16_ss_elect(d, ah, bh, idesc, (it | k16) != 0);
             if constexpr (SPLIT) {
               const uint64_t al = smem_desc_sw128(a_lo + mo + ko, 1024, kBlkBytes);
-              mma_bf16_ss(d, ah, bl, idesc, true);
-              mma_bf16_ss(d, al, bh, idesc, true);
+              mma_bf16_ss_elect(d, ah, bl, idesc, true);
+              mma_bf16_ss_elect(d, al, bh, idesc, true);
             }
           }
         }
-        mma_commit(&bars->empty[stage]);
+        mma_commit_elect(&bars->empty[stage]);
       }
-      mma_commit(&bars->done);
+      mma_commit_elect(&bars->done);
     }
   } else if (GATHER) {
     // ===================== B operand = scale[g][tok] * emb[tok] (layer-0 input), staged by 4 warps =====================

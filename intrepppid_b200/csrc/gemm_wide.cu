@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_wide_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // (whole warp, uniform control flow; one elected lane issues: tc05.cuh)
       constexpr uint32_t idesc = idesc_bf16(kBM, BN, false, false);
       uint32_t it = 0, tl = 0;
       for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -136,16 +136,16 @@ __global__ void __launch_bounds__(192, 1) gemm_nt_wide_kernel(const __grid_const
           for (int k16 = 0; k16 < kBK / 16; ++k16) {
             const uint32_t ko = k16 * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
             const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, 0), bh = smem_desc_sw128(b_hi + ko, 1024, 0);
-            mma_bf16_ss(d_tmem, ah, bh, idesc, (kc | k16) != 0);
+            mma_bf16_ss_elect(d_tmem, ah, bh, idesc, (kc | k16) != 0);
             if constexpr (SPLIT) {
               const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, 0), bl = smem_desc_sw128(b_lo + ko, 1024, 0);
-              mma_bf16_ss(d_tmem, ah, bl, idesc, true);
-              mma_bf16_ss(d_tmem, al, bh, idesc, true);
+              mma_bf16_ss_elect(d_tmem, ah, bl, idesc, true);
+              mma_bf16_ss_elect(d_tmem, al, bh, idesc, true);
             }
           }
-          mma_commit(&bars->empty[stage]);  // stage free once these MMAs have read it
+          mma_commit_elect(&bars->empty[stage]);  // stage free once these MMAs have read it
         }
-        mma_commit(&bars->tfull[acc]);
+        mma_commit_elect(&bars->tfull[acc]);
         ++tl;
       }
     }
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_wide_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // (whole warp, uniform control flow; one elected lane issues: tc05.cuh)
       constexpr uint32_t idesc = idesc_bf16(128, BN, true, true);
       for (int it = 0; it < my_items; ++it) {
         const int stage = it % STAGES;
@@ -337,16 +337,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tn_wide_kernel(const __grid_const
         for (int k16 = 0; k16 < 4; ++k16) {
           const uint32_t ko = k16 * 16 * 128;  // 16 k-rows of 128 bytes inside every block
           const uint64_t ah = smem_desc_sw128(a_hi + ko, 1024, kBlk), bh = smem_desc_sw128(b_hi + ko, 1024, kBlk);
-          mma_bf16_ss(tmem_base, ah, bh, idesc, (it | k16) != 0);
+          mma_bf16_ss_elect(tmem_base, ah, bh, idesc, (it | k16) != 0);
           if constexpr (SPLIT) {
             const uint64_t al = smem_desc_sw128(a_lo + ko, 1024, kBlk), bl = smem_desc_sw128(b_lo + ko, 1024, kBlk);
-            mma_bf16_ss(tmem_base, ah, bl, idesc, true);
-            mma_bf16_ss(tmem_base, al, bh, idesc, true);
+            mma_bf16_ss_elect(tmem_base, ah, bl, idesc, true);
+            mma_bf16_ss_elect(tmem_base, al, bh, idesc, true);
           }
         }
-        mma_commit(&bars->empty[stage]);
+        mma_commit_elect(&bars->empty[stage]);
       }
-      mma_commit(&bars->done);
+      mma_commit_elect(&bars->done);
     }
   }
   __syncthreads();

@@ -118,17 +118,7 @@ __device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)
                : "r"(taddr)
                : "memory");
 }
-// tcgen05.mma / commit issued from WARP-UNIFORM code: all 32 lanes execute the instruction stream, one elected lane issues.  With
-// `if (lane == 0)` around a plain tcgen05.mma, ptxas cannot prove the descriptors uniform and wraps every MMA in an
-// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~100 cycles of issue per MMA, measured: the issue, not the tensor pipe, set the
-// step time).
-__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
-      " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
+// (mma_bf16_ss_elect / mma_commit_elect: tc05.cuh)
 // the same with the A operand in TMEM (lane = M row, 8 columns of packed bf16 pairs per k16 step)
 __device__ __forceinline__ void mma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -144,12 +134,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
-  asm volatile(
-      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
-      " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
-      : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
   asm volatile(
       "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"

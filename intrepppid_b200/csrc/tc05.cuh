@@ -139,6 +139,23 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// The same two, issued from WARP-UNIFORM code: all 32 lanes execute the instruction stream, one elected lane issues.  With
+// `if (lane == 0)` around a plain tcgen05.mma, ptxas cannot prove the descriptors uniform and wraps every MMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop: ~100 cycles of issue per MMA, more than the MMA itself for N <= 128.
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+      " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // byte offset of element (row, 16-byte chunk c) inside a 128B-swizzled tile whose base is 1024-byte aligned
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) { return row * 128u + ((chunk16 ^ (row & 7u)) << 4); }
 
