@@ -228,7 +228,9 @@ __device__ __forceinline__ void load_w_tmem_bwd(uint32_t tb, const float* __rest
 template <int NB, bool SPLIT, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFwdArgs p, const int H) {
   using TT = TileT<NB>;
-  constexpr int NS = TT::NS, JB = TT::JB, NCELL = 2 * JB, NPART = SPLIT ? 2 : 1;
+  // cells per thread: warp `half` takes NFB whole 8-sequence blocks and, for odd NB, one column parity of the middle block, so both
+  // halves carry the same number of cells (NB = 5: 5 + 5 instead of 6 + 4: the publish waits for the slower half)
+  constexpr int NS = TT::NS, NFB = NB / 2, NLD = NFB + (NB & 1), NCELL = 2 * NFB + (NB & 1), NPART = SPLIT ? 2 : 1;
   constexpr int kChunk = TT::kChunk, kHSlice = TT::kHSlice;
   constexpr uint32_t kTmemCols = 512;  // W slice: H/2 columns per part (<= 256), accumulator at column 256
   constexpr uint32_t kDCol = 256;
@@ -324,9 +326,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     PROF_PRINT("fwd mma  [own-wait issue first-remote-wait other-remote-waits]", blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, T);
   } else {
     // ===================== cell warps =====================
-    // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) with the 16x256b shape, 8-column blocks
-    // b = 2 jb + half: rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit
-    // 8 quarter + gq, for the sequences 8 b + 2 tig + (0, 1): whole cells per thread, no exchange between lanes
+    // accumulator read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) with the 16x256b shape, one 8-column block at a
+    // time: rows gq, gq + 8 (first 16 lanes) and gq + 16, gq + 24 (second 16 lanes) = gates i, f, g, o of unit 8 quarter + gq, for
+    // the sequences 8 b + 2 tig + (0, 1): whole cells per thread, no exchange between lanes
     reg_grow<kCellRegs>();
     const int quarter = wid & 3, half = wid >> 2, gq = lane >> 2, tig = lane & 3;
     const int u = kUS * rank + 8 * quarter + gq;
@@ -337,14 +339,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     bool valid[NCELL];
 #pragma unroll
     for (int e = 0; e < NCELL; ++e) {
-      const int b = 2 * (e >> 1) + half;  // (a block b >= NB exists only for odd NB, half 1: its cells are computed and dropped)
-      ncell[e] = 8 * b + 2 * tig + (e & 1);
-      valid[e] = b < NB && ncell[e] < nvalid;
+      const int b = e < 2 * NFB ? half * (NB - NFB) + (e >> 1) : NFB;  // whole blocks of this half | the shared middle block
+      ncell[e] = 8 * b + 2 * tig + (e < 2 * NFB ? (e & 1) : half);
+      valid[e] = ncell[e] < nvalid;
       const int ncl = min(ncell[e], nvalid - 1);
       rowb[e] = (nbase + ncl) * Tmax;
       xoff[e] = (uint32_t)ncl * (uint32_t)Tmax * (uint32_t)H;  // float4 units, relative to the tile's first sequence
     }
-    const int nblk = (NB - half + 1) / 2;  // blocks of this warp
     // layer >= 1: dense input projection rows [N, Tmax, 4H] (GI: one float4 per cell); layer 0: table rows by token
     const float4* const xdense = layer0 ? nullptr : reinterpret_cast<const float4*>(dir ? p.xproj[1] : p.xproj[0]) + (size_t)nbase * Tmax * H + u;
     const float4* const xtab = layer0 ? reinterpret_cast<const float4*>(p.table) + (size_t)((p.table_shared ? 0 : g) * 2 + dir) * (p.V + kPadRows) * H + u : nullptr;
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
     for (int e = 0; e < NCELL; ++e) cst[e] = hv[e] = 0.f;
     const uint32_t my_slot = smem_u32(hB) + (uint32_t)rank * sliceBytes;  // + buffer offset: my slice of the h tile
     unsigned char* const my_slot_ptr = hB + (size_t)rank * sliceBytes;
-    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + kDCol + (uint32_t)(8 * half);
+    const uint32_t taddr = tb + ((uint32_t)(32 * quarter) << 16) + kDCol;
 
     // input projection of the current step (register prefetch: the next step's loads are issued right after this step's values have
     // been consumed and the h slice is on its way; tokens two steps ahead)
@@ -390,15 +391,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       mbar_wait(mma_bar, (uint32_t)(s & 1));
       PROF_MARK(1);
       fence_after_sync();
-      uint32_t ra[JB][4], rb[JB][4];
+      uint32_t ra[NLD][4], rb[NLD][4];
 #pragma unroll
-      for (int jb = 0; jb < JB; ++jb) {
-        if (jb < nblk) {
-          tmem_ld_16x256b_x1(taddr + (uint32_t)(16 * jb), ra[jb]);
-          tmem_ld_16x256b_x1(taddr + (uint32_t)(16 * jb) + (16u << 16), rb[jb]);
-        } else {
-          ra[jb][0] = ra[jb][1] = ra[jb][2] = ra[jb][3] = rb[jb][0] = rb[jb][1] = rb[jb][2] = rb[jb][3] = 0u;
-        }
+      for (int jb = 0; jb < NLD; ++jb) {
+        const uint32_t col = (uint32_t)(8 * (jb < NFB ? half * (NB - NFB) + jb : NFB));
+        tmem_ld_16x256b_x1(taddr + col, ra[jb]);
+        tmem_ld_16x256b_x1(taddr + col + (16u << 16), rb[jb]);
       }
       tmem_wait_ld();
       fence_before_sync();
@@ -409,11 +407,17 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
       __nv_bfloat16 hb16[NCELL], lb16[NCELL];
 #pragma unroll
       for (int e = 0; e < NCELL; ++e) {
-        const int jb = e >> 1, pc = e & 1;
-        gi[e] = sigmoid_f<FAST>(__uint_as_float(ra[jb][pc]) + xc[e].x);
-        gf[e] = sigmoid_f<FAST>(__uint_as_float(ra[jb][2 + pc]) + xc[e].y);
-        gg[e] = tanh_f<FAST>(__uint_as_float(rb[jb][pc]) + xc[e].z);
-        go[e] = sigmoid_f<FAST>(__uint_as_float(rb[jb][2 + pc]) + xc[e].w);
+        uint32_t ai, af, ag, ao;
+        if (e < 2 * NFB) {
+          ai = ra[e >> 1][e & 1]; af = ra[e >> 1][2 + (e & 1)]; ag = rb[e >> 1][e & 1]; ao = rb[e >> 1][2 + (e & 1)];
+        } else {  // the middle block: this half's column parity
+          ai = half ? ra[NLD - 1][1] : ra[NLD - 1][0]; af = half ? ra[NLD - 1][3] : ra[NLD - 1][2];
+          ag = half ? rb[NLD - 1][1] : rb[NLD - 1][0]; ao = half ? rb[NLD - 1][3] : rb[NLD - 1][2];
+        }
+        gi[e] = sigmoid_f<FAST>(__uint_as_float(ai) + xc[e].x);
+        gf[e] = sigmoid_f<FAST>(__uint_as_float(af) + xc[e].y);
+        gg[e] = tanh_f<FAST>(__uint_as_float(ag) + xc[e].z);
+        go[e] = sigmoid_f<FAST>(__uint_as_float(ao) + xc[e].w);
         cst[e] = fmaf(gf[e], cst[e], gi[e] * gg[e]);
         hv[e] = go[e] * tanh_f<FAST>(cst[e]);
         hb16[e] = __float2bfloat16_rn(hv[e]);
@@ -423,10 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
         unsigned char* dst = my_slot_ptr + (size_t)(buf ^ 1) * bufBytes + quarter * kChunk + gq * 2;
 #pragma unroll
         for (int e = 0; e < NCELL; ++e) {
-          if ((e >> 1) < nblk) {
-            *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
-            if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
-          }
+          *reinterpret_cast<__nv_bfloat16*>(dst + ncell[e] * 16) = hb16[e];
+          if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + kHSlice + ncell[e] * 16) = lb16[e];
         }
         PROF_MARK(3);
         fence_async_smem();  // my slice (generic-proxy stores) is read by the bulk copies and by my own tensor core (async proxy)
