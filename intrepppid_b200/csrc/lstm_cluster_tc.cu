@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 
 #include "kernels.h"
@@ -64,8 +65,9 @@ struct TileT {
   static constexpr int NS = 8 * NB;
   static constexpr int kChunk = NS * 16 + 16;   // byte pitch of one 8-row k chunk [NS sequences][16 B] of a B operand tile (+16: bank spread)
   static constexpr int kHSlice = 4 * kChunk;    // forward: h slice of one source CTA and one part: [4 unit chunks][NS sequences][16 B]
-  static constexpr int kXSlice = NS * kUS * 4;  // backward: partial dh of one source CTA for my 32 units: [NS sequences][32 units] fp32
-  static constexpr int JB = (NB + 1) / 2;       // 8-sequence blocks per cell warp (warp `half` takes the blocks b with b % 2 == half)
+  // backward: partial dh of one source CTA for my 32 units: [NS sequences][32 units], fp32 (fp32 mode) or bf16 (bf16 mode: half the
+  // exchange bytes; the partials are rounded to bf16 before the C-way sum, inside that mode's 2e-2 gate)
+  static constexpr int xslice(int elem_bytes) { return NS * kUS * elem_bytes; }
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -102,6 +104,10 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t sbo_
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100); layout type 0 = no swizzle
   return d;
+}
+// 32 lanes x 4 consecutive 32-bit columns -> 4 registers per thread; no wait
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 // 32 lanes x 8 consecutive 32-bit columns -> 8 registers per thread (thread i of the warp reads lane base+i); no wait
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
@@ -501,8 +507,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_cltc_kernel(const LstmFw
 template <int NB, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBwdArgs p, const int H) {
   using TT = TileT<NB>;
-  constexpr int NS = TT::NS, JB = TT::JB, NPART = SPLIT ? 2 : 1;
-  constexpr int kChunk = TT::kChunk, kXSlice = TT::kXSlice;
+  using XT = typename std::conditional<SPLIT, float, __nv_bfloat16>::type;  // element type of the exchanged partial sums
+  constexpr int NS = TT::NS, NPART = SPLIT ? 2 : 1;
+  constexpr int kChunk = TT::kChunk, kXSlice = TT::xslice((int)sizeof(XT));
+  constexpr int NG8 = (NS / 2) / 8, NG4 = ((NS / 2) % 8) / 4;  // read-out per warp: NS/2 columns = NG8 groups of 8 (+ one of 4)
   constexpr bool FAST = !SPLIT;
   const int C = H / kUS, NACC = H / 128;
   constexpr uint32_t kTmemCols = 512;  // W slice: 64 columns per part and accumulator (<= 256), accumulators from column 256
@@ -522,11 +530,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
   constexpr uint32_t kDaPart = 16 * kChunk;
   // partial dh for my 32 units: xbuf[2 buffers][C - 1 remote CTAs][NS sequences][32 units] fp32 (slot of CTA r: (r - rank - 1) mod C)
   // + xown[NS][32]: my own partial.  The idle receive buffer doubles as the staging area of the outgoing slices (see below).
-  float* xbuf = reinterpret_cast<float*>(daB + NPART * kDaPart);
+  XT* xbuf = reinterpret_cast<XT*>(daB + NPART * kDaPart);
   const uint32_t xBufBytes = (uint32_t)(C - 1) * kXSlice;
-  float* xown = xbuf + 2 * (size_t)(xBufBytes / 4);
+  constexpr int kXElems = NS * kUS;  // elements per slice
+  XT* xown = xbuf + 2 * (size_t)(C - 1) * kXElems;
   // xbar[buffer]: "all partials of this step are in place": C - 1 bulk copies (complete_tx) + the two warps that wrote xown
-  uint64_t* xbar = reinterpret_cast<uint64_t*>(xown + kXSlice / 4);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(xown + kXElems);
   uint64_t* da_bar = xbar + 2;   // "the da tile of this step is complete" (all cell threads arrive)
   uint64_t* mma_bar = xbar + 3;  // [2]: "the step's MMAs into accumulator a have completed" (accumulator 0 is sent while 1 is computed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 5);
@@ -645,10 +654,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
     float dc[NB], dhrec[NB];
     // my da values in the B tile: k = 4 lane + gate -> chunk lane/2, bytes (lane & 1) * 8 of the 16-byte row of sequence n
     unsigned char* const da_put = daB + (size_t)(lane >> 1) * kChunk + (size_t)(lane & 1) * 8 + (size_t)s0 * 16;
-    // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) of every accumulator, 8-column groups 2 j + half; lane = unit
+    // read-out: warp (quarter, half) reads TMEM lanes [32 quarter, +32) of every accumulator, columns [half NS/2, +NS/2); lane = unit
     // 128 a + 32 quarter + lane, which CTA 4a + quarter owns as its local unit `lane`
     const int quarter = wid & 3, half = wid >> 2;
-    const int ngrp = (NB - half + 1) / 2;
+    const int xc0 = half * (NS / 2);
     const uint32_t xb_local = smem_u32(xbuf), xbar_local = smem_u32(xbar);
 
     // `in` holds the saved gates / c / dy of the NEXT step (register prefetch: loaded one step ahead, consumed by prep() in the shadow
@@ -735,20 +744,24 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
         mbar_wait(&mma_bar[a], (uint32_t)(s & 1));
         PROF_MARK(5);
         fence_after_sync();
-        uint32_t r[JB][8];
+        uint32_t r[NG8][8], r4[4] = {0u, 0u, 0u, 0u};
+        const uint32_t tcol = tb + ((uint32_t)(32 * quarter) << 16) + kDCol + (uint32_t)(a * NS + xc0);
 #pragma unroll
-        for (int j = 0; j < JB; ++j)
-          if (j < ngrp) tmem_ld8_nowait(tb + ((uint32_t)(32 * quarter) << 16) + kDCol + (uint32_t)(a * NS + 8 * (2 * j + half)), r[j]);
+        for (int j = 0; j < NG8; ++j) tmem_ld8_nowait(tcol + 8 * j, r[j]);
+        if constexpr (NG4 != 0) tmem_ld4_nowait(tcol + 8 * NG8, r4);
         tmem_wait_ld();
         const int owner = 4 * a + quarter;
         const int slot = owner - rank - 1 + (owner > rank ? 0 : C);  // (owner - rank - 1) mod C; == C - 1 for my own units
-        float* stg = owner == rank ? xown : xbuf + (size_t)(s & 1) * (xBufBytes / 4) + (size_t)slot * (kXSlice / 4);
+        XT* stg = (owner == rank ? xown : xbuf + ((size_t)(s & 1) * (C - 1) + slot) * kXElems) + (size_t)xc0 * kUS + lane;
 #pragma unroll
-        for (int j = 0; j < JB; ++j)
-          if (j < ngrp) {
+        for (int j = 0; j < NG8; ++j) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) stg[(8 * (2 * j + half) + i) * kUS + lane] = __uint_as_float(r[j][i]);
-          }
+          for (int i = 0; i < 8; ++i) stg[(8 * j + i) * kUS] = (XT)__uint_as_float(r[j][i]);
+        }
+        if constexpr (NG4 != 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) stg[(8 * NG8 + i) * kUS] = (XT)__uint_as_float(r4[i]);
+        }
         if (owner == rank) {
           __syncwarp();
           mbar_arrive_elect(&xbar[xb]);  // (release: the cell threads that wait on xbar see my rows of xown)
@@ -770,12 +783,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cltc_kernel(const LstmBw
       PROF_MARK(7);
       if (tid == 0 && s + 3 < T) mbar_arrive_expect_tx(&xbar[xb], xBufBytes);  // refilled at step s + 2
       // recurrent gradient of my cells for the next step: sum of the C partials
-      const float* xr = xbuf + (size_t)xb * (xBufBytes / 4) + (size_t)s0 * kUS + lane;
+      const XT* xr = xbuf + (size_t)xb * (C - 1) * kXElems + (size_t)s0 * kUS + lane;
 #pragma unroll
-      for (int e = 0; e < NB; ++e) dhrec[e] = xown[(s0 + e) * kUS + lane];
+      for (int e = 0; e < NB; ++e) dhrec[e] = (float)xown[(s0 + e) * kUS + lane];
       for (int r2 = 0; r2 < C - 1; ++r2) {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) dhrec[e] += xr[(size_t)r2 * (kXSlice / 4) + e * kUS];
+        for (int e = 0; e < NB; ++e) dhrec[e] += (float)xr[(size_t)r2 * kXElems + e * kUS];
       }
       PROF_MARK(8);
     }
@@ -824,7 +837,7 @@ size_t fwd_smem_tc(int H, bool split) {
 template <int NB>
 size_t bwd_smem_tc(int H, bool split) {
   const int npart = split ? 2 : 1, C = H / kUS;
-  return 1024 + (size_t)npart * 16 * TileT<NB>::kChunk + (size_t)(2 * (C - 1) + 1) * TileT<NB>::kXSlice + 64;
+  return 1024 + (size_t)npart * 16 * TileT<NB>::kChunk + (size_t)(2 * (C - 1) + 1) * TileT<NB>::xslice(split ? 4 : 2) + 64;
 }
 
 // clusters of C CTAs of this kernel that are co-resident on the device (cached per kernel and shared-memory size)
