@@ -2,23 +2,25 @@
 // configuration E = H = 256, 3 layers (BASELINE config 5).  Same math and the same HBM layouts as lstm_cluster.cu / lstm_fwd.cu
 // (reference: nn.LSTM inside encoders/awd_lstm.py:35-41,56); the mma.sync cluster kernels stay for the other hidden sizes.
 //
-// A thread-block CLUSTER of C = H/32 CTAs shares one tile of 32 sequences.  CTA r owns hidden units [32r, 32r+32): its 128 gate rows
-// of W_hh stay resident in shared memory for the whole kernel as bf16 hi (+ lo) in the 128-byte-swizzled K-major operand layout, row
-// order L = 4*unit + gate.  Per step and CTA the product is ONE accumulator tile in TMEM:
-//   forward : gates^T[128 rows, 32 seq] = Wslice[128, H] h_{t-1}[H, 32]          (A = W slice K-major, B = h tile, K = H)
-//   backward: dh^T[H units, 32 seq]     = Wslice^T[H, 128] da_t[128, 32]         (A = the SAME bytes read MN-major, B = da tile, K = 128)
-// issued by one thread as tcgen05.mma M=128, N=32 (3 MMAs per product in fp32 mode: hi*hi + hi*lo + lo*hi).  Measured on B200
-// (tools/microbench_cl.cu, profiles/r2_microbench_cl.txt): such an MMA costs ~55 cycles whatever N <= 64 is, i.e. 0.54 us (bf16
-// mode) / 1.35 us (fp32 mode) of tensor time per step, against ~3.3 us of HMMA + ldmatrix time in the mma.sync kernels.
-//   * forward: eight warps read the accumulator (tcgen05.ld: lane = gate row, column = sequence), add the input projection, apply
-//     the gate nonlinearity on all 128 lanes at once (tanh as 2*sigmoid(2x) - 1, so the code is uniform), transpose 4x4 over the four
-//     lanes of a unit so that every lane owns whole cells, update c / h and write their slice of h_t (bf16 hi | lo) in the B-operand
-//     layout of the next step.  The slice goes to the other CTAs with ONE cp.async.bulk shared::cta -> shared::cluster per
-//     destination, counted (complete_tx) on the destination's mbarrier: no cluster barrier in the loop, and the receiving tensor
-//     core reads what the async proxy wrote.
-//   * backward: the cell warps form da_t, store the dgates and write the bf16 da tile; the MMA result -- partial sums for ALL H
-//     units -- is reduce-scattered: every warp sends its TMEM rows to the CTA that owns those units with 16-byte st.async stores
-//     counted on the owner's mbarrier; the owner adds the C partials.
+// A thread-block CLUSTER of C = H/32 CTAs shares one tile of NS = 32 or 40 sequences.  CTA r owns hidden units [32r, 32r+32): its 128
+// gate rows of W_hh stay resident in TENSOR MEMORY for the whole kernel as bf16 hi (+ lo) -- the A operand of TS-mode MMAs.  Per step
+// and CTA the product is one accumulator tile in TMEM:
+//   forward : gates^T[128 rows, NS] = Wslice[128, H] h_{t-1}[H, NS]          (B = h tile in shared memory, K = H)
+//   backward: dh^T[H units, NS]     = Wslice^T[H, 128] da_t[128, NS]         (B = da tile in shared memory, K = 128; H/128 accumulators)
+// issued from warp-uniform code by one elected lane as tcgen05.mma M=128, N=NS (3 MMAs per product in fp32 mode: hi*hi + hi*lo +
+// lo*hi).  Such an MMA costs ~50 cycles whatever N <= 64 is (tools/microbench_cl.cu, profiles/r2_microbench_cl.txt): 0.4 us (bf16
+// mode) / 1.2 us (fp32 mode) of tensor time per step, against ~3.3 us of HMMA + ldmatrix time in the mma.sync kernels.
+//   * forward: eight cell warps read the accumulator with the 16x256b TMEM load shape -- the gate rows are ordered so that every
+//     thread receives i, f, g, o of whole cells (the mma.sync fragment), no lane exchange --, add the input projection (float4 per
+//     cell, register-prefetched one step ahead), update c / h and write their slice of h_t (bf16 hi | lo) directly in the B-operand
+//     layout of the next step.  One warp sends the slice to the other CTAs in ring order, ONE cp.async.bulk shared::cta ->
+//     shared::cluster per destination, counted (complete_tx) on a per-source mbarrier of the receiver: no cluster barrier in the
+//     loop, the receiving tensor core reads what the async proxy wrote, and its MMAs start on the slices that have landed.
+//   * backward: the cell warps form da_t from factors precomputed in the shadow of the previous step's MMAs, store the dgates and
+//     write the bf16 da tile; the MMA result -- partial sums for ALL H units -- is reduce-scattered: the TMEM rows of accumulator a,
+//     lane quarter q belong to CTA 4a + q; they are staged in the idle receive buffer and leave as one bulk copy per destination
+//     (fp32 partials in fp32 mode, bf16 in bf16 mode), counted on the owner's mbarrier; the owner adds the C partials.
+// DESIGN.md section 5 (K2t / K3t) lists the measurements behind each of these choices.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -59,7 +61,6 @@ constexpr int kCellThreads = 32 * kCellWarps;
 // step's state in registers without spilling (a spilled prefetch register turns the prefetch into a blocking load).
 constexpr int kThreads = kCellThreads + 128;
 constexpr int kCellRegs = 208, kAuxRegs = 64;
-constexpr int kWBlk = kRows * 128;      // one [128 gate rows x 64 units] bf16 block of the resident W slice (128-byte swizzle)
 template <int NB>
 struct TileT {
   static constexpr int NS = 8 * NB;
@@ -83,17 +84,6 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_saddr, uint32_t r
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_saddr), "r"(rank));
   return r;
-}
-// bulk copy shared::cta -> shared memory of a CTA of the cluster (async proxy); completes `bytes` on an mbarrier of THAT CTA
-__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
-               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-               : "memory");
-}
-__device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(addr),
-               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(remote_bar)
-               : "memory");
 }
 // shared-memory matrix descriptor without swizzle (K-major "interleaved" canonical layout): core matrices of 8 rows x 16 bytes
 // (128 contiguous bytes); sbo = bytes between 8-row groups along M/N, lbo = bytes between the two 16-byte chunks along K
