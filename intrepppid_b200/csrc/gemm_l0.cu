@@ -24,14 +24,23 @@ namespace {
 
 using namespace tc;
 
-constexpr int kStages = 2;
+// Operand pipeline: the TMA stages (dgates + Hprev, 48 KB in fp32 mode / 24 KB in bf16 mode) and the one-hot tiles (32 KB, written from
+// the token ids by four warps: no HBM latency to hide) are SEPARATE rings.  With one ring of two 80 KB stages only one item's loads
+// were in flight and every item paid part of the TMA latency: 0.32 ms at 54 % of HBM with the tensor pipe 65 % busy -- neither bound.
+// fp32 mode: 3 TMA stages + 2 one-hot tiles (0.319 -> 0.290 ms for the three launches of the family; 4 + 1 measured 0.310: a single
+// one-hot tile serialises the writers with the MMAs); bf16 mode: 5 + 2 (0.204 ms, 85 % of HBM).
+template <bool SPLIT>
+constexpr int ay_stages() { return SPLIT ? 3 : 5; }
+template <bool SPLIT>
+constexpr int oh_stages() { return 2; }
+constexpr int kMaxStagesAY = 5, kMaxStagesOH = 2;
 constexpr int kBlk = 64 * 128;        // one [64 k-rows x 64 columns] bf16 block (128-byte swizzled rows)
 constexpr int kNS = 256;              // one-hot columns (vocabulary slots; V <= 256)
 constexpr int kNOut = 64 + kNS;       // accumulator columns per gate row: [dW_hh (64) | S (256)]
 constexpr uint32_t kTmemCols = 512;   // 320 used
 
 struct Bars {
-  uint64_t full[kStages], empty[kStages], done;
+  uint64_t full[kMaxStagesAY], empty[kMaxStagesAY], ohfull[kMaxStagesOH], ohempty[kMaxStagesOH], done;
   uint32_t tmem_base;
 };
 struct Maps {
@@ -43,10 +52,11 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_constant__ Maps maps, const L0GradArgs p) {
   constexpr int NPART = SPLIT ? 2 : 1;
   constexpr int kABytes = 2 * kBlk, kYBytes = kBlk, kOHBytes = (kNS / 64) * kBlk;
-  constexpr int kStageBytes = NPART * (kABytes + kYBytes) + kOHBytes;
+  constexpr int kStageBytes = NPART * (kABytes + kYBytes), kStages = ay_stages<SPLIT>(), kStagesOH = oh_stages<SPLIT>();
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  Bars* bars = reinterpret_cast<Bars*>(smem + (size_t)kStages * kStageBytes);
+  unsigned char* ohbuf = smem + (size_t)kStages * kStageBytes;  // [kStagesOH][kOHBytes]
+  Bars* bars = reinterpret_cast<Bars*>(ohbuf + (size_t)kStagesOH * kOHBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = blockIdx.y, cta = blockIdx.x, d = p.dir0 + (int)(blockIdx.z >> 1), mh = blockIdx.z & 1;
   const int T = p.lens[p.G + g];
@@ -56,8 +66,12 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bars->full[s], 1 + 128);
+      mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < kStagesOH; ++s) {
+      mbar_init(&bars->ohfull[s], 128);
+      mbar_init(&bars->ohempty[s], 1);
     }
     mbar_init(&bars->done, 1);
     mbar_init_fence();
@@ -68,10 +82,7 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
   // the one-hot regions start as zeros; afterwards only the 64 ones of the previous use of a stage are cleared
-  for (int s = 0; s < kStages; ++s) {
-    uint4* oh = reinterpret_cast<uint4*>(smem + (size_t)s * kStageBytes + NPART * (kABytes + kYBytes));
-    for (int i = tid; i < kOHBytes / 16; i += 192) oh[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  for (int i = tid; i < kStagesOH * kOHBytes / 16; i += 192) reinterpret_cast<uint4*>(ohbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -104,12 +115,13 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
       constexpr uint32_t idesc_hh = idesc_bf16(128, 64, true, true), idesc_s = idesc_bf16(128, kNS, true, true);
       const uint32_t d_hh = tmem_base, d_s = tmem_base + 64;
       for (int it = 0; it < my_items; ++it) {
-        const int stage = it % kStages;
+        const int stage = it % kStages, ohs = it % kStagesOH;
         mbar_wait(&bars->full[stage], (it / kStages) & 1);
+        mbar_wait(&bars->ohfull[ohs], (it / kStagesOH) & 1);
         fence_after_sync();
         const uint32_t a_hi = smem_u32(smem + (size_t)stage * kStageBytes), a_lo = a_hi + kABytes;
         const uint32_t y_hi = a_hi + NPART * kABytes, y_lo = y_hi + kYBytes;
-        const uint32_t oh = a_hi + NPART * (kABytes + kYBytes);
+        const uint32_t oh = smem_u32(ohbuf + (size_t)ohs * kOHBytes);
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
           const uint32_t ko = k16 * 16 * 128;  // 16 k-rows of 128 bytes inside every block
@@ -126,23 +138,24 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
           }
         }
         mma_commit_elect(&bars->empty[stage]);
+        mma_commit_elect(&bars->ohempty[ohs]);
       }
       mma_commit_elect(&bars->done);
     }
   } else {
     // ===================== one-hot writers (4 warps): thread r < 64 owns k-row r of the tile =====================
     const int r = tid - 64;
-    int prev[kStages];
+    int prev[kStagesOH];
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) prev[s] = -1;
+    for (int s = 0; s < kStagesOH; ++s) prev[s] = -1;
     uint32_t it = 0;
     for (int item = cta; item < items; item += p.ctas_per_group, ++it) {
-      const int stage = it % kStages;
+      const int stage = it % kStagesOH;
       const int n = g * p.B + item / tiles_per_seq, t0 = (item % tiles_per_seq) * 64;
       int v = -1;
       if (r < 64 && t0 + r < T) v = p.tok[(size_t)n * p.Tmax + t0 + r];
-      mbar_wait(&bars->empty[stage], ((it / kStages) & 1) ^ 1);
-      unsigned char* oh = smem + (size_t)stage * kStageBytes + NPART * (kABytes + kYBytes);
+      mbar_wait(&bars->ohempty[stage], ((it / kStagesOH) & 1) ^ 1);
+      unsigned char* oh = ohbuf + (size_t)stage * kOHBytes;
       if (r < 64) {
         // element (k-row r, column v) of the MN-major tile: block v/64, 128-byte row r, 16-byte chunk ((v%64)/8) ^ (r%8)
         if (prev[stage] >= 0) *reinterpret_cast<unsigned short*>(oh + prev[stage]) = 0;
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(192, 1) l0_grad_gemm_kernel(const __grid_const
         prev[stage] = off;
       }
       fence_async_smem();
-      mbar_arrive(&bars->full[stage]);
+      mbar_arrive(&bars->ohfull[stage]);
     }
   }
   __syncthreads();
@@ -287,7 +300,8 @@ cudaError_t launch_l0_grads(const L0GradArgs& a0, int precision, cudaStream_t st
   L0GradArgs a = a0;
   a.ctas_per_group = l0_grad_ctas_per_group(a.G, a.ndir);
   const int npart = precision == 0 ? 2 : 1;
-  const size_t smem = 1024 + (size_t)kStages * (npart * 3 * kBlk + (kNS / 64) * kBlk) + sizeof(Bars) + 64;
+  const size_t smem = 1024 + (size_t)(precision == 0 ? ay_stages<true>() : ay_stages<false>()) * npart * 3 * kBlk +
+                      (size_t)(precision == 0 ? oh_stages<true>() : oh_stages<false>()) * (kNS / 64) * kBlk + sizeof(Bars) + 64;
   Maps maps;
   const uint32_t box[3] = {64, 64, 1};
   for (int pl = 0; pl < npart; ++pl) {
