@@ -448,7 +448,8 @@ struct NTTmaMaps {
 };
 constexpr int kNTStoreTile = 32 * 128;  // TSTORE: one staging tile [32 rows x 32 floats]; 4 epilogue warps x (1 or 2) tiles
 
-// TSTORE (C = ..., not +=): the epilogue writes 32x32 blocks into swizzled staging tiles and hands them to the TMA store unit
+// TSTORE (C = ..., not +=; chosen by the launcher only where two staging tiles per epilogue warp fit next to the resident W -- at the
+// headline shapes, with 128 KB of W, they do not, and a single tile measured slower than the thread stores): the epilogue writes 32x32 blocks into swizzled staging tiles and hands them to the TMA store unit
 // (cp.async.bulk.tensor, double buffered per warp) instead of transposing through shared memory and storing row by row from the
 // threads.  Whole 32-row boxes are written: rows t >= T_eff of a live tile receive values nobody reads (the consumers of the input
 // projection and of dY only touch rows t < T_eff).
