@@ -18,6 +18,7 @@
  *                               classifier/head/mlp.py:35-68  MLPHead, BCEWithLogitsLoss, beta mix)
  *   ib200_batch_metrics         e2e/e2e_triplet.py:171-184   (torchmetrics AUROC / AP / MCC / Precision / Recall of the batch)
  *   ib200_adamw_step            e2e/e2e_triplet.py:231-255   (configure_optimizers: torch.optim.AdamW over self.parameters())
+ *   ib200_ranger21_step         e2e/e2e_triplet.py:200-226   (configure_optimizers: ranger21.Ranger21, the factory default; parity unpinned)
  *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
  *   ib200_p2p_allreduce_mean    (no reference counterpart: the reference trains on one device, e2e/e2e_triplet.py:392-400)
  *
@@ -245,6 +246,38 @@ typedef struct ib200_adamw_hyper {
 } ib200_adamw_hyper;
 int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                      float* const* exp_avg_sq, const int64_t* numel, const ib200_adamw_hyper* hyper, void* stream);
+
+/*
+ * Multi-tensor Ranger21: the optimizer the reference's factory default selects (e2e/e2e_triplet.py:200-226 -- ranger21.Ranger21(
+ * self.parameters(), lr, weight_decay=1e-2, use_warmup, warmdown_active, num_batches_per_epoch, num_epochs, warmdown_start_pct=0.72);
+ * intrepppid/__init__.py:37 optimizer_type="ranger21_xx").  Ranger21 is a pinned third-party package
+ * (requirements.txt:65, lessw2020/Ranger21 @ 1a96777) whose source is absent from the image: the arithmetic is the published
+ * algorithm (arXiv:2106.13731) in the step order of oracle/ranger21_restated.py -- PARITY UNPINNED against the package itself.
+ * Covers the AdamW core with positive-negative momentum, adaptive gradient clipping, gradient centralization + normalization, norm
+ * loss, stable weight decay, softplus denominator and lookahead; the learning-rate schedule (warm-up / warm-down) is host logic:
+ * the caller passes lr(step) per tensor.  Two launches per 24 tensors, no host sync.  Like the package, the step rewrites the
+ * gradients in place (clipped, centralized, normalized).
+ *   tensors      HOST array [n]: DEVICE pointers of one parameter's tensors (fp32, contiguous, rows * cols elements each; a 0-d / 1-d
+ *                tensor is one row), `multi_dim` = the parameter has more than one dimension (its rows are centralized; tensors with
+ *                3 dimensions are not supported: the package takes their unit norm over dimension 1 only), `step` = 1-based count
+ *                of this update for this tensor, `lr` = learning rate of this step; grad_ma / neg_grad_ma are the buffer that
+ *                receives this step's momentum and the other one (the package swaps their roles every step: odd steps write
+ *                state["grad_ma"]); lookahead may be NULL when hyper.lookahead_merge == 0
+ *   scratch      n + 1 DEVICE doubles; scratch[n] = variance_normalized of this step afterwards (NaN = the package's RuntimeError)
+ */
+typedef struct ib200_ranger21_tensor {
+  float *param, *grad, *grad_ma, *neg_grad_ma, *variance_ma, *lookahead;
+  int64_t rows, cols;
+  int32_t multi_dim, step;
+  double lr;
+} ib200_ranger21_tensor;
+typedef struct ib200_ranger21_hyper {
+  double beta1, beta2, eps, weight_decay, agc_clip, agc_eps, normloss_factor, softplus_beta, pnm_factor, lookahead_alpha;
+  int32_t use_agc, use_gc, use_gcnorm, use_normloss, use_softplus;
+  int32_t lookahead_merge; /* 1 on the calls that merge the slow weights (every lookahead_mergetime-th) */
+} ib200_ranger21_hyper;
+int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors, const ib200_ranger21_hyper* hyper, double* scratch,
+                        void* stream);
 
 /* Data-parallel gradient exchange (the reference itself is single-GPU, e2e/e2e_triplet.py:392-400): one-shot MEAN all-reduce
  * of a small bucket over NVLink peer memory, in place.  Every rank owns a staging region of 2 * stage_floats floats (two parity halves)

@@ -14,9 +14,9 @@ from torch import nn
 from .classifier.head import MLPHead
 from .e2e.e2e_triplet import StepMasks, TripletE2ENet
 from .encoders.awd_lstm import AWDLSTMEncoder
-from .optim import FusedAdamW
+from .optim import FusedAdamW, FusedRanger21
 
-__all__ = ["intrepppid_network", "AWDLSTMEncoder", "MLPHead", "TripletE2ENet", "StepMasks", "FusedAdamW"]
+__all__ = ["intrepppid_network", "AWDLSTMEncoder", "MLPHead", "TripletE2ENet", "StepMasks", "FusedAdamW", "FusedRanger21"]
 
 
 def intrepppid_network(steps_per_epoch: int, vocab_size: int = 250, embedding_size: int = 64, rnn_num_layers: int = 2,

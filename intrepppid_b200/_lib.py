@@ -35,6 +35,17 @@ class AdamWHyper(C.Structure):
                                                                                                             ("maximize", C.c_int32)]
 
 
+class Ranger21Tensor(C.Structure):
+    _fields_ = [(n, vp) for n in ("param", "grad", "grad_ma", "neg_grad_ma", "variance_ma", "lookahead")] + [
+        ("rows", C.c_int64), ("cols", C.c_int64), ("multi_dim", C.c_int32), ("step", C.c_int32), ("lr", C.c_double)]
+
+
+class Ranger21Hyper(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("beta1", "beta2", "eps", "weight_decay", "agc_clip", "agc_eps", "normloss_factor",
+                                          "softplus_beta", "pnm_factor", "lookahead_alpha")] + [
+        (n, C.c_int32) for n in ("use_agc", "use_gc", "use_gcnorm", "use_normloss", "use_softplus", "lookahead_merge")]
+
+
 class MaskSpec(C.Structure):
     _fields_ = [("out", vp), ("numel", C.c_int64), ("keep_prob", C.c_float), ("row_len", C.c_int32)]
 
@@ -45,7 +56,7 @@ class HeadMasks(C.Structure):
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_status", "ib200_encoder_bwd", "ib200_encoder_bwd_layers",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_batch_metrics", "ib200_draw_masks", "ib200_p2p_allreduce_mean", "ib200_p2p_alloc", "ib200_p2p_open", "ib200_p2p_close", "ib200_p2p_free",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_adamw_step", "ib200_ranger21_step", "ib200_batch_metrics", "ib200_draw_masks", "ib200_p2p_allreduce_mean", "ib200_p2p_alloc", "ib200_p2p_open", "ib200_p2p_close", "ib200_p2p_free",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn", "ib200_dbg_gemm_nt_planes", "ib200_dbg_gemm_tn_planes", "ib200_dbg_l0_scratch_floats",
            "ib200_dbg_l0_grads", "ib200_dbg_gemm_nt_wide", "ib200_dbg_gemm_tn_wide")
 
@@ -84,6 +95,7 @@ def lib() -> C.CDLL:
     L.ib200_pair_score_range.argtypes = [C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64, C.POINTER(HeadParams), vp, vp]
     L.ib200_adamw_step.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64),
                                    C.POINTER(AdamWHyper), vp]
+    L.ib200_ranger21_step.argtypes = [C.c_int32, C.POINTER(Ranger21Tensor), C.POINTER(Ranger21Hyper), vp, vp]
     L.ib200_p2p_allreduce_mean.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_size_t, vp, C.c_size_t, C.c_uint32, vp]
     L.ib200_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     L.ib200_p2p_open.argtypes = [C.c_char_p, C.POINTER(vp)]

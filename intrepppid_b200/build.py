@@ -19,7 +19,7 @@ ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libib200.so")
 TORCH_LIB = os.path.join(PKG, "libib200_torch.so")  # TORCH_LIBRARY shim (csrc/torch_ops.cpp) over the C ABI
 OBJDIR = os.path.join(ROOT, "build", "obj")
-SOURCES = ["capi.cu", "small.cu", "head.cu", "lstm_fwd.cu", "lstm_bwd.cu", "lstm_cluster.cu", "lstm_cluster_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_l0.cu", "gemm_wide.cu", "optim.cu", "metrics.cu", "masks.cu", "p2p.cu"]
+SOURCES = ["capi.cu", "small.cu", "head.cu", "lstm_fwd.cu", "lstm_bwd.cu", "lstm_cluster.cu", "lstm_cluster_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_l0.cu", "gemm_wide.cu", "optim.cu", "ranger21.cu", "metrics.cu", "masks.cu", "p2p.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 if os.environ.get("IB200_PROF"):  # timing experiments only: per-phase cycle counters printed by the tcgen05 cluster kernels

@@ -37,10 +37,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- instrumentation: launch counter (always on) and optional CUDA-event timing per kernel family (bench.py) ----------------
 enum Family { F_LENGTHS, F_L0_TABLE, F_PREP, F_LSTM_FWD_L0, F_LSTM_FWD_UP, F_GEMM_XPROJ, F_LSTM_BWD_UP, F_LSTM_BWD_L0, F_GEMM_DW,
-              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_L0_GRADS, F_ALLREDUCE, F_COUNT };
+              F_DW_REDUCE, F_GEMM_DGRAD, F_EMB_GRAD, F_POOL_FC, F_LOSS_HEAD, F_PAIR_SCORE, F_FILL, F_ADAMW, F_METRICS, F_MASKS, F_L0_GRADS, F_ALLREDUCE, F_RANGER21, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"lengths", "l0_table", "prep_wih", "lstm_fwd_l0", "lstm_fwd_upper", "gemm_nt_xproj",
                                      "lstm_bwd_upper", "lstm_bwd_l0", "gemm_tn_dw", "dw_reduce", "gemm_nt_dgrad", "emb_grad",
-                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks", "l0_grads", "p2p_allreduce"};
+                                     "pool_fc", "loss_head", "pair_score", "fill_zero", "adamw", "batch_metrics", "draw_masks", "l0_grads", "p2p_allreduce", "ranger21"};
 std::atomic<unsigned long long> g_launches{0};
 struct TimingState {
   std::mutex mu;
@@ -945,6 +945,55 @@ int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const
     const cudaError_t e = launch_adamw(n_tensors, params, grads, exp_avg, exp_avg_sq, (const long long*)numel, s, st, &launches);
     g_launches.fetch_add((unsigned long long)launches);
     if (e != cudaSuccess) return cuda_fail(e, "adamw");
+  }
+  return 0;
+}
+
+int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors, const ib200_ranger21_hyper* h, double* scratch,
+                        void* stream) {
+  if (n_tensors < 0 || n_tensors > 4096) return fail(IB200_E_SHAPE, "ib200_ranger21_step: tensor count out of range");
+  if (n_tensors == 0) return 0;
+  if (!tensors || !h || !scratch) return fail(IB200_E_NULL, "ib200_ranger21_step: null pointer");
+  if (!(h->beta1 >= 0. && h->beta1 < 1. && h->beta2 >= 0. && h->beta2 < 1. && h->eps >= 0. && h->weight_decay >= 0.))
+    return fail(IB200_E_SHAPE, "ib200_ranger21_step: hyper-parameters out of range");
+  std::vector<R21Tensor> tb((size_t)n_tensors);
+  double param_size = 0.0;
+  for (int k = 0; k < n_tensors; ++k) {
+    const ib200_ranger21_tensor& t = tensors[k];
+    if (!t.param || !t.grad || !t.grad_ma || !t.neg_grad_ma || !t.variance_ma || (h->lookahead_merge && !t.lookahead))
+      return fail(IB200_E_NULL, "ib200_ranger21_step: null tensor pointer");
+    if (t.rows < 1 || t.cols < 1 || t.rows > INT32_MAX || t.cols > INT32_MAX) return fail(IB200_E_SHAPE, "ib200_ranger21_step: empty or oversized tensor");
+    if (t.step < 1) return fail(IB200_E_SHAPE, "ib200_ranger21_step: step counts from 1");
+    if (!(t.lr >= 0.)) return fail(IB200_E_SHAPE, "ib200_ranger21_step: negative learning rate");
+    // every scalar is derived in double on the host and rounded once, as the package derives them from Python floats
+    const double bc1 = 1.0 - std::pow(h->beta1, (double)t.step), bc2 = 1.0 - std::pow(h->beta2, (double)t.step);
+    R21Tensor& o = tb[(size_t)k];
+    o.p = t.param; o.g = t.grad; o.grad_ma = t.grad_ma; o.neg_grad_ma = t.neg_grad_ma; o.v = t.variance_ma; o.slow = t.lookahead;
+    o.numel = (long long)t.rows * (long long)t.cols;
+    o.inv_bc2 = 1.0 / bc2;
+    o.wd_lr = h->weight_decay * t.lr;
+    o.rows = (int)t.rows; o.cols = (int)t.cols; o.multi_dim = t.multi_dim ? 1 : 0;
+    o.lr = (float)t.lr; o.sqrt_bc2 = (float)std::sqrt(bc2); o.step_size = (float)(t.lr / bc1);
+    param_size += (double)o.numel;
+  }
+  R21Scalars s{};
+  s.param_size = param_size;
+  s.b2 = (float)h->beta2; s.one_minus_b2 = (float)(1.0 - h->beta2);
+  s.b1sq = (float)(h->beta1 * h->beta1); s.one_minus_b1sq = (float)(1.0 - h->beta1 * h->beta1);
+  s.eps = (float)h->eps; s.agc_clip = (float)h->agc_clip; s.agc_eps = (float)h->agc_eps;
+  s.normloss2 = (float)(2.0 * h->normloss_factor); s.softplus_beta = (float)h->softplus_beta;
+  s.pnm_factor = (float)h->pnm_factor; s.one_plus_pnm = (float)(1.0 + h->pnm_factor);
+  s.inv_noise_norm = (float)(1.0 / std::sqrt((1.0 + h->beta2) * (1.0 + h->beta2) + h->beta2 * h->beta2));
+  s.la_alpha = (float)h->lookahead_alpha; s.one_minus_la_alpha = (float)(1.0 - h->lookahead_alpha);
+  s.use_agc = h->use_agc != 0; s.use_gc = h->use_gc != 0; s.use_gcnorm = h->use_gcnorm != 0; s.use_normloss = h->use_normloss != 0;
+  s.use_softplus = h->use_softplus != 0; s.use_decay = h->weight_decay != 0.; s.lookahead_merge = h->lookahead_merge != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  {
+    TimedScope ts__(F_RANGER21, 0, st);
+    const cudaError_t e = launch_ranger21(n_tensors, tb.data(), s, scratch, st, &launches);
+    g_launches.fetch_add((unsigned long long)launches);
+    if (e != cudaSuccess) return cuda_fail(e, "ranger21");
   }
   return 0;
 }

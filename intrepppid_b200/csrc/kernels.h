@@ -255,4 +255,22 @@ struct AdamScalars {
 cudaError_t launch_adamw(int n, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                          const long long* numel, const AdamScalars& s, cudaStream_t st, int* launches);
 
+// ---- multi-tensor Ranger21 (ranger21.cu) -------------------------------------------------------------------------------------
+constexpr int kR21MaxTensors = 24;  // tensors per launch (the table travels in the kernel parameters: 24 x 96 B)
+struct R21Tensor {
+  float* p; float* g; float* grad_ma; const float* neg_grad_ma; float* v; float* slow;
+  long long numel;
+  double inv_bc2, wd_lr;      // 1 / (1 - b2^step); weight_decay * lr(step)
+  int rows, cols, multi_dim;  // rows x cols view (one row for 0-d / 1-d tensors); multi_dim: dim() > 1 (rows are centralized)
+  float lr, sqrt_bc2, step_size;  // lr(step) after warm-up / warm-down; sqrt(1 - b2^step); lr / (1 - b1^step)
+};
+struct R21Scalars {
+  double param_size;  // elements of all tensors of this step
+  float b2, one_minus_b2, b1sq, one_minus_b1sq, eps, agc_clip, agc_eps, normloss2, softplus_beta, pnm_factor, one_plus_pnm,
+      inv_noise_norm, la_alpha, one_minus_la_alpha;
+  int use_agc, use_gc, use_gcnorm, use_normloss, use_softplus, use_decay, lookahead_merge;
+};
+// tensors: HOST array; scratch: n + 1 DEVICE doubles (per-tensor variance sums, then variance_normalized); *launches = kernels launched
+cudaError_t launch_ranger21(int n, const R21Tensor* tensors, const R21Scalars& s, double* scratch, cudaStream_t st, int* launches);
+
 }  // namespace ib200

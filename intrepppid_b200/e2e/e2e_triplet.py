@@ -8,6 +8,7 @@ reference logs; otherwise it is a plain nn.Module and `log` is a no-op (the arit
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -16,6 +17,7 @@ from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts, OneCycleLR
 
 from .. import ops
 from ..optim import FusedAdamW as AdamW  # torch.optim.AdamW's arguments / state layout on the multi-tensor CUDA kernel
+from ..optim import FusedRanger21
 
 try:  # optional orchestration dependencies (absent in the build image)
     import pytorch_lightning as pl
@@ -181,14 +183,17 @@ class TripletE2ENet(_Base):
     def test_step(self, batch, batch_idx):
         return self.step(batch, "test")
 
-    # -- optimizers (e2e_triplet.py:198-255; the AdamW variants step through ib200_adamw_step, Ranger21 stays third-party) ---------
+    # -- optimizers (e2e_triplet.py:198-255): AdamW variants -> ib200_adamw_step, Ranger21 variants -> ib200_ranger21_step ----------
     def configure_optimizers(self):
         if self.optimizer_type in ("ranger21", "ranger21_xx"):
-            from ranger21 import Ranger21  # third-party, same pin as the reference; imported lazily
-
             xx = self.optimizer_type == "ranger21_xx"
-            return Ranger21(self.parameters(), use_warmup=xx, warmdown_active=xx, lr=self.lr, weight_decay=1e-2,
-                            num_batches_per_epoch=self.steps_per_epoch, num_epochs=self.num_epochs, warmdown_start_pct=0.72)
+            kw = dict(use_warmup=xx, warmdown_active=xx, lr=self.lr, weight_decay=1e-2, num_batches_per_epoch=self.steps_per_epoch,
+                      num_epochs=self.num_epochs, warmdown_start_pct=0.72)
+            if os.environ.get("IB200_RANGER21", "fused") == "package":  # the third-party package itself (the reference's pin), when installed
+                from ranger21 import Ranger21
+
+                return Ranger21(self.parameters(), **kw)
+            return FusedRanger21(self.parameters(), **kw)  # parity unpinned against the package: see optim.FusedRanger21
         if self.optimizer_type == "adamw":
             return AdamW(self.parameters(), lr=self.lr)
         if self.optimizer_type == "adamw_1cycle":
