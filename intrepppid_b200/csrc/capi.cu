@@ -958,11 +958,13 @@ int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors,
     return fail(IB200_E_SHAPE, "ib200_ranger21_step: hyper-parameters out of range");
   std::vector<R21Tensor> tb((size_t)n_tensors);
   double param_size = 0.0;
+  float* pnorm = reinterpret_cast<float*>(scratch + 3 + n_tensors);  // row norms follow the 3 + n doubles
   for (int k = 0; k < n_tensors; ++k) {
     const ib200_ranger21_tensor& t = tensors[k];
     if (!t.param || !t.grad || !t.grad_ma || !t.neg_grad_ma || !t.variance_ma || (h->lookahead_merge && !t.lookahead))
       return fail(IB200_E_NULL, "ib200_ranger21_step: null tensor pointer");
-    if (t.rows < 1 || t.cols < 1 || t.rows > INT32_MAX || t.cols > INT32_MAX) return fail(IB200_E_SHAPE, "ib200_ranger21_step: empty or oversized tensor");
+    if (t.rows < 1 || t.cols < 1 || t.rows > INT32_MAX || t.cols > INT32_MAX || t.rows * t.cols > INT32_MAX)
+      return fail(IB200_E_SHAPE, "ib200_ranger21_step: empty or oversized tensor");
     if (t.step < 1) return fail(IB200_E_SHAPE, "ib200_ranger21_step: step counts from 1");
     if (!(t.lr >= 0.)) return fail(IB200_E_SHAPE, "ib200_ranger21_step: negative learning rate");
     // every scalar is derived in double on the host and rounded once, as the package derives them from Python floats
@@ -970,6 +972,8 @@ int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors,
     R21Tensor& o = tb[(size_t)k];
     o.p = t.param; o.g = t.grad; o.grad_ma = t.grad_ma; o.neg_grad_ma = t.neg_grad_ma; o.v = t.variance_ma; o.slow = t.lookahead;
     o.numel = (long long)t.rows * (long long)t.cols;
+    o.pnorm = pnorm;
+    pnorm += t.rows;
     o.inv_bc2 = 1.0 / bc2;
     o.wd_lr = h->weight_decay * t.lr;
     o.rows = (int)t.rows; o.cols = (int)t.cols; o.multi_dim = t.multi_dim ? 1 : 0;

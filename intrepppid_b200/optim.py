@@ -149,7 +149,7 @@ class FusedRanger21(Optimizer):
         self.agc_active, self.agc_clip_val, self.agc_eps = use_adaptive_gradient_clipping, agc_clipping_value, agc_eps
         self.momentum_pnm, self.pnm_momentum_factor = True, pnm_momentum_factor
         self.eps = eps
-        self._scratch = None  # device doubles: per-tensor variance sums + variance_normalized
+        self._scratch = None  # device scratch: per-tensor variance sums + variance_normalized (doubles), row norms (floats)
 
     # -- learning-rate schedule (host logic; the package's warmup_dampening / get_warm_down) ----------------------------------------
     def warmup_dampening(self, lr, step):
@@ -175,7 +175,7 @@ class FusedRanger21(Optimizer):
 
     def variance_normalized(self) -> float:
         """variance_normalized of the most recent step (one device read; NaN is what makes the package raise)."""
-        return float("nan") if self._scratch is None else float(self._scratch[self._n_last].item())
+        return float("nan") if self._scratch is None else float(self._scratch[0].item())
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -239,9 +239,9 @@ class FusedRanger21(Optimizer):
             raise NotImplementedError("FusedRanger21 steps one param_group (the reference passes self.parameters())")
         group = entries[0][0]
         dev = entries[0][1].device
-        if self._scratch is None or self._scratch.numel() < n + 1 or self._scratch.device != dev:
-            self._scratch = torch.zeros(max(64, n + 1), dtype=torch.float64, device=dev)
-        self._n_last = n
+        need = 3 + n + (sum(int(t.rows) for t in tb) + 1) // 2  # 3 + n doubles (vn, 1/vn, counter, sums), then one float per tensor row
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+            self._scratch = torch.zeros(max(64, need), dtype=torch.float64, device=dev)
         hyper = _lib.Ranger21Hyper(float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
                                    float(self.agc_clip_val), float(self.agc_eps), float(self.normloss_factor), float(self.beta_softplus),
                                    float(self.pnm_momentum_factor), float(self.lookahead_alpha), int(bool(self.agc_active)),

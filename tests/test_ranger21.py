@@ -200,8 +200,11 @@ def _run_pair(kw, seed, shapes=SHAPES, steps=12, none_at=1, extra=None):
     return params, P64, P32, mine, o64, om, G64
 
 
+BIG = [(300, 200), (64,), (1000, 64), (64, 512), (7,), (70000,), (3, 40000)]  # past the 48 K-element staging buffer / rows wider than 128
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["ranger21_xx", "ranger21", "no_extras", "two_tables"])
+@pytest.mark.parametrize("variant", ["ranger21_xx", "ranger21", "no_extras", "two_tables", "big_tensors"])
 def test_fused_ranger21_matches_the_restatement(variant):
     from intrepppid_b200 import _lib
 
@@ -213,6 +216,8 @@ def test_fused_ranger21_matches_the_restatement(variant):
                      lookahead_active=False)
     elif variant == "two_tables":
         shapes = SHAPES * 2   # 30 tensors, 29 with a gradient: crosses the 24-tensor kernel-parameter table
+    elif variant == "big_tensors":
+        shapes = BIG
     l0 = _lib.launch_count()
     params, P64, P32, mine, o64, om, G64 = _run_pair(kw, 21, shapes, extra=extra)
     n_live = len(shapes) - 1
@@ -230,7 +235,7 @@ def test_fused_ranger21_matches_the_restatement(variant):
             assert rel_l2(st[name], sr[name]) < 2e-5, (variant, k, name)
         assert float(st["max_variance_ma"].abs().max()) == 0.0
         assert rel_l2(mine[k].grad, G64[k]) < 2e-5 or float(G64[k].abs().max()) == 0.0   # p.grad is rewritten in place like the package's
-    assert torch.equal(mine[0].detach()[0].cpu(), torch.zeros(64))
+    assert torch.equal(mine[0].detach()[0].cpu(), torch.zeros(shapes[0][1]))
     assert om.variance_normalized() > 0
 
 
