@@ -107,6 +107,8 @@ def test_restatement_descends():
 def test_against_the_ranger21_package_when_it_is_importable():
     """THE PIN, for environments that have the reference's dependency installed (not this image: skipped here)."""
     ranger21 = pytest.importorskip("ranger21")
+    if getattr(ranger21, "__file__", None) is None:  # oracle/ref_shim.py seeds sys.modules with a stub of the missing dependency
+        pytest.skip("ranger21 is the reference shim's stub, not the package")
     params, grads = _problem(5)
     mine = [p.clone() for p in params]
     theirs = [torch.nn.Parameter(p.clone()) for p in params]
