@@ -20,6 +20,7 @@
  *   ib200_adamw_step            e2e/e2e_triplet.py:231-255   (configure_optimizers: torch.optim.AdamW over self.parameters())
  *   ib200_ranger21_step         e2e/e2e_triplet.py:200-226   (configure_optimizers: ranger21.Ranger21, the factory default; parity unpinned)
  *   ib200_pair_score            e2e/e2e_triplet.py:105-111 + cli/infer.py:216-225 (head + sigmoid over pairs of cached embeddings)
+ *   ib200_sequence_lengths      encoders/awd_lstm.py:149-150,53-54 on the batch-of-one calls of cli/infer.py:196-225 (lengths only)
  *   ib200_p2p_allreduce_mean    (no reference counterpart: the reference trains on one device, e2e/e2e_triplet.py:392-400)
  *
  * Conventions
@@ -200,6 +201,16 @@ int ib200_pair_score(int32_t M, int32_t H, const float* z, const int32_t* idx_a,
  * proteins, all-gather the [M,H] embeddings, split the pair matrix by rows). */
 int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin, int64_t p_count,
                            const ib200_head_params* params, float* prob_out, void* stream);
+
+/* Per-sequence truncation lengths of BATCH-OF-ONE eval encoder calls -- what `infer from_csv` does for every protein of every row
+ * (cli/infer.py:196-225: each protein goes through TripletE2ENet.forward alone, so it is truncated to its own lengths):
+ *   t1_out[m]   = #{t : tokens[m][t] != 0}                                                 (encoders/awd_lstm.py:149-150, a COUNT)
+ *   teff_out[m] = max_e #{t < t1_out[m] : emb[tokens[m][t]][e] != 0}                        (encoders/awd_lstm.py:53-54, quirk Q2)
+ * Integer bookkeeping for the embedding cache (intrepppid_b200.infer buckets proteins of equal lengths into encoder groups); the
+ * encoder entry points recompute both lengths per group.  tokens [M,T] of `token_dtype` (IB200_TOK_*), emb float [V,H], outputs int32
+ * [M], scratch int32 [V]; 2 <= V <= 28672 as for the encoder.  Ids outside [0, V) are clamped (the encoder call reports them). */
+int ib200_sequence_lengths(int32_t M, int32_t T, int32_t V, int32_t H, const void* tokens, int32_t token_dtype, const float* emb,
+                           int32_t* t1_out, int32_t* teff_out, int32_t* scratch, void* stream);
 
 /*
  * Production-mode dropout masks: every Bernoulli(keep)/keep mask of a step in one launch (the reference draws its 14 masks per step

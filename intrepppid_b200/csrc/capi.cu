@@ -832,6 +832,18 @@ int ib200_pair_score_range(int32_t M, int32_t H, const float* z, int64_t p_begin
   return 0;
 }
 
+int ib200_sequence_lengths(int32_t M, int32_t T, int32_t V, int32_t H, const void* tokens, int32_t token_dtype, const float* emb,
+                           int32_t* t1_out, int32_t* teff_out, int32_t* scratch, void* stream) {
+  if (M < 0 || T < 1 || V < 2 || V > kMaxVocab || H < 1) return fail(IB200_E_SHAPE, "ib200_sequence_lengths: bad shape (2 <= V <= 28672)");
+  if (token_dtype != IB200_TOK_I64 && token_dtype != IB200_TOK_I32 && token_dtype != IB200_TOK_I16 && token_dtype != IB200_TOK_U8)
+    return fail(IB200_E_SHAPE, "ib200_sequence_lengths: unknown token_dtype");
+  if (M == 0) return 0;
+  if (!tokens || !emb || !t1_out || !teff_out || !scratch) return fail(IB200_E_NULL, "ib200_sequence_lengths: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TIMED(F_LENGTHS, 2, launch_seq_lengths(M, T, V, H, tokens, token_dtype, emb, scratch, t1_out, teff_out, st), "sequence lengths");
+  return 0;
+}
+
 int ib200_draw_masks(int32_t n_specs, const ib200_mask_spec* specs, uint64_t seed, uint64_t offset, uint64_t* counters_used, void* stream) {
   if (n_specs < 0) return fail(IB200_E_SHAPE, "ib200_draw_masks: negative mask count");
   if (counters_used) *counters_used = 0;

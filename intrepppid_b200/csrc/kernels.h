@@ -20,6 +20,9 @@ constexpr int kStatusBadToken = 1;            // a token id outside [0, V) was c
 constexpr size_t kLen2MaxSmem = 224 * 1024;   // len2_kernel keeps a [V] histogram + a [V] list in shared memory
 constexpr int kMaxVocab = (int)(kLen2MaxSmem / (2 * sizeof(int)));  // = 28672 vocabulary rows
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st);
+// per-sequence (T1, T_eff) of batch-of-one eval calls; row_kind: scratch [V]
+cudaError_t launch_seq_lengths(int M, int T, int V, int H, const void* tokens, int token_dtype, const float* emb, int* row_kind,
+                               int* t1_out, int* teff_out, cudaStream_t st);
 
 // ---- K1a: layer-0 input-projection table P[g][d][v][4H] (GI order) --------------------------------------------------------
 // Pad replicas: a padded batch makes every short sequence read vocabulary row 0 at the same step (all of them at once at the start

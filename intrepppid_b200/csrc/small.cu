@@ -267,6 +267,82 @@ __global__ void pool_fc_bwd_dw_kernel(int N, int H, const float* __restrict__ dz
   }
 }
 
+
+// ---- per-sequence (T1, T_eff) of a batch-of-one encoder call in eval mode (cli/infer.py:196-225 encodes every protein alone, so
+// each one is truncated to ITS OWN lengths: awd_lstm.py:149-150 and :53-54 on a batch of one).  Bookkeeping for the embedding
+// cache of intrepppid_b200.infer (bucketing by length); the encoder kernels recompute both lengths per group (K0 above).
+__global__ void seq_row_kind_kernel(int V, int H, const float* __restrict__ emb, int* __restrict__ row_kind) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= V) return;
+  int nz = 0;
+  for (int e = lane; e < H; e += 32) nz += emb[(size_t)v * H + e] != 0.0f;
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  if (lane == 0) row_kind[v] = nz == 0 ? 0 : (nz == H ? 1 : 2);  // contributes nothing / to every column / to some columns
+}
+
+template <typename TOK>
+__global__ void __launch_bounds__(256) seq_lengths_kernel(int T, int V, int H, const TOK* __restrict__ tokens,
+                                                          const float* __restrict__ emb, const int* __restrict__ row_kind,
+                                                          int* __restrict__ t1_out, int* __restrict__ teff_out) {
+  extern __shared__ int hist[];  // [V] histogram, then [V] list of partial rows
+  int* partial = hist + V;
+  __shared__ int n_partial, full_sum, t1_s, best_s;
+  const TOK* __restrict__ src = tokens + (size_t)blockIdx.x * T;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) hist[v] = 0;
+  if (threadIdx.x == 0) n_partial = full_sum = t1_s = best_s = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) cnt += ((long long)src[t] != 0);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt != 0) atomicAdd(&t1_s, cnt);
+  __syncthreads();
+  const int T1 = t1_s;  // a COUNT of non-zero ids; the reference then keeps the FIRST T1 positions
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
+    const long long v64 = (long long)src[t];
+    atomicAdd(&hist[v64 < 0 ? 0 : (v64 >= V ? V - 1 : (int)v64)], 1);  // clamped like K0 (the encoder call reports bad ids)
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const int kind = row_kind[v], hv = hist[v];
+    if (kind == 1) mine += hv;
+    else if (kind == 2 && hv != 0) partial[atomicAdd(&n_partial, 1)] = v;
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine != 0) atomicAdd(&full_sum, mine);
+  __syncthreads();
+  int best = 0;
+  if (n_partial == 0) {
+    best = full_sum;
+  } else {
+    for (int e = threadIdx.x; e < H; e += blockDim.x) {
+      int c = full_sum;
+      for (int i = 0; i < n_partial; ++i) c += (emb[(size_t)partial[i] * H + e] != 0.0f) ? hist[partial[i]] : 0;
+      best = max(best, c);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+  }
+  if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(&best_s, best);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    t1_out[blockIdx.x] = T1;
+    teff_out[blockIdx.x] = best_s;
+  }
+}
+
+template <typename TOK>
+cudaError_t launch_seq_lengths_t(int M, int T, int V, int H, const void* tokens, const float* emb, int* row_kind, int* t1_out,
+                                 int* teff_out, cudaStream_t st) {
+  const size_t hist_bytes = 2 * (size_t)V * sizeof(int);
+  if (hist_bytes > kLen2MaxSmem) return cudaErrorInvalidConfiguration;
+  if (hist_bytes > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(seq_lengths_kernel<TOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  seq_row_kind_kernel<<<(V + 7) / 8, 256, 0, st>>>(V, H, emb, row_kind);
+  seq_lengths_kernel<TOK><<<M, 256, hist_bytes, st>>>(T, V, H, (const TOK*)tokens, emb, row_kind, t1_out, teff_out);
+  return cudaGetLastError();
+}
 }  // namespace
 
 cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
@@ -287,6 +363,17 @@ cudaError_t launch_lengths(const LengthArgs& a, cudaStream_t st) {
   nz_rows_kernel<<<dim3((a.V + 7) / 8, a.G), 256, 0, st>>>(a, a.row_kind);
   len2_kernel<<<a.G * a.B, 128, hist_bytes, st>>>(a, a.row_kind);
   return cudaGetLastError();
+}
+
+cudaError_t launch_seq_lengths(int M, int T, int V, int H, const void* tokens, int token_dtype, const float* emb, int* row_kind,
+                               int* t1_out, int* teff_out, cudaStream_t st) {
+  switch (token_dtype) {
+    case IB200_TOK_I64: return launch_seq_lengths_t<long long>(M, T, V, H, tokens, emb, row_kind, t1_out, teff_out, st);
+    case IB200_TOK_I32: return launch_seq_lengths_t<int>(M, T, V, H, tokens, emb, row_kind, t1_out, teff_out, st);
+    case IB200_TOK_I16: return launch_seq_lengths_t<short>(M, T, V, H, tokens, emb, row_kind, t1_out, teff_out, st);
+    case IB200_TOK_U8: return launch_seq_lengths_t<unsigned char>(M, T, V, H, tokens, emb, row_kind, t1_out, teff_out, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 template <int H>

@@ -27,17 +27,26 @@ GROUP_SIZES = (8, 4, 2, 1)  # sequences per encoder group; 8 = one full tile of 
 def batch1_lengths(tokens: torch.Tensor, emb_weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-sequence (T1, T_eff) of a batch-of-one encoder call in eval mode, as int64 tensors [M] on tokens.device.
     T1 = number of non-zero ids (awd_lstm.py:149-150); T_eff = max_e #{t < T1 : emb[x_t, e] != 0} (awd_lstm.py:53-54).
-    Integer bookkeeping for the bucketing only -- the kernels recompute both lengths per group (K0)."""
+    Integer bookkeeping for the bucketing only (`ib200_sequence_lengths`, one CTA per sequence) -- the encoder kernels recompute
+    both lengths per group (K0)."""
+    import ctypes as C
+
+    from . import _lib
+
+    ops._need_cuda(tokens, emb_weight)
     M, T = tokens.shape
-    V = emb_weight.shape[0]
-    tok = tokens.long().clamp(0, V - 1)
-    t1 = (tokens != 0).sum(dim=1)
-    inside = torch.arange(T, device=tokens.device).unsqueeze(0) < t1.unsqueeze(1)
-    hist = torch.zeros(M, V, dtype=torch.float64, device=tokens.device)
-    hist.scatter_add_(1, tok, inside.to(torch.float64))
-    nz = (emb_weight.detach().to(tokens.device) != 0).to(torch.float64)  # [V,E]
-    t_eff = (hist @ nz).max(dim=1).values.round().long()
-    return t1, t_eff
+    V, H = emb_weight.shape
+    if tokens.dtype not in ops._TOKEN_DTYPES:
+        tokens = tokens.long()
+    tokens = tokens.contiguous()
+    emb = ops._f32c(emb_weight.detach())
+    out = torch.empty(2, M, dtype=torch.int32, device=tokens.device)
+    scratch = torch.empty(V, dtype=torch.int32, device=tokens.device)
+    tok_dtype = _lib.TOKEN_DTYPE[str(tokens.dtype).replace("torch.", "")]
+    with torch.cuda.device(tokens.device):
+        _lib.check(_lib.lib().ib200_sequence_lengths(M, T, V, H, tokens.data_ptr(), tok_dtype, emb.data_ptr(), out[0].data_ptr(),
+                                                     out[1].data_ptr(), scratch.data_ptr(), ops._stream()), "ib200_sequence_lengths")
+    return out[0].long(), out[1].long()
 
 
 def plan_buckets(keys: Sequence[Tuple[int, int]], group_sizes: Sequence[int] = GROUP_SIZES,

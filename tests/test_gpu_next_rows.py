@@ -163,6 +163,41 @@ def _proteins(M, T, V, seed):
     return toks
 
 
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.int16, torch.uint8])
+def test_batch1_lengths_match_the_oracle_per_sequence(dtype):
+    """ib200_sequence_lengths against the oracle's own truncation on a batch of one, sequence by sequence (interior zero, all-zero
+    and partially zero vocabulary rows, one full-length and one single-token protein), for every id type of the ABI."""
+    from intrepppid_b200.infer import batch1_lengths
+
+    M, T, V, E = 24, 40, 30, 32
+    P = R.init_params(vocab=V, E=E, L=1, seed=1)
+    P["emb"][7].zero_()       # an all-zero vocabulary row besides the padding row
+    P["emb"][9, :5].zero_()   # a partially zero row
+    g = torch.Generator().manual_seed(2)
+    tok = torch.randint(1, V, (M, T), generator=g)
+    lens = torch.randint(1, T + 1, (M,), generator=g)
+    lens[:4] = torch.tensor([T, T, 1, 5])
+    for m in range(M):
+        tok[m, lens[m]:] = 0
+    tok[6, 2] = 0  # interior <unk>: T1 is a COUNT, so the slice loses the last real token (SURVEY Q1)
+    tok[8, :3] = 7
+    tok[10, :] = 9
+    tok[10, 30:] = 0
+    t1, te = batch1_lengths(tok.to(dtype).cuda(), P["emb"].cuda())
+    assert t1.dtype == te.dtype == torch.int64 and t1.is_cuda
+    for m in range(M):
+        _, info = R.encoder_forward(tok[m:m + 1], P, num_layers=1, bi_reduce="last", training=False)
+        assert (int(t1[m]), int(te[m])) == (info.T1, info.T_eff), m
+    # a vocabulary past the 48 KB default of dynamic shared memory (the opt-in path of the histogram)
+    V2 = 9000
+    emb2 = torch.randn(V2, 32)
+    emb2[0].zero_()
+    tok2 = torch.randint(1, V2, (5, 64), generator=g)
+    tok2[1, 50:] = 0
+    t1b, teb = batch1_lengths(tok2.cuda(), emb2.cuda())
+    assert t1b.tolist() == [64, 50, 64, 64, 64] and teb.tolist() == [64, 50, 64, 64, 64]
+
+
 @pytest.mark.parametrize("bi,L,E", [("last", 2, 64), ("mean", 1, 32), ("max", 2, 96)])
 def test_infer_pairs_equals_the_reference_batch_of_one_loop(bi, L, E, tmp_path):
     from intrepppid_b200 import infer

@@ -85,19 +85,18 @@ def _ragged_tokens(M, T, V, seed):
     return tok
 
 
-def test_batch1_lengths_match_the_oracle_per_sequence():
+def test_batch1_lengths_have_no_cpu_path():
+    from intrepppid_b200 import _lib
     from intrepppid_b200.infer import batch1_lengths
 
-    M, T, V, E = 24, 40, 30, 32
-    P = R.init_params(vocab=V, E=E, L=1, seed=1)
-    P["emb"][7].zero_()       # an all-zero vocabulary row besides the padding row
-    P["emb"][9, :5].zero_()   # a partially zero row
-    tok = _ragged_tokens(M, T, V, 2)
-    tok[8, :3] = 7
-    t1, te = batch1_lengths(tok, P["emb"])
-    for m in range(M):
-        _, info = R.encoder_forward(tok[m:m + 1], P, num_layers=1, bi_reduce="last", training=False)
-        assert (int(t1[m]), int(te[m])) == (info.T1, info.T_eff), m
+    with pytest.raises(_lib.IB200Error):  # (the per-sequence parity against the oracle runs on the GPU: tests/test_gpu_next_rows.py)
+        batch1_lengths(_ragged_tokens(8, 10, 30, 2), torch.randn(30, 32))
+    lib = _lib.lib()
+    assert lib.ib200_sequence_lengths(0, 10, 30, 32, None, 0, None, None, None, None, None) == 0          # nothing to do
+    assert lib.ib200_sequence_lengths(4, 10, 1, 32, None, 0, None, None, None, None, None) == -2          # V < 2
+    assert lib.ib200_sequence_lengths(4, 10, 40000, 32, None, 0, None, None, None, None, None) == -2      # V past the histogram
+    assert lib.ib200_sequence_lengths(4, 10, 30, 32, None, 9, None, None, None, None, None) == -2         # unknown id type
+    assert lib.ib200_sequence_lengths(4, 10, 30, 32, None, 0, None, None, None, None, None) == -1         # null pointers
 
 
 def test_plan_buckets_is_an_exact_partition_into_homogeneous_groups():
