@@ -262,3 +262,36 @@ def test_default_network_trains_with_fused_ranger21():
     assert all(math.isfinite(x) for x in losses) and min(losses[-5:]) < losses[0], losses
     assert net.encoder.embedder.weight.detach()[0].abs().max().item() == 0.0  # padding row untouched
     assert all(p not in opt.state for n, p in net.named_parameters() if "projection" in n)
+
+
+@pytest.mark.gpu
+def test_fused_ranger21_state_dict_round_trip_continues_the_run():
+    """An optimizer checkpoint (state_dict -> a fresh FusedRanger21 -> load_state_dict) continues bit-for-bit: the per-parameter
+    state carries the package's keys; the lookahead counter is an attribute (as in the package) and is restored by the caller."""
+    import copy
+
+    import intrepppid_b200 as ib
+
+    params, grads = _problem(31, steps=9)
+    a = [torch.nn.Parameter(p.clone().cuda()) for p in params]
+    oa = ib.FusedRanger21(a, **KW)
+    for gs in grads[:4]:
+        for p, g in zip(a, gs):
+            p.grad = g.clone().cuda()
+        oa.step()
+    sd = copy.deepcopy(oa.state_dict())
+    assert set(sd["state"][0]) == {"step", "grad_ma", "variance_ma", "lookahead_params", "neg_grad_ma", "max_variance_ma"}
+    assert sd["state"][0]["step"] == 4 and sd["param_groups"][0]["weight_decay"] == 1e-2
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    ob = ib.FusedRanger21(b, **KW)
+    ob.load_state_dict(sd)
+    ob.lookahead_step = oa.lookahead_step
+    for gs in grads[4:]:
+        for pa, pb, g in zip(a, b, gs):
+            pa.grad, pb.grad = g.clone().cuda(), g.clone().cuda()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for pa, pb in zip(a, b):
+        assert torch.equal(pa.detach(), pb.detach())
+    assert ob.state[b[0]]["step"] == 9
