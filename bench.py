@@ -269,7 +269,7 @@ def run_b200(args):
         params = [p for p in net.parameters() if p.requires_grad]
         if optimizer == "adamw":
             opt = FusedAdamW(params, lr=1e-3)  # ib200_adamw_step: one launch over the 23 live tensors
-        else:  # the reference's factory default (e2e_triplet.py:212-224): ib200_ranger21_step, two launches over the live tensors
+        else:  # the reference's factory default (e2e_triplet.py:212-224): ib200_ranger21_step, three launches over the live tensors
             from intrepppid_b200.optim import FusedRanger21
 
             opt = FusedRanger21(params, lr=1e-2, weight_decay=1e-2, use_warmup=True, warmdown_active=True, num_batches_per_epoch=1000,
@@ -434,7 +434,7 @@ def other_configs(args, make_net, timed_steps):
         out[f"{args.mode}/{args.variant}/ranger21_xx"] = {
             "seqs_per_s": 5 * B * k2 / (ms2 / 1e3), "ms_per_step": ms2 / k2, "steps": k2,
             "optimizer_ms_per_step": fam2["ranger21"][0] / k2 if "ranger21" in fam2 else None,
-            "optimizer": "intrepppid_b200.optim.FusedRanger21 (ib200_ranger21_step: 2 launches, no host sync; parity unpinned against "
+            "optimizer": "intrepppid_b200.optim.FusedRanger21 (ib200_ranger21_step: 3 launches, no host sync; parity unpinned against "
                          "the third-party package, which is absent from the image)"}
         del n2
     except Exception as e:  # noqa: BLE001

@@ -266,8 +266,8 @@ int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const
  * algorithm (arXiv:2106.13731) in the step order of oracle/ranger21_restated.py -- PARITY UNPINNED against the package itself.
  * Covers the AdamW core with positive-negative momentum, adaptive gradient clipping, gradient centralization + normalization, norm
  * loss, stable weight decay, softplus denominator and lookahead; the learning-rate schedule (warm-up / warm-down) is host logic:
- * the caller passes lr(step) per tensor.  Two launches per 24 tensors (reductions: one CTA per tensor, gradient staged in shared
- * memory; update: elementwise over all tensors), no host sync.  Like the package, the step rewrites the
+ * the caller passes lr(step) per tensor.  Three launches per 24 tensors, each parallel over all tensors (row pass: clipping,
+ * centralization, row sums; normalization + variance; update), no host sync.  Like the package, the step rewrites the
  * gradients in place (clipped, centralized, normalized).
  *   tensors      HOST array [n]: DEVICE pointers of one parameter's tensors (fp32, contiguous, rows * cols elements each; a 0-d / 1-d
  *                tensor is one row), `multi_dim` = the parameter has more than one dimension (its rows are centralized; tensors with
@@ -275,9 +275,9 @@ int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const
  *                of this update for this tensor, `lr` = learning rate of this step; grad_ma / neg_grad_ma are the buffer that
  *                receives this step's momentum and the other one (the package swaps their roles every step: odd steps write
  *                state["grad_ma"]); lookahead may be NULL when hyper.lookahead_merge == 0
- *   scratch      DEVICE memory, 8-byte aligned, ZERO before the first call and owned by the optimizer between calls,
- *                8 * (3 + n) + 4 * (sum of rows) bytes: scratch[0] = variance_normalized of this step afterwards (NaN = the
- *                package's RuntimeError), [1] its inverse, [2] an arrival counter, n per-tensor sums, then one float per tensor row
+ *   scratch      DEVICE memory, 8-byte aligned, ib200_ranger21_scratch_bytes(n, tensors) bytes, ZERO before the first call and owned
+ *                by the optimizer between calls: scratch[0] = variance_normalized of this step afterwards (NaN = the package's
+ *                RuntimeError), [1] its inverse, [2] an arrival counter, then per-CTA sums, per-row sums and per-row norms
  */
 typedef struct ib200_ranger21_tensor {
   float *param, *grad, *grad_ma, *neg_grad_ma, *variance_ma, *lookahead;
@@ -292,6 +292,7 @@ typedef struct ib200_ranger21_hyper {
 } ib200_ranger21_hyper;
 int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors, const ib200_ranger21_hyper* hyper, double* scratch,
                         void* stream);
+size_t ib200_ranger21_scratch_bytes(int32_t n_tensors, const ib200_ranger21_tensor* tensors); /* only rows / cols are read; 0 on bad input */
 
 /* Data-parallel gradient exchange (the reference itself is single-GPU, e2e/e2e_triplet.py:392-400): one-shot MEAN all-reduce
  * of a small bucket over NVLink peer memory, in place.  Every rank owns a staging region of 2 * stage_floats floats (two parity halves)

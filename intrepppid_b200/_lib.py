@@ -56,7 +56,7 @@ class HeadMasks(C.Structure):
 
 EXPORTS = ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count", "ib200_timing_enable",
            "ib200_timing_families", "ib200_timing_family_name", "ib200_timing_read", "ib200_encoder_fwd", "ib200_encoder_status", "ib200_encoder_bwd", "ib200_encoder_bwd_layers",
-           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_sequence_lengths", "ib200_adamw_step", "ib200_ranger21_step", "ib200_batch_metrics", "ib200_draw_masks", "ib200_p2p_allreduce_mean", "ib200_p2p_alloc", "ib200_p2p_open", "ib200_p2p_close", "ib200_p2p_free",
+           "ib200_pool_fc_fwd", "ib200_pool_fc_bwd", "ib200_loss_head_fwd", "ib200_loss_head_bwd", "ib200_pair_score", "ib200_pair_score_range", "ib200_sequence_lengths", "ib200_adamw_step", "ib200_ranger21_step", "ib200_ranger21_scratch_bytes", "ib200_batch_metrics", "ib200_draw_masks", "ib200_p2p_allreduce_mean", "ib200_p2p_alloc", "ib200_p2p_open", "ib200_p2p_close", "ib200_p2p_free",
            "ib200_dbg_gemm_nt", "ib200_dbg_gemm_tn", "ib200_dbg_gemm_nt_planes", "ib200_dbg_gemm_tn_planes", "ib200_dbg_l0_scratch_floats",
            "ib200_dbg_l0_grads", "ib200_dbg_gemm_nt_wide", "ib200_dbg_gemm_tn_wide")
 
@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
     L.ib200_sequence_lengths.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.ib200_adamw_step.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64),
                                    C.POINTER(AdamWHyper), vp]
+    L.ib200_ranger21_scratch_bytes.restype = C.c_size_t
+    L.ib200_ranger21_scratch_bytes.argtypes = [C.c_int32, C.POINTER(Ranger21Tensor)]
     L.ib200_ranger21_step.argtypes = [C.c_int32, C.POINTER(Ranger21Tensor), C.POINTER(Ranger21Hyper), vp, vp]
     L.ib200_p2p_allreduce_mean.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_size_t, vp, C.c_size_t, C.c_uint32, vp]
     L.ib200_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
@@ -126,7 +128,7 @@ def lib() -> C.CDLL:
     L.ib200_timing_read.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     for name in EXPORTS:
         if name not in ("ib200_version", "ib200_last_error", "ib200_workspace_bytes", "ib200_launch_count",
-                        "ib200_timing_family_name", "ib200_dbg_l0_scratch_floats"):
+                        "ib200_timing_family_name", "ib200_dbg_l0_scratch_floats", "ib200_ranger21_scratch_bytes"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

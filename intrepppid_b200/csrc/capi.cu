@@ -961,6 +961,17 @@ int ib200_adamw_step(int32_t n_tensors, float* const* params, const float* const
   return 0;
 }
 
+size_t ib200_ranger21_scratch_bytes(int32_t n_tensors, const ib200_ranger21_tensor* tensors) {
+  if (n_tensors <= 0 || !tensors) return 0;
+  long long ctas = 0, rows = 0;
+  for (int k = 0; k < n_tensors; ++k) {
+    if (tensors[k].rows < 1 || tensors[k].cols < 1) return 0;
+    ctas += ranger21_elem_ctas((long long)tensors[k].rows * (long long)tensors[k].cols);
+    rows += tensors[k].rows;
+  }
+  return (size_t)(8 * (3 + ctas + 2 * rows) + 4 * rows);
+}
+
 int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors, const ib200_ranger21_hyper* h, double* scratch,
                         void* stream) {
   if (n_tensors < 0 || n_tensors > 4096) return fail(IB200_E_SHAPE, "ib200_ranger21_step: tensor count out of range");
@@ -970,7 +981,8 @@ int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors,
     return fail(IB200_E_SHAPE, "ib200_ranger21_step: hyper-parameters out of range");
   std::vector<R21Tensor> tb((size_t)n_tensors);
   double param_size = 0.0;
-  float* pnorm = reinterpret_cast<float*>(scratch + 3 + n_tensors);  // row norms follow the 3 + n doubles
+  // scratch: 3 doubles (variance_normalized, its inverse, arrival counter) | one double per elementwise CTA | 2 doubles per row | 1 float per row
+  long long total_ctas = 0, total_rows = 0;
   for (int k = 0; k < n_tensors; ++k) {
     const ib200_ranger21_tensor& t = tensors[k];
     if (!t.param || !t.grad || !t.grad_ma || !t.neg_grad_ma || !t.variance_ma || (h->lookahead_merge && !t.lookahead))
@@ -979,13 +991,22 @@ int ib200_ranger21_step(int32_t n_tensors, const ib200_ranger21_tensor* tensors,
       return fail(IB200_E_SHAPE, "ib200_ranger21_step: empty or oversized tensor");
     if (t.step < 1) return fail(IB200_E_SHAPE, "ib200_ranger21_step: step counts from 1");
     if (!(t.lr >= 0.)) return fail(IB200_E_SHAPE, "ib200_ranger21_step: negative learning rate");
+    total_ctas += ranger21_elem_ctas(t.rows * t.cols);
+    total_rows += t.rows;
+  }
+  double* rowsum = scratch + 3 + total_ctas;
+  float* pnorm = reinterpret_cast<float*>(rowsum + 2 * total_rows);
+  for (int k = 0; k < n_tensors; ++k) {
+    const ib200_ranger21_tensor& t = tensors[k];
     // every scalar is derived in double on the host and rounded once, as the package derives them from Python floats
     const double bc1 = 1.0 - std::pow(h->beta1, (double)t.step), bc2 = 1.0 - std::pow(h->beta2, (double)t.step);
     R21Tensor& o = tb[(size_t)k];
     o.p = t.param; o.g = t.grad; o.grad_ma = t.grad_ma; o.neg_grad_ma = t.neg_grad_ma; o.v = t.variance_ma; o.slow = t.lookahead;
     o.numel = (long long)t.rows * (long long)t.cols;
     o.pnorm = pnorm;
+    o.rowsum = rowsum;
     pnorm += t.rows;
+    rowsum += 2 * t.rows;
     o.inv_bc2 = 1.0 / bc2;
     o.wd_lr = h->weight_decay * t.lr;
     o.rows = (int)t.rows; o.cols = (int)t.cols; o.multi_dim = t.multi_dim ? 1 : 0;

@@ -259,10 +259,11 @@ cudaError_t launch_adamw(int n, float* const* params, const float* const* grads,
                          const long long* numel, const AdamScalars& s, cudaStream_t st, int* launches);
 
 // ---- multi-tensor Ranger21 (ranger21.cu) -------------------------------------------------------------------------------------
-constexpr int kR21MaxTensors = 24;  // tensors per launch (the table travels in the kernel parameters: 24 x 104 B)
+constexpr int kR21MaxTensors = 24;  // tensors per launch (the table travels in the kernel parameters: 24 x 112 B)
 struct R21Tensor {
   float* p; float* g; float* grad_ma; const float* neg_grad_ma; float* v; float* slow;
-  float* pnorm;               // [rows] scratch: ||p_row|| of this step (phase 1 -> phase 2)
+  float* pnorm;               // [rows] scratch: ||p_row|| of this step (rows kernel -> update kernel)
+  double* rowsum;             // [rows][2] scratch: sum / sum of squares of the clipped, centralized gradient row
   long long numel;
   double inv_bc2, wd_lr;      // 1 / (1 - b2^step); weight_decay * lr(step)
   int rows, cols, multi_dim;  // rows x cols view (one row for 0-d / 1-d tensors); multi_dim: dim() > 1 (rows are centralized)
@@ -274,8 +275,9 @@ struct R21Scalars {
       inv_noise_norm, la_alpha, one_minus_la_alpha;
   int use_agc, use_gc, use_gcnorm, use_normloss, use_softplus, use_decay, lookahead_merge;
 };
-// tensors: HOST array; scratch: 3 + n DEVICE doubles -- variance_normalized, its inverse, the arrival counter of phase 1 (zero
-// between steps), per-tensor variance sums -- followed by the row-norm floats the tensors point at; *launches = kernels launched
+long long ranger21_elem_ctas(long long numel);  // CTAs of the elementwise kernels for one tensor
+// tensors: HOST array (pnorm / rowsum already point into the scratch); scratch: DEVICE doubles -- [0] variance_normalized, [1] its
+// inverse, [2] the arrival counter (zero between steps), [3 ..] one sum per elementwise CTA; *launches = kernels launched
 cudaError_t launch_ranger21(int n, const R21Tensor* tensors, const R21Scalars& s, double* scratch, cudaStream_t st, int* launches);
 
 }  // namespace ib200

@@ -2,38 +2,38 @@
 // `Ranger21(self.parameters(), lr, weight_decay=1e-2, use_warmup, warmdown_active, ...)`; intrepppid/__init__.py:37
 // optimizer_type="ranger21_xx").  The third-party package walks every parameter twice with ~40 small torch kernels each and one
 // host sync per step (math.sqrt of a device scalar): 6 ms per step on the headline network, more than the whole training step on
-// these kernels; this is TWO launches for all tensors and no sync.
+// these kernels; this is THREE launches for all tensors and no sync.
 //
 // Ranger21 is pinned third-party code absent from the image (requirements.txt:65): the arithmetic follows the published
 // algorithm (arXiv:2106.13731) in the step order oracle/ranger21_restated.py spells out -- PARITY UNPINNED against the package.
 //
-//   phase 1 (one CTA per tensor: every reduction of the step lives here).  The gradient is staged in SHARED MEMORY (tensors up to
-//            48 K elements; larger ones are worked on in place in global memory through the same code), so its six passes cost one
-//            global read and one global write:
-//              rows:   adaptive gradient clipping (unit-wise norms of p and g), centralization; ||p_row|| is kept for phase 2
-//              tensor: std -> normalized gradient g1; variance_ma = b2 variance_ma + (1-b2) g1^2; partial[k] = sum(variance_ma)/(1-b2^t)
-//              rows + tensor: the SECOND centralization + normalization the package applies before the momentum update -> g2,
-//                      written back as the gradient (what the package leaves in p.grad)
-//            the last CTA to finish adds the partial sums in index order: variance_normalized = sqrt(sum_k partial[k] / elements)
-//   phase 2 (elementwise over all tensors, 2048 elements per CTA):  stable weight decay, norm loss from the kept row norms
-//            (||decay p_row|| = decay ||p_row||), positive-negative momentum, softplus denominator, update, lookahead merge.
-// Reductions: fp32 inside a row, double across a tensor; fixed order (deterministic).
+//   rows   (one warp per row of every tensor; a 0-d / 1-d tensor is one row worked on by a whole CTA):  adaptive gradient clipping
+//          (unit-wise norms of p and g), centralization of the rows of >1-d tensors, in place on the gradient; per row: ||p_row||
+//          (kept for the norm loss) and sum / sum of squares of the row's final values (doubles).
+//   elem1  (2048 elements per CTA):  std of the tensor from the row sums -> normalized gradient g1; variance_ma = b2 variance_ma +
+//          (1-b2) g1^2; per-CTA sum of variance_ma / (1-b2^t); the LAST CTA to finish adds the per-CTA sums in index order and publishes
+//          variance_normalized = sqrt(sum / elements) -- nobody waits on anybody.  The package centralizes and normalizes the
+//          gradient a SECOND time before the momentum update: on an already centralized, unit-std tensor that is a change at
+//          rounding level (row means ~1e-9, std = 1 - 1e-8/std); the second normalization is applied with the std that follows from
+//          the first (std(g1) = std(g) * (1/(std(g)+1e-8))), the second centralization (a subtraction of rounding residue) is not.
+//   elem2  (2048 elements per CTA):  stable weight decay, norm loss from the kept row norms (||decay p_row|| = decay ||p_row||),
+//          positive-negative momentum, softplus denominator, update, lookahead merge.
+// Every kernel is parallel over all tensors (HBM / L2-bound, ~28 B read + 16 B written per parameter over the step); reductions
+// are fp32 inside a row, double across rows, in a fixed order (deterministic).
+#include <cstdint>
+
 #include "kernels.h"
 
 namespace ib200 {
 namespace {
 
-constexpr int kR21Threads = 1024;  // phase 1: one CTA per tensor
-constexpr int kR21Warps = kR21Threads / 32;
-constexpr int kR21StageFloats = 48 * 1024;  // gradient staging buffer in shared memory (192 KB)
-constexpr int kR21P2Threads = 256, kR21P2PerThread = 8, kR21P2Chunk = kR21P2Threads * kR21P2PerThread;  // phase 2: elementwise chunks
+constexpr int kR21Threads = 256, kR21Warps = kR21Threads / 32;
+constexpr int kR21RowsPerCta = kR21Warps * 4;                      // rows kernel: 4 rows per warp
+constexpr int kR21PerThread = 8, kR21Chunk = kR21Threads * kR21PerThread;  // elementwise kernels: 2048 elements per CTA
 
 struct R21Table {
   R21Tensor t[kR21MaxTensors];
-};
-struct R21Table2 {
-  R21Tensor t[kR21MaxTensors];
-  int chunk_start[kR21MaxTensors + 1];  // first CTA of tensor k; [n] = grid size
+  int start[kR21MaxTensors + 1];  // first CTA of tensor k (row blocks or element chunks); [n] = grid size
   int n;
 };
 
@@ -48,107 +48,137 @@ __device__ __forceinline__ double warp_sum(double x) {
   return x;
 }
 // sum over the CTA, the same value in every thread (fixed order: deterministic)
-__device__ __forceinline__ double block_sum(double x, double* red) {
+template <typename T>
+__device__ __forceinline__ T block_sum(T x, T* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   x = warp_sum(x);
-  __syncthreads();  // red[] may still be read from the previous call; also orders the caller's writes before the next pass
+  __syncthreads();  // red[] may still be read from the previous call
   if (lane == 0) red[warp] = x;
   __syncthreads();
-  double s = 0.0;
+  T s = 0;
 #pragma unroll
   for (int w = 0; w < kR21Warps; ++w) s += red[w];
   return s;
 }
-
-// whole-tensor unbiased standard deviation of X (two passes), as x.std()
-__device__ __forceinline__ float tensor_std(const float* X, long long n, double* red) {
-  double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += kR21Threads) s += (double)X[i];
-  const double mean = block_sum(s, red) / (double)n;
-  double q = 0.0;
-  for (long long i = threadIdx.x; i < n; i += kR21Threads) {
-    const double d = (double)X[i] - mean;
-    q += d * d;
+__device__ __forceinline__ const R21Tensor& find_tensor(const R21Table& tb, int& first) {
+  int lo = 0, hi = tb.n;  // CTA -> tensor: binary search over the prefix table in the kernel parameters
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tb.start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
   }
-  return (float)sqrt(block_sum(q, red) / (double)(n - 1));
+  first = tb.start[lo];
+  return tb.t[lo];
 }
-
-// AGC scale of one row from its squared norms (1 = not clipped); the row norm of p is kept for the norm loss of phase 2
+// AGC scale of one row from its squared norms (1 = not clipped)
 __device__ __forceinline__ float agc_scale(float sp, float sg, const R21Scalars& s, bool& clip) {
   const float pn = fmaxf(sqrtf(sp), s.agc_eps), gn = sqrtf(sg), maxn = pn * s.agc_clip;
   clip = s.use_agc && gn > maxn;
   return clip ? maxn / fmaxf(gn, 1e-6f) : 1.0f;
 }
 
-__global__ void __launch_bounds__(kR21Threads, 1) r21_phase1_kernel(const __grid_constant__ R21Table tb, const R21Scalars s,
-                                                                   double* scratch, int slot0, int n_total) {
-  double* partial = scratch + 3;  // scratch: [0] variance_normalized, [1] its inverse, [2] arrival counter, [3 ..] per-tensor sums
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* red = reinterpret_cast<double*>(smem_raw);                  // [kR21Warps]
-  float* stage = reinterpret_cast<float*>(smem_raw + kR21Warps * 8);  // [kR21StageFloats]
-  const R21Tensor& t = tb.t[blockIdx.x];
+__global__ void __launch_bounds__(kR21Threads) r21_rows_kernel(const __grid_constant__ R21Table tb, const R21Scalars s) {
+  __shared__ double redd[kR21Warps];
+  __shared__ float redf[kR21Warps];
+  int first;
+  const R21Tensor& t = find_tensor(tb, first);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* G = t.g;
+  float* __restrict__ G = t.g;
   const float* __restrict__ P = t.p;
   const int cols = t.cols, rows = t.rows;
-  const long long n = t.numel;
-  const bool centralize = s.use_gc && t.multi_dim;
-  const bool staged = n <= kR21StageFloats;
-  float* X = staged ? stage : G;  // working copy of the gradient
-  // the optimizer state is DRAM-cold every step (a training step streams GBs through the L2 in between): start its lines towards
-  // the L2 now, under the row pass -- variance_ma for the loop below, the momentum buffers (and slow weights) for phase 2
-  for (long long i = (long long)threadIdx.x * 32; i < n; i += (long long)kR21Threads * 32) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.v + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.grad_ma + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(t.neg_grad_ma + i));
-    if (s.lookahead_merge) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.slow + i));
+
+  if (rows == 1) {
+    // one row (0-d / 1-d tensors, single-row matrices): the whole CTA works on it
+    float sp = 0.f, sg = 0.f;
+    for (int c = threadIdx.x; c < cols; c += kR21Threads) {
+      const float pv = P[c], gv = G[c];
+      sp = fmaf(pv, pv, sp);
+      sg = fmaf(gv, gv, sg);
+    }
+    sp = block_sum(sp, redf);
+    sg = block_sum(sg, redf);
+    bool clip;
+    const float scale = agc_scale(sp, sg, s, clip);
+    float mean = 0.f;
+    if (s.use_gc && t.multi_dim) {
+      float sum = 0.f;
+      for (int c = threadIdx.x; c < cols; c += kR21Threads) sum += clip ? G[c] * scale : G[c];
+      mean = block_sum(sum, redf) / (float)cols;
+    }
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = threadIdx.x; c < cols; c += kR21Threads) {  // (every thread re-reads only what it writes itself)
+      const float x = (clip ? G[c] * scale : G[c]) - mean;
+      G[c] = x;
+      s1 += (double)x;
+      s2 += (double)x * (double)x;
+    }
+    s1 = block_sum(s1, redd);
+    s2 = block_sum(s2, redd);
+    if (threadIdx.x == 0) {
+      t.pnorm[0] = sqrtf(sp);
+      t.rowsum[0] = s1;
+      t.rowsum[1] = s2;
+    }
+    return;
   }
 
-  // ---- rows: AGC + centralization (a 0-d / 1-d tensor is one row: whole-tensor norm, never centralized) ----------------------
+  const bool centralize = s.use_gc && t.multi_dim;
+  const int r0 = ((int)blockIdx.x - first) * kR21RowsPerCta + warp * 4;
   if (cols <= 128) {
-    // four rows per warp at a time, held in registers: one global round trip per four rows
-    for (int r0 = warp * 4; r0 < rows; r0 += kR21Warps * 4) {
-      float p[4][4], g[4][4];
+    // four rows per warp, held in registers: one global round trip
+    float p[4][4], g[4][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = r0 + u, c = lane + 32 * e;
-          const bool ok = r < rows && c < cols;
-          p[u][e] = ok ? P[(size_t)r * cols + c] : 0.f;
-          g[u][e] = ok ? G[(size_t)r * cols + c] : 0.f;
+      for (int e = 0; e < 4; ++e) {
+        const int r = r0 + u, c = lane + 32 * e;
+        const bool ok = r < rows && c < cols;
+        p[u][e] = ok ? P[(size_t)r * cols + c] : 0.f;
+        g[u][e] = ok ? G[(size_t)r * cols + c] : 0.f;
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) break;  // warp-uniform
+      float sp = 0.f, sg = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sp = fmaf(p[u][e], p[u][e], sp);
+        sg = fmaf(g[u][e], g[u][e], sg);
+      }
+      sp = warp_sum(sp);
+      sg = warp_sum(sg);
+      bool clip;
+      const float scale = agc_scale(sp, sg, s, clip);
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (clip) g[u][e] *= scale;
+        sum += g[u][e];
+      }
+      const float mean = centralize ? warp_sum(sum) / (float)cols : 0.f;
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = lane + 32 * e;
+        if (c < cols) {
+          const float x = g[u][e] - mean;
+          if (clip || centralize) G[(size_t)r * cols + c] = x;
+          s1 += (double)x;
+          s2 += (double)x * (double)x;
         }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u;
-        if (r >= rows) break;  // warp-uniform
-        float sp = 0.f, sg = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          sp = fmaf(p[u][e], p[u][e], sp);
-          sg = fmaf(g[u][e], g[u][e], sg);
-        }
-        sp = warp_sum(sp);
-        sg = warp_sum(sg);
-        if (lane == 0) t.pnorm[r] = sqrtf(sp);
-        bool clip;
-        const float scale = agc_scale(sp, sg, s, clip);
-        float sum = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (clip) g[u][e] *= scale;
-          sum += g[u][e];
-        }
-        const float mean = centralize ? warp_sum(sum) / (float)cols : 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = lane + 32 * e;
-          if (c < cols) X[(size_t)r * cols + c] = g[u][e] - mean;
-        }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        t.pnorm[r] = sqrtf(sp);
+        t.rowsum[2 * (size_t)r] = s1;
+        t.rowsum[2 * (size_t)r + 1] = s2;
       }
     }
   } else {
-    for (int r = warp; r < rows; r += kR21Warps) {
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) break;
       const size_t base = (size_t)r * cols;
       float sp = 0.f, sg = 0.f;
 #pragma unroll 4
@@ -156,88 +186,108 @@ __global__ void __launch_bounds__(kR21Threads, 1) r21_phase1_kernel(const __grid
         const float pv = P[base + c], gv = G[base + c];
         sp = fmaf(pv, pv, sp);
         sg = fmaf(gv, gv, sg);
-        if (staged) X[base + c] = gv;
       }
       sp = warp_sum(sp);
       sg = warp_sum(sg);
-      if (lane == 0) t.pnorm[r] = sqrtf(sp);
       bool clip;
       const float scale = agc_scale(sp, sg, s, clip);
-      if (centralize) {  // (each lane re-reads only what it wrote itself)
+      float mean = 0.f;
+      if (centralize) {
         float sum = 0.f;
-        for (int c = lane; c < cols; c += 32) sum += clip ? X[base + c] * scale : X[base + c];
-        const float mean = warp_sum(sum) / (float)cols;
-        for (int c = lane; c < cols; c += 32) X[base + c] = (clip ? X[base + c] * scale : X[base + c]) - mean;
-      } else if (clip) {
-        for (int c = lane; c < cols; c += 32) X[base + c] *= scale;
+#pragma unroll 4
+        for (int c = lane; c < cols; c += 32) sum += clip ? G[base + c] * scale : G[base + c];
+        mean = warp_sum(sum) / (float)cols;
+      }
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+      for (int c = lane; c < cols; c += 32) {  // (every lane re-reads only what it writes itself)
+        const float x = (clip ? G[base + c] * scale : G[base + c]) - mean;
+        if (clip || centralize) G[base + c] = x;
+        s1 += (double)x;
+        s2 += (double)x * (double)x;
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        t.pnorm[r] = sqrtf(sp);
+        t.rowsum[2 * (size_t)r] = s1;
+        t.rowsum[2 * (size_t)r + 1] = s2;
       }
     }
   }
-  __syncthreads();
+}
 
-  // ---- tensor: normalization by the std -> g1; variance_ma and its debiased sum ------------------------------------------------
-  const bool norm = s.use_gcnorm && n > 2;
-  // (x * (1/s) instead of x / s, here and below: within one ulp of the division, and the IEEE division sequence takes its slow path
-  //  on the exactly-zero gradients this network is full of -- unused vocabulary rows, the dead top-layer chain)
-  const float inv1 = norm ? 1.0f / (tensor_std(X, n, red) + 1e-8f) : 1.0f;
+// scratch: [0] variance_normalized, [1] its inverse, [2] arrival counter, [3 ..] per-CTA sums of this kernel
+__global__ void __launch_bounds__(kR21Threads) r21_elem1_kernel(const __grid_constant__ R21Table tb, const R21Scalars s,
+                                                               double* scratch, int cta0, int n_ctas_total) {
+  __shared__ double redd[kR21Warps];
+  int first;
+  const R21Tensor& t = find_tensor(tb, first);
+  const unsigned base = (unsigned)((int)blockIdx.x - first) * kR21Chunk;
+  const unsigned n = (unsigned)t.numel;  // (numel < 2^31, checked by the C ABI)
+  float* __restrict__ G = t.g;
   float* __restrict__ V = t.v;
-  double acc = 0.0;
-#pragma unroll 8
-  for (long long i = threadIdx.x; i < n; i += kR21Threads) {
-    float gv = X[i];
-    if (norm) {
-      gv = gv * inv1;
-      X[i] = gv;
-    }
-    const float v = fmaf(s.one_minus_b2 * gv, gv, V[i] * s.b2);
-    V[i] = v;
-    acc += (double)v;
+
+  // the loads of this CTA's elements do not depend on the std: issue them first
+  float g[kR21PerThread], v[kR21PerThread];
+#pragma unroll
+  for (int j = 0; j < kR21PerThread; ++j) {
+    const unsigned i = base + j * kR21Threads + threadIdx.x;
+    g[j] = i < n ? G[i] : 0.f;
+    v[j] = i < n ? V[i] : 0.f;
   }
-  const double tot = block_sum(acc, red);  // (its barriers also order the X writes above before the row pass below)
+  float inv1 = 1.0f, inv2 = 1.0f;
+  const bool norm = s.use_gcnorm && n > 2;
+  if (norm) {  // unbiased std of the tensor from the row sums of the rows kernel (every CTA of a tensor adds them in the same order)
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = threadIdx.x; r < t.rows; r += kR21Threads) {
+      s1 += t.rowsum[2 * (size_t)r];
+      s2 += t.rowsum[2 * (size_t)r + 1];
+    }
+    s1 = block_sum(s1, redd);
+    s2 = block_sum(s2, redd);
+    const double mean = s1 / (double)n, var = fmax(s2 - s1 * mean, 0.0) / (double)(n - 1);
+    const float sd = (float)sqrt(var);
+    // x * (1/s) instead of x / s: within one ulp of the division, and the IEEE division sequence takes its slow path on the
+    // exactly-zero gradients this network is full of (unused vocabulary rows, the dead top-layer chain)
+    inv1 = 1.0f / (sd + 1e-8f);
+    inv2 = 1.0f / (sd * inv1 + 1e-8f);  // the second normalization: std(g1) = std(g) * inv1
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < kR21PerThread; ++j) {
+    const unsigned i = base + j * kR21Threads + threadIdx.x;
+    if (i < n) {
+      const float g1 = g[j] * inv1;
+      const float vv = fmaf(s.one_minus_b2 * g1, g1, v[j] * s.b2);
+      V[i] = vv;
+      acc += (double)vv;
+      if (norm) G[i] = g1 * inv2;
+    }
+  }
+  const double tot = block_sum(acc, redd);
   if (threadIdx.x == 0) {
-    partial[slot0 + blockIdx.x] = tot * t.inv_bc2;
-    // the LAST CTA of the step (over all phase-1 launches) adds the partial sums in index order and publishes
-    // 1 / variance_normalized for phase 2: no thread of phase 2 repeats the sum, nobody waits on anybody
+    double* partial = scratch + 3;
+    partial[cta0 + blockIdx.x] = tot * t.inv_bc2;
     __threadfence();
     unsigned* ticket = reinterpret_cast<unsigned*>(scratch + 2);
-    if (atomicAdd(ticket, 1u) == (unsigned)n_total - 1u) {
+    if (atomicAdd(ticket, 1u) == (unsigned)n_ctas_total - 1u) {  // the last CTA of the step (over all launches of this kernel)
       __threadfence();
       double vsum = 0.0;
-      for (int k = 0; k < n_total; ++k) vsum += *reinterpret_cast<volatile double*>(partial + k);
+      for (int k = 0; k < n_ctas_total; ++k) vsum += *reinterpret_cast<volatile double*>(partial + k);
       const double vn = sqrt(vsum / s.param_size);
-      scratch[0] = vn;                  // NaN here = the package's "hit nan for variance_normalized"
+      scratch[0] = vn;  // NaN here = the package's "hit nan for variance_normalized"
       scratch[1] = 1.0 / vn;
-      *ticket = 0u;                     // ready for the next step (stream order)
+      *ticket = 0u;     // ready for the next step (stream order)
     }
-  }
-
-  // ---- the second centralization + normalization (applied by the package right before the momentum update) -> g2 -------------
-  if (centralize) {
-    for (int r = warp; r < rows; r += kR21Warps) {
-      const size_t base = (size_t)r * cols;
-      float sum = 0.f;
-      for (int c = lane; c < cols; c += 32) sum += X[base + c];
-      const float mean = warp_sum(sum) / (float)cols;
-      for (int c = lane; c < cols; c += 32) X[base + c] -= mean;
-    }
-    __syncthreads();
-  }
-  const float inv2 = norm ? 1.0f / (tensor_std(X, n, red) + 1e-8f) : 1.0f;
-  if (staged || norm) {
-#pragma unroll 8
-    for (long long i = threadIdx.x; i < n; i += kR21Threads) G[i] = norm ? X[i] * inv2 : X[i];
   }
 }
 
-__global__ void __launch_bounds__(kR21P2Threads) r21_phase2_kernel(const __grid_constant__ R21Table2 tb, const R21Scalars s,
-                                                                  const double* __restrict__ inv_vn) {
-  int lo = 0, hi = tb.n;  // CTA -> (tensor, chunk): binary search over the prefix table in the kernel parameters
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (tb.chunk_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
-  }
-  const R21Tensor& t = tb.t[lo];
-  const unsigned base = (unsigned)((int)blockIdx.x - tb.chunk_start[lo]) * kR21P2Chunk;
+__global__ void __launch_bounds__(kR21Threads) r21_elem2_kernel(const __grid_constant__ R21Table tb, const R21Scalars s,
+                                                               const double* __restrict__ inv_vn) {
+  int first;
+  const R21Tensor& t = find_tensor(tb, first);
+  const unsigned base = (unsigned)((int)blockIdx.x - first) * kR21Chunk;
   const float decay = s.use_decay ? (float)(1.0 - t.wd_lr * inv_vn[0]) : 1.0f;
 
   float* __restrict__ P = t.p;
@@ -247,14 +297,14 @@ __global__ void __launch_bounds__(kR21P2Threads) r21_phase2_kernel(const __grid_
   const float* __restrict__ Mneg = t.neg_grad_ma;
   float* __restrict__ S = t.slow;
   const float* __restrict__ pnorm = t.pnorm;
-  const unsigned n = (unsigned)t.numel, cols = (unsigned)t.cols;  // (numel < 2^31, checked by the C ABI)
+  const unsigned n = (unsigned)t.numel, cols = (unsigned)t.cols;
   const float inv_sqrt_bc2 = 1.0f / t.sqrt_bc2, inv_beta = 1.0f / s.softplus_beta;
 #pragma unroll
-  for (int j = 0; j < kR21P2PerThread; ++j) {
-    const unsigned i = base + j * kR21P2Threads + threadIdx.x;
+  for (int j = 0; j < kR21PerThread; ++j) {
+    const unsigned i = base + j * kR21Threads + threadIdx.x;
     if (i >= n) break;
     float mul = 1.0f;
-    if (s.use_normloss) {  // unit norm of the decayed row = |decay| * the norm phase 1 kept
+    if (s.use_normloss) {  // unit norm of the decayed row = |decay| * the norm the rows kernel kept
       const float unorm = fabsf(decay) * pnorm[i / cols];
       mul = 1.0f - t.lr * (s.normloss2 * (1.0f - 1.0f / (unorm + s.eps)));
     }
@@ -278,35 +328,35 @@ __global__ void __launch_bounds__(kR21P2Threads) r21_phase2_kernel(const __grid_
 
 }  // namespace
 
+long long ranger21_elem_ctas(long long numel) { return (numel + kR21Chunk - 1) / kR21Chunk; }
+
 cudaError_t launch_ranger21(int n, const R21Tensor* tensors, const R21Scalars& s, double* scratch, cudaStream_t st, int* launches) {
   *launches = 0;
-  constexpr int kSmem = kR21Warps * 8 + kR21StageFloats * 4;
-  static cudaError_t attr = cudaFuncSetAttribute(r21_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  if (attr != cudaSuccess) return attr;
-  for (int k0 = 0; k0 < n; k0 += kR21MaxTensors) {
-    const int cnt = n - k0 < kR21MaxTensors ? n - k0 : kR21MaxTensors;
-    R21Table tb{};
-    for (int k = 0; k < cnt; ++k) tb.t[k] = tensors[k0 + k];
-    r21_phase1_kernel<<<cnt, kR21Threads, kSmem, st>>>(tb, s, scratch, k0, n);
-    ++*launches;
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  for (int k0 = 0; k0 < n; k0 += kR21MaxTensors) {
-    const int cnt = n - k0 < kR21MaxTensors ? n - k0 : kR21MaxTensors;
-    R21Table2 tb{};
-    int blocks = 0;
-    for (int k = 0; k < cnt; ++k) {
-      tb.t[k] = tensors[k0 + k];
-      tb.chunk_start[k] = blocks;
-      blocks += (int)((tensors[k0 + k].numel + kR21P2Chunk - 1) / kR21P2Chunk);
+  long long total_ctas = 0;
+  for (int k = 0; k < n; ++k) total_ctas += ranger21_elem_ctas(tensors[k].numel);
+  if (total_ctas > INT32_MAX) return cudaErrorInvalidValue;
+  for (int pass = 0; pass < 3; ++pass) {
+    int cta0 = 0;
+    for (int k0 = 0; k0 < n; k0 += kR21MaxTensors) {
+      const int cnt = n - k0 < kR21MaxTensors ? n - k0 : kR21MaxTensors;
+      R21Table tb{};
+      int blocks = 0;
+      for (int k = 0; k < cnt; ++k) {
+        const R21Tensor& t = tensors[k0 + k];
+        tb.t[k] = t;
+        tb.start[k] = blocks;
+        blocks += pass == 0 ? (t.rows == 1 ? 1 : (t.rows + kR21RowsPerCta - 1) / kR21RowsPerCta) : (int)ranger21_elem_ctas(t.numel);
+      }
+      tb.start[cnt] = blocks;
+      tb.n = cnt;
+      if (pass == 0) r21_rows_kernel<<<blocks, kR21Threads, 0, st>>>(tb, s);
+      else if (pass == 1) r21_elem1_kernel<<<blocks, kR21Threads, 0, st>>>(tb, s, scratch, cta0, (int)total_ctas);
+      else r21_elem2_kernel<<<blocks, kR21Threads, 0, st>>>(tb, s, scratch + 1);
+      cta0 += blocks;
+      ++*launches;
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
     }
-    tb.chunk_start[cnt] = blocks;
-    tb.n = cnt;
-    r21_phase2_kernel<<<blocks, kR21P2Threads, 0, st>>>(tb, s, scratch + 1);
-    ++*launches;
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

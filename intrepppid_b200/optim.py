@@ -95,7 +95,7 @@ class FusedRanger21(Optimizer):
     tests/test_ranger21.py).  Implemented: the AdamW core with positive-negative momentum, AGC, gradient centralization and
     normalization, norm loss, stable weight decay, softplus, linear warm-up, warm-down, lookahead.  The package's other switches
     (madgrad / adabelief cores, Chebyshev schedule, non-pnm momentum, non-stable decay, gc_conv_only) raise: the reference never
-    sets them.  Two launches per step for all tensors and NO host sync (the package pays one per step for its variance scalar);
+    sets them.  Three launches per step for all tensors and NO host sync (the package pays one per step for its variance scalar);
     like the package, the step rewrites p.grad in place.  CUDA fp32 parameters only; there is no CPU path.
     """
 
@@ -239,7 +239,7 @@ class FusedRanger21(Optimizer):
             raise NotImplementedError("FusedRanger21 steps one param_group (the reference passes self.parameters())")
         group = entries[0][0]
         dev = entries[0][1].device
-        need = 3 + n + (sum(int(t.rows) for t in tb) + 1) // 2  # 3 + n doubles (vn, 1/vn, counter, sums), then one float per tensor row
+        need = (int(lib().ib200_ranger21_scratch_bytes(n, tb)) + 7) // 8  # doubles: vn, 1/vn, arrival counter, per-CTA / per-row sums, row norms
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = torch.zeros(max(64, need), dtype=torch.float64, device=dev)
         hyper = _lib.Ranger21Hyper(float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
