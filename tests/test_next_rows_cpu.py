@@ -86,9 +86,10 @@ def _ragged_tokens(M, T, V, seed):
 
 
 def test_batch1_lengths_have_no_cpu_path():
-    from intrepppid_b200 import _lib
+    from intrepppid_b200 import _lib, build
     from intrepppid_b200.infer import batch1_lengths
 
+    build.build()  # (no-op when libib200.so is current)
     with pytest.raises(_lib.IB200Error):  # (the per-sequence parity against the oracle runs on the GPU: tests/test_gpu_next_rows.py)
         batch1_lengths(_ragged_tokens(8, 10, 30, 2), torch.randn(30, 32))
     lib = _lib.lib()

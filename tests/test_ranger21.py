@@ -126,7 +126,9 @@ def test_against_the_ranger21_package_when_it_is_importable():
 # ---- CPU: the product's host side ----------------------------------------------------------------------------------------------------
 def test_fused_ranger21_host_contract():
     import intrepppid_b200 as ib
-    from intrepppid_b200 import _lib
+    from intrepppid_b200 import _lib, build
+
+    build.build()  # (no-op when libib200.so is current)
 
     w = [torch.nn.Parameter(torch.randn(4, 4))]
     with pytest.raises(ValueError):
@@ -156,9 +158,10 @@ def test_fused_ranger21_host_contract():
 def test_ranger21_abi_rejects_bad_arguments_on_the_host():
     import ctypes as C
 
-    from intrepppid_b200 import _lib
+    from intrepppid_b200 import _lib, build
     from intrepppid_b200._lib import Ranger21Hyper, Ranger21Tensor
 
+    build.build()
     lib = _lib.lib()
     h = Ranger21Hyper(0.9, 0.999, 1e-8, 1e-2, 1e-2, 1e-3, 1e-4, 50.0, 1.0, 0.5, 1, 1, 1, 1, 1, 0)
     assert lib.ib200_ranger21_step(0, None, C.byref(h), None, None) == 0
