@@ -298,3 +298,19 @@ def test_fused_ranger21_state_dict_round_trip_continues_the_run():
     for pa, pb in zip(a, b):
         assert torch.equal(pa.detach(), pb.detach())
     assert ob.state[b[0]]["step"] == 9
+
+
+def test_second_centralization_and_normalization_are_rounding_level():
+    """The kernels apply the package's SECOND centralization + normalization of the gradient analytically (csrc/ranger21.cu, elem1):
+    on an already centralized, unit-std tensor the second centralization subtracts rounding residue and the second std follows from
+    the first, std(g1) = std(g) / (std(g) + 1e-8).  Checked here in fp32 against the literal two-pass sequence."""
+    g = torch.Generator().manual_seed(7)
+    for shape in [(256, 64), (250, 64), (256,), (3,), (64, 128), (5, 3, 2, 2)]:
+        x = torch.randn(shape, generator=g) * 0.03
+        lit = RR.normalize_(RR.centralize_(RR.normalize_(RR.centralize_(x.clone()))))        # what the package leaves in p.grad
+        gc = RR.centralize_(x.clone())
+        sd = gc.double().std().float()
+        inv1 = 1.0 / (sd + 1e-8)
+        inv2 = 1.0 / (sd * inv1 + 1e-8)
+        mine = (gc * inv1) * inv2
+        assert rel_l2(mine, lit) < 5e-7, (shape, rel_l2(mine, lit))
